@@ -1,0 +1,42 @@
+// Host-side builders for the tcgen05 conv kernels: tensor maps, tile shapes, tap tables, launches.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/cilrs_b200.h"
+
+namespace cilrs {
+
+struct ConvGemmParams;
+struct WgradParams;
+
+struct BoxShape {
+  int BW, BH, BN;
+  int tiles_w, tiles_h, tiles_n;
+  int m_tiles() const { return tiles_w * tiles_h * tiles_n; }
+};
+// tile of <= 128 output pixels as a (BW x BH x BN) box of the (OW, OH, batch) output volume
+BoxShape choose_box(int ow, int oh, int batch);
+
+int encode_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long stride_w_bytes,
+                    long long stride_h_bytes, long long stride_n_bytes, int box_c, int bw, int bh, int bn, int sw, int sh);
+int encode_2d_map(CUtensorMap* m, const void* base, int inner, int rows, int box_inner, int box_rows);
+
+// ---- plan builders (fill kernel parameter blocks; no launches) ----
+int build_fprop(ConvGemmParams* p, const cilrs_conv_desc* d, const void* x, const void* w, void* y, const float* scale,
+                const float* bias, const void* residual, float* stats, int flags);
+int build_stem_fprop(ConvGemmParams* p, int batch, const void* x_s2d, const void* w, void* y, const float* scale,
+                     const float* bias, float* stats, int flags);
+// stride-1 dgrad: one plan. stride-2: parity (ph, pw) plan; `dy2/w2` optionally fuse the 1x1/2 downsample dgrad
+// into parity (0,0) as an extra tap.
+int build_dgrad(ConvGemmParams* p, const cilrs_conv_desc* d, int ph, int pw, const void* dy, const void* w_dgrad,
+                void* dx, const void* residual, const void* dy2, const void* w2_dgrad);
+int build_wgrad(WgradParams* p, const cilrs_conv_desc* d, const void* dy, const void* x, float* dw);
+int build_stem_wgrad(WgradParams* p, int batch, const void* dy, const void* x_s2d, float* dw);
+
+int launch_conv_gemm(const ConvGemmParams* p, cudaStream_t s);
+int launch_wgrad(const WgradParams* p, cudaStream_t s);
+int conv_out_dim(int in, int k, int stride, int pad);
+
+}  // namespace cilrs

@@ -1,0 +1,181 @@
+// K0: frame preprocessing.
+//   cv2.resize(image, (dst_w, dst_h))  [INTER_LINEAR on uint8 = OpenCV's 11-bit fixed-point bilinear]
+//   -> /255 -> HWC->CHW -> (x - mean) / std            (reference: model/autonomous_drive.py:897-902)
+// One CTA per (frame, output row): the two source rows that output row needs are staged in shared memory with
+// 16-byte coalesced loads, each thread then produces one output pixel (3 channels) in the three output layouts.
+// HBM-bound: only the touched source rows are read (176 of 600 for the 600x800 -> 88x200 case).
+#include "common.cuh"
+#include "../../include/cilrs_b200.h"
+
+namespace cilrs {
+
+struct AxisCoef {
+  int s0, s1;   // source indices
+  int a0, a1;   // 11-bit fixed point weights (sum 2048)
+};
+
+// OpenCV resize (imgproc/src/resize.cpp, INTER_LINEAR, 8u): fx = (float)((d + 0.5) * scale - 0.5); s = floor(fx); fx -= s;
+// clamp; coefficients = cvRound(w * 2048) as short.
+CILRS_DEVINL AxisCoef axis_coef(int d, int ssize, double scale) {
+  const double t = __dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
+  float f = (float)t;
+  int s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  if (s < 0) { s = 0; f = 0.f; }
+  if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+  AxisCoef c;
+  c.s0 = s;
+  c.s1 = min(s + 1, ssize - 1);
+  c.a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  c.a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  return c;
+}
+
+struct PreParams {
+  const uint8_t* src;
+  int batch, src_h, src_w, src_c, reverse, dst_h, dst_w;
+  double scale_x, scale_y;
+  uint8_t* dst_u8;
+  float* dst_f32;
+  __nv_bfloat16* dst_s2d;
+};
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
+  extern __shared__ __align__(16) uint8_t rows[];  // [2][row_bytes_padded]
+  const int dy = blockIdx.x % p.dst_h;
+  const int n = blockIdx.x / p.dst_h;
+  const int row_bytes = p.src_w * p.src_c;
+  const int row_pad = (row_bytes + 15) & ~15;
+  const AxisCoef cy = axis_coef(dy, p.src_h, p.scale_y);
+  const uint8_t* img = p.src + (size_t)n * p.src_h * row_bytes;
+  const uint8_t* r0 = img + (size_t)cy.s0 * row_bytes;
+  const uint8_t* r1 = img + (size_t)cy.s1 * row_bytes;
+  if ((row_bytes & 15) == 0 && (((uintptr_t)p.src) & 15) == 0) {
+    const int nv = row_bytes >> 4;
+    for (int i = threadIdx.x; i < 2 * nv; i += blockDim.x) {
+      const int which = i >= nv;
+      const int j = which ? i - nv : i;
+      const uint4 v = __ldg((const uint4*)(which ? r1 : r0) + j);
+      *((uint4*)(rows + which * row_pad) + j) = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < 2 * row_bytes; i += blockDim.x) {
+      const int which = i >= row_bytes;
+      const int j = which ? i - row_bytes : i;
+      rows[which * row_pad + j] = (which ? r1 : r0)[j];
+    }
+  }
+  __syncthreads();
+
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (int dx = threadIdx.x; dx < p.dst_w; dx += blockDim.x) {
+    const AxisCoef cx = axis_coef(dx, p.src_w, p.scale_x);
+    uint8_t o[3];
+    float f[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int sc = p.reverse ? 2 - c : c;
+      const int h0 = rows[cx.s0 * p.src_c + sc] * cx.a0 + rows[cx.s1 * p.src_c + sc] * cx.a1;
+      const int h1 = rows[row_pad + cx.s0 * p.src_c + sc] * cx.a0 + rows[row_pad + cx.s1 * p.src_c + sc] * cx.a1;
+      const int v = (((cy.a0 * (h0 >> 4)) >> 16) + ((cy.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      o[c] = (uint8_t)v;
+      f[c] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), mean[c]), stdv[c]);
+    }
+    if (p.dst_u8) {
+      uint8_t* d = p.dst_u8 + (((size_t)n * p.dst_h + dy) * p.dst_w + dx) * 3;
+      d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
+    }
+    if (p.dst_f32) {
+      const size_t plane = (size_t)p.dst_h * p.dst_w;
+      float* d = p.dst_f32 + (size_t)n * 3 * plane + (size_t)dy * p.dst_w + dx;
+      d[0] = f[0]; d[plane] = f[1]; d[2 * plane] = f[2];
+    }
+    if (p.dst_s2d) {
+      const int y = dy + 3, x = dx + 3;
+      uint2 v;
+      v.x = pack_bf16x2(f[0], f[1]);
+      v.y = pack_bf16x2(f[2], 0.f);
+      *(uint2*)(p.dst_s2d + (((size_t)n * 47 + (y >> 1)) * 103 + (x >> 1)) * 16 + (y & 1) * 8 + (x & 1) * 4) = v;
+    }
+  }
+  if (p.dst_s2d) {
+    // zero padding of the 94 x 206 padded frame: 3 columns each side of this row, and whole rows 0-2 / 91-93
+    const uint2 z = make_uint2(0u, 0u);
+    const int y = dy + 3;
+    if (threadIdx.x < 6) {
+      const int x = threadIdx.x < 3 ? threadIdx.x : 200 + threadIdx.x;
+      *(uint2*)(p.dst_s2d + (((size_t)n * 47 + (y >> 1)) * 103 + (x >> 1)) * 16 + (y & 1) * 8 + (x & 1) * 4) = z;
+    }
+    if (dy == 0 || dy == p.dst_h - 1) {
+      const int ybase = dy == 0 ? 0 : 91;
+      for (int i = threadIdx.x; i < 3 * 206; i += blockDim.x) {
+        const int yy = ybase + i / 206, x = i % 206;
+        *(uint2*)(p.dst_s2d + (((size_t)n * 47 + (yy >> 1)) * 103 + (x >> 1)) * 16 + (yy & 1) * 8 + (x & 1) * 4) = z;
+      }
+    }
+  }
+}
+
+// image f32 NCHW [B,3,88,200] -> bf16 space-to-depth [B,47,103,16] (zero padded: 3 px each side, 4th channel 0)
+__global__ void __launch_bounds__(256) image_to_s2d_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ dst, int batch) {
+  // one thread per padded pixel (y in [0,94), x in [0,206)) -> 8-byte store
+  const long long total = (long long)batch * 94 * 206;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % 206);
+    const int y = (int)((i / 206) % 94);
+    const int n = (int)(i / (206 * 94));
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+    if (y >= 3 && y < 91 && x >= 3 && x < 203) {
+      const float* s = img + (size_t)n * 3 * 17600 + (size_t)(y - 3) * 200 + (x - 3);
+      f0 = __ldg(s); f1 = __ldg(s + 17600); f2 = __ldg(s + 35200);
+    }
+    uint2 v;
+    v.x = pack_bf16x2(f0, f1);
+    v.y = pack_bf16x2(f2, 0.f);
+    *(uint2*)(dst + (((size_t)n * 47 + (y >> 1)) * 103 + (x >> 1)) * 16 + (y & 1) * 8 + (x & 1) * 4) = v;
+  }
+}
+
+}  // namespace cilrs
+
+using namespace cilrs;
+
+extern "C" {
+
+int cilrs_preprocess_u8(const uint8_t* src, int batch, int src_h, int src_w, int src_c, int reverse, int dst_h, int dst_w,
+                        uint8_t* dst_u8, float* dst_f32, void* dst_s2d, void* stream) {
+  if (!src || batch < 0 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return ERR_INVALID;
+  if (src_c != 3 && src_c != 4) return ERR_INVALID;
+  if (!dst_u8 && !dst_f32 && !dst_s2d) return ERR_INVALID;
+  if (dst_s2d && (dst_h != 88 || dst_w != 200)) return ERR_UNSUPPORTED;
+  const int row_pad = (src_w * src_c + 15) & ~15;
+  if (2 * row_pad > 96 * 1024) return ERR_UNSUPPORTED;
+  if (batch == 0) return OK;
+  PreParams p;
+  p.src = src; p.batch = batch; p.src_h = src_h; p.src_w = src_w; p.src_c = src_c; p.reverse = reverse ? 1 : 0;
+  p.dst_h = dst_h; p.dst_w = dst_w;
+  p.scale_x = (double)src_w / dst_w; p.scale_y = (double)src_h / dst_h;
+  p.dst_u8 = dst_u8; p.dst_f32 = dst_f32; p.dst_s2d = (__nv_bfloat16*)dst_s2d;
+  const size_t smem = 2 * (size_t)row_pad;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return cuda_status(e);
+    smem_set = 96 * 1024;
+  }
+  preprocess_kernel<<<batch * dst_h, 256, smem, (cudaStream_t)stream>>>(p);
+  return cuda_status(cudaGetLastError());
+}
+
+int cilrs_image_to_s2d(const float* image, int batch, void* dst, void* stream) {
+  if (!image || !dst || batch < 0) return ERR_INVALID;
+  if (batch == 0) return OK;
+  const long long total = (long long)batch * 94 * 206;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  image_to_s2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(image, (__nv_bfloat16*)dst, batch);
+  return cuda_status(cudaGetLastError());
+}
+
+}  // extern "C"

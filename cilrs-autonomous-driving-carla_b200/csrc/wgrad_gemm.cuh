@@ -1,0 +1,184 @@
+// Weight-gradient GEMM on tcgen05 tensor cores.
+//
+//   dW[co, tap, ci] = sum over output pixels p of  dY[p, co] * X[p (*stride) + tap offset, ci]
+//
+// The contraction runs over pixels, so both operands are "MN-major" for UMMA: a TMA box of 128 pixels x 64
+// channels lands in shared memory as 128-byte rows (one pixel per row, 128B swizzle) and is consumed as a
+// K(=pixel)-by-64 operand slab. One CTA owns a [128 co] x [g taps x 64 ci] block of dW and a slice of the pixel
+// tiles (split-K over pixels); its accumulator stays in TMEM for the whole slice and is added to the fp32
+// OIHW gradient with red.global.add at the end.
+//   warp 0 : TMA producer      warp 1 : MMA issuer      warps 2..5 : epilogue
+#pragma once
+#include "common.cuh"
+
+namespace cilrs {
+
+constexpr int WG_MAX_TAPS = 16;
+constexpr int WG_THREADS = 192;
+constexpr int WG_SLAB = 128 * 128;  // 128 pixel rows x 64 bf16
+constexpr int WG_MAX_STAGES = 4;
+
+enum WgradColMode : int { WG_COL_REGULAR = 0, WG_COL_CONV1_S2D = 1 };
+
+struct WgradParams {
+  CUtensorMap tmDY;  // (Cout, OW, OH, N), box (64, BW, BH, BN)
+  CUtensorMap tmX;   // (Cin,  W,  H,  N), box (64, BW, BH, BN) with the conv stride as element stride
+  int tiles_w, tiles_h, tiles_n;
+  int BW, BH, BN;
+  int in_sw, in_sh;
+  int co_blocks, m_halves;   // M = 128 rows of the accumulator = m_halves x 64 output channels
+  int ci_chunks;
+  int tap_groups, g;         // g taps per CTA, N = 64 g
+  int split_z;
+  int num_stages;
+  int8_t tap_dw[WG_MAX_TAPS], tap_dh[WG_MAX_TAPS];
+  int16_t tap_id[WG_MAX_TAPS];  // position of the tap inside the kh*kw plane of the OIHW gradient
+  int num_taps;
+  int cout, cin;
+  int co_stride, ci_stride;  // element strides of the fp32 gradient tensor
+  int col_mode;
+  float* grad;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int slabs = 2 + p.g;  // the A side always spans two 64-channel slabs (the second stays zero if m_halves == 1)
+  const int stage_bytes = slabs * WG_SLAB;
+  uint64_t* bars = (uint64_t*)(smem + (size_t)p.num_stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + WG_MAX_STAGES;
+  uint64_t* done_bar = bars + 2 * WG_MAX_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
+
+  {
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* q = (uint4*)smem;
+    const int n16 = p.num_stages * stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += WG_THREADS) q[i] = z;
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmDY);
+    tma_prefetch_desc(&p.tmX);
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item of this CTA
+  int wi = blockIdx.x;
+  const int z = wi % p.split_z; wi /= p.split_z;
+  const int tg = wi % p.tap_groups; wi /= p.tap_groups;
+  const int cic = wi % p.ci_chunks; wi /= p.ci_chunks;
+  const int cob = wi;
+  const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int per = (pix_tiles + p.split_z - 1) / p.split_z;
+  const int pt_begin = z * per;
+  const int pt_end = min(pix_tiles, pt_begin + per);
+  const int valid_rows = p.BW * p.BH * p.BN;
+  const uint32_t tx_bytes = (uint32_t)((p.m_halves + p.g) * valid_rows * 128);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        const int tw = pt % p.tiles_w;
+        const int th = (pt / p.tiles_w) % p.tiles_h;
+        const int tn = pt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* s = smem + (size_t)stage * stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        for (int mh = 0; mh < p.m_halves; ++mh)
+          tma_load_4d(&p.tmDY, &full_bar[stage], s + mh * WG_SLAB, cob * 128 + mh * 64, w0, h0, n0);
+        for (int j = 0; j < p.g; ++j) {
+          const int t = tg * p.g + j;
+          tma_load_4d(&p.tmX, &full_bar[stage], s + (2 + j) * WG_SLAB, cic * 64, w0 * p.in_sw + p.tap_dw[t],
+                      h0 * p.in_sh + p.tap_dh[t], n0);
+        }
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, 64 * p.g, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t first = 1;
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t b_addr = a_addr + 2 * WG_SLAB;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // 8 x (K = 16 pixels = 16 rows of 128 bytes)
+          const uint64_t da = umma_desc_sw128(a_addr + kk * 2048, WG_SLAB, 1024);
+          const uint64_t db = umma_desc_sw128(b_addr + kk * 2048, WG_SLAB, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (first && kk == 0) ? 0u : 1u);
+        }
+        first = 0;
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int co = cob * 128 + row;
+    if (pt_end > pt_begin) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const int ncols = 64 * p.g;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (row < p.m_halves * 64 && co < p.cout) {
+          const int j = c0 >> 6;        // tap within the group
+          const int t = tg * p.g + j;
+          float* gp = p.grad + (size_t)co * p.co_stride;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int cc = (c0 & 63) + e;  // column inside the 64-wide slab
+            int off;
+            if (p.col_mode == WG_COL_REGULAR) {
+              off = (cic * 64 + cc) * p.ci_stride + p.tap_id[t];
+            } else {
+              // conv1 space-to-depth packing: cc = s'*16 + dy*8 + dx*4 + c, tap t = r'
+              const int sp = cc >> 4, dy = (cc >> 3) & 1, dx = (cc >> 2) & 1, c = cc & 3;
+              const int ky = 2 * t + dy, kx = 2 * sp + dx;
+              off = (ky < 7 && kx < 7 && c < 3) ? c * 49 + ky * 7 + kx : -1;
+            }
+            if (off >= 0) atomicAdd(gp + off, __uint_as_float(v[e]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace cilrs

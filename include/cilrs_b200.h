@@ -1,0 +1,100 @@
+/* cilrs_b200 — C-ABI of the B200-native CILRS hot path.
+ *
+ * The reference (rohithr87/CILRS-Autonomous-Driving-CARLA) is pure Python and has no FFI of its own; its hot
+ * path is reached through three Python surfaces, and every entry point below replaces the library call made
+ * underneath one of them (citations are into /root/reference):
+ *
+ *   - AutonomousDriver.preprocess_image      model/autonomous_drive.py:897-902   (cv2.resize + /255 + Normalize)
+ *     prepare_dataset.process_session        model/prepare_dataset.py:56         (cv2.resize)
+ *   - CILRS.forward / loss.backward()        model/autonomous_drive.py:361-399, notebook/notebook.ipynb:549-552
+ *   - optim.Adam(...).step()                 notebook/notebook.ipynb:533-534,555
+ *
+ * Conventions (all entry points):
+ *   - plain C types, raw DEVICE pointers, explicit sizes; `stream` is a cudaStream_t passed as void*.
+ *   - return 0 on success; 1 = invalid argument, 2 = unsupported shape, 3 = workspace too small,
+ *     4 = driver entry point unavailable, >= 1000 = 1000 + cudaError_t of the failed CUDA call.
+ *   - never allocate device memory, never synchronise, never throw. Memory is owned by the caller.
+ *   - activations are NHWC bf16 ("channels-last") inside the conv stack; the public tensors of the
+ *     reference's interface (image f32 NCHW, controls f32 [B,3], pred_speed f32 [B]) keep their layout.
+ */
+#ifndef CILRS_B200_H_
+#define CILRS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CILRS_ABI_VERSION 1
+
+int cilrs_abi_version(void);
+/* human-readable text for a status code returned by any entry point (static storage) */
+const char* cilrs_status_string(int status);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K0  frame preprocessing.  Replaces cv2.resize(image,(200,88)) [INTER_LINEAR, 11-bit fixed point] and
+ *     img/255 -> permute(2,0,1) -> Normalize(mean,std)   (model/autonomous_drive.py:898-901, :481-482, :502-504)
+ *
+ *  src      : uint8 [batch, src_h, src_w, src_c]  (src_c = 3 RGB/BGR or 4 BGRA/RGBA; alpha ignored)
+ *  reverse  : 0 keep channel order, 1 reverse the first three channels (BGR(A) -> RGB; autonomous_drive.py:1551)
+ *  dst_u8   : optional uint8 [batch, dst_h, dst_w, 3]         — bit-exact cv2.resize result (prepare_dataset.py:56)
+ *  dst_f32  : optional float [batch, 3, dst_h, dst_w]         — the tensor preprocess_image returns
+ *  dst_s2d  : optional bf16  [batch, 47, 103, 16]             — conv1-ready space-to-depth layout (only 88x200)
+ *  Only the (src 600x800 -> dst 88x200) geometry has to be fast; any size with src >= dst is accepted.
+ * --------------------------------------------------------------------------------------------------------- */
+int cilrs_preprocess_u8(const uint8_t* src, int batch, int src_h, int src_w, int src_c, int reverse,
+                        int dst_h, int dst_w, uint8_t* dst_u8, float* dst_f32, void* dst_s2d, void* stream);
+
+/* image f32 NCHW [batch,3,88,200] (the tensor CILRS.forward receives) -> conv1-ready bf16 [batch,47,103,16] */
+int cilrs_image_to_s2d(const float* image_nchw, int batch, void* dst_s2d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K1/K2  convolution primitives (replace the cuDNN calls under nn.Conv2d in torchvision resnet34,
+ *        model/autonomous_drive.py:365-369). bf16 NHWC activations, fp32 accumulate on tcgen05 tensor cores.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct cilrs_conv_desc {
+  int batch;
+  int in_h, in_w, in_c; /* input NHWC; in_c multiple of 64 (the 7x7 stem uses the *_stem entry points) */
+  int out_c;            /* multiple of 64 */
+  int kh, kw;           /* 3x3 or 1x1 */
+  int stride;           /* 1 or 2 */
+  int pad;              /* 1 for 3x3, 0 for 1x1 */
+} cilrs_conv_desc;
+
+enum {
+  CILRS_EPI_STATS = 1,      /* also emit per-tile per-channel (sum, sum of squares) for train-mode BatchNorm */
+  CILRS_EPI_SCALE_BIAS = 2, /* y = conv * scale[c] + bias[c]  (folded eval-mode BatchNorm) */
+  CILRS_EPI_RESIDUAL = 4,   /* y += residual */
+  CILRS_EPI_RELU = 8        /* y = max(y, 0) */
+};
+
+/* bytes of packed bf16 weights for fprop / dgrad, and of the stats scratch for a given desc */
+size_t cilrs_conv_packed_weight_bytes(const cilrs_conv_desc* d);
+size_t cilrs_conv_stats_bytes(const cilrs_conv_desc* d); /* floats [m_tiles][2][out_c] */
+int cilrs_conv_stats_tiles(const cilrs_conv_desc* d);
+
+/* fp32 OIHW master weight -> bf16 [tap][out_c][in_c] (fprop) and bf16 [tap][in_c][out_c] (dgrad); either may be NULL */
+int cilrs_conv_pack_weight(const cilrs_conv_desc* d, const float* w_oihw, void* w_fprop, void* w_dgrad, void* stream);
+
+int cilrs_conv_fprop(const cilrs_conv_desc* d, const void* x, const void* w_fprop, void* y, const float* scale,
+                     const float* bias, const void* residual, float* stats, int flags, void* stream);
+/* dx = conv_transpose(dy, w) (+ residual). For stride 2 the four output parities are separate launches. */
+int cilrs_conv_dgrad(const cilrs_conv_desc* d, const void* dy, const void* w_dgrad, void* dx, const void* residual,
+                     void* stream);
+/* dw_oihw (fp32) += dy^T * im2col(x). The caller zeroes dw first. */
+int cilrs_conv_wgrad(const cilrs_conv_desc* d, const void* dy, const void* x, float* dw_oihw, void* stream);
+
+/* the 7x7/2 stem on the space-to-depth input [batch,47,103,16] -> [batch,44,100,64] */
+size_t cilrs_stem_packed_weight_bytes(void);
+int cilrs_stem_pack_weight(const float* w_oihw /* [64,3,7,7] */, void* w_packed, void* stream);
+int cilrs_stem_fprop(int batch, const void* x_s2d, const void* w_packed, void* y, const float* scale, const float* bias,
+                     float* stats, int flags, void* stream);
+int cilrs_stem_wgrad(int batch, const void* dy, const void* x_s2d, float* dw_oihw, void* stream);
+int cilrs_stem_stats_tiles(int batch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CILRS_B200_H_ */
