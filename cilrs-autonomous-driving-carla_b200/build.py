@@ -11,7 +11,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libcilrs_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math"]
+         "-Xcompiler", "-fPIC"]
 
 
 def _sources():

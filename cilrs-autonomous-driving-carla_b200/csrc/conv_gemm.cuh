@@ -11,49 +11,9 @@
 //   warp 0 : TMA producer      warp 1 : MMA issuer (one lane)      warps 2..5 : epilogue (TMEM -> regs -> smem -> HBM)
 #pragma once
 #include "common.cuh"
+#include "conv_params.h"
 
 namespace cilrs {
-
-constexpr int CG_MAX_TAPS = 32;
-constexpr int CG_BLOCK_M = 128;
-constexpr int CG_A_BYTES = CG_BLOCK_M * 128;  // 128 pixel rows x 64 bf16
-constexpr int CG_THREADS = 192;
-constexpr int CG_MAX_STAGES = 8;
-constexpr int CG_STAGING_BYTES = 2 * CG_A_BYTES;  // two 128x64 bf16 output chunks
-constexpr int CG_SMEM_TOTAL = 227 * 1024;
-
-enum ConvEpilogueFlags : int {
-  CG_STATS = 1,       // write per-tile per-channel sum / sum-of-squares of the (bf16-rounded) output
-  CG_SCALE_BIAS = 2,  // y = acc * scale[n] + bias[n]   (folded eval-mode BatchNorm)
-  CG_RESIDUAL = 4,    // y += residual[pixel, n]
-  CG_RELU = 8,        // y = max(y, 0)
-};
-
-struct ConvGemmParams {
-  CUtensorMap tmA[4];
-  CUtensorMap tmB[2];
-  // tiling
-  int tiles_w, tiles_h, tiles_n, n_blocks;
-  int BW, BH, BN;
-  int block_n;
-  int num_taps, chunks;
-  int in_sw, in_sh;
-  int num_stages;
-  int8_t tap_dw[CG_MAX_TAPS], tap_dh[CG_MAX_TAPS];
-  int8_t tap_a[CG_MAX_TAPS], tap_b[CG_MAX_TAPS];
-  int16_t tap_slab[CG_MAX_TAPS];
-  int slab_rows;
-  // output geometry (tile coordinates -> element offset)
-  int n_img, oh, ow;
-  long long out_sn, out_sh, out_sw, out_off;
-  int n_total;
-  __nv_bfloat16* out;
-  const __nv_bfloat16* residual;
-  const float* scale;
-  const float* bias;
-  float* stats;  // [m_tiles][2][n_total]
-  int flags;
-};
 
 __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];

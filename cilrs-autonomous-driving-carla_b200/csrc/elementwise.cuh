@@ -1,0 +1,439 @@
+// HBM-bound kernels around the conv stack: BatchNorm statistics / apply / backward, ReLU, residual add,
+// max-pool (3x3/2, stem) and global average pool. All activations are NHWC bf16, C a multiple of 64; every
+// thread moves 16-byte vectors (8 channels) and keeps its channel group fixed so per-channel parameters live in
+// registers. Reductions are deterministic (fixed partial order, no float atomics).
+#pragma once
+#include "common.cuh"
+
+namespace cilrs {
+
+constexpr int EW_THREADS = 256;
+constexpr int EW_MAX_BLOCKS = 148 * 4;
+
+struct Vec8 {
+  float v[8];
+};
+CILRS_DEVINL Vec8 load8(const __nv_bfloat16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  Vec8 r;
+  r.v[0] = bf16lo(u.x); r.v[1] = bf16hi(u.x); r.v[2] = bf16lo(u.y); r.v[3] = bf16hi(u.y);
+  r.v[4] = bf16lo(u.z); r.v[5] = bf16hi(u.z); r.v[6] = bf16lo(u.w); r.v[7] = bf16hi(u.w);
+  return r;
+}
+CILRS_DEVINL void store8(__nv_bfloat16* p, const Vec8& r) {
+  uint4 u;
+  u.x = pack_bf16x2(r.v[0], r.v[1]); u.y = pack_bf16x2(r.v[2], r.v[3]);
+  u.z = pack_bf16x2(r.v[4], r.v[5]); u.w = pack_bf16x2(r.v[6], r.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+CILRS_DEVINL Vec8 loadf8(const float* p) {
+  Vec8 r;
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+// per-BatchNorm derived vectors, each [C]: scale, shift (forward apply), mean, rstd (backward)
+struct BnVectors {
+  float* scale;
+  float* shift;
+  float* mean;
+  float* rstd;
+};
+
+// ---------------------------------------------------------------------------------------------
+// bn_finalize: per-tile (sum, sumsq) partials -> batch statistics -> scale/shift (+ running stats update)
+//   training: mean = S/n, var_b = Q/n - mean^2 (biased, used to normalise), running_var gets the unbiased one,
+//             momentum 0.1, num_batches_tracked += 1  (torch.nn.BatchNorm2d semantics, torchvision resnet BN layers)
+//   frozen  : statistics come from running_mean / running_var (eval mode)
+// one CTA per 32 channels, 32 tile-slices per channel, double accumulation
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partials, int tiles, int C, double count,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           float* running_mean, float* running_var, long long* nbt,
+                                                           float momentum, float eps, int training, int update_running,
+                                                           BnVectors out) {
+  __shared__ double s_sum[32][33], s_sq[32][33];
+  const int cl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double s = 0.0, q = 0.0;
+  if (training && c < C) {
+    for (int t = slice; t < tiles; t += 32) {
+      s += (double)partials[(size_t)t * 2 * C + c];
+      q += (double)partials[(size_t)t * 2 * C + C + c];
+    }
+  }
+  s_sum[slice][cl] = s;
+  s_sq[slice][cl] = q;
+  __syncthreads();
+  if (slice == 0 && c < C) {
+    float mean, var;
+    if (training) {
+      for (int i = 1; i < 32; ++i) { s += s_sum[i][cl]; q += s_sq[i][cl]; }
+      const double m = s / count;
+      double v = q / count - m * m;
+      if (v < 0.0) v = 0.0;
+      mean = (float)m;
+      var = (float)v;
+      if (update_running) {
+        const double unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    } else {
+      mean = running_mean[c];
+      var = running_var[c];
+    }
+    const float rstd = 1.0f / sqrtf(var + eps);
+    const float sc = gamma[c] * rstd;
+    out.scale[c] = sc;
+    out.shift[c] = beta[c] - mean * sc;
+    out.mean[c] = mean;
+    out.rstd[c] = rstd;
+  }
+  if (training && update_running && nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bn_apply: out = relu?( x*scale + shift  [+ res]  [+ x2*scale2 + shift2] )
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
+                                                              const __nv_bfloat16* __restrict__ x2, const float* __restrict__ scale2,
+                                                              const float* __restrict__ shift2, __nv_bfloat16* __restrict__ out,
+                                                              long long nvec, int C, int relu) {
+  const int groups = C >> 3;
+  const long long stride = (long long)gridDim.x * EW_THREADS;  // multiple of groups (host guarantees)
+  long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+  const int cg = (int)(i % groups) * 8;
+  const Vec8 sc = loadf8(scale + cg), sh = loadf8(shift + cg);
+  Vec8 sc2, sh2;
+  if (x2) { sc2 = loadf8(scale2 + cg); sh2 = loadf8(shift2 + cg); }
+  for (; i < nvec; i += stride) {
+    Vec8 a = load8(x + i * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a.v[k] = fmaf(a.v[k], sc.v[k], sh.v[k]);
+    if (res) {
+      const Vec8 r = load8(res + i * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a.v[k] += r.v[k];
+    }
+    if (x2) {
+      const Vec8 r = load8(x2 + i * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a.v[k] += fmaf(r.v[k], sc2.v[k], sh2.v[k]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a.v[k] = fmaxf(a.v[k], 0.f);
+    }
+    store8(out + i * 8, a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem: out = maxpool3x3/2 pad 1 ( relu( y*scale + shift ) ), argmax position (0..8) kept for the backward
+// y [B,H,W,C] -> out [B,OH,OW,C], OH = (H+1)/2 ...
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                                                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                                                                     uint8_t* __restrict__ argmax, int B, int H, int W, int C, int OH,
+                                                                     int OW) {
+  const int groups = C >> 3;
+  const long long nvec = (long long)B * OH * OW * groups;
+  const long long stride = (long long)gridDim.x * EW_THREADS;
+  long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+  const int cg = (int)(i % groups) * 8;
+  const Vec8 sc = loadf8(scale + cg), sh = loadf8(shift + cg);
+  for (; i < nvec; i += stride) {
+    long long pix = i / groups;
+    const int ow = (int)(pix % OW);
+    const int oh = (int)((pix / OW) % OH);
+    const int n = (int)(pix / ((long long)OW * OH));
+    Vec8 best;
+    int bi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { best.v[k] = -INFINITY; bi[k] = 0; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = oh * 2 - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = ow * 2 - 1 + s;
+        if (w < 0 || w >= W) continue;
+        const Vec8 a = load8(y + (((long long)n * H + h) * W + w) * C + cg);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // round to bf16 first: the comparison must see exactly the values a separate BN+ReLU pass would store
+          const float v = __bfloat162float(__float2bfloat16(fmaxf(fmaf(a.v[k], sc.v[k], sh.v[k]), 0.f)));
+          if (v > best.v[k]) { best.v[k] = v; bi[k] = r * 3 + s; }
+        }
+      }
+    }
+    store8(out + i * 8, best);
+    if (argmax) {
+      uint2 u;
+      u.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+      u.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+      *reinterpret_cast<uint2*>(argmax + i * 8) = u;
+    }
+  }
+}
+
+// global average pool: x [B,P,C] bf16 -> feat [B,C] fp32
+__global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ feat, int B, int P, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int c = i % C, n = i / C;
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += __bfloat162float(x[((long long)n * P + p) * C + c]);
+  feat[i] = s / (float)P;
+}
+// backward: g [B,P,C] bf16 = dfeat[b,c] / P
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, __nv_bfloat16* __restrict__ g, int B, int P, int C) {
+  const long long total = (long long)B * P * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int n = (int)(i / ((long long)P * C));
+    g[i] = __float2bfloat16(dfeat[(long long)n * C + c] / (float)P);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm backward, pass 1 (reduce):  dz = g * (act > 0)   [act == nullptr: no ReLU in between]
+//   bsum[c] = sum dz,  bdot[c] = sum dz * xhat,  xhat = (y - mean) * rstd
+// per-CTA partials in fixed order, the last CTA to finish folds them (threadfence reduction) and also accumulates
+// dgamma += bdot, dbeta += bsum into the fp32 gradient arena.
+// ---------------------------------------------------------------------------------------------
+struct BnBwdReduceParams {
+  const __nv_bfloat16* g;
+  const __nv_bfloat16* act;
+  const __nv_bfloat16* y;
+  const float* mean;
+  const float* rstd;
+  long long nvec;
+  int C;
+  float* partial;       // [gridDim.x][2][C]
+  unsigned int* counter;
+  float* bsum;          // [C]
+  float* bdot;          // [C]
+  float* dgamma;        // += (may be null)
+  float* dbeta;         // +=
+  // stem variant: g is the pooled gradient [B,OH,OW,C] gathered through the arg-max of the 3x3/2 max-pool, and the ReLU
+  // mask is recomputed from y*scale+shift
+  const uint8_t* argmax;
+  const float* scale;
+  const float* shift;
+  int H, W, OH, OW;
+};
+
+CILRS_DEVINL Vec8 stem_gather_grad(const BnBwdReduceParams& p, int n, int h, int w, int cg) {
+  // gradient reaching conv1-output pixel (h, w): every pool window (oh, ow) that contains it and selected it
+  Vec8 acc;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc.v[k] = 0.f;
+  for (int oh = (h) / 2; oh <= (h + 1) / 2; ++oh) {
+    if (oh >= p.OH) continue;
+    const int r = h - (oh * 2 - 1);
+    if (r < 0 || r > 2) continue;
+    for (int ow = (w) / 2; ow <= (w + 1) / 2; ++ow) {
+      if (ow >= p.OW) continue;
+      const int s = w - (ow * 2 - 1);
+      if (s < 0 || s > 2) continue;
+      const long long o = (((long long)n * p.OH + oh) * p.OW + ow) * p.C + cg;
+      const uint2 am = *reinterpret_cast<const uint2*>(p.argmax + o);
+      const Vec8 gv = load8(p.g + o);
+      const int code = r * 3 + s;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int sel = (int)(((k < 4 ? am.x : am.y) >> ((k & 3) * 8)) & 0xFF);
+        if (sel == code) acc.v[k] += gv.v[k];
+      }
+    }
+  }
+  return acc;
+}
+
+template <bool STEM>
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdReduceParams p) {
+  __shared__ float s_red[2 * EW_THREADS][8];  // 16 KB: per-thread partial (sum | dot) vectors
+  __shared__ bool s_last;
+  const int groups = p.C >> 3;
+  const long long stride = (long long)gridDim.x * EW_THREADS;
+  long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+  const int cg = (int)(i % groups) * 8;
+  const Vec8 mean = loadf8(p.mean + cg), rstd = loadf8(p.rstd + cg);
+  Vec8 sc, sh;
+  if (STEM) { sc = loadf8(p.scale + cg); sh = loadf8(p.shift + cg); }
+  float a_sum[8], a_dot[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { a_sum[k] = 0.f; a_dot[k] = 0.f; }
+  for (; i < p.nvec; i += stride) {
+    const Vec8 yv = load8(p.y + i * 8);
+    Vec8 gv;
+    if (STEM) {
+      const long long pix = i / groups;
+      const int w = (int)(pix % p.W);
+      const int h = (int)((pix / p.W) % p.H);
+      const int n = (int)(pix / ((long long)p.W * p.H));
+      gv = stem_gather_grad(p, n, h, w, cg);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (!(fmaf(yv.v[k], sc.v[k], sh.v[k]) > 0.f)) gv.v[k] = 0.f;
+    } else {
+      gv = load8(p.g + i * 8);
+      if (p.act) {
+        const Vec8 av = load8(p.act + i * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (!(av.v[k] > 0.f)) gv.v[k] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a_sum[k] += gv.v[k];
+      a_dot[k] = fmaf(gv.v[k], (yv.v[k] - mean.v[k]) * rstd.v[k], a_dot[k]);
+    }
+  }
+  // threads with the same channel group are EW_THREADS/groups apart in steps of `groups`
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s_red[threadIdx.x][k] = a_sum[k]; s_red[EW_THREADS + threadIdx.x][k] = a_dot[k]; }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    float t_sum[8], t_dot[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t_sum[k] = 0.f; t_dot[k] = 0.f; }
+    for (int t = threadIdx.x; t < EW_THREADS; t += groups) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { t_sum[k] += s_red[t][k]; t_dot[k] += s_red[EW_THREADS + t][k]; }
+    }
+    float* pp = p.partial + (size_t)blockIdx.x * 2 * p.C + threadIdx.x * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { pp[k] = t_sum[k]; pp[p.C + k] = t_dot[k]; }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(p.counter, 1u);
+    s_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    // fold the per-CTA partials: 4 slices of CTAs per channel in parallel, then a fixed-order combine
+    float* s_fin = &s_red[0][0];  // [4][2][C] floats (C <= 512 -> 4096 floats = all of s_red)
+    for (int j = threadIdx.x; j < 4 * p.C; j += EW_THREADS) {
+      const int c = j % p.C, sl = j / p.C;
+      float s = 0.f, d = 0.f;
+      for (unsigned int b = sl; b < gridDim.x; b += 4) {
+        s += p.partial[(size_t)b * 2 * p.C + c];
+        d += p.partial[(size_t)b * 2 * p.C + p.C + c];
+      }
+      s_fin[(sl * 2 + 0) * p.C + c] = s;
+      s_fin[(sl * 2 + 1) * p.C + c] = d;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
+      float s = 0.f, d = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) { s += s_fin[(sl * 2 + 0) * p.C + c]; d += s_fin[(sl * 2 + 1) * p.C + c]; }
+      p.bsum[c] = s;
+      p.bdot[c] = d;
+      if (p.dgamma) p.dgamma[c] += d;
+      if (p.dbeta) p.dbeta[c] += s;
+    }
+    if (threadIdx.x == 0) *p.counter = 0u;  // ready for the next launch / graph replay
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm backward, pass 2 (apply):
+//   training: dy = gamma*rstd * ( dz - bsum/n - xhat * bdot/n )
+//   frozen  : dy = gamma*rstd * dz
+// optionally also stores dz (the gradient that continues down the identity branch)
+// ---------------------------------------------------------------------------------------------
+struct BnBwdApplyParams {
+  const __nv_bfloat16* g;
+  const __nv_bfloat16* act;
+  const __nv_bfloat16* y;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  const float* bsum;
+  const float* bdot;
+  float inv_count;
+  int frozen;
+  long long nvec;
+  int C;
+  __nv_bfloat16* dy;
+  __nv_bfloat16* dz;  // may be null
+  const uint8_t* argmax;
+  const float* scale;
+  const float* shift;
+  int H, W, OH, OW;
+};
+
+template <bool STEM>
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApplyParams p) {
+  const int groups = p.C >> 3;
+  const long long stride = (long long)gridDim.x * EW_THREADS;
+  long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+  const int cg = (int)(i % groups) * 8;
+  const Vec8 mean = loadf8(p.mean + cg), rstd = loadf8(p.rstd + cg), gamma = loadf8(p.gamma + cg);
+  Vec8 k0, k1, sc, sh;
+  {
+    const Vec8 bs = loadf8(p.bsum + cg), bd = loadf8(p.bdot + cg);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      k0.v[k] = p.frozen ? 0.f : bs.v[k] * p.inv_count;
+      k1.v[k] = p.frozen ? 0.f : bd.v[k] * p.inv_count;
+    }
+  }
+  if (STEM) { sc = loadf8(p.scale + cg); sh = loadf8(p.shift + cg); }
+  BnBwdReduceParams gp;  // only the fields the stem gather reads
+  if (STEM) { gp.g = p.g; gp.argmax = p.argmax; gp.OH = p.OH; gp.OW = p.OW; gp.C = p.C; }
+  for (; i < p.nvec; i += stride) {
+    const Vec8 yv = load8(p.y + i * 8);
+    Vec8 gv;
+    if (STEM) {
+      const long long pix = i / groups;
+      const int w = (int)(pix % p.W);
+      const int h = (int)((pix / p.W) % p.H);
+      const int n = (int)(pix / ((long long)p.W * p.H));
+      gv = stem_gather_grad(gp, n, h, w, cg);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (!(fmaf(yv.v[k], sc.v[k], sh.v[k]) > 0.f)) gv.v[k] = 0.f;
+    } else {
+      gv = load8(p.g + i * 8);
+      if (p.act) {
+        const Vec8 av = load8(p.act + i * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (!(av.v[k] > 0.f)) gv.v[k] = 0.f;
+      }
+    }
+    if (p.dz) store8(p.dz + i * 8, gv);
+    Vec8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xhat = (yv.v[k] - mean.v[k]) * rstd.v[k];
+      o.v[k] = gamma.v[k] * rstd.v[k] * (gv.v[k] - k0.v[k] - xhat * k1.v[k]);
+    }
+    store8(p.dy + i * 8, o);
+  }
+}
+
+// grid size for the vector kernels: a multiple of the channel-group count keeps every thread on one channel group
+inline int ew_grid(long long nvec, int C) {
+  const int groups = C >> 3;
+  long long blocks = (nvec + EW_THREADS - 1) / EW_THREADS;
+  if (blocks > EW_MAX_BLOCKS) blocks = EW_MAX_BLOCKS;
+  if (blocks < 1) blocks = 1;
+  // EW_THREADS (256) is a multiple of groups (8..64), so any block count works
+  (void)groups;
+  return (int)blocks;
+}
+
+}  // namespace cilrs

@@ -1,0 +1,766 @@
+// Whole-network plan for the CILRS hot path: ResNet-34 trunk (tcgen05 implicit-GEMM convs + BN/ReLU/pool kernels),
+// heads, losses, backward pass. One C-ABI call per forward / backward; all memory is caller-owned:
+//   params / grads : one flat fp32 arena each, tensors in the reference's named_parameters() order
+//                    (model/autonomous_drive.py:361-399; layout exported by cilrs_model_param_layout)
+//   buffers        : flat fp32 arena of BN running_mean / running_var + int64 num_batches_tracked[36]
+//   workspace      : activations, packed bf16 weights, BN vectors, gradient ping-pong buffers
+#include "conv_params.h"
+#include "conv_host.h"
+#include "elementwise.cuh"
+#include "heads.cuh"
+#include "adam.cuh"
+#include <new>
+#include <string.h>
+#include <vector>
+
+namespace cilrs {
+
+static inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+struct TensorSlot {
+  long long off;   // offset in floats inside the arena
+  long long size;  // elements
+};
+
+struct BnRef {
+  int C;
+  int gamma, beta;  // param slot indices
+  long long rm_off, rv_off;
+  int nbt_idx;
+  float* vec;   // [4][C] scale, shift, mean, rstd   (workspace)
+  float* bred;  // [2][C] bsum, bdot                  (workspace)
+};
+
+struct ConvRef {
+  cilrs_conv_desc d;
+  bool stem;
+  int w;  // param slot
+  __nv_bfloat16 *wf, *wd;
+  BnRef bn;
+  __nv_bfloat16* y;  // raw conv output (pre-BN)
+  int oh, ow;
+};
+
+struct Block {
+  ConvRef a, b, ds;
+  bool has_ds;
+  const __nv_bfloat16* in;
+  __nv_bfloat16* act_a;
+  __nv_bfloat16* out;
+  int in_h, in_w, in_c;
+};
+
+struct Bump {
+  char* base;
+  long long off;
+  void* take(long long bytes) {
+    off = align_up(off, 1024);
+    void* p = base ? (void*)(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+struct Model {
+  int maxB;
+  std::vector<TensorSlot> slots;  // parameter tensors
+  long long param_floats;
+  long long buffer_floats;
+  int num_bn;
+  ConvRef stem;
+  std::vector<Block> blocks;
+  int head_slot0;  // first slot of the heads
+  // bound arenas
+  float* params = nullptr;
+  float* grads = nullptr;
+  float* buffers = nullptr;
+  long long* nbt = nullptr;
+  // workspace
+  __nv_bfloat16* x_s2d;
+  __nv_bfloat16* pool_out;
+  uint8_t* pool_arg;
+  float* stats;          // shared stats-partials scratch
+  float* bwd_partial;    // BN backward partials
+  unsigned int* counters;
+  float* unit_vec;       // [2][64]: ones, zeros (max-pool on already-activated stem output)
+  float* feat;           // [B,512]
+  float* dfeat;
+  HeadsSaved hs;
+  float* loss_out;       // [8]
+  float* dcontrols;      // [B,3]
+  float* dspeed;         // [B]
+  int* err_flag;
+  __nv_bfloat16 *g0, *g1, *ga, *d1, *d2, *dz, *dy_stem;
+  double* sumsq_partial;
+  // plans (tensor maps) for the batch size they were built for
+  int planB = 0;
+  int planMode = -1;
+  std::vector<ConvGemmParams> fwd_plans;
+  std::vector<ConvGemmParams> dgrad_plans;
+  std::vector<WgradParams> wgrad_plans;
+  // resumable backward (so the host can start the allreduce of finished gradient buckets between parts)
+  __nv_bfloat16 *bw_gcur = nullptr, *bw_gnext = nullptr;
+  size_t bw_di = 0, bw_wi = 0;
+};
+
+static int add_slot(Model& m, long long size) {
+  TensorSlot s;
+  s.off = align_up(m.param_floats, 16);
+  s.size = size;
+  m.param_floats = s.off + size;
+  m.slots.push_back(s);
+  return (int)m.slots.size() - 1;
+}
+
+static BnRef make_bn(Model& m, int C) {
+  BnRef b{};
+  b.C = C;
+  b.gamma = add_slot(m, C);
+  b.beta = add_slot(m, C);
+  b.rm_off = m.buffer_floats;
+  b.rv_off = m.buffer_floats + C;
+  m.buffer_floats += 2 * C;
+  b.nbt_idx = m.num_bn++;
+  return b;
+}
+
+static ConvRef make_conv(Model& m, int B, int h, int w, int cin, int cout, int k, int stride) {
+  ConvRef c{};
+  c.stem = false;
+  c.d = cilrs_conv_desc{B, h, w, cin, cout, k, k, stride, k == 3 ? 1 : 0};
+  c.w = add_slot(m, (long long)cout * cin * k * k);
+  c.bn = make_bn(m, cout);
+  c.oh = conv_out_dim(h, k, stride, c.d.pad);
+  c.ow = conv_out_dim(w, k, stride, c.d.pad);
+  return c;
+}
+
+// network topology; also the flat parameter layout (named_parameters order of the reference module)
+static void build_topology(Model& m, int B) {
+  m.param_floats = 0; m.buffer_floats = 0; m.num_bn = 0;
+  m.slots.clear(); m.blocks.clear();
+  m.stem = ConvRef{};
+  m.stem.stem = true;
+  m.stem.d = cilrs_conv_desc{B, 88, 200, 3, 64, 7, 7, 2, 3};
+  m.stem.w = add_slot(m, 64 * 3 * 7 * 7);
+  m.stem.bn = make_bn(m, 64);
+  m.stem.oh = 44; m.stem.ow = 100;
+  const int chans[4] = {64, 128, 256, 512}, nblk[4] = {3, 4, 6, 3};
+  int h = 22, w = 50, cin = 64;
+  for (int s = 0; s < 4; ++s) {
+    for (int b = 0; b < nblk[s]; ++b) {
+      Block blk{};
+      const int stride = (b == 0 && s > 0) ? 2 : 1;
+      const int c = chans[s];
+      blk.in_h = h; blk.in_w = w; blk.in_c = cin;
+      blk.a = make_conv(m, B, h, w, cin, c, 3, stride);
+      blk.b = make_conv(m, B, blk.a.oh, blk.a.ow, c, c, 3, 1);
+      blk.has_ds = (stride != 1 || cin != c);
+      if (blk.has_ds) blk.ds = make_conv(m, B, h, w, cin, c, 1, stride);
+      h = blk.a.oh; w = blk.a.ow; cin = c;
+      m.blocks.push_back(blk);
+    }
+  }
+  m.head_slot0 = (int)m.slots.size();
+  add_slot(m, 128); add_slot(m, 128);          // speed_encoder.0 weight [128,1], bias
+  add_slot(m, 128 * 128); add_slot(m, 128);    // speed_encoder.3
+  for (int k = 0; k < 4; ++k) {
+    add_slot(m, 256 * 640); add_slot(m, 256);  // control_branches.k.0
+    add_slot(m, 256 * 256); add_slot(m, 256);  // .3
+    add_slot(m, 3 * 256); add_slot(m, 3);      // .6
+  }
+  add_slot(m, 256 * 512); add_slot(m, 256);    // speed_predictor.0
+  add_slot(m, 256 * 256); add_slot(m, 256);    // .3
+  add_slot(m, 256); add_slot(m, 1);            // .5
+  m.param_floats = align_up(m.param_floats, 16);
+}
+
+static long long act_elems(int B, int h, int w, int c) { return (long long)B * h * w * c; }
+
+static void carve_conv(Bump& bp, ConvRef& c, int B) {
+  const long long wbytes = c.stem ? 4 * 64 * 64 * 2 : (long long)c.d.kh * c.d.kw * c.d.in_c * c.d.out_c * 2;
+  c.wf = (__nv_bfloat16*)bp.take(wbytes);
+  c.wd = c.stem ? nullptr : (__nv_bfloat16*)bp.take(wbytes);
+  c.y = (__nv_bfloat16*)bp.take(act_elems(B, c.oh, c.ow, c.d.out_c) * 2);
+  c.bn.vec = (float*)bp.take(4LL * c.bn.C * 4);
+  c.bn.bred = (float*)bp.take(2LL * c.bn.C * 4);
+}
+
+static long long carve(Model& m, char* base) {
+  Bump bp{base, 0};
+  const int B = m.maxB;
+  m.x_s2d = (__nv_bfloat16*)bp.take((long long)B * 47 * 103 * 16 * 2);
+  carve_conv(bp, m.stem, B);
+  m.pool_out = (__nv_bfloat16*)bp.take(act_elems(B, 22, 50, 64) * 2);
+  m.pool_arg = (uint8_t*)bp.take(act_elems(B, 22, 50, 64));
+  const __nv_bfloat16* prev = m.pool_out;
+  for (auto& blk : m.blocks) {
+    blk.in = prev;
+    carve_conv(bp, blk.a, B);
+    carve_conv(bp, blk.b, B);
+    if (blk.has_ds) carve_conv(bp, blk.ds, B);
+    blk.act_a = (__nv_bfloat16*)bp.take(act_elems(B, blk.a.oh, blk.a.ow, blk.a.d.out_c) * 2);
+    blk.out = (__nv_bfloat16*)bp.take(act_elems(B, blk.b.oh, blk.b.ow, blk.b.d.out_c) * 2);
+    prev = blk.out;
+  }
+  // stats partial scratch: the stem has the most tiles (<= ceil(B*4400/100) ~ 44*B + slack), 2 x 64 floats each;
+  // deeper layers have fewer tiles x more channels; bound by B*44*100/64 tiles * 2 * 64
+  m.stats = (float*)bp.take(((long long)B * 4400 / 50 + 4400) * 2 * 512 / 4 * 4 + 1024);
+  m.bwd_partial = (float*)bp.take((long long)EW_MAX_BLOCKS * 2 * 512 * 4);
+  m.counters = (unsigned int*)bp.take(64);
+  m.unit_vec = (float*)bp.take(2 * 64 * 4);
+  m.feat = (float*)bp.take((long long)B * 512 * 4);
+  m.dfeat = (float*)bp.take((long long)B * 512 * 4);
+  m.hs.s1 = (float*)bp.take((long long)B * 128 * 4);
+  m.hs.sfeat = (float*)bp.take((long long)B * 128 * 4);
+  m.hs.b1 = (float*)bp.take((long long)B * 256 * 4);
+  m.hs.b2 = (float*)bp.take((long long)B * 256 * 4);
+  m.hs.p1 = (float*)bp.take((long long)B * 256 * 4);
+  m.hs.p2 = (float*)bp.take((long long)B * 256 * 4);
+  m.hs.d_se0 = (float*)bp.take((long long)B * 128 * 4);
+  m.hs.d_se3 = (float*)bp.take((long long)B * 128 * 4);
+  m.hs.d_br0 = (float*)bp.take((long long)B * 256 * 4);
+  m.hs.d_br3 = (float*)bp.take((long long)B * 256 * 4);
+  m.hs.d_br6 = (float*)bp.take((long long)B * 4 * 4);
+  m.hs.d_sp0 = (float*)bp.take((long long)B * 256 * 4);
+  m.hs.d_sp3 = (float*)bp.take((long long)B * 256 * 4);
+  m.hs.d_sp5 = (float*)bp.take((long long)B * 4);
+  m.loss_out = (float*)bp.take(64);
+  m.dcontrols = (float*)bp.take((long long)B * 3 * 4);
+  m.dspeed = (float*)bp.take((long long)B * 4);
+  m.err_flag = (int*)bp.take(64);
+  const long long gmax = act_elems(B, 22, 50, 64) * 2;
+  m.g0 = (__nv_bfloat16*)bp.take(gmax);
+  m.g1 = (__nv_bfloat16*)bp.take(gmax);
+  m.ga = (__nv_bfloat16*)bp.take(gmax);
+  m.d1 = (__nv_bfloat16*)bp.take(gmax);
+  m.d2 = (__nv_bfloat16*)bp.take(gmax);
+  m.dz = (__nv_bfloat16*)bp.take(gmax);
+  m.dy_stem = (__nv_bfloat16*)bp.take(act_elems(B, 44, 100, 64) * 2);
+  m.sumsq_partial = (double*)bp.take(1024 * 8);
+  return align_up(bp.off, 1024);
+}
+
+static void set_batch(ConvRef& c, int B) { c.d.batch = B; }
+
+// ------------------------------------------------------------------------------------------------
+// plan construction: every tensor map for batch B (forward variants, dgrad, wgrad)
+// ------------------------------------------------------------------------------------------------
+enum FwdMode { MODE_TRAIN = 0, MODE_FROZEN = 1, MODE_INFER = 2 };
+
+static int build_plans(Model& m, int B, int mode) {
+  if (B == m.planB && mode == m.planMode) return OK;
+  m.fwd_plans.clear(); m.dgrad_plans.clear(); m.wgrad_plans.clear();
+  int st;
+  set_batch(m.stem, B);
+  const bool infer = mode == MODE_INFER;
+  {
+    ConvGemmParams p;
+    BnRef& bn = m.stem.bn;
+    if (infer) st = build_stem_fprop(&p, B, m.x_s2d, m.stem.wf, m.stem.y, bn.vec, bn.vec + bn.C, nullptr, CG_SCALE_BIAS | CG_RELU);
+    else st = build_stem_fprop(&p, B, m.x_s2d, m.stem.wf, m.stem.y, nullptr, nullptr, m.stats, CG_STATS);
+    if (st) return st;
+    m.fwd_plans.push_back(p);
+  }
+  for (auto& blk : m.blocks) {
+    set_batch(blk.a, B); set_batch(blk.b, B);
+    if (blk.has_ds) set_batch(blk.ds, B);
+    ConvGemmParams p;
+    if (infer) {
+      st = build_fprop(&p, &blk.a.d, blk.in, blk.a.wf, blk.act_a, blk.a.bn.vec, blk.a.bn.vec + blk.a.bn.C, nullptr, nullptr,
+                       CG_SCALE_BIAS | CG_RELU);
+      if (st) return st;
+      m.fwd_plans.push_back(p);
+      const __nv_bfloat16* idn = blk.in;
+      if (blk.has_ds) {
+        st = build_fprop(&p, &blk.ds.d, blk.in, blk.ds.wf, blk.ds.y, blk.ds.bn.vec, blk.ds.bn.vec + blk.ds.bn.C, nullptr, nullptr,
+                         CG_SCALE_BIAS);
+        if (st) return st;
+        m.fwd_plans.push_back(p);
+        idn = blk.ds.y;
+      }
+      st = build_fprop(&p, &blk.b.d, blk.act_a, blk.b.wf, blk.out, blk.b.bn.vec, blk.b.bn.vec + blk.b.bn.C, idn, nullptr,
+                       CG_SCALE_BIAS | CG_RESIDUAL | CG_RELU);
+      if (st) return st;
+      m.fwd_plans.push_back(p);
+    } else {
+      st = build_fprop(&p, &blk.a.d, blk.in, blk.a.wf, blk.a.y, nullptr, nullptr, nullptr, m.stats, CG_STATS);
+      if (st) return st;
+      m.fwd_plans.push_back(p);
+      if (blk.has_ds) {
+        st = build_fprop(&p, &blk.ds.d, blk.in, blk.ds.wf, blk.ds.y, nullptr, nullptr, nullptr, m.stats, CG_STATS);
+        if (st) return st;
+        m.fwd_plans.push_back(p);
+      }
+      st = build_fprop(&p, &blk.b.d, blk.act_a, blk.b.wf, blk.b.y, nullptr, nullptr, nullptr, m.stats, CG_STATS);
+      if (st) return st;
+      m.fwd_plans.push_back(p);
+    }
+  }
+  if (!infer) {
+    // backward plans, in execution order (last block first). Gradient buffers ping-pong g0/g1.
+    __nv_bfloat16* gcur = m.g0;
+    __nv_bfloat16* gnext = m.g1;
+    for (int bi = (int)m.blocks.size() - 1; bi >= 0; --bi) {
+      Block& blk = m.blocks[bi];
+      ConvGemmParams p;
+      WgradParams wp;
+      // conv_b: wgrad(dy_b = d1, act_a), dgrad -> ga
+      st = build_wgrad(&wp, &blk.b.d, m.d1, blk.act_a, m.grads + m.slots[blk.b.w].off);
+      if (st) return st;
+      m.wgrad_plans.push_back(wp);
+      st = build_dgrad(&p, &blk.b.d, 0, 0, m.d1, blk.b.wd, m.ga, nullptr, nullptr, nullptr);
+      if (st) return st;
+      m.dgrad_plans.push_back(p);
+      // conv_a: wgrad(dy_a = d1, in), ds: wgrad(dy_d = d2, in)
+      st = build_wgrad(&wp, &blk.a.d, m.d1, blk.in, m.grads + m.slots[blk.a.w].off);
+      if (st) return st;
+      m.wgrad_plans.push_back(wp);
+      if (blk.has_ds) {
+        st = build_wgrad(&wp, &blk.ds.d, m.d2, blk.in, m.grads + m.slots[blk.ds.w].off);
+        if (st) return st;
+        m.wgrad_plans.push_back(wp);
+      }
+      // dgrad of conv_a into gnext (+ identity path)
+      if (!blk.has_ds) {
+        st = build_dgrad(&p, &blk.a.d, 0, 0, m.d1, blk.a.wd, gnext, m.dz, nullptr, nullptr);
+        if (st) return st;
+        m.dgrad_plans.push_back(p);
+      } else {
+        for (int ph = 0; ph < 2; ++ph)
+          for (int pw = 0; pw < 2; ++pw) {
+            const bool fuse = (ph == 0 && pw == 0);
+            st = build_dgrad(&p, &blk.a.d, ph, pw, m.d1, blk.a.wd, gnext, nullptr, fuse ? m.d2 : nullptr, fuse ? blk.ds.wd : nullptr);
+            if (st) return st;
+            m.dgrad_plans.push_back(p);
+          }
+      }
+      __nv_bfloat16* t = gcur; gcur = gnext; gnext = t;
+    }
+    WgradParams wp;
+    st = build_stem_wgrad(&wp, B, m.dy_stem, m.x_s2d, m.grads + m.slots[m.stem.w].off);
+    if (st) return st;
+    m.wgrad_plans.push_back(wp);
+  }
+  m.planB = B;
+  m.planMode = mode;
+  return OK;
+}
+
+#define CK(call)            \
+  do {                      \
+    int _st = (call);       \
+    if (_st) return _st;    \
+  } while (0)
+#define CKL() CK(cuda_status(cudaGetLastError()))
+
+static int run_bn_finalize(Model& m, const BnRef& bn, int tiles, double count, int training, int update, cudaStream_t s) {
+  BnVectors v{bn.vec, bn.vec + bn.C, bn.vec + 2 * bn.C, bn.vec + 3 * bn.C};
+  bn_finalize_kernel<<<(bn.C + 31) / 32, 1024, 0, s>>>(m.stats, tiles, bn.C, count, m.params + m.slots[bn.gamma].off,
+                                                       m.params + m.slots[bn.beta].off, m.buffers + bn.rm_off, m.buffers + bn.rv_off,
+                                                       m.nbt ? m.nbt + bn.nbt_idx : nullptr, 0.1f, 1e-5f, training, update, v);
+  return cuda_status(cudaGetLastError());
+}
+
+static int run_bn_apply(const __nv_bfloat16* x, const BnRef& bn, const __nv_bfloat16* res, const __nv_bfloat16* x2, const BnRef* bn2,
+                        __nv_bfloat16* out, long long elems, int relu, cudaStream_t s) {
+  const long long nvec = elems / 8;
+  bn_apply_kernel<<<ew_grid(nvec, bn.C), EW_THREADS, 0, s>>>(x, bn.vec, bn.vec + bn.C, res, x2, bn2 ? bn2->vec : nullptr,
+                                                             bn2 ? bn2->vec + bn2->C : nullptr, out, nvec, bn.C, relu);
+  return cuda_status(cudaGetLastError());
+}
+
+static HeadsWeights head_weights(const Model& m, const float* base) {
+  HeadsWeights w;
+  int s = m.head_slot0;
+  auto P = [&](int i) { return base + m.slots[i].off; };
+  w.se0_w = P(s); w.se0_b = P(s + 1); w.se3_w = P(s + 2); w.se3_b = P(s + 3);
+  s += 4;
+  for (int k = 0; k < 4; ++k) {
+    w.br0_w[k] = P(s); w.br0_b[k] = P(s + 1); w.br3_w[k] = P(s + 2); w.br3_b[k] = P(s + 3); w.br6_w[k] = P(s + 4); w.br6_b[k] = P(s + 5);
+    s += 6;
+  }
+  w.sp0_w = P(s); w.sp0_b = P(s + 1); w.sp3_w = P(s + 2); w.sp3_b = P(s + 3); w.sp5_w = P(s + 4); w.sp5_b = P(s + 5);
+  return w;
+}
+
+// re-derive everything that depends on parameter values: packed bf16 conv weights (+ eval-mode BN folding)
+static int refresh(Model& m, int what, cudaStream_t s) {
+  if (!m.params) return ERR_INVALID;
+  if (what & 1) {
+    CK(cilrs_stem_pack_weight(m.params + m.slots[m.stem.w].off, m.stem.wf, s));
+    auto pack = [&](ConvRef& c) { return cilrs_conv_pack_weight(&c.d, m.params + m.slots[c.w].off, c.wf, c.wd, s); };
+    for (auto& blk : m.blocks) {
+      CK(pack(blk.a));
+      CK(pack(blk.b));
+      if (blk.has_ds) CK(pack(blk.ds));
+    }
+  }
+  if (what & 2) {
+    CK(run_bn_finalize(m, m.stem.bn, 0, 1.0, 0, 0, s));
+    for (auto& blk : m.blocks) {
+      CK(run_bn_finalize(m, blk.a.bn, 0, 1.0, 0, 0, s));
+      CK(run_bn_finalize(m, blk.b.bn, 0, 1.0, 0, 0, s));
+      if (blk.has_ds) CK(run_bn_finalize(m, blk.ds.bn, 0, 1.0, 0, 0, s));
+    }
+  }
+  return OK;
+}
+
+static int forward(Model& m, int B, int mode, const float* image, const void* x_s2d_in, const float* speed, const long long* command,
+                   float* controls, float* pred_speed, int update_running, int keep_for_backward, float dropout_p,
+                   unsigned long long seed, cudaStream_t s) {
+  if (B < 1 || B > m.maxB) return ERR_INVALID;
+  if (!m.params || !m.buffers) return ERR_INVALID;
+  CK(build_plans(m, B, mode));
+  if (image) {
+    CK(cilrs_image_to_s2d(image, B, m.x_s2d, s));
+  } else if (x_s2d_in) {
+    if (x_s2d_in != (const void*)m.x_s2d)
+      CK(cuda_status(cudaMemcpyAsync(m.x_s2d, x_s2d_in, (size_t)B * 47 * 103 * 16 * 2, cudaMemcpyDeviceToDevice, s)));
+  } else {
+    return ERR_INVALID;
+  }
+  size_t pi = 0;
+  const int training = mode == MODE_TRAIN;
+  if (mode == MODE_INFER) {
+    CK(launch_conv_gemm(&m.fwd_plans[pi++], s));
+    {
+      const long long nvec = act_elems(B, 22, 50, 64) / 8;
+      bn_relu_maxpool_kernel<<<ew_grid(nvec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.unit_vec, m.unit_vec + 64, m.pool_out, nullptr, B, 44,
+                                                                      100, 64, 22, 50);
+      CKL();
+    }
+    for (auto& blk : m.blocks) {
+      CK(launch_conv_gemm(&m.fwd_plans[pi++], s));
+      if (blk.has_ds) CK(launch_conv_gemm(&m.fwd_plans[pi++], s));
+      CK(launch_conv_gemm(&m.fwd_plans[pi++], s));
+    }
+  } else {
+    CK(launch_conv_gemm(&m.fwd_plans[pi], s));
+    {
+      const ConvGemmParams& p = m.fwd_plans[pi++];
+      CK(run_bn_finalize(m, m.stem.bn, p.tiles_w * p.tiles_h * p.tiles_n, (double)B * 44 * 100, training, update_running, s));
+      const long long nvec = act_elems(B, 22, 50, 64) / 8;
+      bn_relu_maxpool_kernel<<<ew_grid(nvec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.stem.bn.vec, m.stem.bn.vec + 64, m.pool_out,
+                                                                      m.pool_arg, B, 44, 100, 64, 22, 50);
+      CKL();
+    }
+    for (auto& blk : m.blocks) {
+      auto conv_bn = [&](ConvRef& c) -> int {
+        const ConvGemmParams& p = m.fwd_plans[pi];
+        CK(launch_conv_gemm(&m.fwd_plans[pi++], s));
+        return run_bn_finalize(m, c.bn, p.tiles_w * p.tiles_h * p.tiles_n, (double)B * c.oh * c.ow, training, update_running, s);
+      };
+      CK(conv_bn(blk.a));
+      CK(run_bn_apply(blk.a.y, blk.a.bn, nullptr, nullptr, nullptr, blk.act_a, act_elems(B, blk.a.oh, blk.a.ow, blk.a.d.out_c), 1, s));
+      if (blk.has_ds) CK(conv_bn(blk.ds));
+      CK(conv_bn(blk.b));
+      const long long oe = act_elems(B, blk.b.oh, blk.b.ow, blk.b.d.out_c);
+      if (blk.has_ds) CK(run_bn_apply(blk.b.y, blk.b.bn, nullptr, blk.ds.y, &blk.ds.bn, blk.out, oe, 1, s));
+      else CK(run_bn_apply(blk.b.y, blk.b.bn, blk.in, nullptr, nullptr, blk.out, oe, 1, s));
+    }
+  }
+  avgpool_kernel<<<(B * 512 + 255) / 256, 256, 0, s>>>(m.blocks.back().out, m.feat, B, 21, 512);
+  CKL();
+  HeadsFwdParams hp;
+  hp.w = head_weights(m, m.params);
+  if (keep_for_backward) hp.sv = m.hs; else memset(&hp.sv, 0, sizeof(hp.sv));
+  hp.feat = m.feat; hp.speed = speed; hp.command = command; hp.controls = controls; hp.pred_speed = pred_speed;
+  hp.batch = B; hp.dropout_p = dropout_p; hp.seed = seed; hp.error_flag = m.err_flag;
+  heads_fwd_kernel<<<B, HD_THREADS, 0, s>>>(hp);
+  CKL();
+  return OK;
+}
+
+static int run_bn_bwd(Model& m, const BnRef& bn, const __nv_bfloat16* g, const __nv_bfloat16* act, const __nv_bfloat16* y,
+                      long long elems, double count, int frozen, __nv_bfloat16* dy, __nv_bfloat16* dz, cudaStream_t s) {
+  const long long nvec = elems / 8;
+  const int grid = ew_grid(nvec, bn.C);
+  BnBwdReduceParams rp{};
+  rp.g = g; rp.act = act; rp.y = y; rp.mean = bn.vec + 2 * bn.C; rp.rstd = bn.vec + 3 * bn.C; rp.nvec = nvec; rp.C = bn.C;
+  rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + bn.C;
+  rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
+  bn_bwd_reduce_kernel<false><<<grid, EW_THREADS, 0, s>>>(rp);
+  CKL();
+  BnBwdApplyParams ap{};
+  ap.g = g; ap.act = act; ap.y = y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
+  ap.bsum = rp.bsum; ap.bdot = rp.bdot; ap.inv_count = (float)(1.0 / count); ap.frozen = frozen; ap.nvec = nvec; ap.C = bn.C;
+  ap.dy = dy; ap.dz = dz;
+  bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap);
+  CKL();
+  return OK;
+}
+
+// part: -1 = whole backward; 0 = heads + layer4, 1 = layer3, 2 = layer2, 3 = layer1, 4 = stem (must be called in order)
+static int backward(Model& m, int B, int mode, int part, const float* dcontrols, const float* dspeed, const float* speed,
+                    const long long* command, float dropout_p, cudaStream_t s) {
+  if (mode == MODE_INFER) return ERR_INVALID;
+  if (B != m.planB || mode != m.planMode) return ERR_INVALID;  // must follow a forward with keep_for_backward
+  if (!m.grads) return ERR_INVALID;
+  const int frozen = mode == MODE_FROZEN;
+  if (part < -1 || part > 4) return ERR_INVALID;
+  if (part <= 0) {
+  // ---- heads ----
+  HeadsBwdParams bp;
+  bp.w = head_weights(m, m.params); bp.sv = m.hs; bp.dcontrols = dcontrols; bp.dspeed = dspeed; bp.command = command;
+  bp.dfeat = m.dfeat; bp.batch = B; bp.dropout_p = dropout_p;
+  heads_bwd_kernel<<<B, HD_THREADS, 0, s>>>(bp);
+  CKL();
+  {
+    HeadsWgradParams wp;
+    memset(&wp, 0, sizeof(wp));
+    wp.batch = B; wp.command = command; wp.speed = speed;
+    int sidx = m.head_slot0, tiles = 0, nj = 0;
+    auto G = [&](int i) { return m.grads + m.slots[i].off; };
+    auto add = [&](const float* delta, int ldd, const float* x, int ldx, int out, int in, int slot_w, int branch) {
+      HeadsWgradJob& j = wp.job[nj++];
+      j.delta = delta; j.x = x; j.dw = G(slot_w); j.db = G(slot_w + 1); j.out = out; j.in = in; j.ld_delta = ldd; j.ld_x = ldx;
+      j.branch = branch; j.tile_begin = tiles; j.tiles_i = (in + 63) / 64;
+      tiles += j.tiles_i * ((out + 15) / 16);
+    };
+    add(m.hs.d_se0, 128, speed, 1, 128, 1, sidx, -1);
+    add(m.hs.d_se3, 128, m.hs.s1, 128, 128, 128, sidx + 2, -1);
+    sidx += 4;
+    for (int k = 0; k < 4; ++k) {
+      // x of the first branch layer is [feat | sfeat]: two jobs would need two sources; stage it as two column ranges
+      add(m.hs.d_br0, 256, nullptr, 0, 256, 640, sidx, k);      // patched below (combined input)
+      add(m.hs.d_br3, 256, m.hs.b1, 256, 256, 256, sidx + 2, k);
+      add(m.hs.d_br6, 4, m.hs.b2, 256, 3, 256, sidx + 4, k);
+      sidx += 6;
+    }
+    add(m.hs.d_sp0, 256, m.feat, 512, 256, 512, sidx, -1);
+    add(m.hs.d_sp3, 256, m.hs.p1, 256, 256, 256, sidx + 2, -1);
+    add(m.hs.d_sp5, 1, m.hs.p2, 256, 1, 256, sidx + 4, -1);
+    wp.num_jobs = nj;
+    // combined input [B,640] = [feat(512) | sfeat(128)] lives in dfeat-sized scratch: build it once
+    float* comb = (float*)m.ga;  // ga is free until the trunk backward starts (needs B*640*4 bytes)
+    CK(cuda_status(cudaMemcpy2DAsync(comb, 640 * 4, m.feat, 512 * 4, 512 * 4, B, cudaMemcpyDeviceToDevice, s)));
+    CK(cuda_status(cudaMemcpy2DAsync(comb + 512, 640 * 4, m.hs.sfeat, 128 * 4, 128 * 4, B, cudaMemcpyDeviceToDevice, s)));
+    for (int j = 0; j < nj; ++j)
+      if (!wp.job[j].x) { wp.job[j].x = comb; wp.job[j].ld_x = 640; }
+    heads_wgrad_kernel<<<tiles, 256, 0, s>>>(wp);
+    CKL();
+  }
+  // ---- trunk ----
+  avgpool_bwd_kernel<<<(int)((act_elems(B, 3, 7, 512) + 255) / 256), 256, 0, s>>>(m.dfeat, m.g0, B, 21, 512);
+  CKL();
+  m.bw_gcur = m.g0; m.bw_gnext = m.g1; m.bw_di = 0; m.bw_wi = 0;
+  }
+  __nv_bfloat16*& gcur = m.bw_gcur;
+  __nv_bfloat16*& gnext = m.bw_gnext;
+  size_t& di = m.bw_di;
+  size_t& wi = m.bw_wi;
+  // blocks 15..13 = layer4, 12..7 = layer3, 6..3 = layer2, 2..0 = layer1
+  static const int part_hi[4] = {15, 12, 6, 2}, part_lo[4] = {13, 7, 3, 0};
+  const int b_hi = part < 0 ? 15 : (part < 4 ? part_hi[part] : -1);
+  const int b_lo = part < 0 ? 0 : (part < 4 ? part_lo[part] : 0);
+  for (int bi = b_hi; bi >= b_lo; --bi) {
+    Block& blk = m.blocks[bi];
+    const long long oe = act_elems(B, blk.b.oh, blk.b.ow, blk.b.d.out_c);
+    const double cnt = (double)B * blk.b.oh * blk.b.ow;
+    // out = relu(bn_b(y_b) + identity): dz = g * (out > 0)
+    CK(run_bn_bwd(m, blk.b.bn, gcur, blk.out, blk.b.y, oe, cnt, frozen, m.d1, blk.has_ds ? nullptr : m.dz, s));
+    if (blk.has_ds) CK(run_bn_bwd(m, blk.ds.bn, gcur, blk.out, blk.ds.y, oe, cnt, frozen, m.d2, nullptr, s));
+    CK(launch_wgrad(&m.wgrad_plans[wi++], s));       // dW_b
+    CK(launch_conv_gemm(&m.dgrad_plans[di++], s));   // ga = dgrad_b(d1)
+    // act_a = relu(bn_a(y_a))
+    CK(run_bn_bwd(m, blk.a.bn, m.ga, blk.act_a, blk.a.y, oe, cnt, frozen, m.d1, nullptr, s));
+    CK(launch_wgrad(&m.wgrad_plans[wi++], s));       // dW_a
+    if (blk.has_ds) CK(launch_wgrad(&m.wgrad_plans[wi++], s));  // dW_ds
+    const int nd = blk.has_ds ? 4 : 1;
+    for (int k = 0; k < nd; ++k) CK(launch_conv_gemm(&m.dgrad_plans[di++], s));
+    __nv_bfloat16* t = gcur; gcur = gnext; gnext = t;
+  }
+  // ---- stem: max-pool backward + ReLU + BN backward, then wgrad ----
+  if (part < 0 || part == 4) {
+    const BnRef& bn = m.stem.bn;
+    const long long nvec = act_elems(B, 44, 100, 64) / 8;
+    const int grid = ew_grid(nvec, 64);
+    BnBwdReduceParams rp{};
+    rp.g = gcur; rp.y = m.stem.y; rp.mean = bn.vec + 2 * 64; rp.rstd = bn.vec + 3 * 64; rp.nvec = nvec; rp.C = 64;
+    rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + 64;
+    rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
+    rp.argmax = m.pool_arg; rp.scale = bn.vec; rp.shift = bn.vec + 64; rp.H = 44; rp.W = 100; rp.OH = 22; rp.OW = 50;
+    bn_bwd_reduce_kernel<true><<<grid, EW_THREADS, 0, s>>>(rp);
+    CKL();
+    BnBwdApplyParams ap{};
+    ap.g = gcur; ap.y = m.stem.y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
+    ap.bsum = rp.bsum; ap.bdot = rp.bdot; ap.inv_count = (float)(1.0 / ((double)B * 4400.0)); ap.frozen = frozen; ap.nvec = nvec;
+    ap.C = 64; ap.dy = m.dy_stem; ap.argmax = m.pool_arg; ap.scale = bn.vec; ap.shift = bn.vec + 64; ap.H = 44; ap.W = 100;
+    ap.OH = 22; ap.OW = 50;
+    bn_bwd_apply_kernel<true><<<grid, EW_THREADS, 0, s>>>(ap);
+    CKL();
+    CK(launch_wgrad(&m.wgrad_plans[wi++], s));
+  }
+  return OK;
+}
+
+}  // namespace cilrs
+
+using namespace cilrs;
+
+extern "C" {
+
+struct cilrs_model {
+  Model m;
+};
+
+int cilrs_model_param_layout(long long* offsets, long long* sizes, int capacity, long long* total_floats, long long* buffer_floats,
+                             int* num_bn) {
+  Model m;
+  m.maxB = 1;
+  build_topology(m, 1);
+  const int n = (int)m.slots.size();
+  for (int i = 0; i < n && i < capacity; ++i) {
+    if (offsets) offsets[i] = m.slots[i].off;
+    if (sizes) sizes[i] = m.slots[i].size;
+  }
+  if (total_floats) *total_floats = m.param_floats;
+  if (buffer_floats) *buffer_floats = m.buffer_floats;
+  if (num_bn) *num_bn = m.num_bn;
+  return n;
+}
+
+size_t cilrs_model_workspace_bytes(int max_batch) {
+  if (max_batch < 1) return 0;
+  Model m;
+  m.maxB = max_batch;
+  build_topology(m, max_batch);
+  return (size_t)carve(m, nullptr);
+}
+
+int cilrs_model_create(cilrs_model** out, int max_batch, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!out || max_batch < 1 || !workspace) return ERR_INVALID;
+  if (((uintptr_t)workspace) & 1023) return ERR_INVALID;
+  cilrs_model* h = new (std::nothrow) cilrs_model();
+  if (!h) return ERR_INVALID;
+  h->m.maxB = max_batch;
+  build_topology(h->m, max_batch);
+  const long long need = carve(h->m, (char*)workspace);
+  if ((size_t)need > workspace_bytes) {
+    delete h;
+    return ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  // constants: reduction counters, unit scale/shift for the inference max-pool, error flag
+  float unit[128];
+  for (int i = 0; i < 64; ++i) { unit[i] = 1.f; unit[64 + i] = 0.f; }
+  int st = cuda_status(cudaMemsetAsync(h->m.counters, 0, 64, s));
+  if (!st) st = cuda_status(cudaMemsetAsync(h->m.err_flag, 0, 64, s));
+  if (!st) st = cuda_status(cudaMemcpyAsync(h->m.unit_vec, unit, sizeof(unit), cudaMemcpyHostToDevice, s));
+  if (!st) st = cuda_status(cudaStreamSynchronize(s));  // `unit` is a stack buffer; creation is not on the hot path
+  if (st) {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return OK;
+}
+
+void cilrs_model_destroy(cilrs_model* h) { delete h; }
+
+int cilrs_model_bind(cilrs_model* h, float* params, float* grads, float* buffers, long long* num_batches_tracked) {
+  if (!h || !params || !buffers) return ERR_INVALID;
+  if ((((uintptr_t)params) | ((uintptr_t)grads) | ((uintptr_t)buffers)) & 15) return ERR_INVALID;
+  Model& m = h->m;
+  if (m.grads != grads) { m.planB = 0; m.planMode = -1; }  // wgrad plans hold gradient pointers
+  m.params = params; m.grads = grads; m.buffers = buffers; m.nbt = num_batches_tracked;
+  return OK;
+}
+
+int cilrs_model_refresh(cilrs_model* h, int what, void* stream) {
+  if (!h) return ERR_INVALID;
+  return refresh(h->m, what, (cudaStream_t)stream);
+}
+
+int cilrs_model_forward(cilrs_model* h, int batch, int mode, const float* image_nchw, const void* image_s2d, const float* speed,
+                        const long long* command, float* controls, float* pred_speed, int update_running_stats,
+                        int keep_for_backward, float dropout_p, unsigned long long seed, void* stream) {
+  if (!h || !speed || !command || !controls || !pred_speed) return ERR_INVALID;
+  if (mode < 0 || mode > 2) return ERR_INVALID;
+  if (mode == MODE_INFER && keep_for_backward) return ERR_INVALID;
+  return forward(h->m, batch, mode, image_nchw, image_s2d, speed, command, controls, pred_speed, update_running_stats,
+                 keep_for_backward, dropout_p, seed, (cudaStream_t)stream);
+}
+
+int cilrs_model_backward(cilrs_model* h, int batch, int mode, int part, const float* dcontrols, const float* dspeed,
+                         const float* speed, const long long* command, float dropout_p, void* stream) {
+  if (!h || !dcontrols || !dspeed || !speed || !command) return ERR_INVALID;
+  return backward(h->m, batch, mode, part, dcontrols, dspeed, speed, command, dropout_p, (cudaStream_t)stream);
+}
+
+int cilrs_model_backward_part_first_tensor(int part) {
+  static const int first_block[5] = {13, 7, 3, 0, -1};
+  if (part < 0 || part > 4) return -1;
+  if (part == 4) return 0;
+  Model m;
+  m.maxB = 1;
+  build_topology(m, 1);
+  return m.blocks[first_block[part]].a.w;
+}
+
+// debug / test hook: device pointer and NHWC dims of an intermediate activation of the last forward
+//   which: 0 = max-pool output, 1..16 = BasicBlock outputs, 17 = stem conv raw output; dims = {H, W, C}
+void* cilrs_model_debug_activation(cilrs_model* h, int which, int* dims) {
+  if (!h || !dims) return nullptr;
+  Model& m = h->m;
+  if (which == 0) { dims[0] = 22; dims[1] = 50; dims[2] = 64; return m.pool_out; }
+  if (which >= 1 && which <= (int)m.blocks.size()) {
+    Block& b = m.blocks[which - 1];
+    dims[0] = b.b.oh; dims[1] = b.b.ow; dims[2] = b.b.d.out_c;
+    return b.out;
+  }
+  if (which == 17) { dims[0] = 44; dims[1] = 100; dims[2] = 64; return m.stem.y; }
+  return nullptr;
+}
+
+void* cilrs_model_input_s2d(cilrs_model* h) { return h ? (void*)h->m.x_s2d : nullptr; }
+int* cilrs_model_error_flag(cilrs_model* h) { return h ? h->m.err_flag : nullptr; }
+
+int cilrs_loss(const float* controls, const float* pred_speed, const float* targets, const float* speed_target, int batch, int mode,
+               float w_steer, float w_throttle, float w_brake, float w_speed, float grad_scale, float* out6, float* dcontrols,
+               float* dspeed, void* stream) {
+  if (!controls || !pred_speed || !targets || !speed_target || !out6 || batch < 1) return ERR_INVALID;
+  if (mode != 0 && mode != 1) return ERR_INVALID;
+  LossParams p;
+  p.controls = controls; p.pred_speed = pred_speed; p.targets = targets; p.speed_target = speed_target; p.batch = batch; p.mode = mode;
+  p.w_steer = w_steer; p.w_throttle = w_throttle; p.w_brake = w_brake; p.w_speed = w_speed; p.grad_scale = grad_scale;
+  p.out = out6; p.dcontrols = dcontrols; p.dspeed = dspeed;
+  loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p);
+  return cuda_status(cudaGetLastError());
+}
+
+int cilrs_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, long long step, long long* step_dev, float grad_scale, const float* grad_scale_dev,
+                    void* stream) {
+  if (!p || !g || !m || !v || n < 0 || (n & 3) || (step < 1 && !step_dev)) return ERR_INVALID;
+  if ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) return ERR_INVALID;
+  if (n == 0) return OK;
+  AdamParams a;
+  a.p = p; a.g = g; a.m = m; a.v = v; a.n = n; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  a.bias_correction1 = step >= 1 ? (float)(1.0 - pow((double)beta1, (double)step)) : 1.f;
+  a.bias_correction2_sqrt = step >= 1 ? (float)sqrt(1.0 - pow((double)beta2, (double)step)) : 1.f;
+  a.grad_scale = grad_scale; a.grad_scale_dev = grad_scale_dev; a.step_dev = step_dev;
+  if (step_dev) {
+    step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    int st = cuda_status(cudaGetLastError());
+    if (st) return st;
+  }
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  return cuda_status(cudaGetLastError());
+}
+
+int cilrs_grad_sumsq(const float* g, long long n, double* partial_ws /* >= 1024 doubles */, unsigned int* counter_ws /* zeroed */,
+                     float max_norm, float* out2, void* stream) {
+  if (!g || !partial_ws || !counter_ws || !out2 || n < 0 || (n & 3)) return ERR_INVALID;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 592) blocks = 592;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, n, partial_ws, counter_ws, out2, max_norm);
+  return cuda_status(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -10,35 +10,9 @@
 //   warp 0 : TMA producer      warp 1 : MMA issuer      warps 2..5 : epilogue
 #pragma once
 #include "common.cuh"
+#include "conv_params.h"
 
 namespace cilrs {
-
-constexpr int WG_MAX_TAPS = 16;
-constexpr int WG_THREADS = 192;
-constexpr int WG_SLAB = 128 * 128;  // 128 pixel rows x 64 bf16
-constexpr int WG_MAX_STAGES = 4;
-
-enum WgradColMode : int { WG_COL_REGULAR = 0, WG_COL_CONV1_S2D = 1 };
-
-struct WgradParams {
-  CUtensorMap tmDY;  // (Cout, OW, OH, N), box (64, BW, BH, BN)
-  CUtensorMap tmX;   // (Cin,  W,  H,  N), box (64, BW, BH, BN) with the conv stride as element stride
-  int tiles_w, tiles_h, tiles_n;
-  int BW, BH, BN;
-  int in_sw, in_sh;
-  int co_blocks, m_halves;   // M = 128 rows of the accumulator = m_halves x 64 output channels
-  int ci_chunks;
-  int tap_groups, g;         // g taps per CTA, N = 64 g
-  int split_z;
-  int num_stages;
-  int8_t tap_dw[WG_MAX_TAPS], tap_dh[WG_MAX_TAPS];
-  int16_t tap_id[WG_MAX_TAPS];  // position of the tap inside the kh*kw plane of the OIHW gradient
-  int num_taps;
-  int cout, cin;
-  int co_stride, ci_stride;  // element strides of the fp32 gradient tensor
-  int col_mode;
-  float* grad;
-};
 
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];

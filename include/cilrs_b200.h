@@ -94,6 +94,77 @@ int cilrs_stem_fprop(int batch, const void* x_s2d, const void* w_packed, void* y
 int cilrs_stem_wgrad(int batch, const void* dy, const void* x_s2d, float* dw_oihw, void* stream);
 int cilrs_stem_stats_tiles(int batch);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * M1-M5 / B1  the whole CILRS network behind one handle.  Replaces CILRS.forward (model/autonomous_drive.py:389-399)
+ * and the autograd backward the reference gets from loss.backward() (notebook/notebook.ipynb:552).
+ *
+ * Memory model: the caller owns three arenas and a workspace, all device memory:
+ *   params  : fp32, every nn.Parameter of the reference module in named_parameters() order, each tensor starting
+ *             at the offset cilrs_model_param_layout reports (64-byte aligned), OIHW / [out,in] as in the state_dict
+ *   grads   : fp32, same layout; backward ACCUMULATES into it (zero it like optimizer.zero_grad())
+ *   buffers : fp32, for each of the 36 BatchNorms in order: running_mean[C] then running_var[C];
+ *             num_batches_tracked: int64[36]
+ *   workspace : cilrs_model_workspace_bytes(max_batch) bytes, 1024-byte aligned
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct cilrs_model cilrs_model;
+
+/* returns the number of parameter tensors (142); fills offsets/sizes (in floats) for the first `capacity` */
+int cilrs_model_param_layout(long long* offsets, long long* sizes, int capacity, long long* total_floats,
+                             long long* buffer_floats, int* num_bn);
+size_t cilrs_model_workspace_bytes(int max_batch);
+/* creation is the only call that synchronises the stream (it uploads a few constants) */
+int cilrs_model_create(cilrs_model** out, int max_batch, void* workspace, size_t workspace_bytes, void* stream);
+void cilrs_model_destroy(cilrs_model* m);
+int cilrs_model_bind(cilrs_model* m, float* params, float* grads, float* buffers, long long* num_batches_tracked);
+/* call after parameter values changed. what: bit 0 = repack the bf16 conv operands from the fp32 masters,
+ * bit 1 = fold eval-mode BatchNorm (running statistics) into per-channel scale/shift for CILRS_MODE_INFER */
+int cilrs_model_refresh(cilrs_model* m, int what, void* stream);
+
+enum { CILRS_MODE_TRAIN = 0,  /* BN uses batch statistics (module.train()) */
+       CILRS_MODE_FROZEN = 1, /* BN uses running statistics, activations kept: eval() with autograd */
+       CILRS_MODE_INFER = 2   /* eval(), no_grad: BN folded into the conv epilogues */ };
+
+/* image: either f32 NCHW [batch,3,88,200] (image_nchw) or the bf16 space-to-depth tensor K0 produced (image_s2d).
+ * speed f32 [batch], command int64 [batch] in {0..3}; controls f32 [batch,3], pred_speed f32 [batch]. */
+int cilrs_model_forward(cilrs_model* m, int batch, int mode, const float* image_nchw, const void* image_s2d,
+                        const float* speed, const long long* command, float* controls, float* pred_speed,
+                        int update_running_stats, int keep_for_backward, float dropout_p, unsigned long long seed,
+                        void* stream);
+/* gradients of a scalar w.r.t. controls / pred_speed in, parameter gradients accumulated into `grads`.
+ * part = -1 runs the whole backward; parts 0..4 (heads+layer4, layer3, layer2, layer1, stem; in that order) let the
+ * host start the allreduce of the gradient range a part completed while the next part runs (data parallelism). */
+int cilrs_model_backward(cilrs_model* m, int batch, int mode, int part, const float* dcontrols, const float* dspeed,
+                         const float* speed, const long long* command, float dropout_p, void* stream);
+/* first parameter-tensor index (into cilrs_model_param_layout) whose gradient backward part `part` completes;
+ * part p completes tensors [first(p), first(p-1)) with first(-1) = number of tensors */
+int cilrs_model_backward_part_first_tensor(int part);
+void* cilrs_model_input_s2d(cilrs_model* m); /* where K0 may write the conv1-ready frames directly */
+/* test hook: bf16 NHWC activation of the last forward. which: 0 = max-pool output, 1..16 = BasicBlock outputs,
+ * 17 = raw stem conv output; dims receives {H, W, C} */
+void* cilrs_model_debug_activation(cilrs_model* m, int which, int* dims);
+int* cilrs_model_error_flag(cilrs_model* m); /* device int, set to 1 when a command was outside [0,4) */
+
+/* ---------------------------------------------------------------------------------------------------------
+ * L1/L2  losses + their gradients (CILRSLoss.forward notebook/notebook.ipynb:514-527; MSE recipe
+ *        configs/train_config.json:30-32).  mode 0: MSE(controls)+w_speed*MSE(speed); mode 1: weighted L1 + w_speed*MSE.
+ *        out6 = total, control, steer, throttle, brake, speed. dcontrols/dspeed optional.
+ * --------------------------------------------------------------------------------------------------------- */
+int cilrs_loss(const float* controls, const float* pred_speed, const float* targets, const float* speed_target,
+               int batch, int mode, float w_steer, float w_throttle, float w_brake, float w_speed, float grad_scale,
+               float* out6, float* dcontrols, float* dspeed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * O1/O2  optimiser.  torch.optim.Adam(lr, weight_decay) single step over a flat arena (notebook/notebook.ipynb:533-534,555)
+ *        and the squared gradient norm + clip coefficient of clip_grad_norm_ (notebook/notebook.ipynb:553-554).
+ * --------------------------------------------------------------------------------------------------------- */
+/* step: 1-based step number used for the bias corrections; if step_dev (device int64) is given it is incremented on
+ * the stream first and used instead, so a captured CUDA graph of the step stays valid for every step number. */
+int cilrs_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, long long step, long long* step_dev, float grad_scale,
+                    const float* grad_scale_dev, void* stream);
+int cilrs_grad_sumsq(const float* g, long long n, double* partial_ws, unsigned int* counter_ws, float max_norm,
+                     float* out2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
