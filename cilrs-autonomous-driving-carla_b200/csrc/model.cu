@@ -98,6 +98,7 @@ struct Model {
   std::vector<ConvGemmParams> fwd_plans;
   std::vector<ConvGemmParams> dgrad_plans;
   std::vector<WgradParams> wgrad_plans;
+  std::vector<int> wgrad_slot;  // parameter slot each wgrad plan accumulates into (pointer resolved at launch)
   // resumable backward (so the host can start the allreduce of finished gradient buckets between parts)
   __nv_bfloat16 *bw_gcur = nullptr, *bw_gnext = nullptr;
   size_t bw_di = 0, bw_wi = 0;
@@ -250,7 +251,7 @@ enum FwdMode { MODE_TRAIN = 0, MODE_FROZEN = 1, MODE_INFER = 2 };
 
 static int build_plans(Model& m, int B, int mode) {
   if (B == m.planB && mode == m.planMode) return OK;
-  m.fwd_plans.clear(); m.dgrad_plans.clear(); m.wgrad_plans.clear();
+  m.fwd_plans.clear(); m.dgrad_plans.clear(); m.wgrad_plans.clear(); m.wgrad_slot.clear();
   int st;
   set_batch(m.stem, B);
   const bool infer = mode == MODE_INFER;
@@ -306,20 +307,20 @@ static int build_plans(Model& m, int B, int mode) {
       ConvGemmParams p;
       WgradParams wp;
       // conv_b: wgrad(dy_b = d1, act_a), dgrad -> ga
-      st = build_wgrad(&wp, &blk.b.d, m.d1, blk.act_a, m.grads + m.slots[blk.b.w].off);
+      st = build_wgrad(&wp, &blk.b.d, m.d1, blk.act_a, nullptr);
       if (st) return st;
-      m.wgrad_plans.push_back(wp);
+      m.wgrad_plans.push_back(wp); m.wgrad_slot.push_back(blk.b.w);
       st = build_dgrad(&p, &blk.b.d, 0, 0, m.d1, blk.b.wd, m.ga, nullptr, nullptr, nullptr);
       if (st) return st;
       m.dgrad_plans.push_back(p);
       // conv_a: wgrad(dy_a = d1, in), ds: wgrad(dy_d = d2, in)
-      st = build_wgrad(&wp, &blk.a.d, m.d1, blk.in, m.grads + m.slots[blk.a.w].off);
+      st = build_wgrad(&wp, &blk.a.d, m.d1, blk.in, nullptr);
       if (st) return st;
-      m.wgrad_plans.push_back(wp);
+      m.wgrad_plans.push_back(wp); m.wgrad_slot.push_back(blk.a.w);
       if (blk.has_ds) {
-        st = build_wgrad(&wp, &blk.ds.d, m.d2, blk.in, m.grads + m.slots[blk.ds.w].off);
+        st = build_wgrad(&wp, &blk.ds.d, m.d2, blk.in, nullptr);
         if (st) return st;
-        m.wgrad_plans.push_back(wp);
+        m.wgrad_plans.push_back(wp); m.wgrad_slot.push_back(blk.ds.w);
       }
       // dgrad of conv_a into gnext (+ identity path)
       if (!blk.has_ds) {
@@ -338,9 +339,9 @@ static int build_plans(Model& m, int B, int mode) {
       __nv_bfloat16* t = gcur; gcur = gnext; gnext = t;
     }
     WgradParams wp;
-    st = build_stem_wgrad(&wp, B, m.dy_stem, m.x_s2d, m.grads + m.slots[m.stem.w].off);
+    st = build_stem_wgrad(&wp, B, m.dy_stem, m.x_s2d, nullptr);
     if (st) return st;
-    m.wgrad_plans.push_back(wp);
+    m.wgrad_plans.push_back(wp); m.wgrad_slot.push_back(m.stem.w);
   }
   m.planB = B;
   m.planMode = mode;
@@ -407,6 +408,9 @@ static int refresh(Model& m, int what, cudaStream_t s) {
   return OK;
 }
 
+static int heads_forward(Model& m, int B, const float* speed, const long long* command, float* controls, float* pred_speed,
+                         int keep_for_backward, float dropout_p, unsigned long long seed, cudaStream_t s);
+
 static int forward(Model& m, int B, int mode, const float* image, const void* x_s2d_in, const float* speed, const long long* command,
                    float* controls, float* pred_speed, int update_running, int keep_for_backward, float dropout_p,
                    unsigned long long seed, cudaStream_t s) {
@@ -463,6 +467,11 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
   }
   avgpool_kernel<<<(B * 512 + 255) / 256, 256, 0, s>>>(m.blocks.back().out, m.feat, B, 21, 512);
   CKL();
+  return heads_forward(m, B, speed, command, controls, pred_speed, keep_for_backward, dropout_p, seed, s);
+}
+
+static int heads_forward(Model& m, int B, const float* speed, const long long* command, float* controls, float* pred_speed,
+                         int keep_for_backward, float dropout_p, unsigned long long seed, cudaStream_t s) {
   HeadsFwdParams hp;
   hp.w = head_weights(m, m.params);
   if (keep_for_backward) hp.sv = m.hs; else memset(&hp.sv, 0, sizeof(hp.sv));
@@ -471,6 +480,12 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
   heads_fwd_kernel<<<B, HD_THREADS, 0, s>>>(hp);
   CKL();
   return OK;
+}
+
+static int run_wgrad(Model& m, size_t idx, cudaStream_t s) {
+  WgradParams& wp = m.wgrad_plans[idx];
+  wp.grad = m.grads + m.slots[m.wgrad_slot[idx]].off;
+  return launch_wgrad(&wp, s);
 }
 
 static int run_bn_bwd(Model& m, const BnRef& bn, const __nv_bfloat16* g, const __nv_bfloat16* act, const __nv_bfloat16* y,
@@ -492,15 +507,8 @@ static int run_bn_bwd(Model& m, const BnRef& bn, const __nv_bfloat16* g, const _
   return OK;
 }
 
-// part: -1 = whole backward; 0 = heads + layer4, 1 = layer3, 2 = layer2, 3 = layer1, 4 = stem (must be called in order)
-static int backward(Model& m, int B, int mode, int part, const float* dcontrols, const float* dspeed, const float* speed,
-                    const long long* command, float dropout_p, cudaStream_t s) {
-  if (mode == MODE_INFER) return ERR_INVALID;
-  if (B != m.planB || mode != m.planMode) return ERR_INVALID;  // must follow a forward with keep_for_backward
-  if (!m.grads) return ERR_INVALID;
-  const int frozen = mode == MODE_FROZEN;
-  if (part < -1 || part > 4) return ERR_INVALID;
-  if (part <= 0) {
+static int heads_backward(Model& m, int B, const float* dcontrols, const float* dspeed, const float* speed,
+                          const long long* command, float dropout_p, cudaStream_t s) {
   // ---- heads ----
   HeadsBwdParams bp;
   bp.w = head_weights(m, m.params); bp.sv = m.hs; bp.dcontrols = dcontrols; bp.dspeed = dspeed; bp.command = command;
@@ -542,6 +550,19 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     heads_wgrad_kernel<<<tiles, 256, 0, s>>>(wp);
     CKL();
   }
+  return OK;
+}
+
+// part: -1 = whole backward; 0 = heads + layer4, 1 = layer3, 2 = layer2, 3 = layer1, 4 = stem (must be called in order)
+static int backward(Model& m, int B, int mode, int part, const float* dcontrols, const float* dspeed, const float* speed,
+                    const long long* command, float dropout_p, cudaStream_t s) {
+  if (mode == MODE_INFER) return ERR_INVALID;
+  if (B != m.planB || mode != m.planMode) return ERR_INVALID;  // must follow a forward with keep_for_backward
+  if (!m.grads) return ERR_INVALID;
+  const int frozen = mode == MODE_FROZEN;
+  if (part < -1 || part > 4) return ERR_INVALID;
+  if (part <= 0) {
+  CK(heads_backward(m, B, dcontrols, dspeed, speed, command, dropout_p, s));
   // ---- trunk ----
   avgpool_bwd_kernel<<<(int)((act_elems(B, 3, 7, 512) + 255) / 256), 256, 0, s>>>(m.dfeat, m.g0, B, 21, 512);
   CKL();
@@ -562,12 +583,12 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     // out = relu(bn_b(y_b) + identity): dz = g * (out > 0)
     CK(run_bn_bwd(m, blk.b.bn, gcur, blk.out, blk.b.y, oe, cnt, frozen, m.d1, blk.has_ds ? nullptr : m.dz, s));
     if (blk.has_ds) CK(run_bn_bwd(m, blk.ds.bn, gcur, blk.out, blk.ds.y, oe, cnt, frozen, m.d2, nullptr, s));
-    CK(launch_wgrad(&m.wgrad_plans[wi++], s));       // dW_b
+    CK(run_wgrad(m, wi++, s));                       // dW_b
     CK(launch_conv_gemm(&m.dgrad_plans[di++], s));   // ga = dgrad_b(d1)
     // act_a = relu(bn_a(y_a))
     CK(run_bn_bwd(m, blk.a.bn, m.ga, blk.act_a, blk.a.y, oe, cnt, frozen, m.d1, nullptr, s));
-    CK(launch_wgrad(&m.wgrad_plans[wi++], s));       // dW_a
-    if (blk.has_ds) CK(launch_wgrad(&m.wgrad_plans[wi++], s));  // dW_ds
+    CK(run_wgrad(m, wi++, s));                       // dW_a
+    if (blk.has_ds) CK(run_wgrad(m, wi++, s));       // dW_ds
     const int nd = blk.has_ds ? 4 : 1;
     for (int k = 0; k < nd; ++k) CK(launch_conv_gemm(&m.dgrad_plans[di++], s));
     __nv_bfloat16* t = gcur; gcur = gnext; gnext = t;
@@ -591,7 +612,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     ap.OH = 22; ap.OW = 50;
     bn_bwd_apply_kernel<true><<<grid, EW_THREADS, 0, s>>>(ap);
     CKL();
-    CK(launch_wgrad(&m.wgrad_plans[wi++], s));
+    CK(run_wgrad(m, wi++, s));
   }
   return OK;
 }
@@ -664,7 +685,6 @@ int cilrs_model_bind(cilrs_model* h, float* params, float* grads, float* buffers
   if (!h || !params || !buffers) return ERR_INVALID;
   if ((((uintptr_t)params) | ((uintptr_t)grads) | ((uintptr_t)buffers)) & 15) return ERR_INVALID;
   Model& m = h->m;
-  if (m.grads != grads) { m.planB = 0; m.planMode = -1; }  // wgrad plans hold gradient pointers
   m.params = params; m.grads = grads; m.buffers = buffers; m.nbt = num_batches_tracked;
   return OK;
 }
@@ -700,6 +720,28 @@ int cilrs_model_backward_part_first_tensor(int part) {
   return m.blocks[first_block[part]].a.w;
 }
 
+// heads only (test hooks + building block): features [B,512] f32 in, like the trunk would leave them
+int cilrs_model_heads_forward(cilrs_model* h, int batch, const float* feat, const float* speed, const long long* command,
+                              float* controls, float* pred_speed, int keep_for_backward, float dropout_p, unsigned long long seed,
+                              void* stream) {
+  if (!h || !feat || !speed || !command || !controls || !pred_speed) return ERR_INVALID;
+  Model& m = h->m;
+  if (batch < 1 || batch > m.maxB || !m.params) return ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (feat != m.feat) CK(cuda_status(cudaMemcpyAsync(m.feat, feat, (size_t)batch * 512 * 4, cudaMemcpyDeviceToDevice, s)));
+  return heads_forward(m, batch, speed, command, controls, pred_speed, keep_for_backward, dropout_p, seed, s);
+}
+int cilrs_model_heads_backward(cilrs_model* h, int batch, const float* dcontrols, const float* dspeed, const float* speed,
+                               const long long* command, float dropout_p, float* dfeat_out, void* stream) {
+  if (!h || !dcontrols || !dspeed || !speed || !command) return ERR_INVALID;
+  Model& m = h->m;
+  if (batch < 1 || batch > m.maxB || !m.params || !m.grads) return ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(heads_backward(m, batch, dcontrols, dspeed, speed, command, dropout_p, s));
+  if (dfeat_out) CK(cuda_status(cudaMemcpyAsync(dfeat_out, m.dfeat, (size_t)batch * 512 * 4, cudaMemcpyDeviceToDevice, s)));
+  return OK;
+}
+
 // debug / test hook: device pointer and NHWC dims of an intermediate activation of the last forward
 //   which: 0 = max-pool output, 1..16 = BasicBlock outputs, 17 = stem conv raw output; dims = {H, W, C}
 void* cilrs_model_debug_activation(cilrs_model* h, int which, int* dims) {
@@ -717,6 +759,73 @@ void* cilrs_model_debug_activation(cilrs_model* h, int which, int* dims) {
 
 void* cilrs_model_input_s2d(cilrs_model* h) { return h ? (void*)h->m.x_s2d : nullptr; }
 int* cilrs_model_error_flag(cilrs_model* h) { return h ? h->m.err_flag : nullptr; }
+
+
+// ------------------------------------------------------------------------------------------------
+// single-kernel entry points of the BatchNorm / pooling family (used by the unit tests; the network plan above
+// launches the same kernels). `vec` is [4][C] fp32: scale, shift, mean, rstd.
+// ------------------------------------------------------------------------------------------------
+int cilrs_bn_finalize(const float* partials, int tiles, int C, double count, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                      int training, int update_running, float* vec, void* stream) {
+  if (!gamma || !beta || !running_mean || !running_var || !vec || C < 1 || (training && (!partials || tiles < 1))) return ERR_INVALID;
+  BnVectors v{vec, vec + C, vec + 2 * C, vec + 3 * C};
+  bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partials, tiles, C, count, gamma, beta, running_mean,
+                                                                       running_var, num_batches_tracked, momentum, eps, training,
+                                                                       update_running, v);
+  return cuda_status(cudaGetLastError());
+}
+
+int cilrs_bn_apply(const void* x, const float* vec, const void* residual, const void* x2, const float* vec2, void* out,
+                   long long elems, int C, int relu, void* stream) {
+  if (!x || !vec || !out || C < 64 || C % 64 || elems % C) return ERR_INVALID;
+  const long long nvec = elems / 8;
+  bn_apply_kernel<<<ew_grid(nvec, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, vec, vec + C, (const __nv_bfloat16*)residual, (const __nv_bfloat16*)x2, vec2, vec2 ? vec2 + C : nullptr,
+      (__nv_bfloat16*)out, nvec, C, relu);
+  return cuda_status(cudaGetLastError());
+}
+
+int cilrs_bn_relu_maxpool(const void* y, const float* vec, void* out, uint8_t* argmax, int batch, int H, int W, int C, void* stream) {
+  if (!y || !vec || !out || C % 64 || batch < 1) return ERR_INVALID;
+  const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+  const long long nvec = (long long)batch * OH * OW * C / 8;
+  bn_relu_maxpool_kernel<<<ew_grid(nvec, C), EW_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, vec, vec + C,
+                                                                                    (__nv_bfloat16*)out, argmax, batch, H, W, C, OH, OW);
+  return cuda_status(cudaGetLastError());
+}
+
+// BN (+ optional ReLU mask from `act`) backward. workspace: >= (592*2*C + 2*C) floats + one zeroed uint32 counter.
+// stem variant (argmax != NULL): g is the pooled gradient [B,(H+1)/2,(W+1)/2,C] routed through the 3x3/2 max-pool.
+int cilrs_bn_backward(const void* g, const void* act, const void* y, const float* vec, const float* gamma, long long elems, int C,
+                      double count, int frozen, void* dy, void* dz, float* dgamma, float* dbeta, float* workspace,
+                      unsigned int* counter, const uint8_t* argmax, int H, int W, void* stream) {
+  if (!g || !y || !vec || !gamma || !dy || !workspace || !counter || C % 64 || elems % C) return ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long nvec = elems / 8;
+  const int grid = ew_grid(nvec, C);
+  float* bred = workspace + (size_t)EW_MAX_BLOCKS * 2 * C;
+  BnBwdReduceParams rp{};
+  rp.g = (const __nv_bfloat16*)g; rp.act = (const __nv_bfloat16*)act; rp.y = (const __nv_bfloat16*)y;
+  rp.mean = vec + 2 * C; rp.rstd = vec + 3 * C; rp.nvec = nvec; rp.C = C; rp.partial = workspace; rp.counter = counter;
+  rp.bsum = bred; rp.bdot = bred + C; rp.dgamma = dgamma; rp.dbeta = dbeta;
+  BnBwdApplyParams ap{};
+  ap.g = rp.g; ap.act = rp.act; ap.y = rp.y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = gamma; ap.bsum = rp.bsum; ap.bdot = rp.bdot;
+  ap.inv_count = (float)(1.0 / count); ap.frozen = frozen; ap.nvec = nvec; ap.C = C; ap.dy = (__nv_bfloat16*)dy; ap.dz = (__nv_bfloat16*)dz;
+  if (argmax) {
+    rp.argmax = argmax; rp.scale = vec; rp.shift = vec + C; rp.H = H; rp.W = W; rp.OH = (H + 1) / 2; rp.OW = (W + 1) / 2;
+    ap.argmax = argmax; ap.scale = vec; ap.shift = vec + C; ap.H = H; ap.W = W; ap.OH = rp.OH; ap.OW = rp.OW;
+    bn_bwd_reduce_kernel<true><<<grid, EW_THREADS, 0, s>>>(rp);
+    CKL();
+    bn_bwd_apply_kernel<true><<<grid, EW_THREADS, 0, s>>>(ap);
+  } else {
+    bn_bwd_reduce_kernel<false><<<grid, EW_THREADS, 0, s>>>(rp);
+    CKL();
+    bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap);
+  }
+  return cuda_status(cudaGetLastError());
+}
+size_t cilrs_bn_backward_workspace_floats(int C) { return (size_t)EW_MAX_BLOCKS * 2 * C + 2 * (size_t)C; }
 
 int cilrs_loss(const float* controls, const float* pred_speed, const float* targets, const float* speed_target, int batch, int mode,
                float w_steer, float w_throttle, float w_brake, float w_speed, float grad_scale, float* out6, float* dcontrols,

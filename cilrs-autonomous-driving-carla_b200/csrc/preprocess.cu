@@ -145,8 +145,10 @@ extern "C" {
 
 int cilrs_preprocess_u8(const uint8_t* src, int batch, int src_h, int src_w, int src_c, int reverse, int dst_h, int dst_w,
                         uint8_t* dst_u8, float* dst_f32, void* dst_s2d, void* stream) {
-  if (!src || batch < 0 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return ERR_INVALID;
+  if (batch < 0 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return ERR_INVALID;
   if (src_c != 3 && src_c != 4) return ERR_INVALID;
+  if (batch == 0) return OK;  // empty batch: nothing to do (pointers may be null)
+  if (!src) return ERR_INVALID;
   if (!dst_u8 && !dst_f32 && !dst_s2d) return ERR_INVALID;
   if (dst_s2d && (dst_h != 88 || dst_w != 200)) return ERR_UNSUPPORTED;
   const int row_pad = (src_w * src_c + 15) & ~15;

@@ -310,6 +310,8 @@ class CILRS(nn.Module):
         b = speed.shape[0]
         self._ensure(b)
         need_keep = bool(keep)
+        if need_keep:
+            self.flat_gradients()  # the gradient arena must exist (and be bound) before a forward that will be back-propagated
         mode = MODE_TRAIN if self.training else (MODE_FROZEN if need_keep else MODE_INFER)
         self._refresh_if_needed(infer=(mode == MODE_INFER))
         dropout = self.dropout if self.training else 0.0

@@ -144,6 +144,31 @@ void* cilrs_model_input_s2d(cilrs_model* m); /* where K0 may write the conv1-rea
 void* cilrs_model_debug_activation(cilrs_model* m, int which, int* dims);
 int* cilrs_model_error_flag(cilrs_model* m); /* device int, set to 1 when a command was outside [0,4) */
 
+/* heads only (speed encoder + selected branch + speed predictor; model/autonomous_drive.py:371-398) on given
+ * features f32 [batch,512]; the backward also accumulates the head parameter gradients and returns d(features) */
+int cilrs_model_heads_forward(cilrs_model* m, int batch, const float* feat, const float* speed, const long long* command,
+                              float* controls, float* pred_speed, int keep_for_backward, float dropout_p,
+                              unsigned long long seed, void* stream);
+int cilrs_model_heads_backward(cilrs_model* m, int batch, const float* dcontrols, const float* dspeed, const float* speed,
+                               const long long* command, float dropout_p, float* dfeat_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * BatchNorm / ReLU / pooling kernels (replace cuDNN/ATen BatchNorm2d, ReLU, MaxPool2d under torchvision resnet34,
+ * torchvision/models/resnet.py BasicBlock.forward; train-mode statistics come from the conv epilogue partials).
+ * vec = [4][C] fp32 (scale, shift, mean, rstd) written by cilrs_bn_finalize.
+ * --------------------------------------------------------------------------------------------------------- */
+int cilrs_bn_finalize(const float* partials, int tiles, int C, double count, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                      int training, int update_running, float* vec, void* stream);
+int cilrs_bn_apply(const void* x, const float* vec, const void* residual, const void* x2, const float* vec2, void* out,
+                   long long elems, int C, int relu, void* stream);
+int cilrs_bn_relu_maxpool(const void* y, const float* vec, void* out, uint8_t* argmax, int batch, int H, int W, int C,
+                          void* stream);
+int cilrs_bn_backward(const void* g, const void* act, const void* y, const float* vec, const float* gamma, long long elems,
+                      int C, double count, int frozen, void* dy, void* dz, float* dgamma, float* dbeta, float* workspace,
+                      unsigned int* counter, const uint8_t* argmax, int H, int W, void* stream);
+size_t cilrs_bn_backward_workspace_floats(int C);
+
 /* ---------------------------------------------------------------------------------------------------------
  * L1/L2  losses + their gradients (CILRSLoss.forward notebook/notebook.ipynb:514-527; MSE recipe
  *        configs/train_config.json:30-32).  mode 0: MSE(controls)+w_speed*MSE(speed); mode 1: weighted L1 + w_speed*MSE.

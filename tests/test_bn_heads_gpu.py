@@ -1,0 +1,232 @@
+"""Unit parity of the BatchNorm / ReLU / max-pool kernels (forward and backward) and of the fp32 heads, through the C-ABI.
+
+Checker: fp32/fp64 torch autograd of the same operation on the same (bf16-valued) inputs. These kernels are exercised
+in isolation with tight tolerances because in the whole model a single flipped ReLU (bf16 noise upstream) dominates any
+max-norm comparison (see tests/test_model_gpu.py).
+"""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _conv_stats(B, H, W, C, seed):
+    """a raw conv output y (bf16 NHWC) with its stats partials, produced by the real fprop kernel"""
+    from cilrs_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(B, H, W, C, generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randn(C, C, 3, 3, generator=g, device="cuda") * (2.0 / (9 * C)) ** 0.5
+    d = ops.conv_desc(B, H, W, C, C, 3, 1)
+    wf, _ = ops.pack_weight(d, w)
+    y, st = ops.conv_fprop(d, x, wf, stats=True)
+    return y, st
+
+
+def _finalize(st, C, count, gamma, beta, rm, rv, nbt, training, update=1):
+    from cilrs_b200 import _lib
+    vec = torch.empty(4, C, device="cuda")
+    _lib.call("cilrs_bn_finalize", st, st.shape[0] if st is not None else 0, C, ctypes.c_double(count), gamma, beta, rm, rv, nbt,
+              ctypes.c_float(0.1), ctypes.c_float(1e-5), int(training), update, vec, _lib.stream_ptr())
+    return vec
+
+
+@pytest.mark.parametrize("shape", [(6, 11, 25, 128), (3, 22, 50, 64), (9, 3, 7, 512)])
+def test_bn_train_forward_and_running_stats(shape):
+    from cilrs_b200 import _lib
+    B, H, W, C = shape
+    y, st = _conv_stats(B, H, W, C, 1)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    gamma = 1 + 0.3 * torch.randn(C, generator=g, device="cuda")
+    beta = 0.2 * torch.randn(C, generator=g, device="cuda")
+    rm, rv = torch.randn(C, generator=g, device="cuda"), torch.rand(C, generator=g, device="cuda") + 0.5
+    nbt = torch.zeros(1, dtype=torch.long, device="cuda")
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    res = torch.randn(B, H, W, C, generator=g, device="cuda").to(torch.bfloat16)
+    vec = _finalize(st, C, B * H * W, gamma, beta, rm, rv, nbt, True)
+    out = torch.empty_like(y)
+    _lib.call("cilrs_bn_apply", y, vec, res, None, None, out, ctypes.c_longlong(y.numel()), C, 1, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    yf = y.float().permute(0, 3, 1, 2)
+    ref = F.batch_norm(yf, rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5)
+    ref = torch.relu(ref + res.float().permute(0, 3, 1, 2))
+    assert _rel(out.float().permute(0, 3, 1, 2), ref) <= 6e-3
+    assert _rel(rm, rm_ref) <= 1e-5 and _rel(rv, rv_ref) <= 1e-5 and int(nbt) == 1
+    # frozen (eval) statistics + second BN'd input (downsample branch)
+    vec_e = _finalize(None, C, 1.0, gamma, beta, rm, rv, None, False, 0)
+    out2 = torch.empty_like(y)
+    _lib.call("cilrs_bn_apply", y, vec_e, None, res, vec, out2, ctypes.c_longlong(y.numel()), C, 0, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    ref2 = F.batch_norm(yf, rm, rv, gamma, beta, False, 0.1, 1e-5) + F.batch_norm(res.float().permute(0, 3, 1, 2), None, None, gamma, beta, True, 0.1, 1e-5) * 0
+    # second input normalised with `vec` (batch statistics of y): restate directly
+    sc, sh = vec[0], vec[1]
+    ref2 = F.batch_norm(yf, rm, rv, gamma, beta, False, 0.1, 1e-5) + (res.float() * sc + sh).permute(0, 3, 1, 2)
+    assert _rel(out2.float().permute(0, 3, 1, 2), ref2) <= 6e-3
+
+
+@pytest.mark.parametrize("frozen", [0, 1])
+@pytest.mark.parametrize("shape", [(6, 11, 25, 128), (5, 22, 50, 64), (9, 3, 7, 512)])
+def test_bn_relu_backward(shape, frozen):
+    from cilrs_b200 import _lib
+    B, H, W, C = shape
+    y, st = _conv_stats(B, H, W, C, 3)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    gamma = 1 + 0.3 * torch.randn(C, generator=gen, device="cuda")
+    beta = 0.2 * torch.randn(C, generator=gen, device="cuda")
+    rm, rv = 0.1 * torch.randn(C, generator=gen, device="cuda"), torch.rand(C, generator=gen, device="cuda") + 0.5
+    vec = _finalize(st, C, B * H * W, gamma, beta, rm.clone(), rv.clone(), None, not frozen, 0)
+    act = torch.empty_like(y)
+    _lib.call("cilrs_bn_apply", y, vec, None, None, None, act, ctypes.c_longlong(y.numel()), C, 1, _lib.stream_ptr())
+    gup = torch.randn(B, H, W, C, generator=gen, device="cuda").to(torch.bfloat16)
+    dy, dz = torch.empty_like(y), torch.empty_like(y)
+    dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    nws = _lib.lib().cilrs_bn_backward_workspace_floats
+    nws.restype = ctypes.c_size_t
+    ws = torch.empty(nws(C), device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.call("cilrs_bn_backward", gup, act, y, vec, gamma, ctypes.c_longlong(y.numel()), C, ctypes.c_double(B * H * W), frozen, dy, dz,
+              dgamma, dbeta, ws, cnt, None, 0, 0, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    x = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    out = torch.relu(F.batch_norm(x, rm.clone(), rv.clone(), gm, bt, not frozen, 0.1, 1e-5))
+    out.backward(gup.float().permute(0, 3, 1, 2))
+    assert _rel(dy.float().permute(0, 3, 1, 2), x.grad) <= 8e-3
+    assert _rel(dgamma, gm.grad) <= 2e-3 and _rel(dbeta, bt.grad) <= 2e-3
+    assert int(cnt) == 0  # the reduction counter is reset for the next launch / graph replay
+    mask = (act.float() > 0)
+    assert torch.equal(dz.float(), gup.float() * mask)
+
+
+@pytest.mark.parametrize("B", [1, 5])
+def test_stem_bn_relu_maxpool_forward_backward(B):
+    from cilrs_b200 import _lib, ops
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    img = torch.randn(B, 3, 88, 200, generator=gen, device="cuda")
+    w = torch.randn(64, 3, 7, 7, generator=gen, device="cuda") * (2.0 / 147) ** 0.5
+    y, st = ops.stem_fprop(ops.image_to_s2d(img), ops.stem_pack_weight(w), stats=True)
+    C = 64
+    gamma = 1 + 0.3 * torch.randn(C, generator=gen, device="cuda")
+    beta = 0.2 * torch.randn(C, generator=gen, device="cuda")
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    vec = _finalize(st, C, B * 4400, gamma, beta, rm, rv, None, True, 0)
+    pooled = torch.empty(B, 22, 50, C, dtype=torch.bfloat16, device="cuda")
+    arg = torch.empty(B, 22, 50, C, dtype=torch.uint8, device="cuda")
+    _lib.call("cilrs_bn_relu_maxpool", y, vec, pooled, arg, B, 44, 100, C, _lib.stream_ptr())
+    gp = torch.randn(B, 22, 50, C, generator=gen, device="cuda").to(torch.bfloat16)
+    dy = torch.empty_like(y)
+    dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    nws = _lib.lib().cilrs_bn_backward_workspace_floats
+    nws.restype = ctypes.c_size_t
+    ws = torch.empty(nws(C), device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.call("cilrs_bn_backward", gp, None, y, vec, gamma, ctypes.c_longlong(y.numel()), C, ctypes.c_double(B * 4400), 0, dy, None, dgamma,
+              dbeta, ws, cnt, arg, 44, 100, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    x = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    a = torch.relu(F.batch_norm(x, None, None, gm, bt, True, 0.1, 1e-5))
+    a_r = a + (a.to(torch.bfloat16).float() - a).detach()  # the pool compares bf16-rounded activations (straight-through)
+    po = F.max_pool2d(a_r, 3, 2, 1)
+    assert _rel(pooled.float().permute(0, 3, 1, 2), po) <= 8e-3
+    po.backward(gp.float().permute(0, 3, 1, 2))
+    assert _l2(dy.float().permute(0, 3, 1, 2), x.grad) <= 1.5e-2
+    assert _rel(dgamma, gm.grad) <= 1e-2 and _rel(dbeta, bt.grad) <= 1e-2
+
+
+@pytest.mark.parametrize("B", [1, 4, 37])
+def test_heads_forward_backward_fp32_exact(B):
+    """heads on given fp32 features vs the fp64 oracle: 1e-5 (they are fp32 CUDA-core kernels)"""
+    from cilrs_b200 import _lib
+    from cilrs_b200.model import CILRS
+    from oracle import cilrs_oracle as O
+    sd = O.synthetic_state_dict(3)
+    m = CILRS().to("cuda")
+    m.load_state_dict(sd)
+    m._ensure(B)
+    grads = m.flat_gradients()
+    grads.zero_()
+    gen = torch.Generator().manual_seed(B)
+    feat = torch.randn(B, 512, generator=gen).abs()
+    speed = torch.rand(B, generator=gen)
+    command = torch.randint(0, 4, (B,), generator=gen)
+    dctrl, dspd = torch.randn(B, 3, generator=gen), torch.randn(B, generator=gen)
+    controls = torch.empty(B, 3, device="cuda")
+    ps = torch.empty(B, device="cuda")
+    dfeat = torch.empty(B, 512, device="cuda")
+    sp_d, cm_d = speed.cuda(), command.cuda()
+    _lib.call("cilrs_model_heads_forward", m._handle, B, feat.cuda(), sp_d, cm_d, controls, ps, 1, ctypes.c_float(0.0),
+              ctypes.c_ulonglong(1), _lib.stream_ptr())
+    _lib.call("cilrs_model_heads_backward", m._handle, B, dctrl.cuda(), dspd.cuda(), sp_d, cm_d, ctypes.c_float(0.0), dfeat,
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    # oracle: the head part of O.forward on the same features
+    sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()
+            if v.is_floating_point() and not k.startswith("visual_encoder")}
+    f64 = feat.double().clone().requires_grad_(True)
+    s = F.relu(F.linear(speed.double().unsqueeze(1), sd64["speed_encoder.0.weight"], sd64["speed_encoder.0.bias"]))
+    s = F.relu(F.linear(s, sd64["speed_encoder.3.weight"], sd64["speed_encoder.3.bias"]))
+    comb = torch.cat([f64, s], 1)
+    p = F.relu(F.linear(f64, sd64["speed_predictor.0.weight"], sd64["speed_predictor.0.bias"]))
+    p = F.relu(F.linear(p, sd64["speed_predictor.3.weight"], sd64["speed_predictor.3.bias"]))
+    ps64 = F.linear(p, sd64["speed_predictor.5.weight"], sd64["speed_predictor.5.bias"]).squeeze(1)
+    outs = []
+    for k in range(4):
+        pre = "control_branches.%d" % k
+        h = F.relu(F.linear(comb, sd64[pre + ".0.weight"], sd64[pre + ".0.bias"]))
+        h = F.relu(F.linear(h, sd64[pre + ".3.weight"], sd64[pre + ".3.bias"]))
+        outs.append(F.linear(h, sd64[pre + ".6.weight"], sd64[pre + ".6.bias"]))
+    c64 = torch.stack(outs, 0).gather(0, command.view(1, B, 1).expand(1, B, 3)).squeeze(0)
+    ((c64 * dctrl.double()).sum() + (ps64 * dspd.double()).sum()).backward()
+    assert _rel(controls, c64) <= 1e-5 and _rel(ps, ps64) <= 1e-5
+    assert _rel(dfeat, f64.grad) <= 1e-5
+    views = dict(zip([n for n, _ in m.named_parameters()], m._views(grads)))
+    for k, v in sd64.items():
+        ref = v.grad if v.grad is not None else torch.zeros_like(v)
+        assert _rel(views[k], ref) <= 2e-5 or float(ref.abs().max()) == 0.0 and float(views[k].abs().max()) == 0.0, k
+
+
+def test_heads_dropout_statistics():
+    """dropout p>0 cannot match torch's RNG stream: check keep-rate and 1/(1-p) scaling instead"""
+    from cilrs_b200 import _lib
+    from cilrs_b200.model import CILRS
+    m = CILRS(dropout=0.5).to("cuda")
+    B = 256
+    m._ensure(B)
+    feat = torch.rand(B, 512, device="cuda")
+    speed = torch.rand(B, device="cuda")
+    cmd = torch.randint(0, 4, (B,), device="cuda")
+    c0, p0 = torch.empty(B, 3, device="cuda"), torch.empty(B, device="cuda")
+    m.flat_gradients()
+    _lib.call("cilrs_model_heads_forward", m._handle, B, feat, speed, cmd, c0, p0, 1, ctypes.c_float(0.5), ctypes.c_ulonglong(7),
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    # saved post-dropout activations of the first branch layer: about half are zeroed on top of ReLU, survivors doubled
+    _lib.call("cilrs_model_heads_forward", m._handle, B, feat, speed, cmd, c0.clone(), p0.clone(), 1, ctypes.c_float(0.0),
+              ctypes.c_ulonglong(7), _lib.stream_ptr())
+    c1, p1 = torch.empty(B, 3, device="cuda"), torch.empty(B, device="cuda")
+    _lib.call("cilrs_model_heads_forward", m._handle, B, feat, speed, cmd, c1, p1, 1, ctypes.c_float(0.5), ctypes.c_ulonglong(8),
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert not torch.equal(c0, c1)          # different seed -> different mask
+    c2 = torch.empty(B, 3, device="cuda")
+    _lib.call("cilrs_model_heads_forward", m._handle, B, feat, speed, cmd, c2, p1, 1, ctypes.c_float(0.5), ctypes.c_ulonglong(7),
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(c0, c2)              # same seed -> same mask (forward/backward consistency relies on it)
