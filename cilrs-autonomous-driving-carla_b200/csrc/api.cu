@@ -3,7 +3,11 @@
 #include "../../include/cilrs_b200.h"
 #include <stdio.h>
 
+namespace cilrs { long long g_cilrs_launches = 0; }
+
 extern "C" {
+
+long long cilrs_launch_count(void) { return cilrs::g_cilrs_launches; }
 
 int cilrs_abi_version(void) { return CILRS_ABI_VERSION; }
 

@@ -15,6 +15,9 @@ namespace cilrs {
 // ----------------------------------------------------------------------------------------------
 enum : int { OK = 0, ERR_INVALID = 1, ERR_UNSUPPORTED = 2, ERR_WORKSPACE = 3, ERR_DRIVER = 4, ERR_CUDA_BASE = 1000 };
 
+// number of kernel launches issued through this library (bench.py reports it as gpu_launches)
+extern long long g_cilrs_launches;
+
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? OK : ERR_CUDA_BASE + (int)e; }
 
 // ----------------------------------------------------------------------------------------------

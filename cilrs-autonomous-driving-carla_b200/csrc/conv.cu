@@ -340,7 +340,7 @@ int launch_conv_gemm(const ConvGemmParams* p, cudaStream_t s) {
   }
   const int total = p->tiles_w * p->tiles_h * p->tiles_n * p->n_blocks;
   int grid = total < num_sms() ? total : num_sms();
-  conv_gemm_kernel<<<grid, CG_THREADS, CG_SMEM_TOTAL, s>>>(*p);
+  conv_gemm_kernel<<<grid, CG_THREADS, CG_SMEM_TOTAL, s>>>(*p); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -352,7 +352,7 @@ int launch_wgrad(const WgradParams* p, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = p->co_blocks * p->ci_chunks * p->tap_groups * p->split_z;
-  wgrad_gemm_kernel<<<grid, WG_THREADS, CG_SMEM_TOTAL, s>>>(*p);
+  wgrad_gemm_kernel<<<grid, WG_THREADS, CG_SMEM_TOTAL, s>>>(*p); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -409,7 +409,7 @@ int cilrs_conv_pack_weight(const cilrs_conv_desc* d, const float* w, void* wf, v
   int blocks = (int)((total + 255) / 256);
   if (blocks > 2048) blocks = 2048;
   pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, d->out_c, d->in_c,
-                                                               d->kh * d->kw);
+                                                               d->kh * d->kw); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -454,7 +454,7 @@ int cilrs_stem_stats_tiles(int batch) { return batch < 1 ? 0 : choose_box(STEM_O
 
 int cilrs_stem_pack_weight(const float* w, void* wp, void* stream) {
   if (!w || !wp) return ERR_INVALID;
-  pack_stem_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp);
+  pack_stem_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 int cilrs_stem_fprop(int batch, const void* x, const void* w, void* y, const float* scale, const float* bias, float* stats,

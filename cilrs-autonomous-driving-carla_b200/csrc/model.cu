@@ -61,7 +61,41 @@ struct Bump {
   }
 };
 
+// optional per-kernel-class timing (CUDA events around every launch of the plan; used by bench.py's roofline report,
+// never inside a timed region)
+enum ProfClass { PC_FPROP = 0, PC_DGRAD, PC_WGRAD, PC_BN_FWD, PC_BN_BWD, PC_HEADS, PC_OTHER, PC_COUNT };
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int cls; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  ~Prof() { for (auto e : pool) cudaEventDestroy(e); }
+};
+#define PROF(m, cls, s, stmt)                       \
+  do {                                              \
+    if ((m).prof.on) {                              \
+      cudaEvent_t _a = (m).prof.get();              \
+      cudaEventRecord(_a, s);                       \
+      stmt;                                         \
+      cudaEvent_t _b = (m).prof.get();              \
+      cudaEventRecord(_b, s);                       \
+      (m).prof.recs.push_back(Prof::Rec{cls, _a, _b}); \
+    } else {                                        \
+      stmt;                                         \
+    }                                               \
+  } while (0)
+
 struct Model {
+  Prof prof;
   int maxB;
   std::vector<TensorSlot> slots;  // parameter tensors
   long long param_floats;
@@ -359,7 +393,7 @@ static int run_bn_finalize(Model& m, const BnRef& bn, int tiles, double count, i
   BnVectors v{bn.vec, bn.vec + bn.C, bn.vec + 2 * bn.C, bn.vec + 3 * bn.C};
   bn_finalize_kernel<<<(bn.C + 31) / 32, 1024, 0, s>>>(m.stats, tiles, bn.C, count, m.params + m.slots[bn.gamma].off,
                                                        m.params + m.slots[bn.beta].off, m.buffers + bn.rm_off, m.buffers + bn.rv_off,
-                                                       m.nbt ? m.nbt + bn.nbt_idx : nullptr, 0.1f, 1e-5f, training, update, v);
+                                                       m.nbt ? m.nbt + bn.nbt_idx : nullptr, 0.1f, 1e-5f, training, update, v); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -367,7 +401,7 @@ static int run_bn_apply(const __nv_bfloat16* x, const BnRef& bn, const __nv_bflo
                         __nv_bfloat16* out, long long elems, int relu, cudaStream_t s) {
   const long long nvec = elems / 8;
   bn_apply_kernel<<<ew_grid(nvec, bn.C), EW_THREADS, 0, s>>>(x, bn.vec, bn.vec + bn.C, res, x2, bn2 ? bn2->vec : nullptr,
-                                                             bn2 ? bn2->vec + bn2->C : nullptr, out, nvec, bn.C, relu);
+                                                             bn2 ? bn2->vec + bn2->C : nullptr, out, nvec, bn.C, relu); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -428,46 +462,48 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
   size_t pi = 0;
   const int training = mode == MODE_TRAIN;
   if (mode == MODE_INFER) {
-    CK(launch_conv_gemm(&m.fwd_plans[pi++], s));
+    PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi++], s)));
     {
       const long long nvec = act_elems(B, 22, 50, 64) / 8;
       bn_relu_maxpool_kernel<<<ew_grid(nvec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.unit_vec, m.unit_vec + 64, m.pool_out, nullptr, B, 44,
-                                                                      100, 64, 22, 50);
+                                                                      100, 64, 22, 50); ++g_cilrs_launches;
       CKL();
     }
     for (auto& blk : m.blocks) {
-      CK(launch_conv_gemm(&m.fwd_plans[pi++], s));
-      if (blk.has_ds) CK(launch_conv_gemm(&m.fwd_plans[pi++], s));
-      CK(launch_conv_gemm(&m.fwd_plans[pi++], s));
+      PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi++], s)));
+      if (blk.has_ds) PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi++], s)));
+      PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi++], s)));
     }
   } else {
-    CK(launch_conv_gemm(&m.fwd_plans[pi], s));
+    PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi], s)));
     {
       const ConvGemmParams& p = m.fwd_plans[pi++];
-      CK(run_bn_finalize(m, m.stem.bn, p.tiles_w * p.tiles_h * p.tiles_n, (double)B * 44 * 100, training, update_running, s));
+      PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, m.stem.bn, p.tiles_w * p.tiles_h * p.tiles_n, (double)B * 44 * 100, training, update_running, s)));
       const long long nvec = act_elems(B, 22, 50, 64) / 8;
       bn_relu_maxpool_kernel<<<ew_grid(nvec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.stem.bn.vec, m.stem.bn.vec + 64, m.pool_out,
-                                                                      m.pool_arg, B, 44, 100, 64, 22, 50);
+                                                                      m.pool_arg, B, 44, 100, 64, 22, 50); ++g_cilrs_launches;
       CKL();
     }
     for (auto& blk : m.blocks) {
       auto conv_bn = [&](ConvRef& c) -> int {
         const ConvGemmParams& p = m.fwd_plans[pi];
-        CK(launch_conv_gemm(&m.fwd_plans[pi++], s));
-        return run_bn_finalize(m, c.bn, p.tiles_w * p.tiles_h * p.tiles_n, (double)B * c.oh * c.ow, training, update_running, s);
+        PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi++], s)));
+        PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, c.bn, p.tiles_w * p.tiles_h * p.tiles_n, (double)B * c.oh * c.ow, training, update_running, s)));
+        return OK;
       };
       CK(conv_bn(blk.a));
-      CK(run_bn_apply(blk.a.y, blk.a.bn, nullptr, nullptr, nullptr, blk.act_a, act_elems(B, blk.a.oh, blk.a.ow, blk.a.d.out_c), 1, s));
+      PROF(m, PC_BN_FWD, s, CK(run_bn_apply(blk.a.y, blk.a.bn, nullptr, nullptr, nullptr, blk.act_a, act_elems(B, blk.a.oh, blk.a.ow, blk.a.d.out_c), 1, s)));
       if (blk.has_ds) CK(conv_bn(blk.ds));
       CK(conv_bn(blk.b));
       const long long oe = act_elems(B, blk.b.oh, blk.b.ow, blk.b.d.out_c);
-      if (blk.has_ds) CK(run_bn_apply(blk.b.y, blk.b.bn, nullptr, blk.ds.y, &blk.ds.bn, blk.out, oe, 1, s));
-      else CK(run_bn_apply(blk.b.y, blk.b.bn, blk.in, nullptr, nullptr, blk.out, oe, 1, s));
+      if (blk.has_ds) PROF(m, PC_BN_FWD, s, CK(run_bn_apply(blk.b.y, blk.b.bn, nullptr, blk.ds.y, &blk.ds.bn, blk.out, oe, 1, s)));
+      else PROF(m, PC_BN_FWD, s, CK(run_bn_apply(blk.b.y, blk.b.bn, blk.in, nullptr, nullptr, blk.out, oe, 1, s)));
     }
   }
-  avgpool_kernel<<<(B * 512 + 255) / 256, 256, 0, s>>>(m.blocks.back().out, m.feat, B, 21, 512);
+  avgpool_kernel<<<(B * 512 + 255) / 256, 256, 0, s>>>(m.blocks.back().out, m.feat, B, 21, 512); ++g_cilrs_launches;
   CKL();
-  return heads_forward(m, B, speed, command, controls, pred_speed, keep_for_backward, dropout_p, seed, s);
+  PROF(m, PC_HEADS, s, CK(heads_forward(m, B, speed, command, controls, pred_speed, keep_for_backward, dropout_p, seed, s)));
+  return OK;
 }
 
 static int heads_forward(Model& m, int B, const float* speed, const long long* command, float* controls, float* pred_speed,
@@ -477,7 +513,7 @@ static int heads_forward(Model& m, int B, const float* speed, const long long* c
   if (keep_for_backward) hp.sv = m.hs; else memset(&hp.sv, 0, sizeof(hp.sv));
   hp.feat = m.feat; hp.speed = speed; hp.command = command; hp.controls = controls; hp.pred_speed = pred_speed;
   hp.batch = B; hp.dropout_p = dropout_p; hp.seed = seed; hp.error_flag = m.err_flag;
-  heads_fwd_kernel<<<B, HD_THREADS, 0, s>>>(hp);
+  heads_fwd_kernel<<<B, HD_THREADS, 0, s>>>(hp); ++g_cilrs_launches;
   CKL();
   return OK;
 }
@@ -496,13 +532,13 @@ static int run_bn_bwd(Model& m, const BnRef& bn, const __nv_bfloat16* g, const _
   rp.g = g; rp.act = act; rp.y = y; rp.mean = bn.vec + 2 * bn.C; rp.rstd = bn.vec + 3 * bn.C; rp.nvec = nvec; rp.C = bn.C;
   rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + bn.C;
   rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
-  bn_bwd_reduce_kernel<false><<<grid, EW_THREADS, 0, s>>>(rp);
+  bn_bwd_reduce_kernel<false><<<grid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
   CKL();
   BnBwdApplyParams ap{};
   ap.g = g; ap.act = act; ap.y = y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
   ap.bsum = rp.bsum; ap.bdot = rp.bdot; ap.inv_count = (float)(1.0 / count); ap.frozen = frozen; ap.nvec = nvec; ap.C = bn.C;
   ap.dy = dy; ap.dz = dz;
-  bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap);
+  bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
   CKL();
   return OK;
 }
@@ -513,7 +549,7 @@ static int heads_backward(Model& m, int B, const float* dcontrols, const float* 
   HeadsBwdParams bp;
   bp.w = head_weights(m, m.params); bp.sv = m.hs; bp.dcontrols = dcontrols; bp.dspeed = dspeed; bp.command = command;
   bp.dfeat = m.dfeat; bp.batch = B; bp.dropout_p = dropout_p;
-  heads_bwd_kernel<<<B, HD_THREADS, 0, s>>>(bp);
+  heads_bwd_kernel<<<B, HD_THREADS, 0, s>>>(bp); ++g_cilrs_launches;
   CKL();
   {
     HeadsWgradParams wp;
@@ -547,7 +583,7 @@ static int heads_backward(Model& m, int B, const float* dcontrols, const float* 
     CK(cuda_status(cudaMemcpy2DAsync(comb + 512, 640 * 4, m.hs.sfeat, 128 * 4, 128 * 4, B, cudaMemcpyDeviceToDevice, s)));
     for (int j = 0; j < nj; ++j)
       if (!wp.job[j].x) { wp.job[j].x = comb; wp.job[j].ld_x = 640; }
-    heads_wgrad_kernel<<<tiles, 256, 0, s>>>(wp);
+    heads_wgrad_kernel<<<tiles, 256, 0, s>>>(wp); ++g_cilrs_launches;
     CKL();
   }
   return OK;
@@ -562,9 +598,9 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   const int frozen = mode == MODE_FROZEN;
   if (part < -1 || part > 4) return ERR_INVALID;
   if (part <= 0) {
-  CK(heads_backward(m, B, dcontrols, dspeed, speed, command, dropout_p, s));
+  PROF(m, PC_HEADS, s, CK(heads_backward(m, B, dcontrols, dspeed, speed, command, dropout_p, s)));
   // ---- trunk ----
-  avgpool_bwd_kernel<<<(int)((act_elems(B, 3, 7, 512) + 255) / 256), 256, 0, s>>>(m.dfeat, m.g0, B, 21, 512);
+  avgpool_bwd_kernel<<<(int)((act_elems(B, 3, 7, 512) + 255) / 256), 256, 0, s>>>(m.dfeat, m.g0, B, 21, 512); ++g_cilrs_launches;
   CKL();
   m.bw_gcur = m.g0; m.bw_gnext = m.g1; m.bw_di = 0; m.bw_wi = 0;
   }
@@ -581,16 +617,16 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     const long long oe = act_elems(B, blk.b.oh, blk.b.ow, blk.b.d.out_c);
     const double cnt = (double)B * blk.b.oh * blk.b.ow;
     // out = relu(bn_b(y_b) + identity): dz = g * (out > 0)
-    CK(run_bn_bwd(m, blk.b.bn, gcur, blk.out, blk.b.y, oe, cnt, frozen, m.d1, blk.has_ds ? nullptr : m.dz, s));
-    if (blk.has_ds) CK(run_bn_bwd(m, blk.ds.bn, gcur, blk.out, blk.ds.y, oe, cnt, frozen, m.d2, nullptr, s));
-    CK(run_wgrad(m, wi++, s));                       // dW_b
-    CK(launch_conv_gemm(&m.dgrad_plans[di++], s));   // ga = dgrad_b(d1)
+    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd(m, blk.b.bn, gcur, blk.out, blk.b.y, oe, cnt, frozen, m.d1, blk.has_ds ? nullptr : m.dz, s)));
+    if (blk.has_ds) PROF(m, PC_BN_BWD, s, CK(run_bn_bwd(m, blk.ds.bn, gcur, blk.out, blk.ds.y, oe, cnt, frozen, m.d2, nullptr, s)));
+    PROF(m, PC_WGRAD, s, CK(run_wgrad(m, wi++, s)));                       // dW_b
+    PROF(m, PC_DGRAD, s, CK(launch_conv_gemm(&m.dgrad_plans[di++], s)));   // ga = dgrad_b(d1)
     // act_a = relu(bn_a(y_a))
-    CK(run_bn_bwd(m, blk.a.bn, m.ga, blk.act_a, blk.a.y, oe, cnt, frozen, m.d1, nullptr, s));
-    CK(run_wgrad(m, wi++, s));                       // dW_a
-    if (blk.has_ds) CK(run_wgrad(m, wi++, s));       // dW_ds
+    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd(m, blk.a.bn, m.ga, blk.act_a, blk.a.y, oe, cnt, frozen, m.d1, nullptr, s)));
+    PROF(m, PC_WGRAD, s, CK(run_wgrad(m, wi++, s)));                       // dW_a
+    if (blk.has_ds) PROF(m, PC_WGRAD, s, CK(run_wgrad(m, wi++, s)));       // dW_ds
     const int nd = blk.has_ds ? 4 : 1;
-    for (int k = 0; k < nd; ++k) CK(launch_conv_gemm(&m.dgrad_plans[di++], s));
+    for (int k = 0; k < nd; ++k) PROF(m, PC_DGRAD, s, CK(launch_conv_gemm(&m.dgrad_plans[di++], s)));
     __nv_bfloat16* t = gcur; gcur = gnext; gnext = t;
   }
   // ---- stem: max-pool backward + ReLU + BN backward, then wgrad ----
@@ -603,16 +639,16 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + 64;
     rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
     rp.argmax = m.pool_arg; rp.scale = bn.vec; rp.shift = bn.vec + 64; rp.H = 44; rp.W = 100; rp.OH = 22; rp.OW = 50;
-    bn_bwd_reduce_kernel<true><<<grid, EW_THREADS, 0, s>>>(rp);
+    bn_bwd_reduce_kernel<true><<<grid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
     CKL();
     BnBwdApplyParams ap{};
     ap.g = gcur; ap.y = m.stem.y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
     ap.bsum = rp.bsum; ap.bdot = rp.bdot; ap.inv_count = (float)(1.0 / ((double)B * 4400.0)); ap.frozen = frozen; ap.nvec = nvec;
     ap.C = 64; ap.dy = m.dy_stem; ap.argmax = m.pool_arg; ap.scale = bn.vec; ap.shift = bn.vec + 64; ap.H = 44; ap.W = 100;
     ap.OH = 22; ap.OW = 50;
-    bn_bwd_apply_kernel<true><<<grid, EW_THREADS, 0, s>>>(ap);
+    bn_bwd_apply_kernel<true><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
     CKL();
-    CK(run_wgrad(m, wi++, s));
+    PROF(m, PC_WGRAD, s, CK(run_wgrad(m, wi++, s)));
   }
   return OK;
 }
@@ -720,6 +756,32 @@ int cilrs_model_backward_part_first_tensor(int part) {
   return m.blocks[first_block[part]].a.w;
 }
 
+// per-class kernel timing: enable, run forward/backward (not inside a timed region), then collect (synchronises)
+int cilrs_model_profile(cilrs_model* h, int enable) {
+  if (!h) return ERR_INVALID;
+  h->m.prof.on = enable != 0;
+  h->m.prof.used = 0;
+  h->m.prof.recs.clear();
+  return OK;
+}
+// out_ms[7], out_launches[7]: fprop, dgrad, wgrad, bn forward (+pool), bn backward, heads, other
+int cilrs_model_profile_collect(cilrs_model* h, float* out_ms, int* out_launches) {
+  if (!h || !out_ms || !out_launches) return ERR_INVALID;
+  for (int i = 0; i < PC_COUNT; ++i) { out_ms[i] = 0.f; out_launches[i] = 0; }
+  for (auto& r : h->m.prof.recs) {
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e != cudaSuccess) return cuda_status(e);
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, r.a, r.b);
+    if (e != cudaSuccess) return cuda_status(e);
+    out_ms[r.cls] += ms;
+    out_launches[r.cls] += 1;
+  }
+  h->m.prof.used = 0;
+  h->m.prof.recs.clear();
+  return OK;
+}
+
 // heads only (test hooks + building block): features [B,512] f32 in, like the trunk would leave them
 int cilrs_model_heads_forward(cilrs_model* h, int batch, const float* feat, const float* speed, const long long* command,
                               float* controls, float* pred_speed, int keep_for_backward, float dropout_p, unsigned long long seed,
@@ -772,7 +834,7 @@ int cilrs_bn_finalize(const float* partials, int tiles, int C, double count, con
   BnVectors v{vec, vec + C, vec + 2 * C, vec + 3 * C};
   bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partials, tiles, C, count, gamma, beta, running_mean,
                                                                        running_var, num_batches_tracked, momentum, eps, training,
-                                                                       update_running, v);
+                                                                       update_running, v); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -782,7 +844,7 @@ int cilrs_bn_apply(const void* x, const float* vec, const void* residual, const 
   const long long nvec = elems / 8;
   bn_apply_kernel<<<ew_grid(nvec, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, vec, vec + C, (const __nv_bfloat16*)residual, (const __nv_bfloat16*)x2, vec2, vec2 ? vec2 + C : nullptr,
-      (__nv_bfloat16*)out, nvec, C, relu);
+      (__nv_bfloat16*)out, nvec, C, relu); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -791,7 +853,7 @@ int cilrs_bn_relu_maxpool(const void* y, const float* vec, void* out, uint8_t* a
   const int OH = (H + 1) / 2, OW = (W + 1) / 2;
   const long long nvec = (long long)batch * OH * OW * C / 8;
   bn_relu_maxpool_kernel<<<ew_grid(nvec, C), EW_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, vec, vec + C,
-                                                                                    (__nv_bfloat16*)out, argmax, batch, H, W, C, OH, OW);
+                                                                                    (__nv_bfloat16*)out, argmax, batch, H, W, C, OH, OW); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -815,13 +877,13 @@ int cilrs_bn_backward(const void* g, const void* act, const void* y, const float
   if (argmax) {
     rp.argmax = argmax; rp.scale = vec; rp.shift = vec + C; rp.H = H; rp.W = W; rp.OH = (H + 1) / 2; rp.OW = (W + 1) / 2;
     ap.argmax = argmax; ap.scale = vec; ap.shift = vec + C; ap.H = H; ap.W = W; ap.OH = rp.OH; ap.OW = rp.OW;
-    bn_bwd_reduce_kernel<true><<<grid, EW_THREADS, 0, s>>>(rp);
+    bn_bwd_reduce_kernel<true><<<grid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
     CKL();
-    bn_bwd_apply_kernel<true><<<grid, EW_THREADS, 0, s>>>(ap);
+    bn_bwd_apply_kernel<true><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
   } else {
-    bn_bwd_reduce_kernel<false><<<grid, EW_THREADS, 0, s>>>(rp);
+    bn_bwd_reduce_kernel<false><<<grid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
     CKL();
-    bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap);
+    bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
   }
   return cuda_status(cudaGetLastError());
 }
@@ -836,7 +898,7 @@ int cilrs_loss(const float* controls, const float* pred_speed, const float* targ
   p.controls = controls; p.pred_speed = pred_speed; p.targets = targets; p.speed_target = speed_target; p.batch = batch; p.mode = mode;
   p.w_steer = w_steer; p.w_throttle = w_throttle; p.w_brake = w_brake; p.w_speed = w_speed; p.grad_scale = grad_scale;
   p.out = out6; p.dcontrols = dcontrols; p.dspeed = dspeed;
-  loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p);
+  loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -852,13 +914,13 @@ int cilrs_adam_step(float* p, const float* g, float* m, float* v, long long n, f
   a.bias_correction2_sqrt = step >= 1 ? (float)sqrt(1.0 - pow((double)beta2, (double)step)) : 1.f;
   a.grad_scale = grad_scale; a.grad_scale_dev = grad_scale_dev; a.step_dev = step_dev;
   if (step_dev) {
-    step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev); ++g_cilrs_launches;
     int st = cuda_status(cudaGetLastError());
     if (st) return st;
   }
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -868,7 +930,7 @@ int cilrs_grad_sumsq(const float* g, long long n, double* partial_ws /* >= 1024 
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 592) blocks = 592;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, n, partial_ws, counter_ws, out2, max_norm);
+  sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, n, partial_ws, counter_ws, out2, max_norm); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 

@@ -166,7 +166,7 @@ int cilrs_preprocess_u8(const uint8_t* src, int batch, int src_h, int src_w, int
     if (e != cudaSuccess) return cuda_status(e);
     smem_set = 96 * 1024;
   }
-  preprocess_kernel<<<batch * dst_h, 256, smem, (cudaStream_t)stream>>>(p);
+  preprocess_kernel<<<batch * dst_h, 256, smem, (cudaStream_t)stream>>>(p); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -176,7 +176,7 @@ int cilrs_image_to_s2d(const float* image, int batch, void* dst, void* stream) {
   const long long total = (long long)batch * 94 * 206;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  image_to_s2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(image, (__nv_bfloat16*)dst, batch);
+  image_to_s2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(image, (__nv_bfloat16*)dst, batch); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 

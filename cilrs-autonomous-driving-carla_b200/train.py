@@ -13,6 +13,7 @@ import ctypes
 import torch
 
 from . import _lib
+from .ddp import allreduce_ranges, backward_part_ranges, broadcast_parameters
 from .model import MODE_TRAIN
 from .optim import FusedAdam
 
@@ -35,8 +36,12 @@ class FusedTrainer:
         self.frames = frames
         dev = model.flat_parameters().device
         self.dev = dev
+        if use_graph and model.dropout > 0:
+            raise ValueError("use_graph replays one dropout mask; train with dropout through the eager step")
         model.train()
         model._ensure(batch)
+        if self.world > 1:
+            broadcast_parameters(model, 0, process_group)
         self.d_image = torch.zeros(batch, 3, 88, 200, dtype=torch.float32, device=dev) if frames == "f32" else None
         self.d_frames = torch.zeros(batch, 88, 200, 3, dtype=torch.uint8, device=dev) if frames == "u8" else None
         self.d_speed = torch.zeros(batch, dtype=torch.float32, device=dev)
@@ -51,16 +56,7 @@ class FusedTrainer:
         self.norm_cnt = torch.zeros(4, dtype=torch.int32, device=dev)
         self.norm_out = torch.zeros(2, dtype=torch.float32, device=dev)
         self.s2d = model.input_s2d_buffer(batch)
-        lib = _lib.lib()
-        nt = len(model._offsets)
-        firsts = [lib.cilrs_model_backward_part_first_tensor(p) for p in range(5)]
-        bounds = [nt] + firsts
-        # flat-arena element range completed by backward part p
-        self.part_ranges = []
-        for p in range(5):
-            lo = model._offsets[bounds[p + 1]]
-            hi = model._total if p == 0 else model._offsets[bounds[p]]
-            self.part_ranges.append((lo, hi))
+        self.part_ranges = backward_part_ranges(model)
         self.graph = None
         self.kernel_launches = None
         if use_graph:
@@ -91,8 +87,7 @@ class FusedTrainer:
             for part in range(5):
                 _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, part, self.dcontrols, self.dspeed, self.d_speed,
                           self.d_command, ctypes.c_float(m.dropout), sp)
-                lo, hi = self.part_ranges[part]
-                works.append(torch.distributed.all_reduce(g[lo:hi], group=self.pg, async_op=True))
+                works.extend(allreduce_ranges(g, [self.part_ranges[part]], self.pg))
             for w in works:
                 w.wait()
         else:

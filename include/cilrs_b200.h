@@ -32,6 +32,8 @@ extern "C" {
 int cilrs_abi_version(void);
 /* human-readable text for a status code returned by any entry point (static storage) */
 const char* cilrs_status_string(int status);
+/* kernels launched through this library since it was loaded (host-side counter) */
+long long cilrs_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K0  frame preprocessing.  Replaces cv2.resize(image,(200,88)) [INTER_LINEAR, 11-bit fixed point] and
@@ -138,6 +140,10 @@ int cilrs_model_backward(cilrs_model* m, int batch, int mode, int part, const fl
 /* first parameter-tensor index (into cilrs_model_param_layout) whose gradient backward part `part` completes;
  * part p completes tensors [first(p), first(p-1)) with first(-1) = number of tensors */
 int cilrs_model_backward_part_first_tensor(int part);
+/* measurement aid (bench.py roofline): CUDA events around every launch of the plan, summed per kernel class
+ * {conv fprop, conv dgrad, conv wgrad, BN forward + pooling, BN backward, heads, other}. collect() synchronises. */
+int cilrs_model_profile(cilrs_model* m, int enable);
+int cilrs_model_profile_collect(cilrs_model* m, float* out_ms7, int* out_launches7);
 void* cilrs_model_input_s2d(cilrs_model* m); /* where K0 may write the conv1-ready frames directly */
 /* test hook: bf16 NHWC activation of the last forward. which: 0 = max-pool output, 1..16 = BasicBlock outputs,
  * 17 = raw stem conv output; dims receives {H, W, C} */
