@@ -32,12 +32,15 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
-  // zero the operand ring once: rows of an A tile that no TMA box ever writes must read as 0
+  // rows of an A tile that no TMA box ever writes (valid_rows..127) must read as 0: zero them once per stage
   {
-    uint4 z = make_uint4(0, 0, 0, 0);
-    uint4* q = (uint4*)smem;
-    const int n16 = p.num_stages * stage_bytes / 16;
-    for (int i = threadIdx.x; i < n16; i += CG_THREADS) q[i] = z;
+    const int vr = p.BW * p.BH * p.BN;
+    const int n16 = (CG_BLOCK_M - vr) * 8;  // 16-byte units per stage
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int st = 0; st < p.num_stages; ++st) {
+      uint4* q = (uint4*)(smem + (size_t)st * stage_bytes + (size_t)vr * 128);
+      for (int i = threadIdx.x; i < n16; i += CG_THREADS) q[i] = z;
+    }
     fence_proxy_async();
   }
   if (warp == 0 && lane == 0) {

@@ -426,13 +426,13 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApp
 }
 
 // grid size for the vector kernels: a multiple of the channel-group count keeps every thread on one channel group
-inline int ew_grid(long long nvec, int C) {
-  const int groups = C >> 3;
-  long long blocks = (nvec + EW_THREADS - 1) / EW_THREADS;
+// (EW_THREADS = 256 is a multiple of every group count 8..64, so any block count keeps that property.)
+// `per_thread` = vectors each thread should get at least: streaming kernels use 2, reductions 8 (fewer partials to fold).
+inline int ew_grid(long long nvec, int C, int per_thread = 2) {
+  (void)C;
+  long long blocks = (nvec + (long long)EW_THREADS * per_thread - 1) / ((long long)EW_THREADS * per_thread);
   if (blocks > EW_MAX_BLOCKS) blocks = EW_MAX_BLOCKS;
   if (blocks < 1) blocks = 1;
-  // EW_THREADS (256) is a multiple of groups (8..64), so any block count works
-  (void)groups;
   return (int)blocks;
 }
 

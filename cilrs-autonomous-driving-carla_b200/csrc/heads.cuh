@@ -50,19 +50,29 @@ CILRS_DEVINL bool drop_keep(unsigned long long seed, int sample, int site, int j
 CILRS_DEVINL void gemv_rows(const float* __restrict__ W, const float* __restrict__ b, const float* x, int in, int out, float* y,
                             bool relu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = HD_THREADS / 32;
-  for (int o = warp; o < out; o += nwarps) {
-    const float4* wr = reinterpret_cast<const float4*>(W + (size_t)o * in);
-    float acc = 0.f;
-    for (int i = lane; i < in / 4; i += 32) {
-      const float4 w4 = __ldg(wr + i);
+  const int n4 = in >> 2;
+  // four output rows per warp iteration: 4 independent load/FMA chains per lane hide the L2 latency of the weight rows
+  for (int o0 = warp * 4; o0 < out; o0 += nwarps * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < n4; i += 32) {
       const float4 x4 = *reinterpret_cast<const float4*>(x + 4 * i);
-      acc = fmaf(w4.x, x4.x, acc); acc = fmaf(w4.y, x4.y, acc); acc = fmaf(w4.z, x4.z, acc); acc = fmaf(w4.w, x4.w, acc);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (o0 + q < out) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(o0 + q) * in) + i);
+          acc[q] = fmaf(w4.x, x4.x, acc[q]); acc[q] = fmaf(w4.y, x4.y, acc[q]);
+          acc[q] = fmaf(w4.z, x4.z, acc[q]); acc[q] = fmaf(w4.w, x4.w, acc[q]);
+        }
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      float v = acc + b[o];
-      if (relu) v = fmaxf(v, 0.f);
-      y[o] = v;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float r = warp_sum(acc[q]);
+      if (lane == 0 && o0 + q < out) {
+        float v = r + b[o0 + q];
+        if (relu) v = fmaxf(v, 0.f);
+        y[o0 + q] = v;
+      }
     }
   }
 }
@@ -213,10 +223,17 @@ struct HeadsBwdParams {
 // y[i] = sum_o W[o,i] * d[o]  (transposed GEMV; consecutive threads read consecutive i -> coalesced)
 CILRS_DEVINL void gemv_cols(const float* __restrict__ W, const float* d, int in, int out, float* y) {
   for (int i = threadIdx.x; i < in; i += HD_THREADS) {
-    float acc = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int o = 0;
 #pragma unroll 4
-    for (int o = 0; o < out; ++o) acc = fmaf(__ldg(W + (size_t)o * in + i), d[o], acc);
-    y[i] = acc;
+    for (; o + 3 < out; o += 4) {  // 4 independent chains x unroll 4 = 16 loads in flight per thread
+      a0 = fmaf(__ldg(W + (size_t)o * in + i), d[o], a0);
+      a1 = fmaf(__ldg(W + (size_t)(o + 1) * in + i), d[o + 1], a1);
+      a2 = fmaf(__ldg(W + (size_t)(o + 2) * in + i), d[o + 2], a2);
+      a3 = fmaf(__ldg(W + (size_t)(o + 3) * in + i), d[o + 3], a3);
+    }
+    for (; o < out; ++o) a0 = fmaf(__ldg(W + (size_t)o * in + i), d[o], a0);
+    y[i] = (a0 + a1) + (a2 + a3);
   }
 }
 

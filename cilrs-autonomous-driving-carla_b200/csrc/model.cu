@@ -528,11 +528,12 @@ static int run_bn_bwd(Model& m, const BnRef& bn, const __nv_bfloat16* g, const _
                       long long elems, double count, int frozen, __nv_bfloat16* dy, __nv_bfloat16* dz, cudaStream_t s) {
   const long long nvec = elems / 8;
   const int grid = ew_grid(nvec, bn.C);
+  const int rgrid = ew_grid(nvec, bn.C, 8);
   BnBwdReduceParams rp{};
   rp.g = g; rp.act = act; rp.y = y; rp.mean = bn.vec + 2 * bn.C; rp.rstd = bn.vec + 3 * bn.C; rp.nvec = nvec; rp.C = bn.C;
   rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + bn.C;
   rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
-  bn_bwd_reduce_kernel<false><<<grid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
+  bn_bwd_reduce_kernel<false><<<rgrid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
   CKL();
   BnBwdApplyParams ap{};
   ap.g = g; ap.act = act; ap.y = y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
@@ -634,12 +635,13 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     const BnRef& bn = m.stem.bn;
     const long long nvec = act_elems(B, 44, 100, 64) / 8;
     const int grid = ew_grid(nvec, 64);
+    const int rgrid = ew_grid(nvec, 64, 8);
     BnBwdReduceParams rp{};
     rp.g = gcur; rp.y = m.stem.y; rp.mean = bn.vec + 2 * 64; rp.rstd = bn.vec + 3 * 64; rp.nvec = nvec; rp.C = 64;
     rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + 64;
     rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
     rp.argmax = m.pool_arg; rp.scale = bn.vec; rp.shift = bn.vec + 64; rp.H = 44; rp.W = 100; rp.OH = 22; rp.OW = 50;
-    bn_bwd_reduce_kernel<true><<<grid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
+    bn_bwd_reduce_kernel<true><<<rgrid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
     CKL();
     BnBwdApplyParams ap{};
     ap.g = gcur; ap.y = m.stem.y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
@@ -866,6 +868,7 @@ int cilrs_bn_backward(const void* g, const void* act, const void* y, const float
   cudaStream_t s = (cudaStream_t)stream;
   const long long nvec = elems / 8;
   const int grid = ew_grid(nvec, C);
+  const int rgrid = ew_grid(nvec, C, 8);
   float* bred = workspace + (size_t)EW_MAX_BLOCKS * 2 * C;
   BnBwdReduceParams rp{};
   rp.g = (const __nv_bfloat16*)g; rp.act = (const __nv_bfloat16*)act; rp.y = (const __nv_bfloat16*)y;
@@ -877,11 +880,11 @@ int cilrs_bn_backward(const void* g, const void* act, const void* y, const float
   if (argmax) {
     rp.argmax = argmax; rp.scale = vec; rp.shift = vec + C; rp.H = H; rp.W = W; rp.OH = (H + 1) / 2; rp.OW = (W + 1) / 2;
     ap.argmax = argmax; ap.scale = vec; ap.shift = vec + C; ap.H = H; ap.W = W; ap.OH = rp.OH; ap.OW = rp.OW;
-    bn_bwd_reduce_kernel<true><<<grid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
+    bn_bwd_reduce_kernel<true><<<rgrid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
     CKL();
     bn_bwd_apply_kernel<true><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
   } else {
-    bn_bwd_reduce_kernel<false><<<grid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
+    bn_bwd_reduce_kernel<false><<<rgrid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
     CKL();
     bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
   }

@@ -28,11 +28,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
   uint64_t* done_bar = bars + 2 * WG_MAX_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
 
+  // pixel rows no TMA box ever writes (valid_rows..127 of every slab) and the unused second dY slab must read as 0
   {
-    uint4 z = make_uint4(0, 0, 0, 0);
-    uint4* q = (uint4*)smem;
-    const int n16 = p.num_stages * stage_bytes / 16;
-    for (int i = threadIdx.x; i < n16; i += WG_THREADS) q[i] = z;
+    const int vr = p.BW * p.BH * p.BN;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int st = 0; st < p.num_stages; ++st) {
+      for (int sl = 0; sl < slabs; ++sl) {
+        const bool whole = (sl == 1 && p.m_halves == 1);
+        const int first = whole ? 0 : vr;
+        uint4* q = (uint4*)(smem + (size_t)st * stage_bytes + (size_t)sl * WG_SLAB + (size_t)first * 128);
+        const int n16 = (128 - first) * 8;
+        for (int i = threadIdx.x; i < n16; i += WG_THREADS) q[i] = z;
+      }
+    }
     fence_proxy_async();
   }
   if (warp == 0 && lane == 0) {
