@@ -102,7 +102,7 @@ static int pick_block_n(int n_total, int m_tiles) {
 }
 
 static int stages_for(int block_n) {
-  const int avail = CG_SMEM_TOTAL - 1024 - CG_STAGING_BYTES - 1024 - 2048 - 256;
+  const int avail = CG_SMEM_TOTAL - 1024 - CG_STAGING_BYTES - 1024 - 2048 - 4096 - 256;
   int s = avail / (CG_A_BYTES + block_n * 128);
   if (s > CG_MAX_STAGES) s = CG_MAX_STAGES;
   return s;
@@ -331,6 +331,11 @@ int build_stem_wgrad(WgradParams* p, int batch, const void* dy, const void* x_s2
   return encode_stem_map(&p->tmX, x_s2d, batch, b);
 }
 
+int conv_gemm_grid(const ConvGemmParams* p) {
+  const int total = p->tiles_w * p->tiles_h * p->tiles_n * p->n_blocks;
+  return total < num_sms() ? total : num_sms();
+}
+
 int launch_conv_gemm(const ConvGemmParams* p, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -338,8 +343,7 @@ int launch_conv_gemm(const ConvGemmParams* p, cudaStream_t s) {
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
-  const int total = p->tiles_w * p->tiles_h * p->tiles_n * p->n_blocks;
-  int grid = total < num_sms() ? total : num_sms();
+  const int grid = conv_gemm_grid(p);
   conv_gemm_kernel<<<grid, CG_THREADS, CG_SMEM_TOTAL, s>>>(*p); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
@@ -373,6 +377,37 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// all layers in one launch: a CTA transposes a 32(co) x 32(ci) x kk block through shared memory, so the fp32 reads
+// (runs of 32*kk floats) and both bf16 writes (32 consecutive ci resp. co) are coalesced
+__global__ void __launch_bounds__(256) pack_all_kernel(const float* __restrict__ params, const PackJob* __restrict__ jobs, int njobs) {
+  __shared__ float tile[32][32 * 9 + 1];
+  int j = 0;
+  while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].first_block) ++j;
+  const PackJob jb = jobs[j];
+  const int t_idx = blockIdx.x - jb.first_block;
+  const int ci_tiles = jb.cin >> 5;
+  const int co0 = (t_idx / ci_tiles) * 32, ci0 = (t_idx % ci_tiles) * 32;
+  const int kk = jb.kk, run = 32 * kk;
+  const float* w = params + jb.w_off;
+  for (int idx = threadIdx.x; idx < 32 * run; idx += 256) {
+    const int co = idx / run, r = idx - co * run;
+    tile[co][r] = w[((long long)(co0 + co) * jb.cin + ci0) * kk + r];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * run; idx += 256) {
+    const int a = idx & 31, b = (idx >> 5) & 31, t = idx >> 10;  // t < kk
+    // fprop layout [t][co][ci]: a = ci (fastest), b = co
+    jb.wf[((long long)t * jb.cout + co0 + b) * jb.cin + ci0 + a] = __float2bfloat16(tile[b][a * kk + t]);
+    // dgrad layout [t][ci][co]: a = co (fastest), b = ci
+    jb.wd[((long long)t * jb.cin + ci0 + b) * jb.cout + co0 + a] = __float2bfloat16(tile[a][b * kk + t]);
+  }
+}
+
+int launch_pack_all(const float* params, const PackJob* jobs_dev, int njobs, int total_blocks, cudaStream_t s) {
+  pack_all_kernel<<<total_blocks, 256, 0, s>>>(params, jobs_dev, njobs); ++g_cilrs_launches;
+  return cuda_status(cudaGetLastError());
+}
+
 __global__ void pack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // [r'][co][j]
   if (i >= 4 * 64 * 64) return;
@@ -397,7 +432,9 @@ size_t cilrs_conv_packed_weight_bytes(const cilrs_conv_desc* d) {
 int cilrs_conv_stats_tiles(const cilrs_conv_desc* d) {
   if (check_desc(d)) return 0;
   const int OH = conv_out_dim(d->in_h, d->kh, d->stride, d->pad), OW = conv_out_dim(d->in_w, d->kw, d->stride, d->pad);
-  return choose_box(OW, OH, d->batch).m_tiles();
+  const int m_tiles = choose_box(OW, OH, d->batch).m_tiles();
+  const int total = m_tiles * (d->out_c / pick_block_n(d->out_c, m_tiles));
+  return total < num_sms() ? total : num_sms();  // one (sum, sumsq) partial per persistent CTA
 }
 size_t cilrs_conv_stats_bytes(const cilrs_conv_desc* d) { return (size_t)cilrs_conv_stats_tiles(d) * 2 * d->out_c * sizeof(float); }
 
@@ -450,7 +487,11 @@ int cilrs_conv_wgrad(const cilrs_conv_desc* d, const void* dy, const void* x, fl
 }
 
 size_t cilrs_stem_packed_weight_bytes(void) { return 4 * 64 * 64 * 2; }
-int cilrs_stem_stats_tiles(int batch) { return batch < 1 ? 0 : choose_box(STEM_OW, STEM_OH, batch).m_tiles(); }
+int cilrs_stem_stats_tiles(int batch) {
+  if (batch < 1) return 0;
+  const int t = choose_box(STEM_OW, STEM_OH, batch).m_tiles();
+  return t < num_sms() ? t : num_sms();
+}
 
 int cilrs_stem_pack_weight(const float* w, void* wp, void* stream) {
   if (!w || !wp) return ERR_INVALID;

@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
   uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;
   long long* s_rowoff = (long long*)(staging + CG_STAGING_BYTES);  // [128]
   float* s_stat = (float*)(s_rowoff + CG_BLOCK_M);                 // [4][64][2]
-  uint64_t* bars = (uint64_t*)(s_stat + 4 * 64 * 2);
+  float* s_acc = s_stat + 4 * 64 * 2;                              // [2][512] per-CTA running (sum, sumsq) per channel
+  uint64_t* bars = (uint64_t*)(s_acc + 2 * 512);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + CG_MAX_STAGES;
   uint64_t* tfull_bar = bars + 2 * CG_MAX_STAGES;
@@ -138,6 +139,9 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
     const int etid = threadIdx.x - 64; // 0..127
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (p.flags & CG_STATS) {
+      for (int i = etid; i < 2 * 512; i += 128) s_acc[i] = 0.f;  // thread etid owns channels == etid (mod 64) from here on
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_blocks;
       const int n_blk = tile - m_tile * p.n_blocks;
@@ -248,14 +252,22 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
               s += s_stat[(gg * 64 + etid) * 2];
               qq += s_stat[(gg * 64 + etid) * 2 + 1];
             }
-            float* gp = p.stats + (size_t)m_tile * 2 * p.n_total + n_base + etid;
-            gp[0] = s;
-            gp[p.n_total] = qq;
+            s_acc[n_base + etid] += s;          // tiles are visited in a fixed order: deterministic
+            s_acc[512 + n_base + etid] += qq;
           }
         }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if (p.flags & CG_STATS) {
+      // one partial per CTA: stats[blockIdx.x][2][n_total]
+      bar_sync_named(3, 128);
+      float* gp = p.stats + (size_t)blockIdx.x * 2 * p.n_total;
+      for (int i = etid; i < p.n_total; i += 128) {
+        gp[i] = s_acc[i];
+        gp[p.n_total + i] = s_acc[512 + i];
+      }
     }
   }
 

@@ -35,7 +35,17 @@ int build_dgrad(ConvGemmParams* p, const cilrs_conv_desc* d, int ph, int pw, con
 int build_wgrad(WgradParams* p, const cilrs_conv_desc* d, const void* dy, const void* x, float* dw);
 int build_stem_wgrad(WgradParams* p, int batch, const void* dy, const void* x_s2d, float* dw);
 
+// one-launch repack of every 3x3 / 1x1 conv weight of the network (fp32 OIHW masters -> both bf16 operand layouts)
+struct PackJob {
+  long long w_off;  // float offset of the OIHW master inside the parameter arena
+  __nv_bfloat16* wf;
+  __nv_bfloat16* wd;
+  int cout, cin, kk, first_block;
+};
+int launch_pack_all(const float* params, const PackJob* jobs_dev, int njobs, int total_blocks, cudaStream_t s);
+
 int launch_conv_gemm(const ConvGemmParams* p, cudaStream_t s);
+int conv_gemm_grid(const ConvGemmParams* p);  // CTAs launched = number of stats partials
 int launch_wgrad(const WgradParams* p, cudaStream_t s);
 int conv_out_dim(int in, int k, int stride, int pad);
 

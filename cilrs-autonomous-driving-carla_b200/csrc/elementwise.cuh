@@ -220,6 +220,7 @@ struct BnBwdReduceParams {
   float* bdot;          // [C]
   float* dgamma;        // += (may be null)
   float* dbeta;         // +=
+  __nv_bfloat16* dz_out;  // optional: store dz (stem variant: the routed + masked gradient, reused by the apply pass)
   // stem variant: g is the pooled gradient [B,OH,OW,C] gathered through the arg-max of the 3x3/2 max-pool, and the ReLU
   // mask is recomputed from y*scale+shift
   const uint8_t* argmax;
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
           if (!(av.v[k] > 0.f)) gv.v[k] = 0.f;
       }
     }
+    if (p.dz_out) store8(p.dz_out + i * 8, gv);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       a_sum[k] += gv.v[k];
@@ -321,14 +323,17 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
   __syncthreads();
   if (s_last) {
     __threadfence();
-    // fold the per-CTA partials: 4 slices of CTAs per channel in parallel, then a fixed-order combine
-    float* s_fin = &s_red[0][0];  // [4][2][C] floats (C <= 512 -> 4096 floats = all of s_red)
-    for (int j = threadIdx.x; j < 4 * p.C; j += EW_THREADS) {
+    // fold the per-CTA partials: S = 2048/C slices of CTAs per channel in parallel (all 256 threads busy), then a
+    // fixed-order combine -> deterministic
+    float* s_fin = &s_red[0][0];  // [S][2][C] floats = 4096 floats = all of s_red
+    const int S = 2048 / p.C;
+    for (int j = threadIdx.x; j < S * p.C; j += EW_THREADS) {
       const int c = j % p.C, sl = j / p.C;
       float s = 0.f, d = 0.f;
-      for (unsigned int b = sl; b < gridDim.x; b += 4) {
-        s += p.partial[(size_t)b * 2 * p.C + c];
-        d += p.partial[(size_t)b * 2 * p.C + p.C + c];
+#pragma unroll 4
+      for (unsigned int b = sl; b < gridDim.x; b += S) {
+        s += __ldcg(p.partial + (size_t)b * 2 * p.C + c);
+        d += __ldcg(p.partial + (size_t)b * 2 * p.C + p.C + c);
       }
       s_fin[(sl * 2 + 0) * p.C + c] = s;
       s_fin[(sl * 2 + 1) * p.C + c] = d;
@@ -336,8 +341,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
     __syncthreads();
     for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
       float s = 0.f, d = 0.f;
-#pragma unroll
-      for (int sl = 0; sl < 4; ++sl) { s += s_fin[(sl * 2 + 0) * p.C + c]; d += s_fin[(sl * 2 + 1) * p.C + c]; }
+      for (int sl = 0; sl < S; ++sl) { s += s_fin[(sl * 2 + 0) * p.C + c]; d += s_fin[(sl * 2 + 1) * p.C + c]; }
       p.bsum[c] = s;
       p.bdot[c] = d;
       if (p.dgamma) p.dgamma[c] += d;

@@ -80,17 +80,17 @@ struct Prof {
   }
   ~Prof() { for (auto e : pool) cudaEventDestroy(e); }
 };
-#define PROF(m, cls, s, stmt)                       \
+#define PROF(m, cls, s, ...)                        \
   do {                                              \
     if ((m).prof.on) {                              \
       cudaEvent_t _a = (m).prof.get();              \
       cudaEventRecord(_a, s);                       \
-      stmt;                                         \
+      __VA_ARGS__;                                  \
       cudaEvent_t _b = (m).prof.get();              \
       cudaEventRecord(_b, s);                       \
       (m).prof.recs.push_back(Prof::Rec{cls, _a, _b}); \
     } else {                                        \
-      stmt;                                         \
+      __VA_ARGS__;                                  \
     }                                               \
   } while (0)
 
@@ -126,6 +126,8 @@ struct Model {
   int* err_flag;
   __nv_bfloat16 *g0, *g1, *ga, *d1, *d2, *dz, *dy_stem;
   double* sumsq_partial;
+  PackJob* pack_jobs;    // device table for the one-launch weight repack
+  int pack_njobs = 0, pack_blocks = 0;
   // plans (tensor maps) for the batch size they were built for
   int planB = 0;
   int planMode = -1;
@@ -240,7 +242,7 @@ static long long carve(Model& m, char* base) {
   }
   // stats partial scratch: the stem has the most tiles (<= ceil(B*4400/100) ~ 44*B + slack), 2 x 64 floats each;
   // deeper layers have fewer tiles x more channels; bound by B*44*100/64 tiles * 2 * 64
-  m.stats = (float*)bp.take(((long long)B * 4400 / 50 + 4400) * 2 * 512 / 4 * 4 + 1024);
+  m.stats = (float*)bp.take(256LL * 2 * 512 * 4);  // one (sum, sumsq)[C<=512] partial per persistent conv CTA (<= SM count)
   m.bwd_partial = (float*)bp.take((long long)EW_MAX_BLOCKS * 2 * 512 * 4);
   m.counters = (unsigned int*)bp.take(64);
   m.unit_vec = (float*)bp.take(2 * 64 * 4);
@@ -273,6 +275,7 @@ static long long carve(Model& m, char* base) {
   m.dz = (__nv_bfloat16*)bp.take(gmax);
   m.dy_stem = (__nv_bfloat16*)bp.take(act_elems(B, 44, 100, 64) * 2);
   m.sumsq_partial = (double*)bp.take(1024 * 8);
+  m.pack_jobs = (PackJob*)bp.take(64 * sizeof(PackJob));
   return align_up(bp.off, 1024);
 }
 
@@ -424,12 +427,7 @@ static int refresh(Model& m, int what, cudaStream_t s) {
   if (!m.params) return ERR_INVALID;
   if (what & 1) {
     CK(cilrs_stem_pack_weight(m.params + m.slots[m.stem.w].off, m.stem.wf, s));
-    auto pack = [&](ConvRef& c) { return cilrs_conv_pack_weight(&c.d, m.params + m.slots[c.w].off, c.wf, c.wd, s); };
-    for (auto& blk : m.blocks) {
-      CK(pack(blk.a));
-      CK(pack(blk.b));
-      if (blk.has_ds) CK(pack(blk.ds));
-    }
+    CK(launch_pack_all(m.params, m.pack_jobs, m.pack_njobs, m.pack_blocks, s));
   }
   if (what & 2) {
     CK(run_bn_finalize(m, m.stem.bn, 0, 1.0, 0, 0, s));
@@ -478,7 +476,7 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
     PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi], s)));
     {
       const ConvGemmParams& p = m.fwd_plans[pi++];
-      PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, m.stem.bn, p.tiles_w * p.tiles_h * p.tiles_n, (double)B * 44 * 100, training, update_running, s)));
+      PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, m.stem.bn, conv_gemm_grid(&p), (double)B * 44 * 100, training, update_running, s)));
       const long long nvec = act_elems(B, 22, 50, 64) / 8;
       bn_relu_maxpool_kernel<<<ew_grid(nvec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.stem.bn.vec, m.stem.bn.vec + 64, m.pool_out,
                                                                       m.pool_arg, B, 44, 100, 64, 22, 50); ++g_cilrs_launches;
@@ -488,7 +486,7 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
       auto conv_bn = [&](ConvRef& c) -> int {
         const ConvGemmParams& p = m.fwd_plans[pi];
         PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi++], s)));
-        PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, c.bn, p.tiles_w * p.tiles_h * p.tiles_n, (double)B * c.oh * c.ow, training, update_running, s)));
+        PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, c.bn, conv_gemm_grid(&p), (double)B * c.oh * c.ow, training, update_running, s)));
         return OK;
       };
       CK(conv_bn(blk.a));
@@ -528,7 +526,7 @@ static int run_bn_bwd(Model& m, const BnRef& bn, const __nv_bfloat16* g, const _
                       long long elems, double count, int frozen, __nv_bfloat16* dy, __nv_bfloat16* dz, cudaStream_t s) {
   const long long nvec = elems / 8;
   const int grid = ew_grid(nvec, bn.C);
-  const int rgrid = ew_grid(nvec, bn.C, 8);
+  const int rgrid = ew_grid(nvec, bn.C, 16);
   BnBwdReduceParams rp{};
   rp.g = g; rp.act = act; rp.y = y; rp.mean = bn.vec + 2 * bn.C; rp.rstd = bn.vec + 3 * bn.C; rp.nvec = nvec; rp.C = bn.C;
   rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + bn.C;
@@ -635,21 +633,19 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     const BnRef& bn = m.stem.bn;
     const long long nvec = act_elems(B, 44, 100, 64) / 8;
     const int grid = ew_grid(nvec, 64);
-    const int rgrid = ew_grid(nvec, 64, 8);
+    const int rgrid = ew_grid(nvec, 64, 16);
     BnBwdReduceParams rp{};
     rp.g = gcur; rp.y = m.stem.y; rp.mean = bn.vec + 2 * 64; rp.rstd = bn.vec + 3 * 64; rp.nvec = nvec; rp.C = 64;
     rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + 64;
     rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
     rp.argmax = m.pool_arg; rp.scale = bn.vec; rp.shift = bn.vec + 64; rp.H = 44; rp.W = 100; rp.OH = 22; rp.OW = 50;
-    bn_bwd_reduce_kernel<true><<<rgrid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
-    CKL();
+    rp.dz_out = m.dy_stem;  // routed + masked gradient, turned into dy in place by the apply pass
+    PROF(m, PC_BN_BWD, s, { bn_bwd_reduce_kernel<true><<<rgrid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches; CKL(); });
     BnBwdApplyParams ap{};
-    ap.g = gcur; ap.y = m.stem.y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
+    ap.g = m.dy_stem; ap.y = m.stem.y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
     ap.bsum = rp.bsum; ap.bdot = rp.bdot; ap.inv_count = (float)(1.0 / ((double)B * 4400.0)); ap.frozen = frozen; ap.nvec = nvec;
-    ap.C = 64; ap.dy = m.dy_stem; ap.argmax = m.pool_arg; ap.scale = bn.vec; ap.shift = bn.vec + 64; ap.H = 44; ap.W = 100;
-    ap.OH = 22; ap.OW = 50;
-    bn_bwd_apply_kernel<true><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
-    CKL();
+    ap.C = 64; ap.dy = m.dy_stem;
+    PROF(m, PC_BN_BWD, s, { bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches; CKL(); });
     PROF(m, PC_WGRAD, s, CK(run_wgrad(m, wi++, s)));
   }
   return OK;
@@ -705,7 +701,26 @@ int cilrs_model_create(cilrs_model** out, int max_batch, void* workspace, size_t
   // constants: reduction counters, unit scale/shift for the inference max-pool, error flag
   float unit[128];
   for (int i = 0; i < 64; ++i) { unit[i] = 1.f; unit[64 + i] = 0.f; }
+  std::vector<PackJob> jobs;
+  {
+    int blocks = 0;
+    auto add = [&](ConvRef& c) {
+      PackJob j;
+      j.w_off = h->m.slots[c.w].off; j.wf = c.wf; j.wd = c.wd; j.cout = c.d.out_c; j.cin = c.d.in_c; j.kk = c.d.kh * c.d.kw;
+      j.first_block = blocks;
+      blocks += (c.d.out_c / 32) * (c.d.in_c / 32);
+      jobs.push_back(j);
+    };
+    for (auto& blk : h->m.blocks) {
+      add(blk.a);
+      add(blk.b);
+      if (blk.has_ds) add(blk.ds);
+    }
+    h->m.pack_njobs = (int)jobs.size();
+    h->m.pack_blocks = blocks;
+  }
   int st = cuda_status(cudaMemsetAsync(h->m.counters, 0, 64, s));
+  if (!st) st = cuda_status(cudaMemcpyAsync(h->m.pack_jobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, s));
   if (!st) st = cuda_status(cudaMemsetAsync(h->m.err_flag, 0, 64, s));
   if (!st) st = cuda_status(cudaMemcpyAsync(h->m.unit_vec, unit, sizeof(unit), cudaMemcpyHostToDevice, s));
   if (!st) st = cuda_status(cudaStreamSynchronize(s));  // `unit` is a stack buffer; creation is not on the hot path
@@ -868,7 +883,7 @@ int cilrs_bn_backward(const void* g, const void* act, const void* y, const float
   cudaStream_t s = (cudaStream_t)stream;
   const long long nvec = elems / 8;
   const int grid = ew_grid(nvec, C);
-  const int rgrid = ew_grid(nvec, C, 8);
+  const int rgrid = ew_grid(nvec, C, 16);
   float* bred = workspace + (size_t)EW_MAX_BLOCKS * 2 * C;
   BnBwdReduceParams rp{};
   rp.g = (const __nv_bfloat16*)g; rp.act = (const __nv_bfloat16*)act; rp.y = (const __nv_bfloat16*)y;
@@ -879,10 +894,11 @@ int cilrs_bn_backward(const void* g, const void* act, const void* y, const float
   ap.inv_count = (float)(1.0 / count); ap.frozen = frozen; ap.nvec = nvec; ap.C = C; ap.dy = (__nv_bfloat16*)dy; ap.dz = (__nv_bfloat16*)dz;
   if (argmax) {
     rp.argmax = argmax; rp.scale = vec; rp.shift = vec + C; rp.H = H; rp.W = W; rp.OH = (H + 1) / 2; rp.OW = (W + 1) / 2;
-    ap.argmax = argmax; ap.scale = vec; ap.shift = vec + C; ap.H = H; ap.W = W; ap.OH = rp.OH; ap.OW = rp.OW;
+    rp.dz_out = (__nv_bfloat16*)dy;  // routed + masked gradient; the apply pass turns it into dy in place
     bn_bwd_reduce_kernel<true><<<rgrid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
     CKL();
-    bn_bwd_apply_kernel<true><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
+    ap.g = (const __nv_bfloat16*)dy; ap.act = nullptr;
+    bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
   } else {
     bn_bwd_reduce_kernel<false><<<rgrid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
     CKL();

@@ -66,7 +66,7 @@ typedef struct cilrs_conv_desc {
 } cilrs_conv_desc;
 
 enum {
-  CILRS_EPI_STATS = 1,      /* also emit per-tile per-channel (sum, sum of squares) for train-mode BatchNorm */
+  CILRS_EPI_STATS = 1,      /* also emit per-CTA per-channel (sum, sum of squares) partials for train-mode BatchNorm */
   CILRS_EPI_SCALE_BIAS = 2, /* y = conv * scale[c] + bias[c]  (folded eval-mode BatchNorm) */
   CILRS_EPI_RESIDUAL = 4,   /* y += residual */
   CILRS_EPI_RELU = 8        /* y = max(y, 0) */
@@ -74,7 +74,7 @@ enum {
 
 /* bytes of packed bf16 weights for fprop / dgrad, and of the stats scratch for a given desc */
 size_t cilrs_conv_packed_weight_bytes(const cilrs_conv_desc* d);
-size_t cilrs_conv_stats_bytes(const cilrs_conv_desc* d); /* floats [m_tiles][2][out_c] */
+size_t cilrs_conv_stats_bytes(const cilrs_conv_desc* d); /* floats [partials][2][out_c], one partial per persistent CTA */
 int cilrs_conv_stats_tiles(const cilrs_conv_desc* d);
 
 /* fp32 OIHW master weight -> bf16 [tap][out_c][in_c] (fprop) and bf16 [tap][in_c][out_c] (dgrad); either may be NULL */
