@@ -270,6 +270,28 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
   float a_sum[8], a_dot[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { a_sum[k] = 0.f; a_dot[k] = 0.f; }
+  if (!STEM) {
+    // 4 independent vectors per iteration: 12 outstanding 16-byte loads per thread keep HBM busy with ~1 CTA per SM
+    for (; i + 3 * stride < p.nvec; i += 4 * stride) {
+      Vec8 yv[4], gv[4], av[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        yv[u] = load8(p.y + (i + u * stride) * 8);
+        gv[u] = load8(p.g + (i + u * stride) * 8);
+        if (p.act) av[u] = load8(p.act + (i + u * stride) * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float gk = gv[u].v[k];
+          if (p.act && !(av[u].v[k] > 0.f)) gk = 0.f;
+          a_sum[k] += gk;
+          a_dot[k] = fmaf(gk, (yv[u].v[k] - mean.v[k]) * rstd.v[k], a_dot[k]);
+        }
+      }
+    }
+  }
   for (; i < p.nvec; i += stride) {
     const Vec8 yv = load8(p.y + i * 8);
     Vec8 gv;
@@ -430,6 +452,17 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApp
 }
 
 // grid size for the vector kernels: a multiple of the channel-group count keeps every thread on one channel group
+// reductions: ~1 CTA per SM is enough with the 4-way unrolled loop, and keeps the partials the last CTA folds small
+inline int ew_reduce_grid(long long nvec, int C) {
+  long long cap = 16384 / C;  // C=64: 256 -> 148, C=128: 128, C=256: 64, C=512: 32
+  if (cap > 148) cap = 148;
+  if (cap < 16) cap = 16;
+  long long blocks = (nvec + (long long)EW_THREADS * 4 - 1) / ((long long)EW_THREADS * 4);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
 // (EW_THREADS = 256 is a multiple of every group count 8..64, so any block count keeps that property.)
 // `per_thread` = vectors each thread should get at least: streaming kernels use 2, reductions 8 (fewer partials to fold).
 inline int ew_grid(long long nvec, int C, int per_thread = 2) {

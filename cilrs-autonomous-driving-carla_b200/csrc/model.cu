@@ -526,7 +526,7 @@ static int run_bn_bwd(Model& m, const BnRef& bn, const __nv_bfloat16* g, const _
                       long long elems, double count, int frozen, __nv_bfloat16* dy, __nv_bfloat16* dz, cudaStream_t s) {
   const long long nvec = elems / 8;
   const int grid = ew_grid(nvec, bn.C);
-  const int rgrid = ew_grid(nvec, bn.C, 16);
+  const int rgrid = ew_reduce_grid(nvec, bn.C);
   BnBwdReduceParams rp{};
   rp.g = g; rp.act = act; rp.y = y; rp.mean = bn.vec + 2 * bn.C; rp.rstd = bn.vec + 3 * bn.C; rp.nvec = nvec; rp.C = bn.C;
   rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + bn.C;
@@ -633,7 +633,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     const BnRef& bn = m.stem.bn;
     const long long nvec = act_elems(B, 44, 100, 64) / 8;
     const int grid = ew_grid(nvec, 64);
-    const int rgrid = ew_grid(nvec, 64, 16);
+    const int rgrid = ew_grid(nvec, 64, 8);
     BnBwdReduceParams rp{};
     rp.g = gcur; rp.y = m.stem.y; rp.mean = bn.vec + 2 * 64; rp.rstd = bn.vec + 3 * 64; rp.nvec = nvec; rp.C = 64;
     rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + 64;
@@ -883,7 +883,7 @@ int cilrs_bn_backward(const void* g, const void* act, const void* y, const float
   cudaStream_t s = (cudaStream_t)stream;
   const long long nvec = elems / 8;
   const int grid = ew_grid(nvec, C);
-  const int rgrid = ew_grid(nvec, C, 16);
+  const int rgrid = ew_reduce_grid(nvec, C);
   float* bred = workspace + (size_t)EW_MAX_BLOCKS * 2 * C;
   BnBwdReduceParams rp{};
   rp.g = (const __nv_bfloat16*)g; rp.act = (const __nv_bfloat16*)act; rp.y = (const __nv_bfloat16*)y;
