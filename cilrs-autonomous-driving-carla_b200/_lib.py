@@ -18,6 +18,18 @@ class ConvDesc(ctypes.Structure):
                 ("pad", ctypes.c_int)]
 
 
+class FlatConvArgs(ctypes.Structure):
+    """cilrs_flat_conv_args (include/cilrs_b200.h)"""
+    _P, _I, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    _fields_ = [("batch", _I), ("H", _I), ("W", _I), ("in_c", _I), ("out_c", _I), ("dgrad", _I), ("flags", _I),
+                ("x", _P), ("w", _P), ("y", _P), ("scale", _P), ("bias", _P), ("residual", _P), ("mask", _P),
+                ("gamma", _P), ("beta", _P), ("running_mean", _P), ("running_var", _P), ("num_batches_tracked", _P),
+                ("vec", _P), ("momentum", _F), ("eps", _F), ("update_running", _I),
+                ("y1", _P), ("vec1", _P), ("bred1", _P), ("dgamma1", _P), ("dbeta1", _P),
+                ("y2", _P), ("vec2", _P), ("bred2", _P), ("dgamma2", _P), ("dbeta2", _P),
+                ("partials_ws", _P), ("counter_ws", _P)]
+
+
 def lib():
     """Load the shared library (building it is `__graft_entry__.build()` / `python build.py`)."""
     global _lib
@@ -30,7 +42,7 @@ def lib():
         _lib.cilrs_status_string.restype = ctypes.c_char_p
         _lib.cilrs_status_string.argtypes = [ctypes.c_int]
         for name in ("cilrs_conv_packed_weight_bytes", "cilrs_conv_stats_bytes", "cilrs_stem_packed_weight_bytes",
-                     "cilrs_model_workspace_bytes"):
+                     "cilrs_model_workspace_bytes", "cilrs_conv_flat_workspace_floats"):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = ctypes.c_size_t
     return _lib

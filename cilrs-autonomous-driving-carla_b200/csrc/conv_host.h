@@ -10,6 +10,9 @@ namespace cilrs {
 
 struct ConvGemmParams;
 struct WgradParams;
+struct FlatConvParams;
+struct WgradFlatParams;
+struct PadGeom;
 
 struct BoxShape {
   int BW, BH, BN;
@@ -43,6 +46,17 @@ struct PackJob {
   int cout, cin, kk, first_block;
 };
 int launch_pack_all(const float* params, const PackJob* jobs_dev, int njobs, int total_blocks, cudaStream_t s);
+
+// ---- padded-flat 3x3 stride-1 kernels (conv_flat.cu) ----
+int flat_total_rows(int batch, const PadGeom& g);
+// fprop: x [rows][k_channels] -> out [rows][n_total] with w = bf16 [9][n_total][k_channels];
+// dgrad: the same call with dy as x, the dgrad weight pack and dgrad = 1. Epilogue pointers are filled in by the caller.
+int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channels, int n_total, int dgrad, const void* x,
+                    const void* w, void* out, int flags);
+int flat_conv_grid(const FlatConvParams* p);
+int launch_flat_conv(const FlatConvParams* p, cudaStream_t s);
+int build_wgrad_flat(WgradFlatParams* p, int batch, const PadGeom& g, int cin, int cout, const void* dy, const void* x, float* dw);
+int launch_wgrad_flat(const WgradFlatParams* p, cudaStream_t s);
 
 int launch_conv_gemm(const ConvGemmParams* p, cudaStream_t s);
 int conv_gemm_grid(const ConvGemmParams* p);  // CTAs launched = number of stats partials

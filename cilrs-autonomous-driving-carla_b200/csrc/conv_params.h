@@ -74,4 +74,97 @@ struct WgradParams {
   float* grad;
 };
 
+// ------------------------------------------------------------------------------------------------------------------
+// "padded-flat" kernels (3x3 stride-1 convs, the bulk of ResNet-34).
+// Activations live in a padded NHWC layout: image b, row h, column w, channel c sits at flat pixel
+//   f = (b*Hp + h)*Wp + w,   Hp = H + 1, Wp = W + 1,
+// and the extra column / row of every image is all zeros. The left neighbour of column 0 is then the zero column of
+// the previous row, the row above row 0 is the zero row of the previous image, and a 3x3 tap (dh, dw) is the constant
+// flat shift dh*Wp + dw. One TMA load of a slab of (tile rows + 2*(Wp+1)) pixels therefore serves all nine taps: the
+// taps are row-shifted UMMA descriptors into the same shared-memory slab (SWIZZLE_128B is a function of the absolute
+// shared-memory address, so a descriptor may start at any 128-byte row; tools/umma_shift_test.cu).
+// ------------------------------------------------------------------------------------------------------------------
+struct PadGeom {
+  int H, W, Hp, Wp;
+};
+
+constexpr int CF_THREADS = 320;       // warp 0: TMA, warp 1: MMA, warps 2..9: two epilogue groups of 4 warps
+constexpr int CF_MAX_A_STAGES = 4;
+constexpr int CF_MAX_B_STAGES = 20;   // resident-weights mode keeps all taps x chunks (<= 18) in shared memory
+constexpr int CF_MAX_ACC = 8;
+constexpr int CF_STAGING_BYTES = 2 * 128 * 128;  // one 128 x 64 bf16 chunk per epilogue group
+
+enum FlatConvFlags : int {
+  CF_STATS = 1,       // per-channel sum / sum of squares of the bf16 output; the last CTA folds them into the BN vectors
+  CF_SCALE_BIAS = 2,  // y = acc * scale[n] + bias[n]
+  CF_RESIDUAL = 4,    // y += residual[f, n]
+  CF_RELU = 8,        // y = max(y, 0)
+  CF_MASK = 16,       // y = mask[f, n] > 0 ? y : 0          (ReLU backward, fused into the dgrad epilogue)
+  CF_BNBWD = 32,      // per-channel sum(y), sum(y * xhat1) with xhat1 = (y1 - mean1) * rstd1   (BatchNorm backward reduce)
+  CF_BNBWD2 = 64,     // ... and sum(y * xhat2) for a second BatchNorm fed by the same gradient (downsample branch)
+};
+
+struct FlatConvParams {
+  CUtensorMap tmA;  // 2-D (channels, flat pixels), box (64, a_box_rows)
+  CUtensorMap tmB;  // 2-D (channels, taps * n_total), box (64, block_n)
+  int total_rows;
+  PadGeom g;
+  int mt;                      // 128-row sub-tiles per tile (they share every weight tile)
+  int block_n, n_blocks, n_total;
+  int chunks, num_taps;
+  int tap_shift[9];
+  int tap_slab[9];
+  int halo;                    // Wp + 1
+  int a_box_rows, a_boxes;     // slab = a_boxes boxes of a_box_rows rows
+  int a_stages, b_stages, b_resident, acc_sets;
+  int m_tiles;
+  int flags;
+  __nv_bfloat16* out;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* mask;
+  const float* scale;
+  const float* bias;
+  float* partials;             // [gridDim.x][nq][n_total]
+  unsigned int* counter;
+  // CF_STATS: BatchNorm forward finalize (by the last CTA)
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  long long* nbt;
+  float* vec;                  // [4][n_total]: scale, shift, mean, rstd
+  double count;
+  float momentum, eps;
+  int update_running;
+  // CF_BNBWD / CF_BNBWD2
+  const __nv_bfloat16* y1;
+  const float* stat1;          // vec of BN 1 ([4][n_total]; mean at 2n, rstd at 3n)
+  float* bred1;                // [2][n_total]: bsum, bdot
+  float* dgamma1;
+  float* dbeta1;
+  const __nv_bfloat16* y2;
+  const float* stat2;
+  float* bred2;
+  float* dgamma2;
+  float* dbeta2;
+};
+
+constexpr int WF_THREADS = 192;
+constexpr int WF_MAX_STAGES = 4;
+constexpr int WF_MAX_TAPS = 5;
+
+struct WgradFlatParams {
+  CUtensorMap tmDY;  // 2-D (cout, flat pixels), box (64, 128)
+  CUtensorMap tmX;   // 2-D (cin, flat pixels), box (64, x_box_rows)
+  int total_rows, k_tiles;
+  int co_blocks, m_halves, ci_chunks;
+  int tap_groups;
+  int group_first[2], group_count[2];  // taps of each group (consecutive tap ids)
+  int tap_shift[9];
+  int x_box_rows, x_boxes;             // slab rows per stage = x_boxes * x_box_rows
+  int split_z, num_stages;
+  int cout, cin;
+  float* grad;                         // fp32 OIHW
+};
+
 }  // namespace cilrs

@@ -6,6 +6,7 @@ from . import _lib
 from ._lib import ConvDesc
 
 EPI_STATS, EPI_SCALE_BIAS, EPI_RESIDUAL, EPI_RELU = 1, 2, 4, 8
+EPI_MASK, EPI_BNBWD, EPI_BNBWD2 = 16, 32, 64
 
 
 def _need_cuda(*ts):
@@ -63,6 +64,81 @@ def conv_wgrad(d, dy, x):
     _need_cuda(dy, x)
     dw = torch.zeros(d.out_c, d.in_c, d.kh, d.kw, dtype=torch.float32, device=dy.device)
     _lib.call("cilrs_conv_wgrad", d, dy, x, dw, _lib.stream_ptr())
+    return dw
+
+
+def to_padded(x):
+    """dense NHWC [B,H,W,C] -> padded-flat layout [B,H+1,W+1,C] (last row / column of every image zero)."""
+    b, h, w, c = x.shape
+    out = torch.zeros(b, h + 1, w + 1, c, dtype=x.dtype, device=x.device)
+    out[:, :h, :w] = x
+    return out
+
+
+def from_padded(xp, h, w):
+    return xp[:, :h, :w].contiguous()
+
+
+def conv_flat(x_pad, w_pack, out_c, dgrad=False, scale=None, bias=None, residual=None, mask=None, relu=False,
+              bn=None, bnbwd=None, bnbwd2=None):
+    """3x3 stride-1 conv (fprop or dgrad) on padded-flat tensors. x_pad [B,H+1,W+1,Cin] bf16 -> [B,H+1,W+1,out_c].
+    bn = dict(gamma, beta, running_mean, running_var, nbt, update) -> also returns vec [4,out_c] (fused train-mode BN
+    statistics + finalize). bnbwd = dict(y, vec, dgamma, dbeta) -> also returns bred [2,out_c] (fused BN-backward reduce)."""
+    _need_cuda(x_pad, w_pack)
+    b, hp, wp, cin = x_pad.shape
+    dev = x_pad.device
+    y = torch.full((b, hp, wp, out_c), float("nan"), dtype=torch.bfloat16, device=dev)
+    a = _lib.FlatConvArgs()
+    a.batch, a.H, a.W, a.in_c, a.out_c, a.dgrad = b, hp - 1, wp - 1, cin, out_c, int(dgrad)
+    keep = [x_pad, w_pack, y]
+    ptr = lambda t: None if t is None else t.data_ptr()
+    a.x, a.w, a.y = ptr(x_pad), ptr(w_pack), ptr(y)
+    flags = 0
+    if scale is not None:
+        flags |= EPI_SCALE_BIAS
+        a.scale, a.bias = ptr(scale), ptr(bias)
+    if residual is not None:
+        flags |= EPI_RESIDUAL
+        a.residual = ptr(residual)
+    if mask is not None:
+        flags |= EPI_MASK
+        a.mask = ptr(mask)
+    if relu:
+        flags |= EPI_RELU
+    extra = []
+    if bn is not None or bnbwd is not None:
+        ws = torch.zeros(_lib.query("cilrs_conv_flat_workspace_floats", out_c), dtype=torch.float32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        a.partials_ws, a.counter_ws = ptr(ws), ptr(cnt)
+        keep += [ws, cnt]
+    if bn is not None:
+        flags |= EPI_STATS
+        vec = torch.empty(4, out_c, dtype=torch.float32, device=dev)
+        a.gamma, a.beta, a.running_mean, a.running_var = ptr(bn["gamma"]), ptr(bn["beta"]), ptr(bn["running_mean"]), ptr(bn["running_var"])
+        a.num_batches_tracked = ptr(bn.get("nbt"))
+        a.vec, a.momentum, a.eps, a.update_running = ptr(vec), 0.1, 1e-5, int(bn.get("update", 1))
+        extra.append(vec)
+    if bnbwd is not None:
+        flags |= EPI_BNBWD
+        bred = torch.empty(2, out_c, dtype=torch.float32, device=dev)
+        a.y1, a.vec1, a.bred1, a.dgamma1, a.dbeta1 = ptr(bnbwd["y"]), ptr(bnbwd["vec"]), ptr(bred), ptr(bnbwd.get("dgamma")), ptr(bnbwd.get("dbeta"))
+        extra.append(bred)
+        if bnbwd2 is not None:
+            flags |= EPI_BNBWD2
+            bred2 = torch.empty(2, out_c, dtype=torch.float32, device=dev)
+            a.y2, a.vec2, a.bred2, a.dgamma2, a.dbeta2 = ptr(bnbwd2["y"]), ptr(bnbwd2["vec"]), ptr(bred2), ptr(bnbwd2.get("dgamma")), ptr(bnbwd2.get("dbeta"))
+            extra.append(bred2)
+    a.flags = flags
+    _lib.call("cilrs_conv_flat", a, _lib.stream_ptr())
+    return (y, *extra) if extra else y
+
+
+def wgrad_flat(dy_pad, x_pad):
+    _need_cuda(dy_pad, x_pad)
+    b, hp, wp, cout = dy_pad.shape
+    cin = x_pad.shape[3]
+    dw = torch.zeros(cout, cin, 3, 3, dtype=torch.float32, device=dy_pad.device)
+    _lib.call("cilrs_wgrad_flat", b, hp - 1, wp - 1, cin, cout, dy_pad, x_pad, dw, _lib.stream_ptr())
     return dw
 
 

@@ -69,7 +69,11 @@ enum {
   CILRS_EPI_STATS = 1,      /* also emit per-CTA per-channel (sum, sum of squares) partials for train-mode BatchNorm */
   CILRS_EPI_SCALE_BIAS = 2, /* y = conv * scale[c] + bias[c]  (folded eval-mode BatchNorm) */
   CILRS_EPI_RESIDUAL = 4,   /* y += residual */
-  CILRS_EPI_RELU = 8        /* y = max(y, 0) */
+  CILRS_EPI_RELU = 8,       /* y = max(y, 0) */
+  /* padded-flat kernels only (cilrs_conv_flat): */
+  CILRS_EPI_MASK = 16,      /* y = mask > 0 ? y : 0  (ReLU backward fused into the dgrad epilogue) */
+  CILRS_EPI_BNBWD = 32,     /* also reduce sum(y), sum(y * xhat1) per channel = the BatchNorm-backward reductions */
+  CILRS_EPI_BNBWD2 = 64     /* ... and sum(y * xhat2) for a second BatchNorm fed by the same gradient */
 };
 
 /* bytes of packed bf16 weights for fprop / dgrad, and of the stats scratch for a given desc */
@@ -87,6 +91,52 @@ int cilrs_conv_dgrad(const cilrs_conv_desc* d, const void* dy, const void* w_dgr
                      void* stream);
 /* dw_oihw (fp32) += dy^T * im2col(x). The caller zeroes dw first. */
 int cilrs_conv_wgrad(const cilrs_conv_desc* d, const void* dy, const void* x, float* dw_oihw, void* stream);
+
+/* 3x3 stride-1 pad-1 convolutions on the PADDED-FLAT activation layout: a tensor [batch, H+1, W+1, C] bf16 whose last
+ * row and last column of every image are zero, seen as a flat list of (H+1)*(W+1)*batch pixels. A 3x3 tap is then a
+ * constant shift of the flat pixel index, one TMA-loaded slab serves all nine taps, and fprop / dgrad / wgrad of the 29
+ * stride-1 3x3 convolutions of ResNet-34 (torchvision/models/resnet.py BasicBlock.conv1/conv2) run on it.
+ * dgrad = 1: x is dy (in_c = conv output channels), w the dgrad pack, y = dx (out_c = conv input channels).
+ * CILRS_EPI_STATS here also FINALIZES train-mode BatchNorm inside the kernel (last CTA): vec [4][out_c] = scale, shift,
+ * mean, rstd, running statistics updated like torch.nn.BatchNorm2d. CILRS_EPI_BNBWD writes bred [2][out_c] = (sum dz,
+ * sum dz*xhat) and accumulates dgamma / dbeta. */
+typedef struct cilrs_flat_conv_args {
+  int batch, H, W, in_c, out_c;
+  int dgrad;
+  int flags;
+  const void* x;
+  const void* w;
+  void* y;
+  const float* scale;
+  const float* bias;
+  const void* residual; /* padded-flat [rows][out_c] */
+  const void* mask;     /* padded-flat [rows][out_c] */
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  long long* num_batches_tracked;
+  float* vec;
+  float momentum, eps;
+  int update_running;
+  const void* y1;
+  const float* vec1;
+  float* bred1;
+  float* dgamma1;
+  float* dbeta1;
+  const void* y2;
+  const float* vec2;
+  float* bred2;
+  float* dgamma2;
+  float* dbeta2;
+  float* partials_ws;       /* cilrs_conv_flat_workspace_floats(out_c) floats */
+  unsigned int* counter_ws; /* one zeroed uint32, left zero by the kernel */
+} cilrs_flat_conv_args;
+long long cilrs_flat_rows(int batch, int H, int W);
+size_t cilrs_conv_flat_workspace_floats(int out_c);
+int cilrs_conv_flat(const cilrs_flat_conv_args* a, void* stream);
+/* dw_oihw (fp32 [out_c,in_c,3,3]) += dy^T * shifted(x), both padded-flat. The caller zeroes dw first. */
+int cilrs_wgrad_flat(int batch, int H, int W, int in_c, int out_c, const void* dy, const void* x, float* dw_oihw, void* stream);
 
 /* the 7x7/2 stem on the space-to-depth input [batch,47,103,16] -> [batch,44,100,64] */
 size_t cilrs_stem_packed_weight_bytes(void);

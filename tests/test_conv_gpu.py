@@ -188,3 +188,172 @@ def test_stem_wgrad(batch):
     torch.cuda.synchronize()
     ref = torch.nn.grad.conv2d_weight(img.to(torch.bfloat16).float(), (64, 3, 7, 7), dy.float(), stride=2, padding=3)
     _report(f"stem_wgrad{batch}", dw, ref, 2e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# padded-flat kernels (3x3 stride-1): fprop / dgrad / wgrad, fused BatchNorm statistics + finalize, fused ReLU mask +
+# BatchNorm-backward reductions. Same checker (fp32 torch conv of the same bf16-rounded operands).
+# ---------------------------------------------------------------------------------------------------------------
+FLAT_CASES = [
+    # batch, H, W, Cin, Cout
+    (5, 22, 50, 64, 64),
+    (3, 11, 25, 128, 128),
+    (9, 6, 13, 256, 256),
+    (7, 3, 7, 512, 512),
+    (1, 22, 50, 64, 64),
+    (1, 3, 7, 512, 512),
+    (40, 11, 25, 128, 128),
+    (128, 22, 50, 64, 64),
+    (128, 6, 13, 256, 256),
+    (4, 9, 10, 64, 128),
+]
+
+
+def _pads_are_zero(yp, h, w):
+    return float(yp[:, h:, :].float().abs().max()) == 0.0 and float(yp[:, :, w:].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("case", FLAT_CASES)
+def test_flat_fprop(case):
+    ops = _ops()
+    _ref_setup()
+    b, h, w, ci, co = case
+    d = ops.conv_desc(b, h, w, ci, co, 3, 1)
+    x = _mk((b, ci, h, w), 21).to(torch.bfloat16)
+    wt = _mk((co, ci, 3, 3), 22) * (2.0 / (ci * 9)) ** 0.5
+    wf, _ = ops.pack_weight(d, wt)
+    yp = ops.conv_flat(ops.to_padded(_nhwc_bf16(x.float())), wf, co)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), wt.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    _report(f"flat_fprop{case}", ops.from_padded(yp, h, w), ref, 1.2e-2)
+    assert _pads_are_zero(yp, h, w)
+
+
+@pytest.mark.parametrize("case", FLAT_CASES[:7])
+def test_flat_dgrad(case):
+    ops = _ops()
+    _ref_setup()
+    b, h, w, ci, co = case
+    d = ops.conv_desc(b, h, w, ci, co, 3, 1)
+    dy = _mk((b, co, h, w), 23).to(torch.bfloat16)
+    wt = _mk((co, ci, 3, 3), 24) * (2.0 / (co * 9)) ** 0.5
+    _, wd = ops.pack_weight(d, wt)
+    dxp = ops.conv_flat(ops.to_padded(_nhwc_bf16(dy.float())), wd, ci, dgrad=True)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input((b, ci, h, w), wt.to(torch.bfloat16).float(), dy.float(), padding=1)
+    _report(f"flat_dgrad{case}", ops.from_padded(dxp, h, w), ref.permute(0, 2, 3, 1), 1.2e-2)
+    assert _pads_are_zero(dxp, h, w)
+
+
+@pytest.mark.parametrize("case", [(5, 22, 50, 64, 64), (12, 11, 25, 128, 128), (20, 6, 13, 256, 256), (9, 3, 7, 512, 512),
+                                  (128, 11, 25, 128, 128), (3, 9, 10, 64, 128)])
+def test_flat_wgrad(case):
+    ops = _ops()
+    _ref_setup()
+    b, h, w, ci, co = case
+    x = _mk((b, ci, h, w), 25).to(torch.bfloat16)
+    dy = (_mk((b, co, h, w), 26) * 0.1).to(torch.bfloat16)
+    dw = ops.wgrad_flat(ops.to_padded(_nhwc_bf16(dy.float())), ops.to_padded(_nhwc_bf16(x.float())))
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(x.float(), (co, ci, 3, 3), dy.float(), padding=1)
+    _report(f"flat_wgrad{case}", dw, ref, 2e-3)
+
+
+def test_flat_inference_epilogue():
+    ops = _ops()
+    _ref_setup()
+    b, h, w, c = 6, 11, 25, 128
+    d = ops.conv_desc(b, h, w, c, c, 3, 1)
+    x = _mk((b, c, h, w), 27).to(torch.bfloat16)
+    wt = _mk((c, c, 3, 3), 28) * (2.0 / (c * 9)) ** 0.5
+    wf, _ = ops.pack_weight(d, wt)
+    scale = _mk((c,), 29).abs() + 0.5
+    bias = _mk((c,), 30)
+    res = _mk((b, h, w, c), 31).to(torch.bfloat16)
+    yp = ops.conv_flat(ops.to_padded(_nhwc_bf16(x.float())), wf, c, scale=scale, bias=bias, residual=ops.to_padded(res), relu=True)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), wt.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    ref = torch.relu(ref * scale + bias + res.float())
+    _report("flat fused-epilogue", ops.from_padded(yp, h, w), ref, 1.2e-2)
+    assert _pads_are_zero(yp, h, w)
+
+
+@pytest.mark.parametrize("case", [(6, 11, 25, 128), (128, 22, 50, 64), (33, 6, 13, 256), (128, 3, 7, 512)])
+def test_flat_fprop_fused_bn_statistics(case):
+    """train-mode BatchNorm statistics + finalize inside the conv kernel == torch batch_norm statistics of its output"""
+    ops = _ops()
+    _ref_setup()
+    b, h, w, c = case
+    d = ops.conv_desc(b, h, w, c, c, 3, 1)
+    x = _mk((b, c, h, w), 32).to(torch.bfloat16)
+    wt = _mk((c, c, 3, 3), 33) * (2.0 / (c * 9)) ** 0.5
+    wf, _ = ops.pack_weight(d, wt)
+    gamma = 1 + 0.3 * _mk((c,), 34)
+    beta = 0.2 * _mk((c,), 35)
+    rm, rv = _mk((c,), 36), _mk((c,), 37).abs() + 0.5
+    rm0, rv0 = rm.clone(), rv.clone()
+    nbt = torch.zeros(1, dtype=torch.long, device="cuda")
+    for rep in range(2):  # twice: the kernel must leave its counter / workspace reusable
+        yp, vec = ops.conv_flat(ops.to_padded(_nhwc_bf16(x.float())), wf, c,
+                                bn=dict(gamma=gamma, beta=beta, running_mean=rm, running_var=rv, nbt=nbt, update=1 if rep == 0 else 0))
+    torch.cuda.synchronize()
+    y = ops.from_padded(yp, h, w).float()
+    mean = y.mean((0, 1, 2))
+    var = y.var((0, 1, 2), unbiased=False)
+    rstd = 1.0 / torch.sqrt(var + 1e-5)
+    _report("bn mean", vec[2], mean, 2e-4)
+    _report("bn rstd", vec[3], rstd, 1e-4)
+    _report("bn scale", vec[0], gamma * rstd, 1e-4)
+    _report("bn shift", vec[1], beta - mean * gamma * rstd, 2e-4)
+    n = b * h * w
+    _report("running_mean", rm, 0.9 * rm0 + 0.1 * mean, 1e-4)
+    _report("running_var", rv, 0.9 * rv0 + 0.1 * var * n / (n - 1), 1e-4)
+    assert int(nbt) == 1
+
+
+@pytest.mark.parametrize("case", [(6, 11, 25, 128, False), (128, 22, 50, 64, True), (20, 6, 13, 256, True), (128, 3, 7, 512, False)])
+def test_flat_dgrad_fused_relu_mask_and_bn_backward_reduce(case):
+    """dz = (dgrad + residual) * (act > 0) and the BatchNorm-backward reductions sum(dz), sum(dz * xhat) in one kernel"""
+    ops = _ops()
+    _ref_setup()
+    b, h, w, c, two = case
+    d = ops.conv_desc(b, h, w, c, c, 3, 1)
+    dy = _mk((b, c, h, w), 40).to(torch.bfloat16)
+    wt = _mk((c, c, 3, 3), 41) * (2.0 / (c * 9)) ** 0.5
+    _, wd = ops.pack_weight(d, wt)
+    res = _mk((b, h, w, c), 42).to(torch.bfloat16)
+    act = torch.relu(_mk((b, h, w, c), 43)).to(torch.bfloat16)
+    y1 = _mk((b, h, w, c), 44).to(torch.bfloat16)
+    y2 = _mk((b, h, w, c), 45).to(torch.bfloat16)
+
+    def mkvec(y):
+        yf = y.float()
+        mean = yf.mean((0, 1, 2))
+        rstd = 1.0 / torch.sqrt(yf.var((0, 1, 2), unbiased=False) + 1e-5)
+        return torch.stack([torch.ones_like(mean), torch.zeros_like(mean), mean, rstd]).contiguous()
+
+    v1, v2 = mkvec(y1), mkvec(y2)
+    dg1, db1 = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    dg2, db2 = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    out = ops.conv_flat(ops.to_padded(_nhwc_bf16(dy.float())), wd, c, dgrad=True, residual=ops.to_padded(res), mask=ops.to_padded(act),
+                        bnbwd=dict(y=ops.to_padded(y1), vec=v1, dgamma=dg1, dbeta=db1),
+                        bnbwd2=dict(y=ops.to_padded(y2), vec=v2, dgamma=dg2, dbeta=db2) if two else None)
+    torch.cuda.synchronize()
+    dzp, bred1 = out[0], out[1]
+    ref = torch.nn.grad.conv2d_input((b, c, h, w), wt.to(torch.bfloat16).float(), dy.float(), padding=1).permute(0, 2, 3, 1)
+    ref = (ref + res.float()) * (act.float() > 0)
+    dz = ops.from_padded(dzp, h, w)
+    _report("fused dz", dz, ref, 1.2e-2)
+    assert _pads_are_zero(dzp, h, w)
+    dzf = dz.float()  # the reductions are defined on the stored (bf16) dz
+    xhat1 = (y1.float() - v1[2]) * v1[3]
+    _report("bsum", bred1[0], dzf.sum((0, 1, 2)), 2e-4)
+    _report("bdot", bred1[1], (dzf * xhat1).sum((0, 1, 2)), 2e-4)
+    _report("dgamma", dg1, (dzf * xhat1).sum((0, 1, 2)), 2e-4)
+    _report("dbeta", db1, dzf.sum((0, 1, 2)), 2e-4)
+    if two:
+        bred2 = out[2]
+        xhat2 = (y2.float() - v2[2]) * v2[3]
+        _report("bsum2", bred2[0], dzf.sum((0, 1, 2)), 2e-4)
+        _report("bdot2", bred2[1], (dzf * xhat2).sum((0, 1, 2)), 2e-4)
+        _report("dgamma2", dg2, (dzf * xhat2).sum((0, 1, 2)), 2e-4)
