@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcilrs_b200.so")
+# CILRS_B200_LIB selects an instrumented debug build of the same library (tools/); never a different implementation
+LIB_PATH = os.environ.get("CILRS_B200_LIB") or os.path.join(_HERE, "libcilrs_b200.so")
 _lib = None
 
 

@@ -1,6 +1,7 @@
 // Host side of the tcgen05 convolution kernels + their C-ABI entry points (include/cilrs_b200.h).
 #include "conv_gemm.cuh"
 #include "wgrad_gemm.cuh"
+#include "conv_params.h"
 #include "conv_host.h"
 #include <cudaTypedefs.h>
 #include <string.h>
@@ -124,12 +125,21 @@ static int check_desc(const cilrs_conv_desc* d) {
   return OK;
 }
 
+// pixel pitches of a tensor: dense [H][W] or the padded-flat layout of conv_params.h
+static void pitches(const PadGeom* g, int H, int W, int* hp, int* wp) {
+  *hp = g ? g->Hp : H;
+  *wp = g ? g->Wp : W;
+}
+
 int build_fprop(ConvGemmParams* p, const cilrs_conv_desc* d, const void* x, const void* w, void* y, const float* scale,
-                const float* bias, const void* residual, float* stats, int flags) {
+                const float* bias, const void* residual, float* stats, int flags, const PadGeom* gin, const PadGeom* gout) {
   int st = check_desc(d);
   if (st) return st;
   memset(p, 0, sizeof(*p));
   const int OH = conv_out_dim(d->in_h, d->kh, d->stride, d->pad), OW = conv_out_dim(d->in_w, d->kw, d->stride, d->pad);
+  int ihp, iwp, ohp, owp;
+  pitches(gin, d->in_h, d->in_w, &ihp, &iwp);
+  pitches(gout, OH, OW, &ohp, &owp);
   const BoxShape b = choose_box(OW, OH, d->batch);
   set_tiles(p, b);
   p->block_n = pick_block_n(d->out_c, b.m_tiles());
@@ -147,12 +157,12 @@ int build_fprop(ConvGemmParams* p, const cilrs_conv_desc* d, const void* x, cons
     }
   p->slab_rows = d->out_c;
   p->n_img = d->batch; p->oh = OH; p->ow = OW;
-  p->out_sw = d->out_c; p->out_sh = (long long)OW * d->out_c; p->out_sn = (long long)OH * OW * d->out_c; p->out_off = 0;
+  p->out_sw = d->out_c; p->out_sh = (long long)owp * d->out_c; p->out_sn = (long long)ohp * owp * d->out_c; p->out_off = 0;
   p->n_total = d->out_c;
   p->out = (__nv_bfloat16*)y; p->residual = (const __nv_bfloat16*)residual; p->scale = scale; p->bias = bias; p->stats = stats;
   p->flags = flags;
   const long long cb = 2LL * d->in_c;
-  st = encode_nhwc_map(&p->tmA[0], x, d->in_c, d->in_w, d->in_h, d->batch, cb, cb * d->in_w, cb * d->in_w * d->in_h, 64, b.BW,
+  st = encode_nhwc_map(&p->tmA[0], x, d->in_c, d->in_w, d->in_h, d->batch, cb, cb * iwp, cb * iwp * ihp, 64, b.BW,
                        b.BH, b.BN, d->stride, d->stride);
   if (st) return st;
   p->tmA[1] = p->tmA[2] = p->tmA[3] = p->tmA[0];
@@ -195,11 +205,14 @@ int build_stem_fprop(ConvGemmParams* p, int batch, const void* x_s2d, const void
 }
 
 int build_dgrad(ConvGemmParams* p, const cilrs_conv_desc* d, int ph, int pw, const void* dy, const void* wd, void* dx,
-                const void* residual, const void* dy2, const void* w2d) {
+                const void* residual, const void* dy2, const void* w2d, const PadGeom* gin, const PadGeom* gout) {
   int st = check_desc(d);
   if (st) return st;
   memset(p, 0, sizeof(*p));
   const int OH = conv_out_dim(d->in_h, d->kh, d->stride, d->pad), OW = conv_out_dim(d->in_w, d->kw, d->stride, d->pad);
+  int ihp, iwp, ohp, owp;
+  pitches(gin, d->in_h, d->in_w, &ihp, &iwp);
+  pitches(gout, OH, OW, &ohp, &owp);
   const int s = d->stride;
   // output of this launch: input pixels (h, w) with h % s == ph, w % s == pw
   const int TH = (d->in_h - ph + s - 1) / s, TW = (d->in_w - pw + s - 1) / s;
@@ -236,17 +249,17 @@ int build_dgrad(ConvGemmParams* p, const cilrs_conv_desc* d, int ph, int pw, con
   p->slab_rows = d->in_c;
   p->n_img = d->batch; p->oh = TH; p->ow = TW;
   const long long C = d->in_c;
-  p->out_sw = s * C; p->out_sh = (long long)s * d->in_w * C; p->out_sn = (long long)d->in_h * d->in_w * C;
-  p->out_off = ((long long)ph * d->in_w + pw) * C;
+  p->out_sw = s * C; p->out_sh = (long long)s * iwp * C; p->out_sn = (long long)ihp * iwp * C;
+  p->out_off = ((long long)ph * iwp + pw) * C;
   p->n_total = d->in_c;
   p->out = (__nv_bfloat16*)dx; p->residual = (const __nv_bfloat16*)residual;
   p->flags = residual ? CG_RESIDUAL : 0;
   const long long cb = 2LL * d->out_c;
-  st = encode_nhwc_map(&p->tmA[0], dy, d->out_c, OW, OH, d->batch, cb, cb * OW, cb * OW * OH, 64, b.BW, b.BH, b.BN, 1, 1);
+  st = encode_nhwc_map(&p->tmA[0], dy, d->out_c, OW, OH, d->batch, cb, cb * owp, cb * owp * ohp, 64, b.BW, b.BH, b.BN, 1, 1);
   if (st) return st;
   p->tmA[1] = p->tmA[0];
   if (dy2) {
-    st = encode_nhwc_map(&p->tmA[1], dy2, d->out_c, OW, OH, d->batch, cb, cb * OW, cb * OW * OH, 64, b.BW, b.BH, b.BN, 1, 1);
+    st = encode_nhwc_map(&p->tmA[1], dy2, d->out_c, OW, OH, d->batch, cb, cb * owp, cb * owp * ohp, 64, b.BW, b.BH, b.BN, 1, 1);
     if (st) return st;
   }
   p->tmA[2] = p->tmA[3] = p->tmA[0];
@@ -267,11 +280,15 @@ static int wgrad_stages(int g) {
   return s;
 }
 
-int build_wgrad(WgradParams* p, const cilrs_conv_desc* d, const void* dy, const void* x, float* dw) {
+int build_wgrad(WgradParams* p, const cilrs_conv_desc* d, const void* dy, const void* x, float* dw, const PadGeom* gin,
+                const PadGeom* gout) {
   int st = check_desc(d);
   if (st) return st;
   memset(p, 0, sizeof(*p));
   const int OH = conv_out_dim(d->in_h, d->kh, d->stride, d->pad), OW = conv_out_dim(d->in_w, d->kw, d->stride, d->pad);
+  int ihp, iwp, ohp, owp;
+  pitches(gin, d->in_h, d->in_w, &ihp, &iwp);
+  pitches(gout, OH, OW, &ohp, &owp);
   const BoxShape b = choose_box(OW, OH, d->batch);
   p->tiles_w = b.tiles_w; p->tiles_h = b.tiles_h; p->tiles_n = b.tiles_n;
   p->BW = b.BW; p->BH = b.BH; p->BN = b.BN;
@@ -300,10 +317,10 @@ int build_wgrad(WgradParams* p, const cilrs_conv_desc* d, const void* dy, const 
   p->col_mode = WG_COL_REGULAR;
   p->grad = dw;
   const long long cb = 2LL * d->out_c;
-  st = encode_nhwc_map(&p->tmDY, dy, d->out_c, OW, OH, d->batch, cb, cb * OW, cb * OW * OH, 64, b.BW, b.BH, b.BN, 1, 1);
+  st = encode_nhwc_map(&p->tmDY, dy, d->out_c, OW, OH, d->batch, cb, cb * owp, cb * owp * ohp, 64, b.BW, b.BH, b.BN, 1, 1);
   if (st) return st;
   const long long xb = 2LL * d->in_c;
-  st = encode_nhwc_map(&p->tmX, x, d->in_c, d->in_w, d->in_h, d->batch, xb, xb * d->in_w, xb * d->in_w * d->in_h, 64, b.BW, b.BH,
+  st = encode_nhwc_map(&p->tmX, x, d->in_c, d->in_w, d->in_h, d->batch, xb, xb * iwp, xb * iwp * ihp, 64, b.BW, b.BH,
                        b.BN, d->stride, d->stride);
   return st;
 }
@@ -457,7 +474,7 @@ int cilrs_conv_fprop(const cilrs_conv_desc* d, const void* x, const void* w, voi
   if ((flags & CILRS_EPI_SCALE_BIAS) && (!scale || !bias)) return ERR_INVALID;
   if ((flags & CILRS_EPI_RESIDUAL) && !residual) return ERR_INVALID;
   ConvGemmParams p;
-  int st = build_fprop(&p, d, x, w, y, scale, bias, residual, stats, flags);
+  int st = build_fprop(&p, d, x, w, y, scale, bias, residual, stats, flags, nullptr, nullptr);
   if (st) return st;
   return launch_conv_gemm(&p, (cudaStream_t)stream);
 }
@@ -469,7 +486,7 @@ int cilrs_conv_dgrad(const cilrs_conv_desc* d, const void* dy, const void* wd, v
   for (int ph = 0; ph < d->stride; ++ph)
     for (int pw = 0; pw < d->stride; ++pw) {
       ConvGemmParams p;
-      st = build_dgrad(&p, d, ph, pw, dy, wd, dx, residual, nullptr, nullptr);
+      st = build_dgrad(&p, d, ph, pw, dy, wd, dx, residual, nullptr, nullptr, nullptr, nullptr);
       if (st == ERR_UNSUPPORTED && d->kh == 1) continue;  // 1x1/2: odd parities receive no gradient
       if (st) return st;
       st = launch_conv_gemm(&p, (cudaStream_t)stream);
@@ -481,7 +498,7 @@ int cilrs_conv_dgrad(const cilrs_conv_desc* d, const void* dy, const void* wd, v
 int cilrs_conv_wgrad(const cilrs_conv_desc* d, const void* dy, const void* x, float* dw, void* stream) {
   if (!dy || !x || !dw) return ERR_INVALID;
   WgradParams p;
-  int st = build_wgrad(&p, d, dy, x, dw);
+  int st = build_wgrad(&p, d, dy, x, dw, nullptr, nullptr);
   if (st) return st;
   return launch_wgrad(&p, (cudaStream_t)stream);
 }

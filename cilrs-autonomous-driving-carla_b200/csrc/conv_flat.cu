@@ -4,6 +4,8 @@
 #include "wgrad_flat.cuh"
 #include "conv_host.h"
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace cilrs {
 
@@ -28,7 +30,7 @@ static void split_boxes(int rows, int* box_rows, int* boxes) {
 
 static long long flat_smem_fixed(int n_total) {
   return 1024 /* alignment slack */ + CF_STAGING_BYTES + 2 * 4 * 64 * 3 * 4 + 2LL * 3 * n_total * 4 +
-         (2 * CF_MAX_A_STAGES + 2 * CF_MAX_B_STAGES + 2 * CF_MAX_ACC) * 8 + 64;
+         (2 * CF_MAX_A_STAGES + 2 * CF_MAX_B_STAGES + 2 * CF_MAX_ACC) * 8 + 64 + 64;
 }
 
 // Tile-shape choice by a small cost model (clocks per CTA): a (128*mt) x block_n tile issues 9*chunks*mt*4 MMAs of
@@ -93,6 +95,25 @@ static FlatShape choose_flat_shape(int total_rows, int k_channels, int n_total, 
       }
     }
   }
+  // measurement aid: CILRS_FLAT_SHAPE="mt,block_n,resident,a_stages,b_stages" overrides the model (0 stages = keep the model's)
+  if (const char* env = getenv("CILRS_FLAT_SHAPE")) {
+    int mt = 0, bn = 0, res = 0, a_st = 0, b_st = 0;
+    if (sscanf(env, "%d,%d,%d,%d,%d", &mt, &bn, &res, &a_st, &b_st) >= 3 && mt >= 1 && bn >= 64 && n_total % bn == 0 && mt * bn <= 512) {
+      int box_rows, boxes;
+      split_boxes(mt * 128 + 2 * halo, &box_rows, &boxes);
+      const long long a_stage = (long long)box_rows * boxes * 128, b_stage = (long long)bn * 128;
+      if (res) b_st = 9 * chunks;
+      if (a_st < 1) a_st = 2;
+      if (b_st < 1) b_st = (int)((budget - a_st * a_stage) / b_stage);
+      if (b_st > CF_MAX_B_STAGES) b_st = CF_MAX_B_STAGES;
+      if (a_st <= CF_MAX_A_STAGES && b_st >= 1 && a_st * a_stage + b_st * b_stage <= budget && (!res || n_total == bn))
+        best = FlatShape{mt, bn, res, a_st, b_st, box_rows, boxes, 0.0};
+    }
+  }
+  if (getenv("CILRS_FLAT_DEBUG"))
+    fprintf(stderr, "[cilrs flat] rows=%d K=%d N=%d Wp=%d -> mt=%d block_n=%d resident=%d a_stages=%d b_stages=%d a_box=%dx%d cost=%.0f\n",
+            total_rows, k_channels, n_total, g.Wp, best.mt, best.block_n, best.resident, best.a_stages, best.b_stages, best.a_boxes,
+            best.a_box_rows, best.cost);
   return best;
 }
 
@@ -239,6 +260,18 @@ int cilrs_conv_flat(const cilrs_flat_conv_args* a, void* stream) {
   p.y2 = (const __nv_bfloat16*)a->y2; p.stat2 = a->vec2; p.bred2 = a->bred2; p.dgamma2 = a->dgamma2; p.dbeta2 = a->dbeta2;
   return launch_flat_conv(&p, (cudaStream_t)stream);
 }
+
+#ifdef CF_TRACE
+// debug build only: copy out (and reset) the event trace of CTA 0; out = 3 x 2048 uint64, counts = 3 ints
+int cilrs_conv_flat_trace(unsigned long long* out, int* counts) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_cf_trace, sizeof(unsigned long long) * 3 * 2048);
+  cudaMemcpyFromSymbol(counts, g_cf_trace_n, sizeof(int) * 3);
+  int zero[3] = {0, 0, 0};
+  cudaMemcpyToSymbol(g_cf_trace_n, zero, sizeof(zero));
+  return 0;
+}
+#endif
 
 size_t cilrs_conv_flat_workspace_floats(int out_c) { return (size_t)256 * 3 * out_c; }
 

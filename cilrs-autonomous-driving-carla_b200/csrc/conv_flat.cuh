@@ -17,6 +17,19 @@
 
 namespace cilrs {
 
+// optional event trace of CTA 0 (tools/trace_flat.py; compiled in only with -DCF_TRACE)
+#ifdef CF_TRACE
+__device__ unsigned long long g_cf_trace[3][2048];
+__device__ int g_cf_trace_n[3];
+#define CF_EVENT(role, code)                                                              \
+  do {                                                                                    \
+    if (blockIdx.x == 0 && cf_idx[role] < 2048)                                           \
+      g_cf_trace[role][cf_idx[role]++] = ((unsigned long long)clock64() << 16) | (unsigned long long)((code) & 0xFFFF); \
+  } while (0)
+#else
+#define CF_EVENT(role, code) do { } while (0)
+#endif
+
 CILRS_DEVINL void cf_unpack8(const uint4 u, float* f) {
   f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
   f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
@@ -44,6 +57,10 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
   uint64_t* tempty = tfull + CF_MAX_ACC;
   uint32_t* tmem_slot = (uint32_t*)(tempty + CF_MAX_ACC);
   uint32_t* s_flag = tmem_slot + 1;
+#ifdef CF_TRACE
+  uint32_t* cf_idx = s_flag + 1;  // event counters of the three traced roles (shared memory: cheap to bump)
+  if (threadIdx.x < 3) cf_idx[threadIdx.x] = 0;
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -77,6 +94,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
         const int row0 = m_tile * p.mt * 128;
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(&empty_a[as], aph ^ 1);
+          CF_EVENT(0, 0x100 + c);
           mbar_arrive_expect_tx(&full_a[as], (uint32_t)a_stage_bytes);
           uint8_t* dst = sA + (size_t)as * a_stage_bytes;
           for (int bx = 0; bx < p.a_boxes; ++bx)
@@ -85,6 +103,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
           for (int t = 0; t < p.num_taps; ++t) {
             if (!p.b_resident || first) {
               if (!p.b_resident) mbar_wait(&empty_b[bs], bph ^ 1);
+              CF_EVENT(0, 0x200 + t);
               mbar_arrive_expect_tx(&full_b[bs], (uint32_t)b_stage_bytes);
               tma_load_2d(&p.tmB, &full_b[bs], sB + (size_t)bs * b_stage_bytes, c * 64, p.tap_slab[t] * p.n_total + n_blk * p.block_n);
             }
@@ -96,44 +115,60 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.block_n, 0, 0);
-      int as = 0, bs = 0, acc = 0;
-      uint32_t aph = 0, bph = 0, accph = 0;
-      bool first = true;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], accph ^ 1);
+    // The whole warp runs the loop so every address / descriptor stays in uniform registers and an MMA costs ~8
+    // instructions; one elected lane issues. (With a lone lane inside a divergent branch each tcgen05.mma cost ~90
+    // clocks of instruction issue - more than the 32..64 clocks the tensor core needs for N = 64..128;
+    // tools/umma_rate_test2.cu.) The CTA owns all 512 TMEM columns, so the allocation starts at column 0.
+    if (tmem_base != 0) __trap();
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(128, p.block_n, 0, 0);
+    const uint64_t descA0 = umma_desc_sw128(smem_u32(sA), 16, 1024);
+    const uint64_t descB0 = umma_desc_sw128(smem_u32(sB), 16, 1024);
+    const uint32_t a_stage_units = (uint32_t)(a_stage_bytes >> 4), b_stage_units = (uint32_t)(b_stage_bytes >> 4);
+    int as = 0, bs = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, accph = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], accph ^ 1);
+      tc_fence_after();
+      if (leader) CF_EVENT(1, 0x300);
+      const uint32_t d_base = (uint32_t)(acc * acc_stride);
+      for (int c = 0; c < p.chunks; ++c) {
+        mbar_wait(&full_a[as], aph);
         tc_fence_after();
-        const uint32_t d_base = tmem_base + (uint32_t)(acc * acc_stride);
-        for (int c = 0; c < p.chunks; ++c) {
-          mbar_wait(&full_a[as], aph);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + (size_t)as * a_stage_bytes);
-          for (int t = 0; t < p.num_taps; ++t) {
-            if (!p.b_resident || first) {
-              mbar_wait(&full_b[bs], bph);
-              tc_fence_after();
-            }
-            const uint32_t b_addr = smem_u32(sB + (size_t)bs * b_stage_bytes);
+        if (leader) CF_EVENT(1, 0x100 + c);
+        const uint64_t da_stage = descA0 + (uint64_t)((uint32_t)as * a_stage_units);
+        for (int t = 0; t < p.num_taps; ++t) {
+          if (!p.b_resident || first) {
+            mbar_wait(&full_b[bs], bph);
+            tc_fence_after();
+          }
+          if (leader) CF_EVENT(1, 0x200 + t);
+          const uint64_t db = descB0 + (uint64_t)((uint32_t)bs * b_stage_units);
+          const uint64_t da_tap = da_stage + (uint64_t)((uint32_t)(p.halo + p.tap_shift[t]) * 8u);  // 128-byte rows, in 16-byte units
+          if (leader) {
             for (int m = 0; m < p.mt; ++m) {
-              const uint32_t a_addr = a_base + (uint32_t)((m * 128 + p.halo + p.tap_shift[t]) * 128);
+              const uint64_t da = da_tap + (uint64_t)((uint32_t)m * 1024u);
+              const uint32_t d = d_base + (uint32_t)(m * p.block_n);
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
-                const uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
-                umma_bf16(d_base + (uint32_t)(m * p.block_n), da, db, idesc, (c | t | kk) != 0 ? 1u : 0u);
-              }
+              for (int kk = 0; kk < 4; ++kk) umma_bf16(d, da + kk * 2, db + kk * 2, idesc, (c | t | kk) != 0 ? 1u : 0u);
             }
             if (!p.b_resident) umma_commit(&empty_b[bs]);
-            if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
           }
-          umma_commit(&empty_a[as]);
-          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+          __syncwarp();
+          if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
         }
-        umma_commit(&tfull[acc]);
-        if (++acc == p.acc_sets) { acc = 0; accph ^= 1; }
-        first = false;
+        if (leader) umma_commit(&empty_a[as]);
+        __syncwarp();
+        if (++as == p.a_stages) { as = 0; aph ^= 1; }
       }
+      if (leader) {
+        umma_commit(&tfull[acc]);
+        CF_EVENT(1, 0x400);
+      }
+      __syncwarp();
+      if (++acc == p.acc_sets) { acc = 0; accph ^= 1; }
+      first = false;
     }
   } else {
     // ================= epilogue: 2 groups x 4 warps; a group handles every other 128 x 64 unit =================
@@ -163,6 +198,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
       const int row0 = m_tile * p.mt * 128;
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
+      if (ew == 0 && lane == 0) CF_EVENT(2, 0x500);
       for (int m = 0; m < p.mt; ++m) {
         const int f = row0 + m * 128 + row;
         bool valid = f < p.total_rows;
@@ -182,6 +218,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
           tmem_ld_32x32(taddr, v);
           tmem_ld_32x32(taddr + 32, v + 32);
           tmem_ld_wait();
+          if (ew == 0 && lane == 0) CF_EVENT(2, 0x601);
           if (p.flags & CF_SCALE_BIAS) {
 #pragma unroll
             for (int j = 0; j < 64; ++j)
@@ -217,7 +254,9 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = 0u;
           }
+          if (ew == 0 && lane == 0) CF_EVENT(2, 0x602);
           bar_sync_named(bar_id, 128);  // the group's previous unit no longer reads the staging buffer
+          if (ew == 0 && lane == 0) CF_EVENT(2, 0x603);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             uint4 o;
@@ -228,6 +267,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
             *(uint4*)(sbuf + row * 128 + ((j ^ (row & 7)) << 4)) = o;
           }
           bar_sync_named(bar_id, 128);
+          if (ew == 0 && lane == 0) CF_EVENT(2, 0x604);
           // coalesced write-out: 8 consecutive threads cover one 128-byte row
           const int fb = row0 + m * 128;
 #pragma unroll
@@ -239,6 +279,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
               *(uint4*)(p.out + (long long)(fb + r) * p.n_total + n_base + c16 * 8) = o;
             }
           }
+          if (ew == 0 && lane == 0) CF_EVENT(2, 0x605);
           if (do_stats) {
             // column phase: thread (cp, rg) owns channel pair cp over the 32 rows of row group rg
             const int cp = etid & 31, rg = etid >> 5;
@@ -280,6 +321,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
                 }
               }
             }
+            if (ew == 0 && lane == 0) CF_EVENT(2, 0x606);
             float* st = g_stat + (rg * 64 + cp * 2) * 3;
             st[0] = s0; st[1] = q0; st[2] = t0;
             st[3] = s1; st[4] = q1; st[5] = t1;
@@ -299,6 +341,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
           }
         }
       }
+      if (ew == 0 && lane == 0) CF_EVENT(2, 0x600);
       // all of this warp's reads of the accumulator set are complete: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -309,6 +352,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     if (do_stats) {
       // ---- per-CTA partial, then the last CTA to finish folds all partials and finalizes ----
       const int tid = ew * 32 + lane;  // 0..255
+      if (tid == 0) CF_EVENT(2, 0x700);
       bar_sync_named(3, 256);
       float* gp = p.partials + (size_t)blockIdx.x * nq * p.n_total;
       for (int i = tid; i < nq * p.n_total; i += 256) gp[i] = s_acc[i] + s_acc[3 * p.n_total + i];
@@ -319,6 +363,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
         *s_flag = (done == gridDim.x - 1) ? 1u : 0u;
       }
       bar_sync_named(3, 256);
+      if (tid == 0) CF_EVENT(2, 0x701);
       if (*s_flag) {
         __threadfence();
         double* s_fold = (double*)staging;  // [slices][nq][n_total] doubles <= 24 KB
@@ -350,6 +395,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
           }
         }
         bar_sync_named(3, 256);
+        if (tid == 0) CF_EVENT(2, 0x702);
         for (int c = tid; c < p.n_total; c += 256) {
           double S[3] = {0.0, 0.0, 0.0};
           for (int sl = 0; sl < slices; ++sl)
@@ -387,6 +433,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
           }
         }
         if (tid == 0) {
+          CF_EVENT(2, 0x703);
           *p.counter = 0u;  // ready for the next launch / graph replay
           if (!bwd && p.update_running && p.nbt) *p.nbt += 1;
         }
@@ -396,6 +443,9 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
+#ifdef CF_TRACE
+  if (blockIdx.x == 0 && threadIdx.x < 3) g_cf_trace_n[threadIdx.x] = (int)cf_idx[threadIdx.x];
+#endif
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, 512);

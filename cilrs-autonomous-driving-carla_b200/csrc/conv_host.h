@@ -27,15 +27,17 @@ int encode_nhwc_map(CUtensorMap* m, const void* base, int C, int W, int H, int N
 int encode_2d_map(CUtensorMap* m, const void* base, int inner, int rows, int box_inner, int box_rows);
 
 // ---- plan builders (fill kernel parameter blocks; no launches) ----
+// gin / gout: padded-flat geometry (conv_params.h) of the input / output tensor, nullptr = dense NHWC
 int build_fprop(ConvGemmParams* p, const cilrs_conv_desc* d, const void* x, const void* w, void* y, const float* scale,
-                const float* bias, const void* residual, float* stats, int flags);
+                const float* bias, const void* residual, float* stats, int flags, const PadGeom* gin, const PadGeom* gout);
 int build_stem_fprop(ConvGemmParams* p, int batch, const void* x_s2d, const void* w, void* y, const float* scale,
                      const float* bias, float* stats, int flags);
 // stride-1 dgrad: one plan. stride-2: parity (ph, pw) plan; `dy2/w2` optionally fuse the 1x1/2 downsample dgrad
 // into parity (0,0) as an extra tap.
 int build_dgrad(ConvGemmParams* p, const cilrs_conv_desc* d, int ph, int pw, const void* dy, const void* w_dgrad,
-                void* dx, const void* residual, const void* dy2, const void* w2_dgrad);
-int build_wgrad(WgradParams* p, const cilrs_conv_desc* d, const void* dy, const void* x, float* dw);
+                void* dx, const void* residual, const void* dy2, const void* w2_dgrad, const PadGeom* gin, const PadGeom* gout);
+int build_wgrad(WgradParams* p, const cilrs_conv_desc* d, const void* dy, const void* x, float* dw, const PadGeom* gin,
+                const PadGeom* gout);
 int build_stem_wgrad(WgradParams* p, int batch, const void* dy, const void* x_s2d, float* dw);
 
 // one-launch repack of every 3x3 / 1x1 conv weight of the network (fp32 OIHW masters -> both bf16 operand layouts)

@@ -4,6 +4,7 @@
 // registers. Reductions are deterministic (fixed partial order, no float atomics).
 #pragma once
 #include "common.cuh"
+#include "conv_params.h"
 
 namespace cilrs {
 
@@ -32,6 +33,27 @@ CILRS_DEVINL Vec8 loadf8(const float* p) {
   r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
   return r;
 }
+
+// Walks the pixels a thread visits (constant pixel stride) through the padded-flat layout (conv_params.h: PadGeom) and tells
+// whether the current one is a real pixel or a padding pixel, which must be written as zero and never read.
+// A dense tensor is the geometry {1, 1, 1, 1}: every pixel is valid.
+struct PadWalk {
+  unsigned int w, h, sw, sh, Wp, Hp, W, H;
+  CILRS_DEVINL void init(long long pix, long long stride, const PadGeom& g) {
+    Wp = (unsigned int)g.Wp; Hp = (unsigned int)g.Hp; W = (unsigned int)g.W; H = (unsigned int)g.H;
+    w = (unsigned int)(pix % Wp);
+    h = (unsigned int)((pix / Wp) % Hp);
+    sw = (unsigned int)(stride % Wp);
+    sh = (unsigned int)((stride / Wp) % Hp);
+  }
+  CILRS_DEVINL bool valid() const { return w < W && h < H; }
+  CILRS_DEVINL void next() {
+    w += sw; h += sh;
+    if (w >= Wp) { w -= Wp; ++h; }
+    if (h >= Hp) h -= Hp;
+  }
+};
+CILRS_DEVINL void store8_zero(__nv_bfloat16* p) { *reinterpret_cast<uint4*>(p) = make_uint4(0, 0, 0, 0); }
 
 // per-BatchNorm derived vectors, each [C]: scale, shift (forward apply), mean, rstd (backward)
 struct BnVectors {
@@ -101,7 +123,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
                                                               const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                                                               const __nv_bfloat16* __restrict__ x2, const float* __restrict__ scale2,
                                                               const float* __restrict__ shift2, __nv_bfloat16* __restrict__ out,
-                                                              long long nvec, int C, int relu) {
+                                                              long long nvec, int C, int relu, const PadGeom g) {
   const int groups = C >> 3;
   const long long stride = (long long)gridDim.x * EW_THREADS;  // multiple of groups (host guarantees)
   long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
@@ -109,7 +131,10 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
   const Vec8 sc = loadf8(scale + cg), sh = loadf8(shift + cg);
   Vec8 sc2, sh2;
   if (x2) { sc2 = loadf8(scale2 + cg); sh2 = loadf8(shift2 + cg); }
-  for (; i < nvec; i += stride) {
+  PadWalk walk;
+  walk.init(i / groups, stride / groups, g);
+  for (; i < nvec; i += stride, walk.next()) {
+    if (!walk.valid()) { store8_zero(out + i * 8); continue; }
     Vec8 a = load8(x + i * 8);
 #pragma unroll
     for (int k = 0; k < 8; ++k) a.v[k] = fmaf(a.v[k], sc.v[k], sh.v[k]);
@@ -138,7 +163,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
 __global__ void __launch_bounds__(EW_THREADS) bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                                                                      uint8_t* __restrict__ argmax, int B, int H, int W, int C, int OH,
-                                                                     int OW) {
+                                                                     int OW, int OHp, int OWp) {
   const int groups = C >> 3;
   const long long nvec = (long long)B * OH * OW * groups;
   const long long stride = (long long)gridDim.x * EW_THREADS;
@@ -171,7 +196,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_maxpool_kernel(const __nv_
         }
       }
     }
-    store8(out + i * 8, best);
+    store8(out + ((((long long)n * OHp + oh) * OWp + ow) * groups) * 8 + cg, best);  // padded-flat output, dense argmax
     if (argmax) {
       uint2 u;
       u.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
@@ -181,22 +206,28 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_maxpool_kernel(const __nv_
   }
 }
 
-// global average pool: x [B,P,C] bf16 -> feat [B,C] fp32
-__global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ feat, int B, int P, int C) {
+// global average pool: x padded-flat [B,Hp,Wp,C] bf16 -> feat [B,C] fp32 (padding pixels are zero, so the sum runs over all of them)
+__global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ feat, int B, int C, const PadGeom g) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int c = i % C, n = i / C;
+  const int PP = g.Hp * g.Wp;
   float s = 0.f;
-  for (int p = 0; p < P; ++p) s += __bfloat162float(x[((long long)n * P + p) * C + c]);
-  feat[i] = s / (float)P;
+  for (int p = 0; p < PP; ++p) s += __bfloat162float(x[((long long)n * PP + p) * C + c]);
+  feat[i] = s / (float)(g.H * g.W);
 }
-// backward: g [B,P,C] bf16 = dfeat[b,c] / P
-__global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, __nv_bfloat16* __restrict__ g, int B, int P, int C) {
-  const long long total = (long long)B * P * C;
+// backward: g padded-flat [B,Hp,Wp,C] bf16 = dfeat[b,c] / (H*W) on real pixels, 0 on padding
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, __nv_bfloat16* __restrict__ gout, int B, int C, const PadGeom g) {
+  const int PP = g.Hp * g.Wp;
+  const long long total = (long long)B * PP * C;
+  const float inv = 1.f / (float)(g.H * g.W);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
-    const int n = (int)(i / ((long long)P * C));
-    g[i] = __float2bfloat16(dfeat[(long long)n * C + c] / (float)P);
+    const long long pix = i / C;
+    const int n = (int)(pix / PP);
+    const int q = (int)(pix - (long long)n * PP);
+    const bool valid = (q % g.Wp) < g.W && (q / g.Wp) < g.H;
+    gout[i] = __float2bfloat16(valid ? dfeat[(long long)n * C + c] * inv : 0.f);
   }
 }
 
@@ -227,6 +258,8 @@ struct BnBwdReduceParams {
   const float* scale;
   const float* shift;
   int H, W, OH, OW;
+  int OHp, OWp;  // stem variant: padded-flat geometry of the pooled gradient g
+  PadGeom geom;  // regular variant: padded-flat geometry of g / act / y / dz_out ({1,1,1,1} = dense)
 };
 
 CILRS_DEVINL Vec8 stem_gather_grad(const BnBwdReduceParams& p, int n, int h, int w, int cg) {
@@ -242,9 +275,9 @@ CILRS_DEVINL Vec8 stem_gather_grad(const BnBwdReduceParams& p, int n, int h, int
       if (ow >= p.OW) continue;
       const int s = w - (ow * 2 - 1);
       if (s < 0 || s > 2) continue;
-      const long long o = (((long long)n * p.OH + oh) * p.OW + ow) * p.C + cg;
+      const long long o = (((long long)n * p.OH + oh) * p.OW + ow) * p.C + cg;  // arg-max codes are stored densely
       const uint2 am = *reinterpret_cast<const uint2*>(p.argmax + o);
-      const Vec8 gv = load8(p.g + o);
+      const Vec8 gv = load8(p.g + (((long long)n * p.OHp + oh) * p.OWp + ow) * p.C + cg);
       const int code = r * 3 + s;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -270,29 +303,17 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
   float a_sum[8], a_dot[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { a_sum[k] = 0.f; a_dot[k] = 0.f; }
-  if (!STEM) {
-    // 4 independent vectors per iteration: 12 outstanding 16-byte loads per thread keep HBM busy with ~1 CTA per SM
-    for (; i + 3 * stride < p.nvec; i += 4 * stride) {
-      Vec8 yv[4], gv[4], av[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        yv[u] = load8(p.y + (i + u * stride) * 8);
-        gv[u] = load8(p.g + (i + u * stride) * 8);
-        if (p.act) av[u] = load8(p.act + (i + u * stride) * 8);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float gk = gv[u].v[k];
-          if (p.act && !(av[u].v[k] > 0.f)) gk = 0.f;
-          a_sum[k] += gk;
-          a_dot[k] = fmaf(gk, (yv[u].v[k] - mean.v[k]) * rstd.v[k], a_dot[k]);
-        }
+  PadWalk walk;
+  if (!STEM) walk.init(i / groups, stride / groups, p.geom);
+  for (; i < p.nvec; i += stride) {
+    if (!STEM) {
+      const bool ok = walk.valid();
+      walk.next();
+      if (!ok) {  // padding pixel: g may hold stale data there; it contributes nothing and dz stays zero
+        if (p.dz_out) store8_zero(p.dz_out + i * 8);
+        continue;
       }
     }
-  }
-  for (; i < p.nvec; i += stride) {
     const Vec8 yv = load8(p.y + i * 8);
     Vec8 gv;
     if (STEM) {
@@ -398,6 +419,7 @@ struct BnBwdApplyParams {
   const float* scale;
   const float* shift;
   int H, W, OH, OW;
+  PadGeom geom;       // padded-flat geometry of g / act / y / dy / dz ({1,1,1,1} = dense)
 };
 
 template <bool STEM>
@@ -418,8 +440,19 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApp
   }
   if (STEM) { sc = loadf8(p.scale + cg); sh = loadf8(p.shift + cg); }
   BnBwdReduceParams gp;  // only the fields the stem gather reads
-  if (STEM) { gp.g = p.g; gp.argmax = p.argmax; gp.OH = p.OH; gp.OW = p.OW; gp.C = p.C; }
+  if (STEM) { gp.g = p.g; gp.argmax = p.argmax; gp.OH = p.OH; gp.OW = p.OW; gp.OHp = p.OH; gp.OWp = p.OW; gp.C = p.C; }
+  PadWalk walk;
+  if (!STEM) walk.init(i / groups, stride / groups, p.geom);
   for (; i < p.nvec; i += stride) {
+    if (!STEM) {
+      const bool ok = walk.valid();
+      walk.next();
+      if (!ok) {
+        store8_zero(p.dy + i * 8);
+        if (p.dz) store8_zero(p.dz + i * 8);
+        continue;
+      }
+    }
     const Vec8 yv = load8(p.y + i * 8);
     Vec8 gv;
     if (STEM) {

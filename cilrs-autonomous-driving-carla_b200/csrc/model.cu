@@ -34,11 +34,19 @@ struct BnRef {
 struct ConvRef {
   cilrs_conv_desc d;
   bool stem;
-  int w;  // param slot
+  bool flat;  // 3x3 stride 1: runs on the padded-flat kernels (conv_flat.cuh / wgrad_flat.cuh)
+  int w;      // param slot
   __nv_bfloat16 *wf, *wd;
   BnRef bn;
-  __nv_bfloat16* y;  // raw conv output (pre-BN)
+  __nv_bfloat16* y;  // raw conv output (pre-BN), padded-flat (the stem's is dense)
   int oh, ow;
+  PadGeom gin, gout;  // padded-flat geometry of the input / output tensors
+};
+
+// indices into the plan vectors of the model (-1 = not used by this block / mode)
+struct BlockPlan {
+  int f_a_old = -1, f_a_flat = -1, f_ds_old = -1, f_b_flat = -1;
+  int w_b = -1, d_b = -1, w_a_flat = -1, w_a_old = -1, w_ds_old = -1, d_a_flat = -1, d_a_old = -1;  // d_a_old: first of 4 parity plans
 };
 
 struct Block {
@@ -48,6 +56,7 @@ struct Block {
   __nv_bfloat16* act_a;
   __nv_bfloat16* out;
   int in_h, in_w, in_c;
+  BlockPlan pl;
 };
 
 struct Bump {
@@ -124,20 +133,20 @@ struct Model {
   float* dcontrols;      // [B,3]
   float* dspeed;         // [B]
   int* err_flag;
-  __nv_bfloat16 *g0, *g1, *ga, *d1, *d2, *dz, *dy_stem;
+  __nv_bfloat16 *g0, *g1, *ga, *d1, *d2, *dy_stem;
   double* sumsq_partial;
   PackJob* pack_jobs;    // device table for the one-launch weight repack
   int pack_njobs = 0, pack_blocks = 0;
   // plans (tensor maps) for the batch size they were built for
   int planB = 0;
   int planMode = -1;
-  std::vector<ConvGemmParams> fwd_plans;
-  std::vector<ConvGemmParams> dgrad_plans;
-  std::vector<WgradParams> wgrad_plans;
-  std::vector<int> wgrad_slot;  // parameter slot each wgrad plan accumulates into (pointer resolved at launch)
+  std::vector<ConvGemmParams> old_plans;     // generic kernel: stem, stride-2 and 1x1 convs (fprop and dgrad)
+  std::vector<WgradParams> wold_plans;
+  std::vector<FlatConvParams> flat_plans;    // padded-flat kernel: 3x3 stride-1 fprop and dgrad
+  std::vector<WgradFlatParams> wflat_plans;
+  int stem_fwd = -1, stem_wgrad = -1;
   // resumable backward (so the host can start the allreduce of finished gradient buckets between parts)
   __nv_bfloat16 *bw_gcur = nullptr, *bw_gnext = nullptr;
-  size_t bw_di = 0, bw_wi = 0;
 };
 
 static int add_slot(Model& m, long long size) {
@@ -164,11 +173,14 @@ static BnRef make_bn(Model& m, int C) {
 static ConvRef make_conv(Model& m, int B, int h, int w, int cin, int cout, int k, int stride) {
   ConvRef c{};
   c.stem = false;
+  c.flat = (k == 3 && stride == 1);
   c.d = cilrs_conv_desc{B, h, w, cin, cout, k, k, stride, k == 3 ? 1 : 0};
   c.w = add_slot(m, (long long)cout * cin * k * k);
   c.bn = make_bn(m, cout);
   c.oh = conv_out_dim(h, k, stride, c.d.pad);
   c.ow = conv_out_dim(w, k, stride, c.d.pad);
+  c.gin = PadGeom{h, w, h + 1, w + 1};
+  c.gout = PadGeom{c.oh, c.ow, c.oh + 1, c.ow + 1};
   return c;
 }
 
@@ -213,12 +225,15 @@ static void build_topology(Model& m, int B) {
 }
 
 static long long act_elems(int B, int h, int w, int c) { return (long long)B * h * w * c; }
+static long long pad_elems(int B, const PadGeom& g, int c) { return (long long)B * g.Hp * g.Wp * c; }
+static const PadGeom kGeom0{22, 50, 23, 51};   // layer1 / max-pool output
+static const PadGeom kDense{1, 1, 1, 1};       // "every pixel is real" for the elementwise kernels
 
 static void carve_conv(Bump& bp, ConvRef& c, int B) {
   const long long wbytes = c.stem ? 4 * 64 * 64 * 2 : (long long)c.d.kh * c.d.kw * c.d.in_c * c.d.out_c * 2;
   c.wf = (__nv_bfloat16*)bp.take(wbytes);
   c.wd = c.stem ? nullptr : (__nv_bfloat16*)bp.take(wbytes);
-  c.y = (__nv_bfloat16*)bp.take(act_elems(B, c.oh, c.ow, c.d.out_c) * 2);
+  c.y = (__nv_bfloat16*)bp.take((c.stem ? act_elems(B, c.oh, c.ow, c.d.out_c) : pad_elems(B, c.gout, c.d.out_c)) * 2);
   c.bn.vec = (float*)bp.take(4LL * c.bn.C * 4);
   c.bn.bred = (float*)bp.take(2LL * c.bn.C * 4);
 }
@@ -228,7 +243,7 @@ static long long carve(Model& m, char* base) {
   const int B = m.maxB;
   m.x_s2d = (__nv_bfloat16*)bp.take((long long)B * 47 * 103 * 16 * 2);
   carve_conv(bp, m.stem, B);
-  m.pool_out = (__nv_bfloat16*)bp.take(act_elems(B, 22, 50, 64) * 2);
+  m.pool_out = (__nv_bfloat16*)bp.take(pad_elems(B, kGeom0, 64) * 2);
   m.pool_arg = (uint8_t*)bp.take(act_elems(B, 22, 50, 64));
   const __nv_bfloat16* prev = m.pool_out;
   for (auto& blk : m.blocks) {
@@ -236,8 +251,8 @@ static long long carve(Model& m, char* base) {
     carve_conv(bp, blk.a, B);
     carve_conv(bp, blk.b, B);
     if (blk.has_ds) carve_conv(bp, blk.ds, B);
-    blk.act_a = (__nv_bfloat16*)bp.take(act_elems(B, blk.a.oh, blk.a.ow, blk.a.d.out_c) * 2);
-    blk.out = (__nv_bfloat16*)bp.take(act_elems(B, blk.b.oh, blk.b.ow, blk.b.d.out_c) * 2);
+    blk.act_a = (__nv_bfloat16*)bp.take(pad_elems(B, blk.a.gout, blk.a.d.out_c) * 2);
+    blk.out = (__nv_bfloat16*)bp.take(pad_elems(B, blk.b.gout, blk.b.d.out_c) * 2);
     prev = blk.out;
   }
   // stats partial scratch: the stem has the most tiles (<= ceil(B*4400/100) ~ 44*B + slack), 2 x 64 floats each;
@@ -266,13 +281,12 @@ static long long carve(Model& m, char* base) {
   m.dcontrols = (float*)bp.take((long long)B * 3 * 4);
   m.dspeed = (float*)bp.take((long long)B * 4);
   m.err_flag = (int*)bp.take(64);
-  const long long gmax = act_elems(B, 22, 50, 64) * 2;
+  const long long gmax = pad_elems(B, kGeom0, 64) * 2;  // the largest padded-flat activation (layer1)
   m.g0 = (__nv_bfloat16*)bp.take(gmax);
   m.g1 = (__nv_bfloat16*)bp.take(gmax);
   m.ga = (__nv_bfloat16*)bp.take(gmax);
   m.d1 = (__nv_bfloat16*)bp.take(gmax);
   m.d2 = (__nv_bfloat16*)bp.take(gmax);
-  m.dz = (__nv_bfloat16*)bp.take(gmax);
   m.dy_stem = (__nv_bfloat16*)bp.take(act_elems(B, 44, 100, 64) * 2);
   m.sumsq_partial = (double*)bp.take(1024 * 8);
   m.pack_jobs = (PackJob*)bp.take(64 * sizeof(PackJob));
@@ -286,111 +300,125 @@ static void set_batch(ConvRef& c, int B) { c.d.batch = B; }
 // ------------------------------------------------------------------------------------------------
 enum FwdMode { MODE_TRAIN = 0, MODE_FROZEN = 1, MODE_INFER = 2 };
 
-static int build_plans(Model& m, int B, int mode) {
-  if (B == m.planB && mode == m.planMode) return OK;
-  m.fwd_plans.clear(); m.dgrad_plans.clear(); m.wgrad_plans.clear(); m.wgrad_slot.clear();
-  int st;
-  set_batch(m.stem, B);
-  const bool infer = mode == MODE_INFER;
-  {
-    ConvGemmParams p;
-    BnRef& bn = m.stem.bn;
-    if (infer) st = build_stem_fprop(&p, B, m.x_s2d, m.stem.wf, m.stem.y, bn.vec, bn.vec + bn.C, nullptr, CG_SCALE_BIAS | CG_RELU);
-    else st = build_stem_fprop(&p, B, m.x_s2d, m.stem.wf, m.stem.y, nullptr, nullptr, m.stats, CG_STATS);
-    if (st) return st;
-    m.fwd_plans.push_back(p);
-  }
-  for (auto& blk : m.blocks) {
-    set_batch(blk.a, B); set_batch(blk.b, B);
-    if (blk.has_ds) set_batch(blk.ds, B);
-    ConvGemmParams p;
-    if (infer) {
-      st = build_fprop(&p, &blk.a.d, blk.in, blk.a.wf, blk.act_a, blk.a.bn.vec, blk.a.bn.vec + blk.a.bn.C, nullptr, nullptr,
-                       CG_SCALE_BIAS | CG_RELU);
-      if (st) return st;
-      m.fwd_plans.push_back(p);
-      const __nv_bfloat16* idn = blk.in;
-      if (blk.has_ds) {
-        st = build_fprop(&p, &blk.ds.d, blk.in, blk.ds.wf, blk.ds.y, blk.ds.bn.vec, blk.ds.bn.vec + blk.ds.bn.C, nullptr, nullptr,
-                         CG_SCALE_BIAS);
-        if (st) return st;
-        m.fwd_plans.push_back(p);
-        idn = blk.ds.y;
-      }
-      st = build_fprop(&p, &blk.b.d, blk.act_a, blk.b.wf, blk.out, blk.b.bn.vec, blk.b.bn.vec + blk.b.bn.C, idn, nullptr,
-                       CG_SCALE_BIAS | CG_RESIDUAL | CG_RELU);
-      if (st) return st;
-      m.fwd_plans.push_back(p);
-    } else {
-      st = build_fprop(&p, &blk.a.d, blk.in, blk.a.wf, blk.a.y, nullptr, nullptr, nullptr, m.stats, CG_STATS);
-      if (st) return st;
-      m.fwd_plans.push_back(p);
-      if (blk.has_ds) {
-        st = build_fprop(&p, &blk.ds.d, blk.in, blk.ds.wf, blk.ds.y, nullptr, nullptr, nullptr, m.stats, CG_STATS);
-        if (st) return st;
-        m.fwd_plans.push_back(p);
-      }
-      st = build_fprop(&p, &blk.b.d, blk.act_a, blk.b.wf, blk.b.y, nullptr, nullptr, nullptr, m.stats, CG_STATS);
-      if (st) return st;
-      m.fwd_plans.push_back(p);
-    }
-  }
-  if (!infer) {
-    // backward plans, in execution order (last block first). Gradient buffers ping-pong g0/g1.
-    __nv_bfloat16* gcur = m.g0;
-    __nv_bfloat16* gnext = m.g1;
-    for (int bi = (int)m.blocks.size() - 1; bi >= 0; --bi) {
-      Block& blk = m.blocks[bi];
-      ConvGemmParams p;
-      WgradParams wp;
-      // conv_b: wgrad(dy_b = d1, act_a), dgrad -> ga
-      st = build_wgrad(&wp, &blk.b.d, m.d1, blk.act_a, nullptr);
-      if (st) return st;
-      m.wgrad_plans.push_back(wp); m.wgrad_slot.push_back(blk.b.w);
-      st = build_dgrad(&p, &blk.b.d, 0, 0, m.d1, blk.b.wd, m.ga, nullptr, nullptr, nullptr);
-      if (st) return st;
-      m.dgrad_plans.push_back(p);
-      // conv_a: wgrad(dy_a = d1, in), ds: wgrad(dy_d = d2, in)
-      st = build_wgrad(&wp, &blk.a.d, m.d1, blk.in, nullptr);
-      if (st) return st;
-      m.wgrad_plans.push_back(wp); m.wgrad_slot.push_back(blk.a.w);
-      if (blk.has_ds) {
-        st = build_wgrad(&wp, &blk.ds.d, m.d2, blk.in, nullptr);
-        if (st) return st;
-        m.wgrad_plans.push_back(wp); m.wgrad_slot.push_back(blk.ds.w);
-      }
-      // dgrad of conv_a into gnext (+ identity path)
-      if (!blk.has_ds) {
-        st = build_dgrad(&p, &blk.a.d, 0, 0, m.d1, blk.a.wd, gnext, m.dz, nullptr, nullptr);
-        if (st) return st;
-        m.dgrad_plans.push_back(p);
-      } else {
-        for (int ph = 0; ph < 2; ++ph)
-          for (int pw = 0; pw < 2; ++pw) {
-            const bool fuse = (ph == 0 && pw == 0);
-            st = build_dgrad(&p, &blk.a.d, ph, pw, m.d1, blk.a.wd, gnext, nullptr, fuse ? m.d2 : nullptr, fuse ? blk.ds.wd : nullptr);
-            if (st) return st;
-            m.dgrad_plans.push_back(p);
-          }
-      }
-      __nv_bfloat16* t = gcur; gcur = gnext; gnext = t;
-    }
-    WgradParams wp;
-    st = build_stem_wgrad(&wp, B, m.dy_stem, m.x_s2d, nullptr);
-    if (st) return st;
-    m.wgrad_plans.push_back(wp); m.wgrad_slot.push_back(m.stem.w);
-  }
-  m.planB = B;
-  m.planMode = mode;
-  return OK;
-}
-
 #define CK(call)            \
   do {                      \
     int _st = (call);       \
     if (_st) return _st;    \
   } while (0)
 #define CKL() CK(cuda_status(cudaGetLastError()))
+
+static int add_old(Model& m, const ConvGemmParams& p) { m.old_plans.push_back(p); return (int)m.old_plans.size() - 1; }
+static int add_flat(Model& m, const FlatConvParams& p) { m.flat_plans.push_back(p); return (int)m.flat_plans.size() - 1; }
+
+static int build_plans(Model& m, int B, int mode) {
+  if (B == m.planB && mode == m.planMode) return OK;
+  m.old_plans.clear(); m.wold_plans.clear(); m.flat_plans.clear(); m.wflat_plans.clear();
+  set_batch(m.stem, B);
+  const bool infer = mode == MODE_INFER;
+  const bool training = mode == MODE_TRAIN;
+  {
+    ConvGemmParams p;
+    BnRef& bn = m.stem.bn;
+    if (infer) CK(build_stem_fprop(&p, B, m.x_s2d, m.stem.wf, m.stem.y, bn.vec, bn.vec + bn.C, nullptr, CG_SCALE_BIAS | CG_RELU));
+    else CK(build_stem_fprop(&p, B, m.x_s2d, m.stem.wf, m.stem.y, nullptr, nullptr, m.stats, CG_STATS));
+    m.stem_fwd = add_old(m, p);
+  }
+  for (auto& blk : m.blocks) {
+    set_batch(blk.a, B); set_batch(blk.b, B);
+    if (blk.has_ds) set_batch(blk.ds, B);
+    blk.pl = BlockPlan{};
+    ConvGemmParams p;
+    FlatConvParams f;
+    // ---- forward ----
+    // conv_a: inference fuses folded BN + ReLU and writes act_a directly; training writes the raw output (+ BN statistics)
+    if (blk.a.flat) {
+      const int fl = infer ? (CF_SCALE_BIAS | CF_RELU) : (training ? CF_STATS : 0);
+      CK(build_flat_conv(&f, B, blk.a.gin, blk.a.d.in_c, blk.a.d.out_c, 0, blk.in, blk.a.wf, infer ? blk.act_a : blk.a.y, fl));
+      if (infer) { f.scale = blk.a.bn.vec; f.bias = blk.a.bn.vec + blk.a.bn.C; }
+      blk.pl.f_a_flat = add_flat(m, f);
+    } else {
+      if (infer) CK(build_fprop(&p, &blk.a.d, blk.in, blk.a.wf, blk.act_a, blk.a.bn.vec, blk.a.bn.vec + blk.a.bn.C, nullptr, nullptr,
+                                CG_SCALE_BIAS | CG_RELU, &blk.a.gin, &blk.a.gout));
+      else CK(build_fprop(&p, &blk.a.d, blk.in, blk.a.wf, blk.a.y, nullptr, nullptr, nullptr, m.stats, CG_STATS, &blk.a.gin, &blk.a.gout));
+      blk.pl.f_a_old = add_old(m, p);
+    }
+    if (blk.has_ds) {
+      if (infer) CK(build_fprop(&p, &blk.ds.d, blk.in, blk.ds.wf, blk.ds.y, blk.ds.bn.vec, blk.ds.bn.vec + blk.ds.bn.C, nullptr, nullptr,
+                                CG_SCALE_BIAS, &blk.ds.gin, &blk.ds.gout));
+      else CK(build_fprop(&p, &blk.ds.d, blk.in, blk.ds.wf, blk.ds.y, nullptr, nullptr, nullptr, m.stats, CG_STATS, &blk.ds.gin, &blk.ds.gout));
+      blk.pl.f_ds_old = add_old(m, p);
+    }
+    {
+      const int fl = infer ? (CF_SCALE_BIAS | CF_RESIDUAL | CF_RELU) : (training ? CF_STATS : 0);
+      CK(build_flat_conv(&f, B, blk.b.gin, blk.b.d.in_c, blk.b.d.out_c, 0, blk.act_a, blk.b.wf, infer ? blk.out : blk.b.y, fl));
+      if (infer) {
+        f.scale = blk.b.bn.vec; f.bias = blk.b.bn.vec + blk.b.bn.C;
+        f.residual = blk.has_ds ? blk.ds.y : blk.in;
+      }
+      blk.pl.f_b_flat = add_flat(m, f);
+    }
+  }
+  if (!infer) {
+    // backward plans. Gradient buffers ping-pong g0/g1 (gcur = masked gradient dz of the current block's output).
+    __nv_bfloat16* gcur = m.g0;
+    __nv_bfloat16* gnext = m.g1;
+    for (int bi = (int)m.blocks.size() - 1; bi >= 0; --bi) {
+      Block& blk = m.blocks[bi];
+      ConvGemmParams p;
+      FlatConvParams f;
+      WgradParams wp;
+      WgradFlatParams wf;
+      // conv_b: dW_b = wgrad(dy_b = d1, act_a);  ga = relu'(act_a) * dgrad_b(d1), + the BN_a backward reductions
+      CK(build_wgrad_flat(&wf, B, blk.b.gin, blk.b.d.in_c, blk.b.d.out_c, m.d1, blk.act_a, nullptr));
+      m.wflat_plans.push_back(wf); blk.pl.w_b = (int)m.wflat_plans.size() - 1;
+      CK(build_flat_conv(&f, B, blk.b.gin, blk.b.d.out_c, blk.b.d.in_c, 1, m.d1, blk.b.wd, m.ga, CF_MASK | CF_BNBWD));
+      f.mask = blk.act_a; f.y1 = blk.a.y; f.stat1 = blk.a.bn.vec; f.bred1 = blk.a.bn.bred;
+      blk.pl.d_b = add_flat(m, f);
+      // conv_a: dW_a = wgrad(dy_a = d1, in); downsample: dW_ds = wgrad(dy_ds = d2, in)
+      if (blk.a.flat) {
+        CK(build_wgrad_flat(&wf, B, blk.a.gin, blk.a.d.in_c, blk.a.d.out_c, m.d1, blk.in, nullptr));
+        m.wflat_plans.push_back(wf); blk.pl.w_a_flat = (int)m.wflat_plans.size() - 1;
+      } else {
+        CK(build_wgrad(&wp, &blk.a.d, m.d1, blk.in, nullptr, &blk.a.gin, &blk.a.gout));
+        m.wold_plans.push_back(wp); blk.pl.w_a_old = (int)m.wold_plans.size() - 1;
+      }
+      if (blk.has_ds) {
+        CK(build_wgrad(&wp, &blk.ds.d, m.d2, blk.in, nullptr, &blk.ds.gin, &blk.ds.gout));
+        m.wold_plans.push_back(wp); blk.pl.w_ds_old = (int)m.wold_plans.size() - 1;
+      }
+      // gradient of the block input: dgrad_a(d1) + identity path (dz of this block) | + dgrad_ds(d2)
+      if (blk.a.flat) {
+        int fl = CF_RESIDUAL;
+        if (bi > 0) fl |= CF_MASK | CF_BNBWD | (m.blocks[bi - 1].has_ds ? CF_BNBWD2 : 0);
+        CK(build_flat_conv(&f, B, blk.a.gin, blk.a.d.out_c, blk.a.d.in_c, 1, m.d1, blk.a.wd, gnext, fl));
+        f.residual = gcur;
+        if (bi > 0) {
+          Block& pb = m.blocks[bi - 1];
+          f.mask = blk.in;  // = output of the previous block
+          f.y1 = pb.b.y; f.stat1 = pb.b.bn.vec; f.bred1 = pb.b.bn.bred;
+          if (pb.has_ds) { f.y2 = pb.ds.y; f.stat2 = pb.ds.bn.vec; f.bred2 = pb.ds.bn.bred; }
+        }
+        blk.pl.d_a_flat = add_flat(m, f);
+      } else {
+        for (int ph = 0; ph < 2; ++ph)
+          for (int pw = 0; pw < 2; ++pw) {
+            const bool fuse = (ph == 0 && pw == 0);
+            CK(build_dgrad(&p, &blk.a.d, ph, pw, m.d1, blk.a.wd, gnext, nullptr, fuse ? m.d2 : nullptr, fuse ? blk.ds.wd : nullptr,
+                           &blk.a.gin, &blk.a.gout));
+            const int idx = add_old(m, p);
+            if (fuse) blk.pl.d_a_old = idx;
+          }
+      }
+      __nv_bfloat16* t = gcur; gcur = gnext; gnext = t;
+    }
+    WgradParams wp;
+    CK(build_stem_wgrad(&wp, B, m.dy_stem, m.x_s2d, nullptr));
+    m.wold_plans.push_back(wp); m.stem_wgrad = (int)m.wold_plans.size() - 1;
+  }
+  m.planB = B;
+  m.planMode = mode;
+  return OK;
+}
 
 static int run_bn_finalize(Model& m, const BnRef& bn, int tiles, double count, int training, int update, cudaStream_t s) {
   BnVectors v{bn.vec, bn.vec + bn.C, bn.vec + 2 * bn.C, bn.vec + 3 * bn.C};
@@ -400,12 +428,26 @@ static int run_bn_finalize(Model& m, const BnRef& bn, int tiles, double count, i
   return cuda_status(cudaGetLastError());
 }
 
-static int run_bn_apply(const __nv_bfloat16* x, const BnRef& bn, const __nv_bfloat16* res, const __nv_bfloat16* x2, const BnRef* bn2,
-                        __nv_bfloat16* out, long long elems, int relu, cudaStream_t s) {
-  const long long nvec = elems / 8;
+// out = relu?( bn(x) [+ res] [+ bn2(x2)] ) on padded-flat tensors of geometry g
+static int run_bn_apply(int B, const PadGeom& g, const __nv_bfloat16* x, const BnRef& bn, const __nv_bfloat16* res, const __nv_bfloat16* x2,
+                        const BnRef* bn2, __nv_bfloat16* out, int relu, cudaStream_t s) {
+  const long long nvec = pad_elems(B, g, bn.C) / 8;
   bn_apply_kernel<<<ew_grid(nvec, bn.C), EW_THREADS, 0, s>>>(x, bn.vec, bn.vec + bn.C, res, x2, bn2 ? bn2->vec : nullptr,
-                                                             bn2 ? bn2->vec + bn2->C : nullptr, out, nvec, bn.C, relu); ++g_cilrs_launches;
+                                                             bn2 ? bn2->vec + bn2->C : nullptr, out, nvec, bn.C, relu, g); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
+}
+
+// flat conv with the train-mode BatchNorm statistics + finalize fused (pointers bound at launch time)
+static int launch_flat_fwd(Model& m, int idx, const BnRef& bn, double count, int update_running, cudaStream_t s) {
+  FlatConvParams f = m.flat_plans[idx];
+  if (f.flags & CF_STATS) {
+    f.partials = m.stats; f.counter = m.counters + 1;
+    f.gamma = m.params + m.slots[bn.gamma].off; f.beta = m.params + m.slots[bn.beta].off;
+    f.running_mean = m.buffers + bn.rm_off; f.running_var = m.buffers + bn.rv_off;
+    f.nbt = m.nbt ? m.nbt + bn.nbt_idx : nullptr;
+    f.vec = bn.vec; f.count = count; f.momentum = 0.1f; f.eps = 1e-5f; f.update_running = update_running;
+  }
+  return launch_flat_conv(&f, s);
 }
 
 static HeadsWeights head_weights(const Model& m, const float* base) {
@@ -457,48 +499,47 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
   } else {
     return ERR_INVALID;
   }
-  size_t pi = 0;
   const int training = mode == MODE_TRAIN;
+  const long long pool_vec = act_elems(B, 22, 50, 64) / 8;
+  PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.old_plans[m.stem_fwd], s)));
   if (mode == MODE_INFER) {
-    PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi++], s)));
-    {
-      const long long nvec = act_elems(B, 22, 50, 64) / 8;
-      bn_relu_maxpool_kernel<<<ew_grid(nvec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.unit_vec, m.unit_vec + 64, m.pool_out, nullptr, B, 44,
-                                                                      100, 64, 22, 50); ++g_cilrs_launches;
-      CKL();
-    }
+    bn_relu_maxpool_kernel<<<ew_grid(pool_vec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.unit_vec, m.unit_vec + 64, m.pool_out, nullptr, B, 44,
+                                                                        100, 64, 22, 50, kGeom0.Hp, kGeom0.Wp); ++g_cilrs_launches;
+    CKL();
     for (auto& blk : m.blocks) {
-      PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi++], s)));
-      if (blk.has_ds) PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi++], s)));
-      PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi++], s)));
+      if (blk.pl.f_a_flat >= 0) PROF(m, PC_FPROP, s, CK(launch_flat_conv(&m.flat_plans[blk.pl.f_a_flat], s)));
+      else PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.old_plans[blk.pl.f_a_old], s)));
+      if (blk.has_ds) PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.old_plans[blk.pl.f_ds_old], s)));
+      PROF(m, PC_FPROP, s, CK(launch_flat_conv(&m.flat_plans[blk.pl.f_b_flat], s)));
     }
   } else {
-    PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi], s)));
-    {
-      const ConvGemmParams& p = m.fwd_plans[pi++];
-      PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, m.stem.bn, conv_gemm_grid(&p), (double)B * 44 * 100, training, update_running, s)));
-      const long long nvec = act_elems(B, 22, 50, 64) / 8;
-      bn_relu_maxpool_kernel<<<ew_grid(nvec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.stem.bn.vec, m.stem.bn.vec + 64, m.pool_out,
-                                                                      m.pool_arg, B, 44, 100, 64, 22, 50); ++g_cilrs_launches;
-      CKL();
-    }
+    PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, m.stem.bn, conv_gemm_grid(&m.old_plans[m.stem_fwd]), (double)B * 44 * 100, training,
+                                             update_running, s)));
+    bn_relu_maxpool_kernel<<<ew_grid(pool_vec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.stem.bn.vec, m.stem.bn.vec + 64, m.pool_out,
+                                                                        m.pool_arg, B, 44, 100, 64, 22, 50, kGeom0.Hp, kGeom0.Wp); ++g_cilrs_launches;
+    CKL();
     for (auto& blk : m.blocks) {
-      auto conv_bn = [&](ConvRef& c) -> int {
-        const ConvGemmParams& p = m.fwd_plans[pi];
-        PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.fwd_plans[pi++], s)));
-        PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, c.bn, conv_gemm_grid(&p), (double)B * c.oh * c.ow, training, update_running, s)));
+      // raw conv output + BN vectors: fused in the flat kernel (training), or generic kernel + finalize kernel
+      auto conv_bn = [&](ConvRef& c, int flat_idx, int old_idx) -> int {
+        const double count = (double)B * c.oh * c.ow;
+        if (flat_idx >= 0) {
+          PROF(m, PC_FPROP, s, CK(launch_flat_fwd(m, flat_idx, c.bn, count, update_running, s)));
+          if (!training) PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, c.bn, 0, count, 0, 0, s)));
+        } else {
+          PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.old_plans[old_idx], s)));
+          PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, c.bn, conv_gemm_grid(&m.old_plans[old_idx]), count, training, update_running, s)));
+        }
         return OK;
       };
-      CK(conv_bn(blk.a));
-      PROF(m, PC_BN_FWD, s, CK(run_bn_apply(blk.a.y, blk.a.bn, nullptr, nullptr, nullptr, blk.act_a, act_elems(B, blk.a.oh, blk.a.ow, blk.a.d.out_c), 1, s)));
-      if (blk.has_ds) CK(conv_bn(blk.ds));
-      CK(conv_bn(blk.b));
-      const long long oe = act_elems(B, blk.b.oh, blk.b.ow, blk.b.d.out_c);
-      if (blk.has_ds) PROF(m, PC_BN_FWD, s, CK(run_bn_apply(blk.b.y, blk.b.bn, nullptr, blk.ds.y, &blk.ds.bn, blk.out, oe, 1, s)));
-      else PROF(m, PC_BN_FWD, s, CK(run_bn_apply(blk.b.y, blk.b.bn, blk.in, nullptr, nullptr, blk.out, oe, 1, s)));
+      CK(conv_bn(blk.a, blk.pl.f_a_flat, blk.pl.f_a_old));
+      PROF(m, PC_BN_FWD, s, CK(run_bn_apply(B, blk.a.gout, blk.a.y, blk.a.bn, nullptr, nullptr, nullptr, blk.act_a, 1, s)));
+      if (blk.has_ds) CK(conv_bn(blk.ds, -1, blk.pl.f_ds_old));
+      CK(conv_bn(blk.b, blk.pl.f_b_flat, -1));
+      if (blk.has_ds) PROF(m, PC_BN_FWD, s, CK(run_bn_apply(B, blk.b.gout, blk.b.y, blk.b.bn, nullptr, blk.ds.y, &blk.ds.bn, blk.out, 1, s)));
+      else PROF(m, PC_BN_FWD, s, CK(run_bn_apply(B, blk.b.gout, blk.b.y, blk.b.bn, blk.in, nullptr, nullptr, blk.out, 1, s)));
     }
   }
-  avgpool_kernel<<<(B * 512 + 255) / 256, 256, 0, s>>>(m.blocks.back().out, m.feat, B, 21, 512); ++g_cilrs_launches;
+  avgpool_kernel<<<(B * 512 + 255) / 256, 256, 0, s>>>(m.blocks.back().out, m.feat, B, 512, m.blocks.back().b.gout); ++g_cilrs_launches;
   CKL();
   PROF(m, PC_HEADS, s, CK(heads_forward(m, B, speed, command, controls, pred_speed, keep_for_backward, dropout_p, seed, s)));
   return OK;
@@ -516,30 +557,52 @@ static int heads_forward(Model& m, int B, const float* speed, const long long* c
   return OK;
 }
 
-static int run_wgrad(Model& m, size_t idx, cudaStream_t s) {
-  WgradParams& wp = m.wgrad_plans[idx];
-  wp.grad = m.grads + m.slots[m.wgrad_slot[idx]].off;
+// ---- backward building blocks ----
+static int run_wgrad_old(Model& m, int idx, int slot, cudaStream_t s) {
+  WgradParams wp = m.wold_plans[idx];
+  wp.grad = m.grads + m.slots[slot].off;
   return launch_wgrad(&wp, s);
 }
+static int run_wgrad_flat(Model& m, int idx, int slot, cudaStream_t s) {
+  WgradFlatParams wp = m.wflat_plans[idx];
+  wp.grad = m.grads + m.slots[slot].off;
+  return launch_wgrad_flat(&wp, s);
+}
+// flat dgrad with the fused ReLU mask + BatchNorm-backward reductions: bind workspace and dgamma / dbeta at launch time
+static int launch_flat_bwd(Model& m, int idx, const BnRef* bn1, const BnRef* bn2, cudaStream_t s) {
+  FlatConvParams f = m.flat_plans[idx];
+  if (f.flags & CF_BNBWD) {
+    f.partials = m.stats; f.counter = m.counters + 1;
+    f.dgamma1 = m.grads + m.slots[bn1->gamma].off; f.dbeta1 = m.grads + m.slots[bn1->beta].off;
+    if (f.flags & CF_BNBWD2) { f.dgamma2 = m.grads + m.slots[bn2->gamma].off; f.dbeta2 = m.grads + m.slots[bn2->beta].off; }
+  }
+  return launch_flat_conv(&f, s);
+}
 
-static int run_bn_bwd(Model& m, const BnRef& bn, const __nv_bfloat16* g, const __nv_bfloat16* act, const __nv_bfloat16* y,
-                      long long elems, double count, int frozen, __nv_bfloat16* dy, __nv_bfloat16* dz, cudaStream_t s) {
-  const long long nvec = elems / 8;
-  const int grid = ew_grid(nvec, bn.C);
-  const int rgrid = ew_reduce_grid(nvec, bn.C);
+// standalone BatchNorm-backward reduce (where no flat dgrad produces the gradient): dz = g * (act > 0) written in place,
+// bred = (sum dz, sum dz * xhat), dgamma / dbeta accumulated
+static int run_bn_bwd_reduce(Model& m, int B, const PadGeom& g, const BnRef& bn, __nv_bfloat16* grad, const __nv_bfloat16* act,
+                             const __nv_bfloat16* y, cudaStream_t s) {
+  const long long nvec = pad_elems(B, g, bn.C) / 8;
   BnBwdReduceParams rp{};
-  rp.g = g; rp.act = act; rp.y = y; rp.mean = bn.vec + 2 * bn.C; rp.rstd = bn.vec + 3 * bn.C; rp.nvec = nvec; rp.C = bn.C;
+  rp.g = grad; rp.act = act; rp.y = y; rp.mean = bn.vec + 2 * bn.C; rp.rstd = bn.vec + 3 * bn.C; rp.nvec = nvec; rp.C = bn.C;
   rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + bn.C;
   rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
-  bn_bwd_reduce_kernel<false><<<rgrid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
-  CKL();
+  rp.dz_out = grad; rp.geom = g;
+  bn_bwd_reduce_kernel<false><<<ew_reduce_grid(nvec, bn.C), EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+// dy = gamma * rstd * (dz - bsum/n - xhat * bdot/n)   (frozen: gamma * rstd * dz); dz is already ReLU-masked
+static int run_bn_bwd_apply(Model& m, int B, const PadGeom& g, const BnRef& bn, const __nv_bfloat16* dz, const __nv_bfloat16* y,
+                            double count, int frozen, __nv_bfloat16* dy, cudaStream_t s) {
+  const long long nvec = pad_elems(B, g, bn.C) / 8;
   BnBwdApplyParams ap{};
-  ap.g = g; ap.act = act; ap.y = y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
-  ap.bsum = rp.bsum; ap.bdot = rp.bdot; ap.inv_count = (float)(1.0 / count); ap.frozen = frozen; ap.nvec = nvec; ap.C = bn.C;
-  ap.dy = dy; ap.dz = dz;
-  bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
-  CKL();
-  return OK;
+  ap.g = dz; ap.act = nullptr; ap.y = y; ap.mean = bn.vec + 2 * bn.C; ap.rstd = bn.vec + 3 * bn.C;
+  ap.gamma = m.params + m.slots[bn.gamma].off; ap.bsum = bn.bred; ap.bdot = bn.bred + bn.C; ap.inv_count = (float)(1.0 / count);
+  ap.frozen = frozen; ap.nvec = nvec; ap.C = bn.C; ap.dy = dy; ap.dz = nullptr; ap.geom = g;
+  bn_bwd_apply_kernel<false><<<ew_grid(nvec, bn.C), EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
+  return cuda_status(cudaGetLastError());
 }
 
 static int heads_backward(Model& m, int B, const float* dcontrols, const float* dspeed, const float* speed,
@@ -597,35 +660,42 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   const int frozen = mode == MODE_FROZEN;
   if (part < -1 || part > 4) return ERR_INVALID;
   if (part <= 0) {
-  PROF(m, PC_HEADS, s, CK(heads_backward(m, B, dcontrols, dspeed, speed, command, dropout_p, s)));
-  // ---- trunk ----
-  avgpool_bwd_kernel<<<(int)((act_elems(B, 3, 7, 512) + 255) / 256), 256, 0, s>>>(m.dfeat, m.g0, B, 21, 512); ++g_cilrs_launches;
-  CKL();
-  m.bw_gcur = m.g0; m.bw_gnext = m.g1; m.bw_di = 0; m.bw_wi = 0;
+    PROF(m, PC_HEADS, s, CK(heads_backward(m, B, dcontrols, dspeed, speed, command, dropout_p, s)));
+    // ---- trunk: gradient of the last block's output, then its ReLU mask + BN_b reductions ----
+    Block& last = m.blocks.back();
+    avgpool_bwd_kernel<<<(int)((pad_elems(B, last.b.gout, 512) + 255) / 256), 256, 0, s>>>(m.dfeat, m.g0, B, 512, last.b.gout); ++g_cilrs_launches;
+    CKL();
+    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_reduce(m, B, last.b.gout, last.b.bn, m.g0, last.out, last.b.y, s)));
+    m.bw_gcur = m.g0; m.bw_gnext = m.g1;
   }
   __nv_bfloat16*& gcur = m.bw_gcur;
   __nv_bfloat16*& gnext = m.bw_gnext;
-  size_t& di = m.bw_di;
-  size_t& wi = m.bw_wi;
   // blocks 15..13 = layer4, 12..7 = layer3, 6..3 = layer2, 2..0 = layer1
   static const int part_hi[4] = {15, 12, 6, 2}, part_lo[4] = {13, 7, 3, 0};
   const int b_hi = part < 0 ? 15 : (part < 4 ? part_hi[part] : -1);
   const int b_lo = part < 0 ? 0 : (part < 4 ? part_lo[part] : 0);
   for (int bi = b_hi; bi >= b_lo; --bi) {
     Block& blk = m.blocks[bi];
-    const long long oe = act_elems(B, blk.b.oh, blk.b.ow, blk.b.d.out_c);
+    const PadGeom& go = blk.b.gout;
     const double cnt = (double)B * blk.b.oh * blk.b.ow;
-    // out = relu(bn_b(y_b) + identity): dz = g * (out > 0)
-    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd(m, blk.b.bn, gcur, blk.out, blk.b.y, oe, cnt, frozen, m.d1, blk.has_ds ? nullptr : m.dz, s)));
-    if (blk.has_ds) PROF(m, PC_BN_BWD, s, CK(run_bn_bwd(m, blk.ds.bn, gcur, blk.out, blk.ds.y, oe, cnt, frozen, m.d2, nullptr, s)));
-    PROF(m, PC_WGRAD, s, CK(run_wgrad(m, wi++, s)));                       // dW_b
-    PROF(m, PC_DGRAD, s, CK(launch_conv_gemm(&m.dgrad_plans[di++], s)));   // ga = dgrad_b(d1)
-    // act_a = relu(bn_a(y_a))
-    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd(m, blk.a.bn, m.ga, blk.act_a, blk.a.y, oe, cnt, frozen, m.d1, nullptr, s)));
-    PROF(m, PC_WGRAD, s, CK(run_wgrad(m, wi++, s)));                       // dW_a
-    if (blk.has_ds) PROF(m, PC_WGRAD, s, CK(run_wgrad(m, wi++, s)));       // dW_ds
-    const int nd = blk.has_ds ? 4 : 1;
-    for (int k = 0; k < nd; ++k) PROF(m, PC_DGRAD, s, CK(launch_conv_gemm(&m.dgrad_plans[di++], s)));
+    // gcur = dz of this block's output (ReLU-masked), with the reductions of bn_b (and bn_ds) already in their bred
+    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.b.bn, gcur, blk.b.y, cnt, frozen, m.d1, s)));
+    if (blk.has_ds) PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.ds.bn, gcur, blk.ds.y, cnt, frozen, m.d2, s)));
+    PROF(m, PC_WGRAD, s, CK(run_wgrad_flat(m, blk.pl.w_b, blk.b.w, s)));            // dW_b
+    PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_b, &blk.a.bn, nullptr, s))); // ga = dz_a (+ BN_a reductions)
+    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.a.bn, m.ga, blk.a.y, cnt, frozen, m.d1, s)));
+    if (blk.pl.w_a_flat >= 0) PROF(m, PC_WGRAD, s, CK(run_wgrad_flat(m, blk.pl.w_a_flat, blk.a.w, s)));
+    else PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, blk.pl.w_a_old, blk.a.w, s)));
+    if (blk.has_ds) PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, blk.pl.w_ds_old, blk.ds.w, s)));
+    if (blk.pl.d_a_flat >= 0) {
+      Block* pb = bi > 0 ? &m.blocks[bi - 1] : nullptr;
+      PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_a_flat, pb ? &pb->b.bn : nullptr, (pb && pb->has_ds) ? &pb->ds.bn : nullptr, s)));
+    } else {
+      for (int k = 0; k < 4; ++k) PROF(m, PC_DGRAD, s, CK(launch_conv_gemm(&m.old_plans[blk.pl.d_a_old + k], s)));
+      // the parity launches write the raw gradient of the previous block's output: mask + reduce it here
+      Block& pb = m.blocks[bi - 1];
+      PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_reduce(m, B, pb.b.gout, pb.b.bn, gnext, pb.out, pb.b.y, s)));
+    }
     __nv_bfloat16* t = gcur; gcur = gnext; gnext = t;
   }
   // ---- stem: max-pool backward + ReLU + BN backward, then wgrad ----
@@ -639,14 +709,15 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + 64;
     rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
     rp.argmax = m.pool_arg; rp.scale = bn.vec; rp.shift = bn.vec + 64; rp.H = 44; rp.W = 100; rp.OH = 22; rp.OW = 50;
+    rp.OHp = kGeom0.Hp; rp.OWp = kGeom0.Wp; rp.geom = kDense;
     rp.dz_out = m.dy_stem;  // routed + masked gradient, turned into dy in place by the apply pass
     PROF(m, PC_BN_BWD, s, { bn_bwd_reduce_kernel<true><<<rgrid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches; CKL(); });
     BnBwdApplyParams ap{};
     ap.g = m.dy_stem; ap.y = m.stem.y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
     ap.bsum = rp.bsum; ap.bdot = rp.bdot; ap.inv_count = (float)(1.0 / ((double)B * 4400.0)); ap.frozen = frozen; ap.nvec = nvec;
-    ap.C = 64; ap.dy = m.dy_stem;
+    ap.C = 64; ap.dy = m.dy_stem; ap.geom = kDense;
     PROF(m, PC_BN_BWD, s, { bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches; CKL(); });
-    PROF(m, PC_WGRAD, s, CK(run_wgrad(m, wi++, s)));
+    PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, m.stem_wgrad, m.stem.w, s)));
   }
   return OK;
 }
@@ -719,7 +790,9 @@ int cilrs_model_create(cilrs_model** out, int max_batch, void* workspace, size_t
     h->m.pack_njobs = (int)jobs.size();
     h->m.pack_blocks = blocks;
   }
-  int st = cuda_status(cudaMemsetAsync(h->m.counters, 0, 64, s));
+  // the padding pixels of every padded-flat tensor must read as zero from the first step on (kernels keep them zero)
+  int st = cuda_status(cudaMemsetAsync(workspace, 0, (size_t)need, s));
+  if (!st) st = cuda_status(cudaMemsetAsync(h->m.counters, 0, 64, s));
   if (!st) st = cuda_status(cudaMemcpyAsync(h->m.pack_jobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, s));
   if (!st) st = cuda_status(cudaMemsetAsync(h->m.err_flag, 0, 64, s));
   if (!st) st = cuda_status(cudaMemcpyAsync(h->m.unit_vec, unit, sizeof(unit), cudaMemcpyHostToDevice, s));
@@ -822,17 +895,18 @@ int cilrs_model_heads_backward(cilrs_model* h, int batch, const float* dcontrols
 }
 
 // debug / test hook: device pointer and NHWC dims of an intermediate activation of the last forward
-//   which: 0 = max-pool output, 1..16 = BasicBlock outputs, 17 = stem conv raw output; dims = {H, W, C}
+//   which: 0 = max-pool output, 1..16 = BasicBlock outputs, 17 = stem conv raw output;
+//   dims = {H, W, C, Hp, Wp}: the tensor is [batch, Hp, Wp, C] with the real pixels in [:, :H, :W] (padded-flat layout)
 void* cilrs_model_debug_activation(cilrs_model* h, int which, int* dims) {
   if (!h || !dims) return nullptr;
   Model& m = h->m;
-  if (which == 0) { dims[0] = 22; dims[1] = 50; dims[2] = 64; return m.pool_out; }
+  if (which == 0) { dims[0] = 22; dims[1] = 50; dims[2] = 64; dims[3] = kGeom0.Hp; dims[4] = kGeom0.Wp; return m.pool_out; }
   if (which >= 1 && which <= (int)m.blocks.size()) {
     Block& b = m.blocks[which - 1];
-    dims[0] = b.b.oh; dims[1] = b.b.ow; dims[2] = b.b.d.out_c;
+    dims[0] = b.b.oh; dims[1] = b.b.ow; dims[2] = b.b.d.out_c; dims[3] = b.b.gout.Hp; dims[4] = b.b.gout.Wp;
     return b.out;
   }
-  if (which == 17) { dims[0] = 44; dims[1] = 100; dims[2] = 64; return m.stem.y; }
+  if (which == 17) { dims[0] = 44; dims[1] = 100; dims[2] = 64; dims[3] = 44; dims[4] = 100; return m.stem.y; }
   return nullptr;
 }
 
@@ -855,32 +929,49 @@ int cilrs_bn_finalize(const float* partials, int tiles, int C, double count, con
   return cuda_status(cudaGetLastError());
 }
 
+// pad_h, pad_w > 0: the tensors are padded-flat [batch, pad_h + 1, pad_w + 1, C] (elems counts the padding pixels too)
+static int abi_geom(int pad_h, int pad_w, long long elems, int C, PadGeom* g) {
+  if (pad_h <= 0 && pad_w <= 0) { *g = kDense; return OK; }
+  if (pad_h <= 0 || pad_w <= 0) return ERR_INVALID;
+  *g = PadGeom{pad_h, pad_w, pad_h + 1, pad_w + 1};
+  return (elems % ((long long)g->Hp * g->Wp * C)) ? ERR_INVALID : OK;
+}
+
 int cilrs_bn_apply(const void* x, const float* vec, const void* residual, const void* x2, const float* vec2, void* out,
-                   long long elems, int C, int relu, void* stream) {
+                   long long elems, int C, int relu, int pad_h, int pad_w, void* stream) {
   if (!x || !vec || !out || C < 64 || C % 64 || elems % C) return ERR_INVALID;
+  PadGeom g;
+  CK(abi_geom(pad_h, pad_w, elems, C, &g));
   const long long nvec = elems / 8;
   bn_apply_kernel<<<ew_grid(nvec, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, vec, vec + C, (const __nv_bfloat16*)residual, (const __nv_bfloat16*)x2, vec2, vec2 ? vec2 + C : nullptr,
-      (__nv_bfloat16*)out, nvec, C, relu); ++g_cilrs_launches;
+      (__nv_bfloat16*)out, nvec, C, relu, g); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
-int cilrs_bn_relu_maxpool(const void* y, const float* vec, void* out, uint8_t* argmax, int batch, int H, int W, int C, void* stream) {
+// padded_out != 0: out is padded-flat [batch, OH + 1, OW + 1, C] (its padding pixels are not written); argmax stays dense
+int cilrs_bn_relu_maxpool(const void* y, const float* vec, void* out, uint8_t* argmax, int batch, int H, int W, int C, int padded_out,
+                          void* stream) {
   if (!y || !vec || !out || C % 64 || batch < 1) return ERR_INVALID;
   const int OH = (H + 1) / 2, OW = (W + 1) / 2;
   const long long nvec = (long long)batch * OH * OW * C / 8;
-  bn_relu_maxpool_kernel<<<ew_grid(nvec, C), EW_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, vec, vec + C,
-                                                                                    (__nv_bfloat16*)out, argmax, batch, H, W, C, OH, OW); ++g_cilrs_launches;
+  bn_relu_maxpool_kernel<<<ew_grid(nvec, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y, vec, vec + C, (__nv_bfloat16*)out, argmax, batch, H, W, C, OH, OW, padded_out ? OH + 1 : OH,
+      padded_out ? OW + 1 : OW); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
 // BN (+ optional ReLU mask from `act`) backward. workspace: >= (592*2*C + 2*C) floats + one zeroed uint32 counter.
-// stem variant (argmax != NULL): g is the pooled gradient [B,(H+1)/2,(W+1)/2,C] routed through the 3x3/2 max-pool.
+// stem variant (argmax != NULL): g is the pooled gradient [B,(H+1)/2,(W+1)/2,C] routed through the 3x3/2 max-pool; with
+// pad_h > 0 that pooled gradient is padded-flat [B,(H+1)/2+1,(W+1)/2+1,C].
+// regular variant with pad_h, pad_w > 0: g / act / y / dy / dz are padded-flat [batch, pad_h+1, pad_w+1, C].
 int cilrs_bn_backward(const void* g, const void* act, const void* y, const float* vec, const float* gamma, long long elems, int C,
                       double count, int frozen, void* dy, void* dz, float* dgamma, float* dbeta, float* workspace,
-                      unsigned int* counter, const uint8_t* argmax, int H, int W, void* stream) {
+                      unsigned int* counter, const uint8_t* argmax, int H, int W, int pad_h, int pad_w, void* stream) {
   if (!g || !y || !vec || !gamma || !dy || !workspace || !counter || C % 64 || elems % C) return ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
+  PadGeom geom = kDense;
+  if (!argmax) CK(abi_geom(pad_h, pad_w, elems, C, &geom));
   const long long nvec = elems / 8;
   const int grid = ew_grid(nvec, C);
   const int rgrid = ew_reduce_grid(nvec, C);
@@ -888,14 +979,16 @@ int cilrs_bn_backward(const void* g, const void* act, const void* y, const float
   BnBwdReduceParams rp{};
   rp.g = (const __nv_bfloat16*)g; rp.act = (const __nv_bfloat16*)act; rp.y = (const __nv_bfloat16*)y;
   rp.mean = vec + 2 * C; rp.rstd = vec + 3 * C; rp.nvec = nvec; rp.C = C; rp.partial = workspace; rp.counter = counter;
-  rp.bsum = bred; rp.bdot = bred + C; rp.dgamma = dgamma; rp.dbeta = dbeta;
+  rp.bsum = bred; rp.bdot = bred + C; rp.dgamma = dgamma; rp.dbeta = dbeta; rp.geom = geom;
   BnBwdApplyParams ap{};
   ap.g = rp.g; ap.act = rp.act; ap.y = rp.y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = gamma; ap.bsum = rp.bsum; ap.bdot = rp.bdot;
   ap.inv_count = (float)(1.0 / count); ap.frozen = frozen; ap.nvec = nvec; ap.C = C; ap.dy = (__nv_bfloat16*)dy; ap.dz = (__nv_bfloat16*)dz;
+  ap.geom = geom;
   if (argmax) {
     rp.argmax = argmax; rp.scale = vec; rp.shift = vec + C; rp.H = H; rp.W = W; rp.OH = (H + 1) / 2; rp.OW = (W + 1) / 2;
+    rp.OHp = pad_h > 0 ? rp.OH + 1 : rp.OH; rp.OWp = pad_h > 0 ? rp.OW + 1 : rp.OW;
     rp.dz_out = (__nv_bfloat16*)dy;  // routed + masked gradient; the apply pass turns it into dy in place
-    bn_bwd_reduce_kernel<true><<<rgrid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
+    bn_bwd_reduce_kernel<true><<<ew_grid(nvec, C, 8), EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
     CKL();
     ap.g = (const __nv_bfloat16*)dy; ap.act = nullptr;
     bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;

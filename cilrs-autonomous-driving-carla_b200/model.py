@@ -346,14 +346,15 @@ class CILRS(nn.Module):
         return self._workspace[start:start + n].view(torch.bfloat16).view(batch, 47, 103, 16)
 
     def debug_activation(self, which, batch):
-        """Test hook: bf16 [batch,H,W,C] activation of the last forward (0 = max-pool out, 1..16 = block outputs)."""
+        """Test hook: bf16 [batch,H,W,C] activation of the last forward (0 = max-pool out, 1..16 = block outputs).
+        Inside the plan the tensors are in the padded-flat layout [batch,H+1,W+1,C]; the real pixels are returned."""
         lib = _lib.lib()
         lib.cilrs_model_debug_activation.restype = ctypes.c_void_p
-        dims = (ctypes.c_int * 3)()
+        dims = (ctypes.c_int * 5)()
         ptr = lib.cilrs_model_debug_activation(self._handle, int(which), dims)
         if not ptr:
             raise ValueError("no such activation")
-        h, w, c = dims[0], dims[1], dims[2]
+        h, w, c, hp, wp = dims[0], dims[1], dims[2], dims[3], dims[4]
         start = ptr - self._workspace.data_ptr()
-        n = batch * h * w * c * 2
-        return self._workspace[start:start + n].view(torch.bfloat16).view(batch, h, w, c)
+        n = batch * hp * wp * c * 2
+        return self._workspace[start:start + n].view(torch.bfloat16).view(batch, hp, wp, c)[:, :h, :w]

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CILRS_ABI_VERSION 1
+#define CILRS_ABI_VERSION 2
 
 int cilrs_abi_version(void);
 /* human-readable text for a status code returned by any entry point (static storage) */
@@ -195,8 +195,9 @@ int cilrs_model_backward_part_first_tensor(int part);
 int cilrs_model_profile(cilrs_model* m, int enable);
 int cilrs_model_profile_collect(cilrs_model* m, float* out_ms7, int* out_launches7);
 void* cilrs_model_input_s2d(cilrs_model* m); /* where K0 may write the conv1-ready frames directly */
-/* test hook: bf16 NHWC activation of the last forward. which: 0 = max-pool output, 1..16 = BasicBlock outputs,
- * 17 = raw stem conv output; dims receives {H, W, C} */
+/* test hook: bf16 activation of the last forward. which: 0 = max-pool output, 1..16 = BasicBlock outputs,
+ * 17 = raw stem conv output; dims receives {H, W, C, Hp, Wp}: the tensor is [batch, Hp, Wp, C] with the real pixels in
+ * [:, :H, :W] (padded-flat layout; the stem output is dense, Hp = H, Wp = W) */
 void* cilrs_model_debug_activation(cilrs_model* m, int which, int* dims);
 int* cilrs_model_error_flag(cilrs_model* m); /* device int, set to 1 when a command was outside [0,4) */
 
@@ -216,13 +217,17 @@ int cilrs_model_heads_backward(cilrs_model* m, int batch, const float* dcontrols
 int cilrs_bn_finalize(const float* partials, int tiles, int C, double count, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                       int training, int update_running, float* vec, void* stream);
+/* pad_h, pad_w > 0 (both): every activation argument is in the padded-flat layout [batch, pad_h+1, pad_w+1, C] (see
+ * cilrs_conv_flat) and `elems` counts the padding pixels too; they are written as zeros and never read. 0, 0 = dense NHWC. */
 int cilrs_bn_apply(const void* x, const float* vec, const void* residual, const void* x2, const float* vec2, void* out,
-                   long long elems, int C, int relu, void* stream);
+                   long long elems, int C, int relu, int pad_h, int pad_w, void* stream);
+/* padded_out != 0: out is padded-flat [batch, (H+1)/2+1, (W+1)/2+1, C] (padding pixels untouched); argmax stays dense */
 int cilrs_bn_relu_maxpool(const void* y, const float* vec, void* out, uint8_t* argmax, int batch, int H, int W, int C,
-                          void* stream);
+                          int padded_out, void* stream);
+/* stem variant (argmax != NULL): pad_h > 0 means the pooled gradient g is padded-flat */
 int cilrs_bn_backward(const void* g, const void* act, const void* y, const float* vec, const float* gamma, long long elems,
                       int C, double count, int frozen, void* dy, void* dz, float* dgamma, float* dbeta, float* workspace,
-                      unsigned int* counter, const uint8_t* argmax, int H, int W, void* stream);
+                      unsigned int* counter, const uint8_t* argmax, int H, int W, int pad_h, int pad_w, void* stream);
 size_t cilrs_bn_backward_workspace_floats(int C);
 
 /* ---------------------------------------------------------------------------------------------------------

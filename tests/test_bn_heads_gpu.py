@@ -61,7 +61,7 @@ def test_bn_train_forward_and_running_stats(shape):
     res = torch.randn(B, H, W, C, generator=g, device="cuda").to(torch.bfloat16)
     vec = _finalize(st, C, B * H * W, gamma, beta, rm, rv, nbt, True)
     out = torch.empty_like(y)
-    _lib.call("cilrs_bn_apply", y, vec, res, None, None, out, ctypes.c_longlong(y.numel()), C, 1, _lib.stream_ptr())
+    _lib.call("cilrs_bn_apply", y, vec, res, None, None, out, ctypes.c_longlong(y.numel()), C, 1, 0, 0, _lib.stream_ptr())
     torch.cuda.synchronize()
     yf = y.float().permute(0, 3, 1, 2)
     ref = F.batch_norm(yf, rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5)
@@ -71,7 +71,7 @@ def test_bn_train_forward_and_running_stats(shape):
     # frozen (eval) statistics + second BN'd input (downsample branch)
     vec_e = _finalize(None, C, 1.0, gamma, beta, rm, rv, None, False, 0)
     out2 = torch.empty_like(y)
-    _lib.call("cilrs_bn_apply", y, vec_e, None, res, vec, out2, ctypes.c_longlong(y.numel()), C, 0, _lib.stream_ptr())
+    _lib.call("cilrs_bn_apply", y, vec_e, None, res, vec, out2, ctypes.c_longlong(y.numel()), C, 0, 0, 0, _lib.stream_ptr())
     torch.cuda.synchronize()
     ref2 = F.batch_norm(yf, rm, rv, gamma, beta, False, 0.1, 1e-5) + F.batch_norm(res.float().permute(0, 3, 1, 2), None, None, gamma, beta, True, 0.1, 1e-5) * 0
     # second input normalised with `vec` (batch statistics of y): restate directly
@@ -92,7 +92,7 @@ def test_bn_relu_backward(shape, frozen):
     rm, rv = 0.1 * torch.randn(C, generator=gen, device="cuda"), torch.rand(C, generator=gen, device="cuda") + 0.5
     vec = _finalize(st, C, B * H * W, gamma, beta, rm.clone(), rv.clone(), None, not frozen, 0)
     act = torch.empty_like(y)
-    _lib.call("cilrs_bn_apply", y, vec, None, None, None, act, ctypes.c_longlong(y.numel()), C, 1, _lib.stream_ptr())
+    _lib.call("cilrs_bn_apply", y, vec, None, None, None, act, ctypes.c_longlong(y.numel()), C, 1, 0, 0, _lib.stream_ptr())
     gup = torch.randn(B, H, W, C, generator=gen, device="cuda").to(torch.bfloat16)
     dy, dz = torch.empty_like(y), torch.empty_like(y)
     dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
@@ -101,7 +101,7 @@ def test_bn_relu_backward(shape, frozen):
     ws = torch.empty(nws(C), device="cuda")
     cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
     _lib.call("cilrs_bn_backward", gup, act, y, vec, gamma, ctypes.c_longlong(y.numel()), C, ctypes.c_double(B * H * W), frozen, dy, dz,
-              dgamma, dbeta, ws, cnt, None, 0, 0, _lib.stream_ptr())
+              dgamma, dbeta, ws, cnt, None, 0, 0, 0, 0, _lib.stream_ptr())
     torch.cuda.synchronize()
     x = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
     gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
@@ -128,7 +128,7 @@ def test_stem_bn_relu_maxpool_forward_backward(B):
     vec = _finalize(st, C, B * 4400, gamma, beta, rm, rv, None, True, 0)
     pooled = torch.empty(B, 22, 50, C, dtype=torch.bfloat16, device="cuda")
     arg = torch.empty(B, 22, 50, C, dtype=torch.uint8, device="cuda")
-    _lib.call("cilrs_bn_relu_maxpool", y, vec, pooled, arg, B, 44, 100, C, _lib.stream_ptr())
+    _lib.call("cilrs_bn_relu_maxpool", y, vec, pooled, arg, B, 44, 100, C, 0, _lib.stream_ptr())
     gp = torch.randn(B, 22, 50, C, generator=gen, device="cuda").to(torch.bfloat16)
     dy = torch.empty_like(y)
     dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
@@ -137,7 +137,7 @@ def test_stem_bn_relu_maxpool_forward_backward(B):
     ws = torch.empty(nws(C), device="cuda")
     cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
     _lib.call("cilrs_bn_backward", gp, None, y, vec, gamma, ctypes.c_longlong(y.numel()), C, ctypes.c_double(B * 4400), 0, dy, None, dgamma,
-              dbeta, ws, cnt, arg, 44, 100, _lib.stream_ptr())
+              dbeta, ws, cnt, arg, 44, 100, 0, 0, _lib.stream_ptr())
     torch.cuda.synchronize()
     x = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
     gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
@@ -148,6 +148,55 @@ def test_stem_bn_relu_maxpool_forward_backward(B):
     po.backward(gp.float().permute(0, 3, 1, 2))
     assert _l2(dy.float().permute(0, 3, 1, 2), x.grad) <= 1.5e-2
     assert _rel(dgamma, gm.grad) <= 1e-2 and _rel(dbeta, bt.grad) <= 1e-2
+
+
+@pytest.mark.parametrize("shape", [(6, 11, 25, 128), (3, 22, 50, 64), (9, 3, 7, 512)])
+def test_padded_flat_layout_bn_apply_and_backward_equal_the_dense_kernels(shape):
+    """the same kernels on the padded-flat layout [B,H+1,W+1,C]: identical results on the real pixels, exact zeros on the
+    padding pixels, and stale values in the padding of the incoming gradient are never read"""
+    from cilrs_b200 import _lib, ops
+    B, H, W, C = shape
+    y, st = _conv_stats(B, H, W, C, 11)
+    gen = torch.Generator(device="cuda").manual_seed(12)
+    gamma = 1 + 0.3 * torch.randn(C, generator=gen, device="cuda")
+    beta = 0.2 * torch.randn(C, generator=gen, device="cuda")
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    vec = _finalize(st, C, B * H * W, gamma, beta, rm, rv, None, True, 0)
+    res = torch.randn(B, H, W, C, generator=gen, device="cuda").to(torch.bfloat16)
+    out_d = torch.empty_like(y)
+    _lib.call("cilrs_bn_apply", y, vec, res, None, None, out_d, ctypes.c_longlong(y.numel()), C, 1, 0, 0, _lib.stream_ptr())
+    yp, resp = ops.to_padded(y), ops.to_padded(res)
+    out_p = torch.full_like(yp, float("nan"))
+    _lib.call("cilrs_bn_apply", yp, vec, resp, None, None, out_p, ctypes.c_longlong(yp.numel()), C, 1, H, W, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(ops.from_padded(out_p, H, W), out_d)
+    assert float(out_p[:, H:].float().abs().max()) == 0.0 and float(out_p[:, :, W:].float().abs().max()) == 0.0
+    # backward: dense vs padded (gradient padding filled with garbage on purpose)
+    gup = torch.randn(B, H, W, C, generator=gen, device="cuda").to(torch.bfloat16)
+    nws = _lib.lib().cilrs_bn_backward_workspace_floats
+    nws.restype = ctypes.c_size_t
+    outs = []
+    for padded in (False, True):
+        g_in = gup
+        a_in, y_in = out_d, y
+        if padded:
+            g_in = torch.full((B, H + 1, W + 1, C), 7.0, dtype=torch.bfloat16, device="cuda")
+            g_in[:, :H, :W] = gup
+            a_in, y_in = ops.to_padded(out_d), yp
+        dy, dz = torch.full_like(y_in, float("nan")), torch.full_like(y_in, float("nan"))
+        dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        ws = torch.empty(nws(C), device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.call("cilrs_bn_backward", g_in, a_in, y_in, vec, gamma, ctypes.c_longlong(y_in.numel()), C, ctypes.c_double(B * H * W), 0, dy, dz,
+                  dgamma, dbeta, ws, cnt, None, 0, 0, H if padded else 0, W if padded else 0, _lib.stream_ptr())
+        torch.cuda.synchronize()
+        outs.append((dy, dz, dgamma, dbeta))
+    (dy_d, dz_d, dg_d, db_d), (dy_p, dz_p, dg_p, db_p) = outs
+    assert torch.equal(ops.from_padded(dz_p, H, W), dz_d)
+    assert float(dy_p[:, H:].float().abs().max()) == 0.0 and float(dy_p[:, :, W:].float().abs().max()) == 0.0
+    assert float(dz_p[:, H:].float().abs().max()) == 0.0 and float(dz_p[:, :, W:].float().abs().max()) == 0.0
+    assert _rel(dg_p, dg_d) <= 1e-4 and _rel(db_p, db_d) <= 1e-4      # different partial order
+    assert _rel(ops.from_padded(dy_p, H, W).float(), dy_d.float()) <= 8e-3
 
 
 @pytest.mark.parametrize("B", [1, 4, 37])
