@@ -28,92 +28,114 @@ static void split_boxes(int rows, int* box_rows, int* boxes) {
   *boxes = n;
 }
 
-static long long flat_smem_fixed(int n_total) {
-  return 1024 /* alignment slack */ + CF_STAGING_BYTES + 2 * 4 * 64 * 3 * 4 + 2LL * 3 * n_total * 4 +
+static long long flat_smem_fixed(int block_n) {
+  return 1024 /* alignment slack */ + 8LL * 3 * block_n * 4 /* warp-private statistics */ +
          (2 * CF_MAX_A_STAGES + 2 * CF_MAX_B_STAGES + 2 * CF_MAX_ACC) * 8 + 64 + 64;
 }
 
-// Tile-shape choice by a small cost model (clocks per CTA): a (128*mt) x block_n tile issues 9*chunks*mt*4 MMAs of
-// block_n*2/4... clocks and pulls one activation slab per chunk plus (unless resident) one weight tile per tap and chunk
-// through L2->SMEM at ~min(64, 6300/active CTAs) bytes per clock; tiles are dealt round-robin to <= #SM persistent CTAs.
+// Tile-shape choice by a small cost model in clocks per CTA, calibrated on B200 traces (tools/trace_flat.py):
+//  * a tcgen05.mma 128 x N x 16 takes max(N/2, shared-memory operand fetch (4096 + 32 N bytes at 128 B/clk)) clocks:
+//    48 / 64 / 128 for N = 64 / 128 / 256;
+//  * every mbarrier round trip of the issuing warp (one per weight stage = `tap_group` taps) costs ~550 clocks of which the
+//    tensor-core queue hides ~3.3 MMAs;
+//  * a 128 x 64 epilogue unit costs ~2000 clocks and is only hidden behind the MMAs of a following tile;
+//  * activations + weights cross L2->SMEM at ~min(64, 6300 / active CTAs) bytes per clock.
 struct FlatShape {
-  int mt, block_n, resident, a_stages, b_stages, a_box_rows, a_boxes;
+  int mt, block_n, resident, tap_group, a_stages, b_stages, a_box_rows, a_boxes;
   double cost;
 };
+
+static bool flat_stages(long long budget, int chunks, int n_blocks, int bn, long long a_stage, int resident, int G, int* a_st, int* b_st) {
+  const long long b_stage = (long long)G * bn * 128;
+  if (resident) {
+    if (n_blocks != 1 || G != 9 || chunks > CF_MAX_B_STAGES) return false;
+    const long long left = budget - chunks * b_stage;
+    if (left < 2 * a_stage) return false;
+    *b_st = chunks;
+    *a_st = (int)(left / a_stage) > CF_MAX_A_STAGES ? CF_MAX_A_STAGES : (int)(left / a_stage);
+    return true;
+  }
+  long long left = budget - 2 * a_stage;
+  if (left < 2 * b_stage) return false;
+  int nb = (int)(left / b_stage);
+  if (nb > CF_MAX_B_STAGES) nb = CF_MAX_B_STAGES;
+  if (nb * G > 18) nb = (18 + G - 1) / G;  // more than two chunks of weights in flight buys nothing
+  if (nb < 2) nb = 2;
+  left -= nb * b_stage;
+  *b_st = nb;
+  *a_st = left >= a_stage ? 3 : 2;
+  return true;
+}
 
 static FlatShape choose_flat_shape(int total_rows, int k_channels, int n_total, const PadGeom& g) {
   const int sms = sm_count();
   const int chunks = k_channels / 64;
   const int halo = g.Wp + 1;
-  const long long budget = CG_SMEM_TOTAL - flat_smem_fixed(n_total);
   FlatShape best{};
   best.cost = 1e30;
   const int bns[3] = {256, 128, 64};
   const int mts[3] = {1, 2, 4};
+  const int groups[4] = {9, 3, 2, 1};
   for (int bi = 0; bi < 3; ++bi) {
     const int bn = bns[bi];
     if (n_total % bn) continue;
     const int n_blocks = n_total / bn;
+    const long long budget = CG_SMEM_TOTAL - flat_smem_fixed(bn);
+    const double mma_clk = bn == 64 ? 48.0 : (bn == 128 ? 64.0 : 128.0);
     for (int mi = 0; mi < 3; ++mi) {
       const int mt = mts[mi];
-      if (mt * bn > 256) continue;
+      if (mt * bn > 512) continue;
       int box_rows, boxes;
       split_boxes(mt * 128 + 2 * halo, &box_rows, &boxes);
       const long long a_stage = (long long)box_rows * boxes * 128;
-      const long long b_stage = (long long)bn * 128;
-      for (int res = 0; res < 2; ++res) {
-        if (res && n_blocks != 1) continue;
+      for (int gi = 0; gi < 4; ++gi) {
+        const int res = gi == 0;
+        const int G = res ? 9 : groups[gi];
         int a_st, b_st;
-        if (res) {
-          b_st = 9 * chunks;
-          if (b_st > CF_MAX_B_STAGES) continue;
-          const long long left = budget - b_st * b_stage;
-          if (left < 2 * a_stage) continue;
-          a_st = (int)(left / a_stage);
-          if (a_st > CF_MAX_A_STAGES) a_st = CF_MAX_A_STAGES;
-        } else {
-          a_st = 2;
-          long long left = budget - a_st * a_stage;
-          if (left < 3 * b_stage) continue;
-          b_st = (int)(left / b_stage);
-          if (b_st > 16) b_st = 16;
-          left -= b_st * b_stage;
-          if (left >= a_stage) a_st = 3;
-        }
+        if (!flat_stages(budget, chunks, n_blocks, bn, a_stage, res, G, &a_st, &b_st)) continue;
         const int m_tiles = (total_rows + mt * 128 - 1) / (mt * 128);
         const long long tiles = (long long)m_tiles * n_blocks;
-        const int active = tiles < sms ? (int)tiles : sms;
+        int active = tiles < sms ? (int)tiles : sms;
+        active -= active % n_blocks;  // the grid is a multiple of n_blocks (one channel block per CTA)
+        if (active < 1) continue;
         const double bw = 6300.0 / active < 64.0 ? 6300.0 / active : 64.0;
-        const double mma = 9.0 * chunks * mt * bn * 2.0;
-        const double bytes = (double)chunks * a_stage + (res ? 0.0 : 9.0 * chunks * b_stage);
-        const double tile_clk = (mma > bytes / bw ? mma : bytes / bw) + 600.0;  // + pipeline fill / epilogue tail
-        const long long rounds = (tiles + active - 1) / active;
-        const double cost = rounds * tile_clk;
-        if (cost < best.cost * 0.98) {
-          best = FlatShape{mt, bn, res, a_st, b_st, box_rows, boxes, cost};
+        const double exposed = 550.0 - 3.3 * mma_clk > 60.0 ? 550.0 - 3.3 * mma_clk : 60.0;
+        double chunk_clk = 0.0;
+        for (int t0 = 0; t0 < 9; t0 += G) {
+          const int cnt = 9 - t0 < G ? 9 - t0 : G;
+          chunk_clk += cnt * mt * 4 * mma_clk + exposed;
         }
+        const double mma = chunks * chunk_clk;
+        const double bytes = (double)chunks * a_stage + (res ? 0.0 : 9.0 * chunks * bn * 128.0);
+        const double tile_clk = mma > bytes / bw ? mma : bytes / bw;
+        const long long rounds = (tiles + active - 1) / active;
+        const double units = mt * (bn / 64) * 0.5;                      // per epilogue group
+        const int acc_sets = 512 / (mt * bn);
+        // the epilogue of a tile hides behind the next tile's MMAs only with >= 2 accumulator sets and a next tile
+        const double epi_tail = units * 2000.0 * (acc_sets >= 2 ? 1.0 : (double)rounds);
+        const double cost = rounds * tile_clk + 1500.0 + epi_tail;
+        if (cost < best.cost * 0.99) best = FlatShape{mt, bn, res, G, a_st, b_st, box_rows, boxes, cost};
       }
     }
   }
-  // measurement aid: CILRS_FLAT_SHAPE="mt,block_n,resident,a_stages,b_stages" overrides the model (0 stages = keep the model's)
+  // measurement aid: CILRS_FLAT_SHAPE="mt,block_n,resident,tap_group" overrides the model
   if (const char* env = getenv("CILRS_FLAT_SHAPE")) {
-    int mt = 0, bn = 0, res = 0, a_st = 0, b_st = 0;
-    if (sscanf(env, "%d,%d,%d,%d,%d", &mt, &bn, &res, &a_st, &b_st) >= 3 && mt >= 1 && bn >= 64 && n_total % bn == 0 && mt * bn <= 512) {
-      int box_rows, boxes;
+    int mt = 0, bn = 0, res = 0, G = 0;
+    if (sscanf(env, "%d,%d,%d,%d", &mt, &bn, &res, &G) == 4 && (mt == 1 || mt == 2 || mt == 4) && bn >= 64 && n_total % bn == 0 &&
+        mt * bn <= 512 && G >= 1 && G <= 9) {
+      int box_rows, boxes, a_st, b_st;
       split_boxes(mt * 128 + 2 * halo, &box_rows, &boxes);
-      const long long a_stage = (long long)box_rows * boxes * 128, b_stage = (long long)bn * 128;
-      if (res) b_st = 9 * chunks;
-      if (a_st < 1) a_st = 2;
-      if (b_st < 1) b_st = (int)((budget - a_st * a_stage) / b_stage);
-      if (b_st > CF_MAX_B_STAGES) b_st = CF_MAX_B_STAGES;
-      if (a_st <= CF_MAX_A_STAGES && b_st >= 1 && a_st * a_stage + b_st * b_stage <= budget && (!res || n_total == bn))
-        best = FlatShape{mt, bn, res, a_st, b_st, box_rows, boxes, 0.0};
+      const long long a_stage = (long long)box_rows * boxes * 128;
+      const long long budget = CG_SMEM_TOTAL - flat_smem_fixed(bn);
+      if (res) G = 9;
+      if (flat_stages(budget, chunks, n_total / bn, bn, a_stage, res, G, &a_st, &b_st))
+        best = FlatShape{mt, bn, res, G, a_st, b_st, box_rows, boxes, 0.0};
     }
   }
   if (getenv("CILRS_FLAT_DEBUG"))
-    fprintf(stderr, "[cilrs flat] rows=%d K=%d N=%d Wp=%d -> mt=%d block_n=%d resident=%d a_stages=%d b_stages=%d a_box=%dx%d cost=%.0f\n",
-            total_rows, k_channels, n_total, g.Wp, best.mt, best.block_n, best.resident, best.a_stages, best.b_stages, best.a_boxes,
-            best.a_box_rows, best.cost);
+    fprintf(stderr, "[cilrs flat] rows=%d K=%d N=%d Wp=%d -> mt=%d block_n=%d resident=%d tap_group=%d a_stages=%d b_stages=%d a_box=%dx%d cost=%.0f\n",
+            total_rows, k_channels, n_total, g.Wp, best.mt, best.block_n, best.resident, best.tap_group, best.a_stages, best.b_stages,
+            best.a_boxes, best.a_box_rows, best.cost);
   return best;
 }
 
@@ -145,7 +167,7 @@ int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channe
   p->chunks = k_channels / 64;
   p->halo = g.Wp + 1;
   p->a_box_rows = sh.a_box_rows; p->a_boxes = sh.a_boxes;
-  p->a_stages = sh.a_stages; p->b_stages = sh.b_stages; p->b_resident = sh.resident;
+  p->a_stages = sh.a_stages; p->b_stages = sh.b_stages; p->b_resident = sh.resident; p->tap_group = sh.tap_group;
   int sets = 512 / (sh.mt * sh.block_n);
   p->acc_sets = sets > CF_MAX_ACC ? CF_MAX_ACC : sets;
   p->m_tiles = (p->total_rows + sh.mt * 128 - 1) / (sh.mt * 128);
@@ -159,18 +181,26 @@ int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channe
 
 int flat_conv_grid(const FlatConvParams* p) {
   const long long total = (long long)p->m_tiles * p->n_blocks;
-  return total < sm_count() ? (int)total : sm_count();
+  int grid = total < sm_count() ? (int)total : sm_count();
+  return grid - grid % p->n_blocks;  // a multiple of n_blocks: every CTA then only ever sees one channel block
 }
 
 int launch_flat_conv(const FlatConvParams* p, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_flat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_flat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL);
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
   if ((p->flags & (CF_STATS | CF_BNBWD)) && (!p->partials || !p->counter)) return ERR_INVALID;
-  conv_flat_kernel<<<flat_conv_grid(p), CF_THREADS, CG_SMEM_TOTAL, s>>>(*p); ++g_cilrs_launches;
+  const int grid = flat_conv_grid(p);
+  if (p->mt == 1) conv_flat_kernel<1><<<grid, CF_THREADS, CG_SMEM_TOTAL, s>>>(*p);
+  else if (p->mt == 2) conv_flat_kernel<2><<<grid, CF_THREADS, CG_SMEM_TOTAL, s>>>(*p);
+  else if (p->mt == 4) conv_flat_kernel<4><<<grid, CF_THREADS, CG_SMEM_TOTAL, s>>>(*p);
+  else return ERR_INVALID;
+  ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -186,12 +216,10 @@ int build_wgrad_flat(WgradFlatParams* p, int batch, const PadGeom& g, int cin, i
   p->co_blocks = (cout + 127) / 128;
   p->m_halves = cout >= 128 ? 2 : 1;
   p->ci_chunks = cin / 64;
-  p->tap_groups = 2;
-  p->group_first[0] = 0; p->group_count[0] = 5;
-  p->group_first[1] = 5; p->group_count[1] = 4;
+  p->tap_groups = 3;  // one filter row (dw = -1, 0, +1) per CTA: a single N = 192 MMA over a 130-pixel slab
   for (int r = 0; r < 3; ++r)
     for (int s = 0; s < 3; ++s) p->tap_shift[r * 3 + s] = (r - 1) * g.Wp + (s - 1);
-  split_boxes(128 + g.Wp + 1, &p->x_box_rows, &p->x_boxes);
+  split_boxes(128 + 2, &p->x_box_rows, &p->x_boxes);
   const int base = p->co_blocks * p->ci_chunks * p->tap_groups;
   int z = sm_count() / base;
   if (z < 1) z = 1;

@@ -30,25 +30,54 @@ __device__ int g_cf_trace_n[3];
 #define CF_EVENT(role, code) do { } while (0)
 #endif
 
-CILRS_DEVINL void cf_unpack8(const uint4 u, float* f) {
-  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
-  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+// 256-bit global accesses (one full 32-byte sector per thread)
+CILRS_DEVINL void ldg256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+CILRS_DEVINL void stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// one row (64 bf16 = 128 bytes) of a padded-flat tensor -> 32 packed registers
+CILRS_DEVINL void load_row64(const __nv_bfloat16* p, uint32_t* r) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ldg256(p + j * 16, r + j * 8);
 }
 
+// Column sums across the warp without shared memory: every lane holds one row x[0..63]; after five butterfly steps lane l
+// holds the sums over all 32 rows of columns 2l and 2l+1 (62 shuffles). Destroys x.
+CILRS_DEVINL float2 warp_colsum64(float* x, int lane) {
+#pragma unroll
+  for (int half = 32; half >= 2; half >>= 1) {
+    const int bit = half >> 1;
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? x[i] : x[i + half];
+      const float keep = up ? x[i + half] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  return make_float2(x[0], x[1]);
+}
+
+template <int MT>
 __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_constant__ FlatConvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // aligned by pointer arithmetic on the __shared__ array (not through an integer cast) so that the compiler keeps the
+  // shared address space and emits LDS/STS instead of generic loads/stores
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   const int a_stage_bytes = p.a_boxes * p.a_box_rows * 128;
-  const int b_stage_bytes = p.block_n * 128;
+  const int b_tap_bytes = p.block_n * 128;
+  const int b_stage_bytes = p.tap_group * b_tap_bytes;  // one stage = the weight tiles of `tap_group` consecutive taps
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)p.a_stages * a_stage_bytes;
-  uint8_t* staging = sB + (size_t)p.b_stages * b_stage_bytes;
-  float* s_stat = (float*)(staging + CF_STAGING_BYTES);  // [2 groups][4 warps][64 ch][3]
-  float* s_acc = s_stat + 2 * 4 * 64 * 3;                // [2 groups][3][n_total]
-  uint64_t* bars = (uint64_t*)(s_acc + 2 * 3 * p.n_total);
+  float* s_wacc = (float*)(sB + (size_t)p.b_stages * b_stage_bytes);  // [8 epilogue warps][3][block_n] running statistics
+  uint64_t* bars = (uint64_t*)(s_wacc + 8 * 3 * p.block_n);
   uint64_t* full_a = bars;
   uint64_t* empty_a = full_a + CF_MAX_A_STAGES;
   uint64_t* full_b = empty_a + CF_MAX_A_STAGES;
@@ -80,7 +109,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p.m_tiles * p.n_blocks;
-  const int acc_stride = p.mt * p.block_n;  // TMEM columns per accumulator set
+  const int acc_stride = MT * p.block_n;  // TMEM columns per accumulator set
+  const int n_groups = (p.num_taps + p.tap_group - 1) / p.tap_group;
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -91,7 +121,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_blocks;
         const int n_blk = tile - m_tile * p.n_blocks;
-        const int row0 = m_tile * p.mt * 128;
+        const int row0 = m_tile * MT * 128;
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(&empty_a[as], aph ^ 1);
           CF_EVENT(0, 0x100 + c);
@@ -100,12 +130,16 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
           for (int bx = 0; bx < p.a_boxes; ++bx)
             tma_load_2d(&p.tmA, &full_a[as], dst + (size_t)bx * p.a_box_rows * 128, c * 64, row0 - p.halo + bx * p.a_box_rows);
           if (++as == p.a_stages) { as = 0; aph ^= 1; }
-          for (int t = 0; t < p.num_taps; ++t) {
+          for (int gi = 0; gi < n_groups; ++gi) {
+            const int t0 = gi * p.tap_group;
+            const int cnt = min(p.tap_group, p.num_taps - t0);
             if (!p.b_resident || first) {
               if (!p.b_resident) mbar_wait(&empty_b[bs], bph ^ 1);
-              CF_EVENT(0, 0x200 + t);
-              mbar_arrive_expect_tx(&full_b[bs], (uint32_t)b_stage_bytes);
-              tma_load_2d(&p.tmB, &full_b[bs], sB + (size_t)bs * b_stage_bytes, c * 64, p.tap_slab[t] * p.n_total + n_blk * p.block_n);
+              CF_EVENT(0, 0x200 + gi);
+              mbar_arrive_expect_tx(&full_b[bs], (uint32_t)(cnt * b_tap_bytes));
+              for (int j = 0; j < cnt; ++j)
+                tma_load_2d(&p.tmB, &full_b[bs], sB + (size_t)bs * b_stage_bytes + (size_t)j * b_tap_bytes, c * 64,
+                            p.tap_slab[t0 + j] * p.n_total + n_blk * p.block_n);
             }
             if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
           }
@@ -125,6 +159,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     const uint64_t descA0 = umma_desc_sw128(smem_u32(sA), 16, 1024);
     const uint64_t descB0 = umma_desc_sw128(smem_u32(sB), 16, 1024);
     const uint32_t a_stage_units = (uint32_t)(a_stage_bytes >> 4), b_stage_units = (uint32_t)(b_stage_bytes >> 4);
+    const uint32_t b_tap_units = (uint32_t)(b_tap_bytes >> 4);
     int as = 0, bs = 0, acc = 0;
     uint32_t aph = 0, bph = 0, accph = 0;
     bool first = true;
@@ -138,20 +173,26 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
         tc_fence_after();
         if (leader) CF_EVENT(1, 0x100 + c);
         const uint64_t da_stage = descA0 + (uint64_t)((uint32_t)as * a_stage_units);
-        for (int t = 0; t < p.num_taps; ++t) {
+        for (int gi = 0; gi < n_groups; ++gi) {
+          const int t0 = gi * p.tap_group;
+          const int cnt = min(p.tap_group, p.num_taps - t0);
           if (!p.b_resident || first) {
             mbar_wait(&full_b[bs], bph);
             tc_fence_after();
           }
-          if (leader) CF_EVENT(1, 0x200 + t);
-          const uint64_t db = descB0 + (uint64_t)((uint32_t)bs * b_stage_units);
-          const uint64_t da_tap = da_stage + (uint64_t)((uint32_t)(p.halo + p.tap_shift[t]) * 8u);  // 128-byte rows, in 16-byte units
+          if (leader) CF_EVENT(1, 0x200 + gi);
+          const uint64_t db_stage = descB0 + (uint64_t)((uint32_t)bs * b_stage_units);
           if (leader) {
-            for (int m = 0; m < p.mt; ++m) {
-              const uint64_t da = da_tap + (uint64_t)((uint32_t)m * 1024u);
-              const uint32_t d = d_base + (uint32_t)(m * p.block_n);
+            for (int j = 0; j < cnt; ++j) {
+              const uint64_t db = db_stage + (uint64_t)((uint32_t)j * b_tap_units);
+              const uint64_t da_tap = da_stage + (uint64_t)((uint32_t)(p.halo + p.tap_shift[t0 + j]) * 8u);  // 128-byte rows, in 16-byte units
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) umma_bf16(d, da + kk * 2, db + kk * 2, idesc, (c | t | kk) != 0 ? 1u : 0u);
+              for (int m = 0; m < MT; ++m) {
+                const uint64_t da = da_tap + (uint64_t)((uint32_t)m * 1024u);
+                const uint32_t d = d_base + (uint32_t)(m * p.block_n);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_bf16(d, da + kk * 2, db + kk * 2, idesc, (c | (t0 + j) | kk) != 0 ? 1u : 0u);
+              }
             }
             if (!p.b_resident) umma_commit(&empty_b[bs]);
           }
@@ -172,21 +213,21 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     }
   } else {
     // ================= epilogue: 2 groups x 4 warps; a group handles every other 128 x 64 unit =================
+    // Register-direct: TMEM -> registers -> (scale/bias, residual, ReLU mask) -> bf16 -> 256-bit global stores; per-channel
+    // statistics by a shuffle butterfly into warp-private accumulators. No shared-memory staging and no barriers: the
+    // tensor core's operand fetch already saturates the 128 B/clk of shared memory (conv_flat.cu).
     const int ew = warp - 2;
     const int grp = ew >> 2;
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;          // accumulator row
-    const int etid = (ew & 3) * 32 + lane;  // 0..127 inside the group
-    const int bar_id = 1 + grp;
-    uint8_t* sbuf = staging + grp * (CF_STAGING_BYTES / 2);
-    float* g_stat = s_stat + grp * (4 * 64 * 3);
-    float* g_acc = s_acc + grp * (3 * p.n_total);
     const bool do_stats = (p.flags & (CF_STATS | CF_BNBWD)) != 0;
     const bool bwd = (p.flags & CF_BNBWD) != 0;
     const bool bwd2 = (p.flags & CF_BNBWD2) != 0;
     const int nq = bwd2 ? 3 : 2;
+    float* w_acc = s_wacc + ew * (3 * p.block_n);  // this warp's running sums [3][block_n]
     if (do_stats) {
-      for (int i = etid; i < 3 * p.n_total; i += 128) g_acc[i] = 0.f;
+      for (int i = lane; i < 3 * p.block_n; i += 32) w_acc[i] = 0.f;
+      __syncwarp();
     }
     int acc = 0;
     uint32_t accph = 0;
@@ -195,13 +236,15 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_blocks;
       const int n_blk = tile - m_tile * p.n_blocks;
-      const int row0 = m_tile * p.mt * 128;
+      const int row0 = m_tile * MT * 128;
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
       if (ew == 0 && lane == 0) CF_EVENT(2, 0x500);
-      for (int m = 0; m < p.mt; ++m) {
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
         const int f = row0 + m * 128 + row;
-        bool valid = f < p.total_rows;
+        const bool in_range = f < p.total_rows;
+        bool valid = in_range;
         if (valid) {
           const unsigned int uf = (unsigned int)f;
           const unsigned int wq = uf / (unsigned int)p.g.Wp;
@@ -209,6 +252,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
           const unsigned int h = wq % (unsigned int)p.g.Hp;
           valid = (w < (unsigned int)p.g.W) && (h < (unsigned int)p.g.H);
         }
+#pragma unroll 1
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
           if (((uc++) & 1u) != (uint32_t)grp) continue;
           const int n_base = n_blk * p.block_n + chunk * 64;
@@ -225,120 +269,73 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
               v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), __ldg(p.scale + n_base + j), __ldg(p.bias + n_base + j)));
           }
           if ((p.flags & CF_RESIDUAL) && valid) {
-            const uint4* rp = (const uint4*)(p.residual + goff);
+            uint32_t r[32];
+            load_row64(p.residual + goff, r);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float r[8];
-              cf_unpack8(__ldg(rp + j), r);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[j * 8 + e] = __float_as_uint(__uint_as_float(v[j * 8 + e]) + r[e]);
+            for (int j = 0; j < 32; ++j) {
+              v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) + bf16lo(r[j]));
+              v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) + bf16hi(r[j]));
             }
           }
           if ((p.flags & CF_MASK) && valid) {
-            const uint4* mp = (const uint4*)(p.mask + goff);
+            uint32_t r[32];
+            load_row64(p.mask + goff, r);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float r[8];
-              cf_unpack8(__ldg(mp + j), r);
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (!(r[e] > 0.f)) v[j * 8 + e] = 0u;
+            for (int j = 0; j < 32; ++j) {
+              if (!(bf16lo(r[j]) > 0.f)) v[2 * j] = 0u;
+              if (!(bf16hi(r[j]) > 0.f)) v[2 * j + 1] = 0u;
             }
           }
           if (p.flags & CF_RELU) {
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
           }
-          if (!valid) {
-            // padding pixels of the layout (and rows past the end): they stay exact zeros in memory and in the statistics
+          uint32_t u[32];
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = 0u;
-          }
-          if (ew == 0 && lane == 0) CF_EVENT(2, 0x602);
-          bar_sync_named(bar_id, 128);  // the group's previous unit no longer reads the staging buffer
-          if (ew == 0 && lane == 0) CF_EVENT(2, 0x603);
+          for (int j = 0; j < 32; ++j)
+            u[j] = valid ? pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) : 0u;  // padding pixels stay exact zeros
+          if (in_range) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
-            o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
-            o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
-            o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
-            *(uint4*)(sbuf + row * 128 + ((j ^ (row & 7)) << 4)) = o;
-          }
-          bar_sync_named(bar_id, 128);
-          if (ew == 0 && lane == 0) CF_EVENT(2, 0x604);
-          // coalesced write-out: 8 consecutive threads cover one 128-byte row
-          const int fb = row0 + m * 128;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int u = it * 128 + etid;
-            const int r = u >> 3, c16 = u & 7;
-            if (fb + r < p.total_rows) {
-              const uint4 o = *(const uint4*)(sbuf + r * 128 + ((c16 ^ (r & 7)) << 4));
-              *(uint4*)(p.out + (long long)(fb + r) * p.n_total + n_base + c16 * 8) = o;
-            }
+            for (int j = 0; j < 4; ++j) stg256(p.out + goff + j * 16, u + j * 8);
           }
           if (ew == 0 && lane == 0) CF_EVENT(2, 0x605);
           if (do_stats) {
-            // column phase: thread (cp, rg) owns channel pair cp over the 32 rows of row group rg
-            const int cp = etid & 31, rg = etid >> 5;
-            const int c16 = cp >> 2, sub = (cp & 3) * 4;
-            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f, t0 = 0.f, t1 = 0.f;
-            if (!bwd) {
-#pragma unroll 8
-              for (int rr = 0; rr < 32; ++rr) {
-                const int r = rg * 32 + rr;
-                const uint32_t u = *(const uint32_t*)(sbuf + r * 128 + ((c16 ^ (r & 7)) << 4) + sub);
-                const float a = bf16lo(u), b = bf16hi(u);
-                s0 += a; s1 += b;
-                q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
-              }
-            } else {
-              const int ch = n_base + cp * 2;
-              const float m1a = __ldg(p.stat1 + 2 * p.n_total + ch), m1b = __ldg(p.stat1 + 2 * p.n_total + ch + 1);
-              const float r1a = __ldg(p.stat1 + 3 * p.n_total + ch), r1b = __ldg(p.stat1 + 3 * p.n_total + ch + 1);
-              float m2a = 0.f, m2b = 0.f, r2a = 0.f, r2b = 0.f;
-              if (bwd2) {
-                m2a = __ldg(p.stat2 + 2 * p.n_total + ch); m2b = __ldg(p.stat2 + 2 * p.n_total + ch + 1);
-                r2a = __ldg(p.stat2 + 3 * p.n_total + ch); r2b = __ldg(p.stat2 + 3 * p.n_total + ch + 1);
-              }
-              const int last = p.total_rows - 1;
-#pragma unroll 8
-              for (int rr = 0; rr < 32; ++rr) {
-                const int r = rg * 32 + rr;
-                const uint32_t u = *(const uint32_t*)(sbuf + r * 128 + ((c16 ^ (r & 7)) << 4) + sub);
-                const float a = bf16lo(u), b = bf16hi(u);
-                const long long fo = (long long)min(fb + r, last) * p.n_total + ch;  // rows past the end hold dz = 0
-                const uint32_t yu = __ldg((const unsigned int*)(p.y1 + fo));
-                s0 += a; s1 += b;
-                q0 = fmaf(a, (bf16lo(yu) - m1a) * r1a, q0);
-                q1 = fmaf(b, (bf16hi(yu) - m1b) * r1b, q1);
-                if (bwd2) {
-                  const uint32_t y2u = __ldg((const unsigned int*)(p.y2 + fo));
-                  t0 = fmaf(a, (bf16lo(y2u) - m2a) * r2a, t0);
-                  t1 = fmaf(b, (bf16hi(y2u) - m2b) * r2b, t1);
-                }
-              }
-            }
-            if (ew == 0 && lane == 0) CF_EVENT(2, 0x606);
-            float* st = g_stat + (rg * 64 + cp * 2) * 3;
-            st[0] = s0; st[1] = q0; st[2] = t0;
-            st[3] = s1; st[4] = q1; st[5] = t1;
-            bar_sync_named(bar_id, 128);
-            if (etid < 64) {
-              float s = 0.f, qq = 0.f, tt = 0.f;
+            // statistics of the stored (bf16-rounded) values
+            float* wa = w_acc + chunk * 64 + 2 * lane;
+            float x[64];
 #pragma unroll
-              for (int gg = 0; gg < 4; ++gg) {
-                s += g_stat[(gg * 64 + etid) * 3];
-                qq += g_stat[(gg * 64 + etid) * 3 + 1];
-                tt += g_stat[(gg * 64 + etid) * 3 + 2];
+            for (int j = 0; j < 32; ++j) { x[2 * j] = bf16lo(u[j]); x[2 * j + 1] = bf16hi(u[j]); }
+            const float2 s0 = warp_colsum64(x, lane);
+            wa[0] += s0.x; wa[1] += s0.y;
+            if (!bwd) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { const float a = bf16lo(u[j]), b = bf16hi(u[j]); x[2 * j] = a * a; x[2 * j + 1] = b * b; }
+              const float2 s1 = warp_colsum64(x, lane);
+              wa[p.block_n] += s1.x; wa[p.block_n + 1] += s1.y;
+            } else {
+              // sum dz * y (raw); the finalize turns it into sum dz * xhat = rstd * (sum dz*y - mean * sum dz)
+              uint32_t r[32];
+              if (valid) load_row64(p.y1 + goff, r);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                x[2 * j] = valid ? bf16lo(u[j]) * bf16lo(r[j]) : 0.f;
+                x[2 * j + 1] = valid ? bf16hi(u[j]) * bf16hi(r[j]) : 0.f;
               }
-              g_acc[n_base + etid] += s;  // units are visited in a fixed order: deterministic
-              g_acc[p.n_total + n_base + etid] += qq;
-              g_acc[2 * p.n_total + n_base + etid] += tt;
+              const float2 s1 = warp_colsum64(x, lane);
+              wa[p.block_n] += s1.x; wa[p.block_n + 1] += s1.y;
+              if (bwd2) {
+                if (valid) load_row64(p.y2 + goff, r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  x[2 * j] = valid ? bf16lo(u[j]) * bf16lo(r[j]) : 0.f;
+                  x[2 * j + 1] = valid ? bf16hi(u[j]) * bf16hi(r[j]) : 0.f;
+                }
+                const float2 s2 = warp_colsum64(x, lane);
+                wa[2 * p.block_n] += s2.x; wa[2 * p.block_n + 1] += s2.y;
+              }
             }
           }
+          if (ew == 0 && lane == 0) CF_EVENT(2, 0x606);
         }
       }
       if (ew == 0 && lane == 0) CF_EVENT(2, 0x600);
@@ -350,81 +347,86 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     }
 
     if (do_stats) {
-      // ---- per-CTA partial, then the last CTA to finish folds all partials and finalizes ----
+      // ---- per-CTA partial (the eight warps' sums in a fixed order), then the last CTA to finish folds all partials ----
       const int tid = ew * 32 + lane;  // 0..255
       if (tid == 0) CF_EVENT(2, 0x700);
       bar_sync_named(3, 256);
-      float* gp = p.partials + (size_t)blockIdx.x * nq * p.n_total;
-      for (int i = tid; i < nq * p.n_total; i += 256) gp[i] = s_acc[i] + s_acc[3 * p.n_total + i];
-      __threadfence();
+      // this CTA's sums (the eight warps in a fixed order) go into the global per-channel accumulators [3][n_total] with
+      // red.global.add; the last CTA to arrive reads them, finalizes and re-zeroes them for the next launch
+      const int nb = blockIdx.x % p.n_blocks;  // gridDim.x is a multiple of n_blocks: one channel block per CTA
+      for (int i = tid; i < nq * p.block_n; i += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) t += s_wacc[wv * 3 * p.block_n + i];
+        const int k = i / p.block_n, c = i - k * p.block_n;
+        atomicAdd(p.partials + k * p.n_total + nb * p.block_n + c, t);
+      }
       bar_sync_named(3, 256);
       if (tid == 0) {
+        // release: the barrier ordered every thread's atomics before this fence (cumulativity); acquire after the count
+        __threadfence();
         const unsigned int done = atomicAdd(p.counter, 1u);
-        *s_flag = (done == gridDim.x - 1) ? 1u : 0u;
+        const bool last = (done == gridDim.x - 1);
+        if (last) __threadfence();
+        *s_flag = last ? 1u : 0u;
       }
       bar_sync_named(3, 256);
       if (tid == 0) CF_EVENT(2, 0x701);
       if (*s_flag) {
-        __threadfence();
-        double* s_fold = (double*)staging;  // [slices][nq][n_total] doubles <= 24 KB
-        const int quads = p.n_total >> 2;
-        const int slices = 256 / quads;     // n_total 64 -> 16, 512 -> 2
-        {
-          const int qd = tid % quads, sl = tid / quads;
-          double a[3][4];
+        // per-channel inputs of the finalize (loads issued together, one L2 round trip)
+        float pre[2][4];
 #pragma unroll
-          for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) a[k][e] = 0.0;
-          if (sl < slices) {
-#pragma unroll 4
-            for (unsigned int b = sl; b < gridDim.x; b += slices) {
-              const float* bp = p.partials + (size_t)b * nq * p.n_total + qd * 4;
-#pragma unroll
-              for (int k = 0; k < 3; ++k) {
-                if (k < nq) {
-                  const float4 x = __ldcg((const float4*)(bp + k * p.n_total));
-                  a[k][0] += (double)x.x; a[k][1] += (double)x.y; a[k][2] += (double)x.z; a[k][3] += (double)x.w;
-                }
-              }
+        for (int it = 0; it < 2; ++it) {
+          const int c = tid + it * 256;
+          if (c < p.n_total) {
+            if (!bwd) {
+              pre[it][0] = __ldg(p.gamma + c); pre[it][1] = __ldg(p.beta + c);
+              pre[it][2] = p.update_running ? p.running_mean[c] : 0.f; pre[it][3] = p.update_running ? p.running_var[c] : 0.f;
+            } else {
+              pre[it][0] = __ldg(p.stat1 + 2 * p.n_total + c); pre[it][1] = __ldg(p.stat1 + 3 * p.n_total + c);
+              pre[it][2] = bwd2 ? __ldg(p.stat2 + 2 * p.n_total + c) : 0.f; pre[it][3] = bwd2 ? __ldg(p.stat2 + 3 * p.n_total + c) : 0.f;
             }
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) s_fold[((size_t)sl * 3 + k) * p.n_total + qd * 4 + e] = a[k][e];
           }
         }
-        bar_sync_named(3, 256);
-        if (tid == 0) CF_EVENT(2, 0x702);
-        for (int c = tid; c < p.n_total; c += 256) {
-          double S[3] = {0.0, 0.0, 0.0};
-          for (int sl = 0; sl < slices; ++sl)
+        const double inv_count = 1.0 / p.count;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) S[k] += s_fold[((size_t)sl * 3 + k) * p.n_total + c];
+        for (int it = 0; it < 2; ++it) {
+          const int c = tid + it * 256;
+          if (c >= p.n_total) break;
+          double S[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            if (k < nq) {
+              S[k] = (double)__ldcg(p.partials + k * p.n_total + c);
+              p.partials[k * p.n_total + c] = 0.f;
+            }
+          }
           if (!bwd) {
-            const double mean_d = S[0] / p.count;
-            double var_d = S[1] / p.count - mean_d * mean_d;
+            const double mean_d = S[0] * inv_count;
+            double var_d = S[1] * inv_count - mean_d * mean_d;
             if (var_d < 0.0) var_d = 0.0;
             const float mean = (float)mean_d, var = (float)var_d;
             if (p.update_running) {
-              const double unbiased = p.count > 1.0 ? var_d * p.count / (p.count - 1.0) : var_d;
-              p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
-              p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)unbiased;
+              const float unbiased = p.count > 1.0 ? (float)(var_d * (p.count / (p.count - 1.0))) : var;
+              p.running_mean[c] = (1.f - p.momentum) * pre[it][2] + p.momentum * mean;
+              p.running_var[c] = (1.f - p.momentum) * pre[it][3] + p.momentum * unbiased;
             }
             const float rstd = 1.0f / sqrtf(var + p.eps);
-            const float sc = p.gamma[c] * rstd;
+            const float sc = pre[it][0] * rstd;
             p.vec[c] = sc;
-            p.vec[p.n_total + c] = p.beta[c] - mean * sc;
+            p.vec[p.n_total + c] = pre[it][1] - mean * sc;
             p.vec[2 * p.n_total + c] = mean;
             p.vec[3 * p.n_total + c] = rstd;
           } else {
-            const float bs = (float)S[0], bd1 = (float)S[1];
+            // sum dz * xhat = rstd * (sum dz * y - mean * sum dz)
+            const float bs = (float)S[0];
+            const float bd1 = (float)((double)pre[it][1] * (S[1] - (double)pre[it][0] * S[0]));
             p.bred1[c] = bs;
             p.bred1[p.n_total + c] = bd1;
             if (p.dgamma1) p.dgamma1[c] += bd1;
             if (p.dbeta1) p.dbeta1[c] += bs;
             if (bwd2) {
-              const float bd2 = (float)S[2];
+              const float bd2 = (float)((double)pre[it][3] * (S[2] - (double)pre[it][2] * S[0]));
               p.bred2[c] = bs;
               p.bred2[p.n_total + c] = bd2;
               if (p.dgamma2) p.dgamma2[c] += bd2;

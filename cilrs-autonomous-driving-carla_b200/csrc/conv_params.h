@@ -90,7 +90,7 @@ struct PadGeom {
 
 constexpr int CF_THREADS = 320;       // warp 0: TMA, warp 1: MMA, warps 2..9: two epilogue groups of 4 warps
 constexpr int CF_MAX_A_STAGES = 4;
-constexpr int CF_MAX_B_STAGES = 20;   // resident-weights mode keeps all taps x chunks (<= 18) in shared memory
+constexpr int CF_MAX_B_STAGES = 16;
 constexpr int CF_MAX_ACC = 8;
 constexpr int CF_STAGING_BYTES = 2 * 128 * 128;  // one 128 x 64 bf16 chunk per epilogue group
 
@@ -116,6 +116,7 @@ struct FlatConvParams {
   int tap_slab[9];
   int halo;                    // Wp + 1
   int a_box_rows, a_boxes;     // slab = a_boxes boxes of a_box_rows rows
+  int tap_group;               // taps per weight stage (one mbarrier round trip per group); 9 with resident weights
   int a_stages, b_stages, b_resident, acc_sets;
   int m_tiles;
   int flags;
@@ -124,7 +125,7 @@ struct FlatConvParams {
   const __nv_bfloat16* mask;
   const float* scale;
   const float* bias;
-  float* partials;             // [gridDim.x][nq][n_total]
+  float* partials;             // [3][n_total] global accumulators (zero on entry, left zero by the kernel)
   unsigned int* counter;
   // CF_STATS: BatchNorm forward finalize (by the last CTA)
   const float* gamma;
@@ -158,8 +159,7 @@ struct WgradFlatParams {
   CUtensorMap tmX;   // 2-D (cin, flat pixels), box (64, x_box_rows)
   int total_rows, k_tiles;
   int co_blocks, m_halves, ci_chunks;
-  int tap_groups;
-  int group_first[2], group_count[2];  // taps of each group (consecutive tap ids)
+  int tap_groups;                      // 3: one filter row per CTA
   int tap_shift[9];
   int x_box_rows, x_boxes;             // slab rows per stage = x_boxes * x_box_rows
   int split_z, num_stages;

@@ -124,6 +124,7 @@ struct Model {
   uint8_t* pool_arg;
   float* stats;          // shared stats-partials scratch
   float* bwd_partial;    // BN backward partials
+  float* stat_acc;
   unsigned int* counters;
   float* unit_vec;       // [2][64]: ones, zeros (max-pool on already-activated stem output)
   float* feat;           // [B,512]
@@ -259,6 +260,7 @@ static long long carve(Model& m, char* base) {
   // deeper layers have fewer tiles x more channels; bound by B*44*100/64 tiles * 2 * 64
   m.stats = (float*)bp.take(256LL * 2 * 512 * 4);  // one (sum, sumsq)[C<=512] partial per persistent conv CTA (<= SM count)
   m.bwd_partial = (float*)bp.take((long long)EW_MAX_BLOCKS * 2 * 512 * 4);
+  m.stat_acc = (float*)bp.take(3 * 512 * 4);  // flat kernels: per-channel statistics accumulators (kept zero between launches)
   m.counters = (unsigned int*)bp.take(64);
   m.unit_vec = (float*)bp.take(2 * 64 * 4);
   m.feat = (float*)bp.take((long long)B * 512 * 4);
@@ -441,7 +443,7 @@ static int run_bn_apply(int B, const PadGeom& g, const __nv_bfloat16* x, const B
 static int launch_flat_fwd(Model& m, int idx, const BnRef& bn, double count, int update_running, cudaStream_t s) {
   FlatConvParams f = m.flat_plans[idx];
   if (f.flags & CF_STATS) {
-    f.partials = m.stats; f.counter = m.counters + 1;
+    f.partials = m.stat_acc; f.counter = m.counters + 1;
     f.gamma = m.params + m.slots[bn.gamma].off; f.beta = m.params + m.slots[bn.beta].off;
     f.running_mean = m.buffers + bn.rm_off; f.running_var = m.buffers + bn.rv_off;
     f.nbt = m.nbt ? m.nbt + bn.nbt_idx : nullptr;
@@ -572,7 +574,7 @@ static int run_wgrad_flat(Model& m, int idx, int slot, cudaStream_t s) {
 static int launch_flat_bwd(Model& m, int idx, const BnRef* bn1, const BnRef* bn2, cudaStream_t s) {
   FlatConvParams f = m.flat_plans[idx];
   if (f.flags & CF_BNBWD) {
-    f.partials = m.stats; f.counter = m.counters + 1;
+    f.partials = m.stat_acc; f.counter = m.counters + 1;
     f.dgamma1 = m.grads + m.slots[bn1->gamma].off; f.dbeta1 = m.grads + m.slots[bn1->beta].off;
     if (f.flags & CF_BNBWD2) { f.dgamma2 = m.grads + m.slots[bn2->gamma].off; f.dbeta2 = m.grads + m.slots[bn2->beta].off; }
   }

@@ -3,11 +3,12 @@
 //   dW[co, tap, ci] = sum over flat pixels f of  dY[f, co] * X[f + shift_tap, ci]
 //
 // dY is zero on the padding pixels of the layout, so the sum may run over every flat pixel. Both operands are
-// "MN-major" (one pixel per 128-byte shared-memory row = the K index). Per 128-pixel K tile ONE slab of
-// (128 + Wp + 1) pixels of X is loaded; the taps of the CTA's tap group are row-shifted descriptors into it (the old
-// kernel loaded one X box per tap). A CTA owns [128 co] x [64 ci] x [4 or 5 taps] and a slice of the K tiles; the
-// accumulator stays in TMEM for the whole slice and is added to the fp32 OIHW gradient with red.global.add.
-//   warp 0 : TMA producer      warp 1 : MMA issuer      warps 2..5 : epilogue
+// "MN-major" (one pixel per 128-byte shared-memory row = the K index). A CTA owns [128 co] x [64 ci] x [one filter row =
+// 3 taps] and a slice of the 128-pixel K tiles. Per K tile ONE slab of 130 pixels of X is loaded; the three taps
+// (dw = -1, 0, +1) are ONE tcgen05.mma with N = 192 whose B descriptor walks its three 64-column slabs with a leading
+// byte offset of 128 = one pixel row, i.e. the slabs are the same shared-memory data shifted by one pixel each.
+// The accumulator stays in TMEM for the whole slice and is added to the fp32 OIHW gradient with red.global.add.
+//   warp 0 : TMA producer      warp 1 : MMA issuer (whole warp, one elected lane issues)      warps 2..5 : epilogue
 #pragma once
 #include "common.cuh"
 #include "conv_params.h"
@@ -16,7 +17,7 @@ namespace cilrs {
 
 __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_constant__ WgradFlatParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -59,14 +60,13 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
   // work item of this CTA
   int wi = blockIdx.x;
   const int z = wi % p.split_z; wi /= p.split_z;
-  const int tg = wi % p.tap_groups; wi /= p.tap_groups;
+  const int tg = wi % 3; wi /= 3;   // filter row dh = tg - 1
   const int cic = wi % p.ci_chunks; wi /= p.ci_chunks;
   const int cob = wi;
   const int per = (p.k_tiles + p.split_z - 1) / p.split_z;
   const int kt_begin = z * per;
   const int kt_end = min(p.k_tiles, kt_begin + per);
-  const int t_first = p.group_first[tg], t_count = p.group_count[tg];
-  const int min_shift = p.tap_shift[t_first];  // tap shifts increase with the tap id
+  const int min_shift = p.tap_shift[tg * 3];  // dw = -1 of this filter row
   const uint32_t tx_bytes = (uint32_t)(p.m_halves * WG_SLAB + x_bytes);
 
   if (warp == 0) {
@@ -86,31 +86,34 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t first = 1;
-      for (int kt = kt_begin; kt < kt_end; ++kt) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t x_addr = a_addr + 2 * WG_SLAB;
-        for (int j = 0; j < t_count; ++j) {
-          const uint32_t b_addr = x_addr + (uint32_t)((p.tap_shift[t_first + j] - min_shift) * 128);
+    // whole warp in uniform control flow (descriptors stay in uniform registers), one elected lane issues.
+    // One CTA per SM (shared memory) and the first allocation of the SM: the accumulator starts at TMEM column 0.
+    if (tmem_base != 0) __trap();
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(128, 192, 1, 1);
+    const uint64_t descA0 = umma_desc_sw128(smem_u32(smem), WG_SLAB, 1024);             // two 64-co slabs 16 KB apart
+    const uint64_t descB0 = umma_desc_sw128(smem_u32(smem) + 2 * WG_SLAB, 128, 1024);   // three 64-ci slabs one pixel row apart
+    const uint32_t stage_units = (uint32_t)(stage_bytes >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t first = 1;
+    for (int kt = kt_begin; kt < kt_end; ++kt) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint64_t da = descA0 + (uint64_t)((uint32_t)stage * stage_units);
+      const uint64_t db = descB0 + (uint64_t)((uint32_t)stage * stage_units);
+      if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {  // 8 x (K = 16 pixels = 16 rows of 128 bytes)
-            const uint64_t da = umma_desc_sw128(a_addr + kk * 2048, WG_SLAB, 1024);
-            const uint64_t db = umma_desc_sw128(b_addr + kk * 2048, WG_SLAB, 1024);
-            umma_bf16(tmem_base + (uint32_t)(j * 64), da, db, idesc, (first && kk == 0) ? 0u : 1u);
-          }
-        }
-        first = 0;
+        for (int kk = 0; kk < 8; ++kk)  // 8 x (K = 16 pixels = 16 rows of 128 bytes = 128 sixteen-byte units)
+          umma_bf16(0u, da + kk * 128, db + kk * 128, idesc, (first && kk == 0) ? 0u : 1u);
         umma_commit(&empty_bar[stage]);
-        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(done_bar);
+      __syncwarp();
+      first = 0;
+      if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
     }
+    if (leader) umma_commit(done_bar);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -118,14 +121,13 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
     if (kt_end > kt_begin) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
-      const int ncols = 64 * t_count;
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
+      for (int c0 = 0; c0 < 192; c0 += 32) {
         uint32_t v[32];
         __syncwarp();
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
         if (row < p.m_halves * 64 && co < p.cout) {
-          const int t = t_first + (c0 >> 6);
+          const int t = tg * 3 + (c0 >> 6);
           float* gp = p.grad + ((size_t)co * p.cin + cic * 64 + (c0 & 63)) * 9 + t;
 #pragma unroll
           for (int e = 0; e < 32; ++e) atomicAdd(gp + e * 9, __uint_as_float(v[e]));
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 

@@ -129,7 +129,7 @@ typedef struct cilrs_flat_conv_args {
   float* bred2;
   float* dgamma2;
   float* dbeta2;
-  float* partials_ws;       /* cilrs_conv_flat_workspace_floats(out_c) floats */
+  float* partials_ws;       /* cilrs_conv_flat_workspace_floats(out_c) floats, ZEROED; left zero by the kernel */
   unsigned int* counter_ws; /* one zeroed uint32, left zero by the kernel */
 } cilrs_flat_conv_args;
 long long cilrs_flat_rows(int batch, int H, int W);

@@ -43,16 +43,17 @@ for name, h, w, c in layers:
         for bn in (64, 128, 256):
             if c % bn or mt * bn > 512:
                 continue
-            for r in (0, 1):
-                for a_st in (2, 3):
-                    os.environ["CILRS_FLAT_SHAPE"] = "%d,%d,%d,%d,0" % (mt, bn, r, a_st)
-                    try:
-                        t = timeit_hot(lambda: _lib.call("cilrs_conv_flat", a, sp))
-                    except RuntimeError as e:
-                        continue
-                    res.append((t, mt, bn, r, a_st))
+            for r, G in ((1, 9), (0, 3), (0, 2), (0, 1)):
+                os.environ["CILRS_FLAT_SHAPE"] = "%d,%d,%d,%d" % (mt, bn, r, G)
+                os.environ["CILRS_FLAT_DEBUG"] = "1"
+                try:
+                    t = timeit_hot(lambda: _lib.call("cilrs_conv_flat", a, sp))
+                except RuntimeError as e:
+                    continue
+                res.append((t, mt, bn, r, G))
     del os.environ["CILRS_FLAT_SHAPE"]
+    del os.environ["CILRS_FLAT_DEBUG"]
     t_auto = timeit_hot(lambda: _lib.call("cilrs_conv_flat", a, sp))
     res.sort()
     print("%s %s auto %.1f us (%.0f TF) | best:" % (name, mode, t_auto * 1e3, flops / t_auto / 1e9),
-          "  ".join("%.1fus mt%d bn%d r%d a%d" % (t * 1e3, mt, bn, r, a_st) for t, mt, bn, r, a_st in res[:8]))
+          "  ".join("%.1fus mt%d bn%d r%d G%d" % (t * 1e3, mt, bn, r, G) for t, mt, bn, r, G in res[:10]))
