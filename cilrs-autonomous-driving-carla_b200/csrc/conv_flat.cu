@@ -207,7 +207,7 @@ int launch_flat_conv(const FlatConvParams* p, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // wgrad
 // ------------------------------------------------------------------------------------------------
-int build_wgrad_flat(WgradFlatParams* p, int batch, const PadGeom& g, int cin, int cout, const void* dy, const void* x, float* dw) {
+int build_wgrad_flat(WgradFlatParams* p, int batch, const PadGeom& g, int cin, int cout, const void* dy, const void* x, float* scratch) {
   if (batch < 1 || g.H < 1 || g.W < 1 || g.Hp < g.H || g.Wp <= g.W || g.Wp < 3) return ERR_INVALID;
   if (cin % 64 || cout % 64 || cin < 64 || cout < 64) return ERR_UNSUPPORTED;
   memset(p, 0, sizeof(*p));
@@ -231,7 +231,7 @@ int build_wgrad_flat(WgradFlatParams* p, int batch, const PadGeom& g, int cin, i
   if (st < 2) return ERR_UNSUPPORTED;
   p->num_stages = st;
   p->cout = cout; p->cin = cin;
-  p->grad = dw;
+  p->scratch = scratch;
   int e = encode_2d_map(&p->tmDY, dy, cout, p->total_rows, 64, 128);
   if (e) return e;
   return encode_2d_map(&p->tmX, x, cin, p->total_rows, 64, p->x_box_rows);
@@ -245,7 +245,24 @@ int launch_wgrad_flat(const WgradFlatParams* p, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = p->co_blocks * p->ci_chunks * p->tap_groups * p->split_z;
+  if ((long long)grid * 128 * 192 * 4 > WF_SCRATCH_BYTES || !p->scratch) return ERR_WORKSPACE;
   wgrad_flat_kernel<<<grid, WF_THREADS, CG_SMEM_TOTAL, s>>>(*p); ++g_cilrs_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+// append the reduction of one flat wgrad to a job list (the list is a kernel parameter, see wgrad_reduce_kernel)
+int add_wgrad_reduce_job(WgradReduceJobs* jobs, const WgradFlatParams* p, long long grad_off) {
+  if (jobs->n >= 16) return ERR_INVALID;
+  WgradReduceJob& j = jobs->job[jobs->n++];
+  j.scratch = p->scratch; j.grad_off = grad_off; j.cout = p->cout; j.cin = p->cin; j.ci_chunks = p->ci_chunks; j.split_z = p->split_z;
+  j.first_block = jobs->total_blocks;
+  jobs->total_blocks += p->cout * p->ci_chunks;
+  return OK;
+}
+
+int launch_wgrad_reduce(const WgradReduceJobs* jobs, float* grads, cudaStream_t s) {
+  if (jobs->n == 0) return OK;
+  wgrad_reduce_kernel<<<jobs->total_blocks, 192, 0, s>>>(*jobs, grads); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -303,13 +320,22 @@ int cilrs_conv_flat_trace(unsigned long long* out, int* counts) {
 
 size_t cilrs_conv_flat_workspace_floats(int out_c) { return (size_t)256 * 3 * out_c; }
 
-int cilrs_wgrad_flat(int batch, int H, int W, int in_c, int out_c, const void* dy, const void* x, float* dw_oihw, void* stream) {
-  if (!dy || !x || !dw_oihw) return ERR_INVALID;
+size_t cilrs_wgrad_flat_workspace_bytes(void) { return (size_t)WF_SCRATCH_BYTES; }
+
+int cilrs_wgrad_flat(int batch, int H, int W, int in_c, int out_c, const void* dy, const void* x, float* dw_oihw, float* scratch_ws,
+                     void* stream) {
+  if (!dy || !x || !dw_oihw || !scratch_ws) return ERR_INVALID;
   const PadGeom g{H, W, H + 1, W + 1};
   WgradFlatParams p;
-  int st = build_wgrad_flat(&p, batch, g, in_c, out_c, dy, x, dw_oihw);
+  int st = build_wgrad_flat(&p, batch, g, in_c, out_c, dy, x, scratch_ws);
   if (st) return st;
-  return launch_wgrad_flat(&p, (cudaStream_t)stream);
+  st = launch_wgrad_flat(&p, (cudaStream_t)stream);
+  if (st) return st;
+  WgradReduceJobs jobs;
+  jobs.n = 0; jobs.total_blocks = 0;
+  st = add_wgrad_reduce_job(&jobs, &p, 0);
+  if (st) return st;
+  return launch_wgrad_reduce(&jobs, dw_oihw, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -57,8 +57,12 @@ int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channe
                     const void* w, void* out, int flags);
 int flat_conv_grid(const FlatConvParams* p);
 int launch_flat_conv(const FlatConvParams* p, cudaStream_t s);
-int build_wgrad_flat(WgradFlatParams* p, int batch, const PadGeom& g, int cin, int cout, const void* dy, const void* x, float* dw);
+struct WgradReduceJobs;
+// scratch: WF_SCRATCH_BYTES of split-K partial tiles, folded into the OIHW gradient by the reduce launch
+int build_wgrad_flat(WgradFlatParams* p, int batch, const PadGeom& g, int cin, int cout, const void* dy, const void* x, float* scratch);
 int launch_wgrad_flat(const WgradFlatParams* p, cudaStream_t s);
+int add_wgrad_reduce_job(WgradReduceJobs* jobs, const WgradFlatParams* p, long long grad_off);
+int launch_wgrad_reduce(const WgradReduceJobs* jobs, float* grads, cudaStream_t s);
 
 int launch_conv_gemm(const ConvGemmParams* p, cudaStream_t s);
 int conv_gemm_grid(const ConvGemmParams* p);  // CTAs launched = number of stats partials

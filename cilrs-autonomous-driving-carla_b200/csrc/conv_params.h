@@ -164,7 +164,20 @@ struct WgradFlatParams {
   int x_box_rows, x_boxes;             // slab rows per stage = x_boxes * x_box_rows
   int split_z, num_stages;
   int cout, cin;
-  float* grad;                         // fp32 OIHW
+  float* scratch;                      // split-K partial tiles [tile][z][128][192] fp32 (wgrad_reduce_kernel folds them)
 };
+
+struct WgradReduceJob {
+  const float* scratch;
+  long long grad_off;   // float offset of the OIHW gradient inside the gradient arena
+  int cout, cin, ci_chunks, split_z;
+  int first_block;      // CTAs [first_block, first_block + cout * ci_chunks) belong to this job
+};
+struct WgradReduceJobs {  // passed by value as the kernel parameter: no device-side table
+  int n, total_blocks;
+  WgradReduceJob job[16];
+};
+
+constexpr long long WF_SCRATCH_BYTES = 160LL * 128 * 192 * 4;  // >= (#CTAs <= SM count) tiles of 128 x 192 fp32 per convolution
 
 }  // namespace cilrs

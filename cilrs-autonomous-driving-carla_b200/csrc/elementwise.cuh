@@ -245,7 +245,7 @@ struct BnBwdReduceParams {
   const float* rstd;
   long long nvec;
   int C;
-  float* partial;       // [gridDim.x][2][C]
+  float* partial;       // [2][C] global accumulators, zero on entry and left zero
   unsigned int* counter;
   float* bsum;          // [C]
   float* bdot;          // [C]
@@ -263,26 +263,40 @@ struct BnBwdReduceParams {
 };
 
 CILRS_DEVINL Vec8 stem_gather_grad(const BnBwdReduceParams& p, int n, int h, int w, int cg) {
-  // gradient reaching conv1-output pixel (h, w): every pool window (oh, ow) that contains it and selected it
+  // gradient reaching conv1-output pixel (h, w): every pool window (oh, ow) that contains it and selected it.
+  // Windows: oh in {h/2, (h+1)/2}, ow in {w/2, (w+1)/2} (the two coincide for even coordinates). All four loads are issued
+  // before any use.
   Vec8 acc;
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc.v[k] = 0.f;
-  for (int oh = (h) / 2; oh <= (h + 1) / 2; ++oh) {
-    if (oh >= p.OH) continue;
-    const int r = h - (oh * 2 - 1);
-    if (r < 0 || r > 2) continue;
-    for (int ow = (w) / 2; ow <= (w + 1) / 2; ++ow) {
-      if (ow >= p.OW) continue;
-      const int s = w - (ow * 2 - 1);
-      if (s < 0 || s > 2) continue;
-      const long long o = (((long long)n * p.OH + oh) * p.OW + ow) * p.C + cg;  // arg-max codes are stored densely
-      const uint2 am = *reinterpret_cast<const uint2*>(p.argmax + o);
-      const Vec8 gv = load8(p.g + (((long long)n * p.OHp + oh) * p.OWp + ow) * p.C + cg);
-      const int code = r * 3 + s;
+  uint2 am[4];
+  uint4 gq[4];
+  int code[4];
+  bool ok[4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int oh = (h + a) >> 1, ow = (w + b) >> 1;
+      const int r = h - (oh * 2 - 1), s = w - (ow * 2 - 1);
+      const int q = a * 2 + b;
+      ok[q] = oh < p.OH && ow < p.OW && r >= 0 && r <= 2 && s >= 0 && s <= 2 && !(a == 1 && (h & 1) == 0) && !(b == 1 && (w & 1) == 0);
+      code[q] = r * 3 + s;
+      if (ok[q]) {
+        am[q] = *reinterpret_cast<const uint2*>(p.argmax + (((long long)n * p.OH + oh) * p.OW + ow) * p.C + cg);  // dense codes
+        gq[q] = *reinterpret_cast<const uint4*>(p.g + (((long long)n * p.OHp + oh) * p.OWp + ow) * p.C + cg);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (ok[q]) {
+      const uint32_t gw[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int sel = (int)(((k < 4 ? am.x : am.y) >> ((k & 3) * 8)) & 0xFF);
-        if (sel == code) acc.v[k] += gv.v[k];
+        const int sel = (int)(((k < 4 ? am[q].x : am[q].y) >> ((k & 3) * 8)) & 0xFF);
+        const float gv = (k & 1) ? bf16hi(gw[k >> 1]) : bf16lo(gw[k >> 1]);
+        if (sel == code[q]) acc.v[k] += gv;
       }
     }
   }
@@ -303,42 +317,61 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
   float a_sum[8], a_dot[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { a_sum[k] = 0.f; a_dot[k] = 0.f; }
-  PadWalk walk;
-  if (!STEM) walk.init(i / groups, stride / groups, p.geom);
-  for (; i < p.nvec; i += stride) {
-    if (!STEM) {
-      const bool ok = walk.valid();
-      walk.next();
-      if (!ok) {  // padding pixel: g may hold stale data there; it contributes nothing and dz stays zero
-        if (p.dz_out) store8_zero(p.dz_out + i * 8);
-        continue;
+  if (!STEM) {
+    // four vectors per iteration, all loads issued before the first use (12 x 16 bytes in flight per thread)
+    PadWalk walk;
+    walk.init(i / groups, stride / groups, p.geom);
+    for (; i < p.nvec; i += 4 * stride) {
+      bool ok[4], in[4];
+      Vec8 yv[4], gv[4], av[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        in[u] = i + u * stride < p.nvec;
+        ok[u] = in[u] && walk.valid();
+        walk.next();
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ok[u]) {
+          const long long o = (i + u * stride) * 8;
+          yv[u] = load8(p.y + o);
+          gv[u] = load8(p.g + o);
+          if (p.act) av[u] = load8(p.act + o);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long o = (i + u * stride) * 8;
+        if (ok[u]) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (p.act && !(av[u].v[k] > 0.f)) gv[u].v[k] = 0.f;
+            a_sum[k] += gv[u].v[k];
+            a_dot[k] = fmaf(gv[u].v[k], (yv[u].v[k] - mean.v[k]) * rstd.v[k], a_dot[k]);
+          }
+          if (p.dz_out) store8(p.dz_out + o, gv[u]);
+        } else if (in[u] && p.dz_out) {
+          store8_zero(p.dz_out + o);  // padding pixel: g may hold stale data there; it contributes nothing and dz stays zero
+        }
       }
     }
-    const Vec8 yv = load8(p.y + i * 8);
-    Vec8 gv;
-    if (STEM) {
+  } else {
+    for (; i < p.nvec; i += stride) {
+      const Vec8 yv = load8(p.y + i * 8);
       const long long pix = i / groups;
       const int w = (int)(pix % p.W);
       const int h = (int)((pix / p.W) % p.H);
       const int n = (int)(pix / ((long long)p.W * p.H));
-      gv = stem_gather_grad(p, n, h, w, cg);
+      Vec8 gv = stem_gather_grad(p, n, h, w, cg);
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         if (!(fmaf(yv.v[k], sc.v[k], sh.v[k]) > 0.f)) gv.v[k] = 0.f;
-    } else {
-      gv = load8(p.g + i * 8);
-      if (p.act) {
-        const Vec8 av = load8(p.act + i * 8);
+      if (p.dz_out) store8(p.dz_out + i * 8, gv);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (!(av.v[k] > 0.f)) gv.v[k] = 0.f;
+      for (int k = 0; k < 8; ++k) {
+        a_sum[k] += gv.v[k];
+        a_dot[k] = fmaf(gv.v[k], (yv.v[k] - mean.v[k]) * rstd.v[k], a_dot[k]);
       }
-    }
-    if (p.dz_out) store8(p.dz_out + i * 8, gv);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      a_sum[k] += gv.v[k];
-      a_dot[k] = fmaf(gv.v[k], (yv.v[k] - mean.v[k]) * rstd.v[k], a_dot[k]);
     }
   }
   // threads with the same channel group are EW_THREADS/groups apart in steps of `groups`
@@ -353,38 +386,24 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
 #pragma unroll
       for (int k = 0; k < 8; ++k) { t_sum[k] += s_red[t][k]; t_dot[k] += s_red[EW_THREADS + t][k]; }
     }
-    float* pp = p.partial + (size_t)blockIdx.x * 2 * p.C + threadIdx.x * 8;
+    // global per-channel accumulators [2][C] (zero on entry, re-zeroed by the last CTA)
+    float* pp = p.partial + threadIdx.x * 8;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { pp[k] = t_sum[k]; pp[p.C + k] = t_dot[k]; }
+    for (int k = 0; k < 8; ++k) { atomicAdd(pp + k, t_sum[k]); atomicAdd(pp + p.C + k, t_dot[k]); }
   }
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     const unsigned int done = atomicAdd(p.counter, 1u);
     s_last = (done == gridDim.x - 1);
+    if (s_last) __threadfence();
   }
   __syncthreads();
   if (s_last) {
-    __threadfence();
-    // fold the per-CTA partials: S = 2048/C slices of CTAs per channel in parallel (all 256 threads busy), then a
-    // fixed-order combine -> deterministic
-    float* s_fin = &s_red[0][0];  // [S][2][C] floats = 4096 floats = all of s_red
-    const int S = 2048 / p.C;
-    for (int j = threadIdx.x; j < S * p.C; j += EW_THREADS) {
-      const int c = j % p.C, sl = j / p.C;
-      float s = 0.f, d = 0.f;
-#pragma unroll 4
-      for (unsigned int b = sl; b < gridDim.x; b += S) {
-        s += __ldcg(p.partial + (size_t)b * 2 * p.C + c);
-        d += __ldcg(p.partial + (size_t)b * 2 * p.C + p.C + c);
-      }
-      s_fin[(sl * 2 + 0) * p.C + c] = s;
-      s_fin[(sl * 2 + 1) * p.C + c] = d;
-    }
-    __syncthreads();
     for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
-      float s = 0.f, d = 0.f;
-      for (int sl = 0; sl < S; ++sl) { s += s_fin[(sl * 2 + 0) * p.C + c]; d += s_fin[(sl * 2 + 1) * p.C + c]; }
+      const float s = __ldcg(p.partial + c), d = __ldcg(p.partial + p.C + c);
+      p.partial[c] = 0.f;
+      p.partial[p.C + c] = 0.f;
       p.bsum[c] = s;
       p.bdot[c] = d;
       if (p.dgamma) p.dgamma[c] += d;
@@ -487,11 +506,9 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApp
 // grid size for the vector kernels: a multiple of the channel-group count keeps every thread on one channel group
 // reductions: ~1 CTA per SM is enough with the 4-way unrolled loop, and keeps the partials the last CTA folds small
 inline int ew_reduce_grid(long long nvec, int C) {
-  long long cap = 16384 / C;  // C=64: 256 -> 148, C=128: 128, C=256: 64, C=512: 32
-  if (cap > 148) cap = 148;
-  if (cap < 16) cap = 16;
+  (void)C;
   long long blocks = (nvec + (long long)EW_THREADS * 4 - 1) / ((long long)EW_THREADS * 4);
-  if (blocks > cap) blocks = cap;
+  if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }

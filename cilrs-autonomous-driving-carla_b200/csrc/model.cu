@@ -145,6 +145,9 @@ struct Model {
   std::vector<WgradParams> wold_plans;
   std::vector<FlatConvParams> flat_plans;    // padded-flat kernel: 3x3 stride-1 fprop and dgrad
   std::vector<WgradFlatParams> wflat_plans;
+  std::vector<long long> wflat_grad_off;     // gradient-arena offset each flat wgrad plan reduces into
+  WgradReduceJobs red_jobs[4];               // split-K reductions of the flat wgrads, one launch per backward part (layer4..layer1)
+  float* wscratch = nullptr;                 // WF_SCRATCH_BYTES per flat 3x3 convolution
   int stem_fwd = -1, stem_wgrad = -1;
   // resumable backward (so the host can start the allreduce of finished gradient buckets between parts)
   __nv_bfloat16 *bw_gcur = nullptr, *bw_gnext = nullptr;
@@ -291,6 +294,7 @@ static long long carve(Model& m, char* base) {
   m.d2 = (__nv_bfloat16*)bp.take(gmax);
   m.dy_stem = (__nv_bfloat16*)bp.take(act_elems(B, 44, 100, 64) * 2);
   m.sumsq_partial = (double*)bp.take(1024 * 8);
+  m.wscratch = (float*)bp.take(29LL * WF_SCRATCH_BYTES);
   m.pack_jobs = (PackJob*)bp.take(64 * sizeof(PackJob));
   return align_up(bp.off, 1024);
 }
@@ -314,7 +318,8 @@ static int add_flat(Model& m, const FlatConvParams& p) { m.flat_plans.push_back(
 
 static int build_plans(Model& m, int B, int mode) {
   if (B == m.planB && mode == m.planMode) return OK;
-  m.old_plans.clear(); m.wold_plans.clear(); m.flat_plans.clear(); m.wflat_plans.clear();
+  m.old_plans.clear(); m.wold_plans.clear(); m.flat_plans.clear(); m.wflat_plans.clear(); m.wflat_grad_off.clear();
+  for (int i = 0; i < 4; ++i) { m.red_jobs[i].n = 0; m.red_jobs[i].total_blocks = 0; }
   set_batch(m.stem, B);
   const bool infer = mode == MODE_INFER;
   const bool training = mode == MODE_TRAIN;
@@ -371,15 +376,21 @@ static int build_plans(Model& m, int B, int mode) {
       WgradParams wp;
       WgradFlatParams wf;
       // conv_b: dW_b = wgrad(dy_b = d1, act_a);  ga = relu'(act_a) * dgrad_b(d1), + the BN_a backward reductions
-      CK(build_wgrad_flat(&wf, B, blk.b.gin, blk.b.d.in_c, blk.b.d.out_c, m.d1, blk.act_a, nullptr));
-      m.wflat_plans.push_back(wf); blk.pl.w_b = (int)m.wflat_plans.size() - 1;
+      const int part = bi >= 13 ? 0 : (bi >= 7 ? 1 : (bi >= 3 ? 2 : 3));
+      auto add_wflat = [&](const ConvRef& c, const __nv_bfloat16* dy, const __nv_bfloat16* x, int* idx) -> int {
+        float* scratch = (float*)((char*)m.wscratch + (long long)m.wflat_plans.size() * WF_SCRATCH_BYTES);
+        CK(build_wgrad_flat(&wf, B, c.gin, c.d.in_c, c.d.out_c, dy, x, scratch));
+        m.wflat_plans.push_back(wf);
+        *idx = (int)m.wflat_plans.size() - 1;
+        return add_wgrad_reduce_job(&m.red_jobs[part], &wf, m.slots[c.w].off);
+      };
+      CK(add_wflat(blk.b, m.d1, blk.act_a, &blk.pl.w_b));
       CK(build_flat_conv(&f, B, blk.b.gin, blk.b.d.out_c, blk.b.d.in_c, 1, m.d1, blk.b.wd, m.ga, CF_MASK | CF_BNBWD));
       f.mask = blk.act_a; f.y1 = blk.a.y; f.stat1 = blk.a.bn.vec; f.bred1 = blk.a.bn.bred;
       blk.pl.d_b = add_flat(m, f);
       // conv_a: dW_a = wgrad(dy_a = d1, in); downsample: dW_ds = wgrad(dy_ds = d2, in)
       if (blk.a.flat) {
-        CK(build_wgrad_flat(&wf, B, blk.a.gin, blk.a.d.in_c, blk.a.d.out_c, m.d1, blk.in, nullptr));
-        m.wflat_plans.push_back(wf); blk.pl.w_a_flat = (int)m.wflat_plans.size() - 1;
+        CK(add_wflat(blk.a, m.d1, blk.in, &blk.pl.w_a_flat));
       } else {
         CK(build_wgrad(&wp, &blk.a.d, m.d1, blk.in, nullptr, &blk.a.gin, &blk.a.gout));
         m.wold_plans.push_back(wp); blk.pl.w_a_old = (int)m.wold_plans.size() - 1;
@@ -565,11 +576,7 @@ static int run_wgrad_old(Model& m, int idx, int slot, cudaStream_t s) {
   wp.grad = m.grads + m.slots[slot].off;
   return launch_wgrad(&wp, s);
 }
-static int run_wgrad_flat(Model& m, int idx, int slot, cudaStream_t s) {
-  WgradFlatParams wp = m.wflat_plans[idx];
-  wp.grad = m.grads + m.slots[slot].off;
-  return launch_wgrad_flat(&wp, s);
-}
+static int run_wgrad_flat(Model& m, int idx, cudaStream_t s) { return launch_wgrad_flat(&m.wflat_plans[idx], s); }
 // flat dgrad with the fused ReLU mask + BatchNorm-backward reductions: bind workspace and dgamma / dbeta at launch time
 static int launch_flat_bwd(Model& m, int idx, const BnRef* bn1, const BnRef* bn2, cudaStream_t s) {
   FlatConvParams f = m.flat_plans[idx];
@@ -588,7 +595,7 @@ static int run_bn_bwd_reduce(Model& m, int B, const PadGeom& g, const BnRef& bn,
   const long long nvec = pad_elems(B, g, bn.C) / 8;
   BnBwdReduceParams rp{};
   rp.g = grad; rp.act = act; rp.y = y; rp.mean = bn.vec + 2 * bn.C; rp.rstd = bn.vec + 3 * bn.C; rp.nvec = nvec; rp.C = bn.C;
-  rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + bn.C;
+  rp.partial = m.stat_acc; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + bn.C;
   rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
   rp.dz_out = grad; rp.geom = g;
   bn_bwd_reduce_kernel<false><<<ew_reduce_grid(nvec, bn.C), EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
@@ -683,10 +690,10 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     // gcur = dz of this block's output (ReLU-masked), with the reductions of bn_b (and bn_ds) already in their bred
     PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.b.bn, gcur, blk.b.y, cnt, frozen, m.d1, s)));
     if (blk.has_ds) PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.ds.bn, gcur, blk.ds.y, cnt, frozen, m.d2, s)));
-    PROF(m, PC_WGRAD, s, CK(run_wgrad_flat(m, blk.pl.w_b, blk.b.w, s)));            // dW_b
+    PROF(m, PC_WGRAD, s, CK(run_wgrad_flat(m, blk.pl.w_b, s)));            // dW_b
     PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_b, &blk.a.bn, nullptr, s))); // ga = dz_a (+ BN_a reductions)
     PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.a.bn, m.ga, blk.a.y, cnt, frozen, m.d1, s)));
-    if (blk.pl.w_a_flat >= 0) PROF(m, PC_WGRAD, s, CK(run_wgrad_flat(m, blk.pl.w_a_flat, blk.a.w, s)));
+    if (blk.pl.w_a_flat >= 0) PROF(m, PC_WGRAD, s, CK(run_wgrad_flat(m, blk.pl.w_a_flat, s)));
     else PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, blk.pl.w_a_old, blk.a.w, s)));
     if (blk.has_ds) PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, blk.pl.w_ds_old, blk.ds.w, s)));
     if (blk.pl.d_a_flat >= 0) {
@@ -700,6 +707,9 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     }
     __nv_bfloat16* t = gcur; gcur = gnext; gnext = t;
   }
+  // fold the split-K partial tiles of this part's flat wgrads into the OIHW gradients (one launch per layer group)
+  for (int pt = 0; pt < 4; ++pt)
+    if (part < 0 || part == pt) PROF(m, PC_WGRAD, s, CK(launch_wgrad_reduce(&m.red_jobs[pt], m.grads, s)));
   // ---- stem: max-pool backward + ReLU + BN backward, then wgrad ----
   if (part < 0 || part == 4) {
     const BnRef& bn = m.stem.bn;
@@ -708,7 +718,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     const int rgrid = ew_grid(nvec, 64, 8);
     BnBwdReduceParams rp{};
     rp.g = gcur; rp.y = m.stem.y; rp.mean = bn.vec + 2 * 64; rp.rstd = bn.vec + 3 * 64; rp.nvec = nvec; rp.C = 64;
-    rp.partial = m.bwd_partial; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + 64;
+    rp.partial = m.stat_acc; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + 64;
     rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
     rp.argmax = m.pool_arg; rp.scale = bn.vec; rp.shift = bn.vec + 64; rp.H = 44; rp.W = 100; rp.OH = 22; rp.OW = 50;
     rp.OHp = kGeom0.Hp; rp.OWp = kGeom0.Wp; rp.geom = kDense;
@@ -963,7 +973,8 @@ int cilrs_bn_relu_maxpool(const void* y, const float* vec, void* out, uint8_t* a
   return cuda_status(cudaGetLastError());
 }
 
-// BN (+ optional ReLU mask from `act`) backward. workspace: >= (592*2*C + 2*C) floats + one zeroed uint32 counter.
+// BN (+ optional ReLU mask from `act`) backward. workspace: cilrs_bn_backward_workspace_floats(C) floats whose first 2*C are
+// ZERO on entry (global accumulators; left zero) + one zeroed uint32 counter.
 // stem variant (argmax != NULL): g is the pooled gradient [B,(H+1)/2,(W+1)/2,C] routed through the 3x3/2 max-pool; with
 // pad_h > 0 that pooled gradient is padded-flat [B,(H+1)/2+1,(W+1)/2+1,C].
 // regular variant with pad_h, pad_w > 0: g / act / y / dy / dz are padded-flat [batch, pad_h+1, pad_w+1, C].

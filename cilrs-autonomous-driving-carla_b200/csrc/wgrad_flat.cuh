@@ -7,7 +7,9 @@
 // 3 taps] and a slice of the 128-pixel K tiles. Per K tile ONE slab of 130 pixels of X is loaded; the three taps
 // (dw = -1, 0, +1) are ONE tcgen05.mma with N = 192 whose B descriptor walks its three 64-column slabs with a leading
 // byte offset of 128 = one pixel row, i.e. the slabs are the same shared-memory data shifted by one pixel each.
-// The accumulator stays in TMEM for the whole slice and is added to the fp32 OIHW gradient with red.global.add.
+// The accumulator stays in TMEM for the whole slice. Split-K partials are NOT combined with atomics (3.5 M scattered
+// red.global.add per conv cost 25 us, twice the MMA time): every CTA stores its 128 x 192 fp32 tile with coalesced 256-bit
+// stores to a scratch slot, and wgrad_reduce_kernel sums the slots in a fixed order into the OIHW gradient (deterministic).
 //   warp 0 : TMA producer      warp 1 : MMA issuer (whole warp, one elected lane issues)      warps 2..5 : epilogue
 #pragma once
 #include "common.cuh"
@@ -117,7 +119,9 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int co = cob * 128 + row;
+    // scratch slot of this CTA: [tile = (cob, cic, tg)][z][128 rows][192 columns = 3 taps x 64 ci] fp32
+    const int tile = (cob * p.ci_chunks + cic) * 3 + tg;
+    float* dst = p.scratch + (((size_t)tile * p.split_z + z) * 128 + row) * 192;
     if (kt_end > kt_begin) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
@@ -126,13 +130,16 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
         __syncwarp();
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (row < p.m_halves * 64 && co < p.cout) {
-          const int t = tg * 3 + (c0 >> 6);
-          float* gp = p.grad + ((size_t)co * p.cin + cic * 64 + (c0 & 63)) * 9 + t;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) atomicAdd(gp + e * 9, __uint_as_float(v[e]));
-        }
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + c0 + j * 8), "r"(v[j * 8]), "r"(v[j * 8 + 1]),
+                       "r"(v[j * 8 + 2]), "r"(v[j * 8 + 3]), "r"(v[j * 8 + 4]), "r"(v[j * 8 + 5]), "r"(v[j * 8 + 6]), "r"(v[j * 8 + 7])
+                       : "memory");
       }
+    } else {
+      // a K slice past the end (split_z does not divide the tile count): the reducer still reads this slot
+      const uint4 zz = make_uint4(0, 0, 0, 0);
+      for (int c0 = 0; c0 < 192; c0 += 4) *(uint4*)(dst + c0) = zz;
     }
   }
   tc_fence_before();
@@ -141,6 +148,36 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
     __syncwarp();
     tmem_dealloc(tmem_base, 256);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Split-K reduction of the flat wgrad partials into the fp32 OIHW gradient (accumulating: grad += sum over z).
+// One CTA per (output channel co, 64-channel input chunk): its 192 threads sum, for each of the three filter rows, the
+// z partial rows (coalesced 768-byte reads), permute through shared memory into the OIHW order ci*9 + tap and add the
+// 576 contiguous floats to the gradient. All flat convolutions of a backward part are served by one launch (job table).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) wgrad_reduce_kernel(const __grid_constant__ WgradReduceJobs jobs, float* __restrict__ grads) {
+  __shared__ float s_out[576];
+  int j = 0;
+  while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.job[j + 1].first_block) ++j;
+  const WgradReduceJob& jb = jobs.job[j];
+  const int u = blockIdx.x - jb.first_block;
+  const int co = u / jb.ci_chunks, cic = u - co * jb.ci_chunks;
+  const int cob = co >> 7, row = co & 127;
+  const int t = threadIdx.x;  // column of the 192-wide tile: tap-in-row (t >> 6), input channel (t & 63)
+#pragma unroll
+  for (int tg = 0; tg < 3; ++tg) {
+    const int tile = (cob * jb.ci_chunks + cic) * 3 + tg;
+    const float* src = jb.scratch + (((size_t)tile * jb.split_z) * 128 + row) * 192 + t;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int z = 0; z < jb.split_z; ++z) acc += __ldcg(src + (size_t)z * 128 * 192);
+    s_out[(t & 63) * 9 + tg * 3 + (t >> 6)] = acc;
+  }
+  __syncthreads();
+  float* g = grads + jb.grad_off + ((size_t)co * jb.cin + cic * 64) * 9;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) g[k * 192 + t] += s_out[k * 192 + t];
 }
 
 }  // namespace cilrs

@@ -135,8 +135,11 @@ typedef struct cilrs_flat_conv_args {
 long long cilrs_flat_rows(int batch, int H, int W);
 size_t cilrs_conv_flat_workspace_floats(int out_c);
 int cilrs_conv_flat(const cilrs_flat_conv_args* a, void* stream);
-/* dw_oihw (fp32 [out_c,in_c,3,3]) += dy^T * shifted(x), both padded-flat. The caller zeroes dw first. */
-int cilrs_wgrad_flat(int batch, int H, int W, int in_c, int out_c, const void* dy, const void* x, float* dw_oihw, void* stream);
+/* dw_oihw (fp32 [out_c,in_c,3,3]) += dy^T * shifted(x), both padded-flat (two launches: split-K partial tiles into
+ * scratch_ws, then a fixed-order reduction into dw: deterministic, no atomics). scratch_ws: cilrs_wgrad_flat_workspace_bytes(). */
+size_t cilrs_wgrad_flat_workspace_bytes(void);
+int cilrs_wgrad_flat(int batch, int H, int W, int in_c, int out_c, const void* dy, const void* x, float* dw_oihw,
+                     float* scratch_ws, void* stream);
 
 /* the 7x7/2 stem on the space-to-depth input [batch,47,103,16] -> [batch,44,100,64] */
 size_t cilrs_stem_packed_weight_bytes(void);
@@ -224,7 +227,8 @@ int cilrs_bn_apply(const void* x, const float* vec, const void* residual, const 
 /* padded_out != 0: out is padded-flat [batch, (H+1)/2+1, (W+1)/2+1, C] (padding pixels untouched); argmax stays dense */
 int cilrs_bn_relu_maxpool(const void* y, const float* vec, void* out, uint8_t* argmax, int batch, int H, int W, int C,
                           int padded_out, void* stream);
-/* stem variant (argmax != NULL): pad_h > 0 means the pooled gradient g is padded-flat */
+/* stem variant (argmax != NULL): pad_h > 0 means the pooled gradient g is padded-flat.
+ * workspace: cilrs_bn_backward_workspace_floats(C) floats, the first 2*C ZERO on entry (left zero); counter: zeroed uint32 */
 int cilrs_bn_backward(const void* g, const void* act, const void* y, const float* vec, const float* gamma, long long elems,
                       int C, double count, int frozen, void* dy, void* dz, float* dgamma, float* dbeta, float* workspace,
                       unsigned int* counter, const uint8_t* argmax, int H, int W, int pad_h, int pad_w, void* stream);

@@ -98,7 +98,7 @@ def test_bn_relu_backward(shape, frozen):
     dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     nws = _lib.lib().cilrs_bn_backward_workspace_floats
     nws.restype = ctypes.c_size_t
-    ws = torch.empty(nws(C), device="cuda")
+    ws = torch.zeros(nws(C), device="cuda")
     cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
     _lib.call("cilrs_bn_backward", gup, act, y, vec, gamma, ctypes.c_longlong(y.numel()), C, ctypes.c_double(B * H * W), frozen, dy, dz,
               dgamma, dbeta, ws, cnt, None, 0, 0, 0, 0, _lib.stream_ptr())
@@ -134,7 +134,7 @@ def test_stem_bn_relu_maxpool_forward_backward(B):
     dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     nws = _lib.lib().cilrs_bn_backward_workspace_floats
     nws.restype = ctypes.c_size_t
-    ws = torch.empty(nws(C), device="cuda")
+    ws = torch.zeros(nws(C), device="cuda")
     cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
     _lib.call("cilrs_bn_backward", gp, None, y, vec, gamma, ctypes.c_longlong(y.numel()), C, ctypes.c_double(B * 4400), 0, dy, None, dgamma,
               dbeta, ws, cnt, arg, 44, 100, 0, 0, _lib.stream_ptr())
@@ -185,7 +185,7 @@ def test_padded_flat_layout_bn_apply_and_backward_equal_the_dense_kernels(shape)
             a_in, y_in = ops.to_padded(out_d), yp
         dy, dz = torch.full_like(y_in, float("nan")), torch.full_like(y_in, float("nan"))
         dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-        ws = torch.empty(nws(C), device="cuda")
+        ws = torch.zeros(nws(C), device="cuda")
         cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
         _lib.call("cilrs_bn_backward", g_in, a_in, y_in, vec, gamma, ctypes.c_longlong(y_in.numel()), C, ctypes.c_double(B * H * W), 0, dy, dz,
                   dgamma, dbeta, ws, cnt, None, 0, 0, H if padded else 0, W if padded else 0, _lib.stream_ptr())

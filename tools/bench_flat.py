@@ -52,6 +52,7 @@ for name, h, w, c, count in layers:
     bred = torch.zeros(2, c, device="cuda")
     dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
     dw = torch.zeros(c, c, 3, 3, device="cuda")
+    wsw = torch.empty(_lib.query("cilrs_wgrad_flat_workspace_bytes") // 4, device="cuda")
     a = _lib.FlatConvArgs()
     a.batch, a.H, a.W, a.in_c, a.out_c, a.dgrad, a.flags = B, h, w, c, c, 0, ops.EPI_STATS
     a.x, a.w, a.y = P(x), P(wf), P(out)
@@ -71,7 +72,7 @@ for name, h, w, c, count in layers:
     f_f = lambda: _lib.call("cilrs_conv_flat", a, sp)
     f_p = lambda: _lib.call("cilrs_conv_flat", p, sp)
     f_d = lambda: _lib.call("cilrs_conv_flat", g, sp)
-    f_w = lambda: _lib.call("cilrs_wgrad_flat", B, h, w, c, c, dy, x, dw, sp)
+    f_w = lambda: _lib.call("cilrs_wgrad_flat", B, h, w, c, c, dy, x, dw, wsw, sp)
     flops = 2.0 * B * h * w * c * c * 9
     t_p, t_f, t_d, t_w = timeit(f_p), timeit(f_f), timeit(f_d), timeit(f_w)
     h_p, h_f, h_d, h_w = timeit_hot(f_p), timeit_hot(f_f), timeit_hot(f_d), timeit_hot(f_w)

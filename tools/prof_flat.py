@@ -21,6 +21,7 @@ gamma, beta, rm, rv = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda"
 vec = torch.zeros(4, c, device="cuda"); vec[3] = 1
 bred = torch.zeros(2, c, device="cuda"); dg = torch.zeros(c, device="cuda"); db = torch.zeros(c, device="cuda")
 dw = torch.zeros(c, c, 3, 3, device="cuda")
+wsw = torch.empty(_lib.query("cilrs_wgrad_flat_workspace_bytes") // 4, device="cuda")
 a = _lib.FlatConvArgs()
 a.batch, a.H, a.W, a.in_c, a.out_c = B, h, w, c, c
 a.partials_ws, a.counter_ws = P(ws), P(cnt)
@@ -36,7 +37,7 @@ elif mode == "dgrad":
 sp = _lib.stream_ptr()
 for _ in range(6):
     if mode == "wgrad":
-        _lib.call("cilrs_wgrad_flat", B, h, w, c, c, dy, x, dw, sp)
+        _lib.call("cilrs_wgrad_flat", B, h, w, c, c, dy, x, dw, wsw, sp)
     else:
         _lib.call("cilrs_conv_flat", a, sp)
 torch.cuda.synchronize()
