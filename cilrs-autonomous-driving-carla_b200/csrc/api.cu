@@ -3,7 +3,15 @@
 #include "../../include/cilrs_b200.h"
 #include <stdio.h>
 
-namespace cilrs { long long g_cilrs_launches = 0; }
+#include <stdlib.h>
+namespace cilrs {
+long long g_cilrs_launches = 0;
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) on = getenv("CILRS_NO_PDL") ? 0 : 1;
+  return on != 0;
+}
+}  // namespace cilrs
 
 extern "C" {
 

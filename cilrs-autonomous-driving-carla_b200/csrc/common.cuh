@@ -164,6 +164,31 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N, int a_mn_major
   return d;
 }
 
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the step is launched with the programmatic-stream-serialization
+// attribute, lets its successor start launching as soon as all of its own CTAs are resident (launch_dependents at the
+// top) and blocks before its first global-memory access until the predecessor grid has completed and flushed (wait).
+// The successor's launch latency and prologue (barrier init, TMEM allocation, descriptor prefetch) then overlap the
+// predecessor's tail. Without the launch attribute both instructions are no-ops.
+// ----------------------------------------------------------------------------------------------
+CILRS_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+CILRS_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+CILRS_DEVINL void pdl_entry() { pdl_launch_dependents(); pdl_wait(); }
+
+bool pdl_enabled();  // api.cu: false when CILRS_NO_PDL is set
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // named barrier for a subset of warps
 CILRS_DEVINL void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 

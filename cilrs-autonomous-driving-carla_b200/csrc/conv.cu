@@ -361,8 +361,8 @@ int launch_conv_gemm(const ConvGemmParams* p, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = conv_gemm_grid(p);
-  conv_gemm_kernel<<<grid, CG_THREADS, CG_SMEM_TOTAL, s>>>(*p); ++g_cilrs_launches;
-  return cuda_status(cudaGetLastError());
+  ++g_cilrs_launches;
+  return cuda_status(launch_pdl(conv_gemm_kernel, dim3(grid), dim3(CG_THREADS), CG_SMEM_TOTAL, s, *p));
 }
 
 int launch_wgrad(const WgradParams* p, cudaStream_t s) {
@@ -373,8 +373,8 @@ int launch_wgrad(const WgradParams* p, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = p->co_blocks * p->ci_chunks * p->tap_groups * p->split_z;
-  wgrad_gemm_kernel<<<grid, WG_THREADS, CG_SMEM_TOTAL, s>>>(*p); ++g_cilrs_launches;
-  return cuda_status(cudaGetLastError());
+  ++g_cilrs_launches;
+  return cuda_status(launch_pdl(wgrad_gemm_kernel, dim3(grid), dim3(WG_THREADS), CG_SMEM_TOTAL, s, *p));
 }
 
 // ------------------------------------------------------------------------------------------------

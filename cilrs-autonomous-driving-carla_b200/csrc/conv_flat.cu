@@ -196,12 +196,10 @@ int launch_flat_conv(const FlatConvParams* p, cudaStream_t s) {
   }
   if ((p->flags & (CF_STATS | CF_BNBWD)) && (!p->partials || !p->counter)) return ERR_INVALID;
   const int grid = flat_conv_grid(p);
-  if (p->mt == 1) conv_flat_kernel<1><<<grid, CF_THREADS, CG_SMEM_TOTAL, s>>>(*p);
-  else if (p->mt == 2) conv_flat_kernel<2><<<grid, CF_THREADS, CG_SMEM_TOTAL, s>>>(*p);
-  else if (p->mt == 4) conv_flat_kernel<4><<<grid, CF_THREADS, CG_SMEM_TOTAL, s>>>(*p);
-  else return ERR_INVALID;
+  void (*kernel)(FlatConvParams) = p->mt == 1 ? conv_flat_kernel<1> : (p->mt == 2 ? conv_flat_kernel<2> : (p->mt == 4 ? conv_flat_kernel<4> : nullptr));
+  if (!kernel) return ERR_INVALID;
   ++g_cilrs_launches;
-  return cuda_status(cudaGetLastError());
+  return cuda_status(launch_pdl(kernel, dim3(grid), dim3(CF_THREADS), CG_SMEM_TOTAL, s, *p));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -246,8 +244,8 @@ int launch_wgrad_flat(const WgradFlatParams* p, cudaStream_t s) {
   }
   const int grid = p->co_blocks * p->ci_chunks * p->tap_groups * p->split_z;
   if ((long long)grid * 128 * 192 * 4 > WF_SCRATCH_BYTES || !p->scratch) return ERR_WORKSPACE;
-  wgrad_flat_kernel<<<grid, WF_THREADS, CG_SMEM_TOTAL, s>>>(*p); ++g_cilrs_launches;
-  return cuda_status(cudaGetLastError());
+  ++g_cilrs_launches;
+  return cuda_status(launch_pdl(wgrad_flat_kernel, dim3(grid), dim3(WF_THREADS), CG_SMEM_TOTAL, s, *p));
 }
 
 // append the reduction of one flat wgrad to a job list (the list is a kernel parameter, see wgrad_reduce_kernel)
@@ -262,8 +260,8 @@ int add_wgrad_reduce_job(WgradReduceJobs* jobs, const WgradFlatParams* p, long l
 
 int launch_wgrad_reduce(const WgradReduceJobs* jobs, float* grads, cudaStream_t s) {
   if (jobs->n == 0) return OK;
-  wgrad_reduce_kernel<<<jobs->total_blocks, 192, 0, s>>>(*jobs, grads); ++g_cilrs_launches;
-  return cuda_status(cudaGetLastError());
+  ++g_cilrs_launches;
+  return cuda_status(launch_pdl(wgrad_reduce_kernel, dim3(jobs->total_blocks), dim3(192), 0, s, *jobs, grads));
 }
 
 }  // namespace cilrs

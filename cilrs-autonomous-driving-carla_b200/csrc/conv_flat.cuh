@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
   if (threadIdx.x < 3) cf_idx[threadIdx.x] = 0;
 #endif
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above is local to the CTA; from here on the predecessor's results are read
 
   const int total_tiles = p.m_tiles * p.n_blocks;
   const int acc_stride = MT * p.block_n;  // TMEM columns per accumulator set

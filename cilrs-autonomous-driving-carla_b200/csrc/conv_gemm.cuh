@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
+  pdl_launch_dependents();
   // rows of an A tile that no TMA box ever writes (valid_rows..127) must read as 0: zero them once per stage
   {
     const int vr = p.BW * p.BH * p.BN;
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = m_tiles * p.n_blocks;

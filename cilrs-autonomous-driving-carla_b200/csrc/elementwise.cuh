@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                                            float momentum, float eps, int training, int update_running,
                                                            BnVectors out) {
   __shared__ double s_sum[32][33], s_sq[32][33];
+  pdl_entry();
   const int cl = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double s = 0.0, q = 0.0;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
                                                               const __nv_bfloat16* __restrict__ x2, const float* __restrict__ scale2,
                                                               const float* __restrict__ shift2, __nv_bfloat16* __restrict__ out,
                                                               long long nvec, int C, int relu, const PadGeom g) {
+  pdl_entry();
   const int groups = C >> 3;
   const long long stride = (long long)gridDim.x * EW_THREADS;  // multiple of groups (host guarantees)
   long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_maxpool_kernel(const __nv_
                                                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                                                                      uint8_t* __restrict__ argmax, int B, int H, int W, int C, int OH,
                                                                      int OW, int OHp, int OWp) {
+  pdl_entry();
   const int groups = C >> 3;
   const long long nvec = (long long)B * OH * OW * groups;
   const long long stride = (long long)gridDim.x * EW_THREADS;
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_maxpool_kernel(const __nv_
 
 // global average pool: x padded-flat [B,Hp,Wp,C] bf16 -> feat [B,C] fp32 (padding pixels are zero, so the sum runs over all of them)
 __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ feat, int B, int C, const PadGeom g) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int c = i % C, n = i / C;
@@ -218,6 +222,7 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __res
 }
 // backward: g padded-flat [B,Hp,Wp,C] bf16 = dfeat[b,c] / (H*W) on real pixels, 0 on padding
 __global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, __nv_bfloat16* __restrict__ gout, int B, int C, const PadGeom g) {
+  pdl_entry();
   const int PP = g.Hp * g.Wp;
   const long long total = (long long)B * PP * C;
   const float inv = 1.f / (float)(g.H * g.W);
@@ -307,6 +312,7 @@ template <bool STEM>
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdReduceParams p) {
   __shared__ float s_red[2 * EW_THREADS][8];  // 16 KB: per-thread partial (sum | dot) vectors
   __shared__ bool s_last;
+  pdl_entry();
   const int groups = p.C >> 3;
   const long long stride = (long long)gridDim.x * EW_THREADS;
   long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
@@ -443,6 +449,7 @@ struct BnBwdApplyParams {
 
 template <bool STEM>
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApplyParams p) {
+  pdl_entry();
   const int groups = p.C >> 3;
   const long long stride = (long long)gridDim.x * EW_THREADS;
   long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x;

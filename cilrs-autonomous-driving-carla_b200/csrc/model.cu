@@ -435,19 +435,21 @@ static int build_plans(Model& m, int B, int mode) {
 
 static int run_bn_finalize(Model& m, const BnRef& bn, int tiles, double count, int training, int update, cudaStream_t s) {
   BnVectors v{bn.vec, bn.vec + bn.C, bn.vec + 2 * bn.C, bn.vec + 3 * bn.C};
-  bn_finalize_kernel<<<(bn.C + 31) / 32, 1024, 0, s>>>(m.stats, tiles, bn.C, count, m.params + m.slots[bn.gamma].off,
-                                                       m.params + m.slots[bn.beta].off, m.buffers + bn.rm_off, m.buffers + bn.rv_off,
-                                                       m.nbt ? m.nbt + bn.nbt_idx : nullptr, 0.1f, 1e-5f, training, update, v); ++g_cilrs_launches;
-  return cuda_status(cudaGetLastError());
+  ++g_cilrs_launches;
+  return cuda_status(launch_pdl(bn_finalize_kernel, dim3((bn.C + 31) / 32), dim3(1024), 0, s, (const float*)m.stats, tiles, bn.C, count,
+                                (const float*)(m.params + m.slots[bn.gamma].off), (const float*)(m.params + m.slots[bn.beta].off),
+                                m.buffers + bn.rm_off, m.buffers + bn.rv_off, m.nbt ? m.nbt + bn.nbt_idx : (long long*)nullptr, 0.1f, 1e-5f,
+                                training, update, v));
 }
 
 // out = relu?( bn(x) [+ res] [+ bn2(x2)] ) on padded-flat tensors of geometry g
 static int run_bn_apply(int B, const PadGeom& g, const __nv_bfloat16* x, const BnRef& bn, const __nv_bfloat16* res, const __nv_bfloat16* x2,
                         const BnRef* bn2, __nv_bfloat16* out, int relu, cudaStream_t s) {
   const long long nvec = pad_elems(B, g, bn.C) / 8;
-  bn_apply_kernel<<<ew_grid(nvec, bn.C), EW_THREADS, 0, s>>>(x, bn.vec, bn.vec + bn.C, res, x2, bn2 ? bn2->vec : nullptr,
-                                                             bn2 ? bn2->vec + bn2->C : nullptr, out, nvec, bn.C, relu, g); ++g_cilrs_launches;
-  return cuda_status(cudaGetLastError());
+  ++g_cilrs_launches;
+  return cuda_status(launch_pdl(bn_apply_kernel, dim3(ew_grid(nvec, bn.C)), dim3(EW_THREADS), 0, s, x, (const float*)bn.vec,
+                                (const float*)(bn.vec + bn.C), res, x2, (const float*)(bn2 ? bn2->vec : nullptr),
+                                (const float*)(bn2 ? bn2->vec + bn2->C : nullptr), out, nvec, bn.C, relu, g));
 }
 
 // flat conv with the train-mode BatchNorm statistics + finalize fused (pointers bound at launch time)
@@ -598,8 +600,8 @@ static int run_bn_bwd_reduce(Model& m, int B, const PadGeom& g, const BnRef& bn,
   rp.partial = m.stat_acc; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + bn.C;
   rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
   rp.dz_out = grad; rp.geom = g;
-  bn_bwd_reduce_kernel<false><<<ew_reduce_grid(nvec, bn.C), EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
-  return cuda_status(cudaGetLastError());
+  ++g_cilrs_launches;
+  return cuda_status(launch_pdl(bn_bwd_reduce_kernel<false>, dim3(ew_reduce_grid(nvec, bn.C)), dim3(EW_THREADS), 0, s, rp));
 }
 
 // dy = gamma * rstd * (dz - bsum/n - xhat * bdot/n)   (frozen: gamma * rstd * dz); dz is already ReLU-masked
@@ -610,8 +612,8 @@ static int run_bn_bwd_apply(Model& m, int B, const PadGeom& g, const BnRef& bn, 
   ap.g = dz; ap.act = nullptr; ap.y = y; ap.mean = bn.vec + 2 * bn.C; ap.rstd = bn.vec + 3 * bn.C;
   ap.gamma = m.params + m.slots[bn.gamma].off; ap.bsum = bn.bred; ap.bdot = bn.bred + bn.C; ap.inv_count = (float)(1.0 / count);
   ap.frozen = frozen; ap.nvec = nvec; ap.C = bn.C; ap.dy = dy; ap.dz = nullptr; ap.geom = g;
-  bn_bwd_apply_kernel<false><<<ew_grid(nvec, bn.C), EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
-  return cuda_status(cudaGetLastError());
+  ++g_cilrs_launches;
+  return cuda_status(launch_pdl(bn_bwd_apply_kernel<false>, dim3(ew_grid(nvec, bn.C)), dim3(EW_THREADS), 0, s, ap));
 }
 
 static int heads_backward(Model& m, int B, const float* dcontrols, const float* dspeed, const float* speed,
@@ -723,12 +725,12 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     rp.argmax = m.pool_arg; rp.scale = bn.vec; rp.shift = bn.vec + 64; rp.H = 44; rp.W = 100; rp.OH = 22; rp.OW = 50;
     rp.OHp = kGeom0.Hp; rp.OWp = kGeom0.Wp; rp.geom = kDense;
     rp.dz_out = m.dy_stem;  // routed + masked gradient, turned into dy in place by the apply pass
-    PROF(m, PC_BN_BWD, s, { bn_bwd_reduce_kernel<true><<<rgrid, EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches; CKL(); });
+    PROF(m, PC_BN_BWD, s, { ++g_cilrs_launches; CK(cuda_status(launch_pdl(bn_bwd_reduce_kernel<true>, dim3(rgrid), dim3(EW_THREADS), 0, s, rp))); });
     BnBwdApplyParams ap{};
     ap.g = m.dy_stem; ap.y = m.stem.y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
     ap.bsum = rp.bsum; ap.bdot = rp.bdot; ap.inv_count = (float)(1.0 / ((double)B * 4400.0)); ap.frozen = frozen; ap.nvec = nvec;
     ap.C = 64; ap.dy = m.dy_stem; ap.geom = kDense;
-    PROF(m, PC_BN_BWD, s, { bn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches; CKL(); });
+    PROF(m, PC_BN_BWD, s, { ++g_cilrs_launches; CK(cuda_status(launch_pdl(bn_bwd_apply_kernel<false>, dim3(grid), dim3(EW_THREADS), 0, s, ap))); });
     PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, m.stem_wgrad, m.stem.w, s)));
   }
   return OK;

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
   uint64_t* done_bar = bars + 2 * WF_MAX_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
 
+  pdl_launch_dependents();
   if (p.m_halves == 1) {
     // the A side always spans two 64-channel slabs; with 64 output channels the second one stays zero
     const uint4 z = make_uint4(0, 0, 0, 0);
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   // work item of this CTA
   int wi = blockIdx.x;
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(192) wgrad_reduce_kernel(const __grid_constant__ WgradReduceJobs jobs, float* __restrict__ grads) {
   __shared__ float s_out[576];
+  pdl_entry();
   int j = 0;
   while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.job[j + 1].first_block) ++j;
   const WgradReduceJob& jb = jobs.job[j];

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
   uint64_t* done_bar = bars + 2 * WG_MAX_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
 
+  pdl_launch_dependents();
   // pixel rows no TMA box ever writes (valid_rows..127 of every slab) and the unused second dY slab must read as 0
   {
     const int vr = p.BW * p.BH * p.BN;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   // work item of this CTA
   int wi = blockIdx.x;
