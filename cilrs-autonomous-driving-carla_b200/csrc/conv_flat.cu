@@ -260,8 +260,13 @@ int add_wgrad_reduce_job(WgradReduceJobs* jobs, const WgradFlatParams* p, long l
 
 int launch_wgrad_reduce(const WgradReduceJobs* jobs, float* grads, cudaStream_t s) {
   if (jobs->n == 0) return OK;
+  // 192 threads per K-slice chain; more chains when the split is deep (layer1: 49 slices)
+  int max_z = 1;
+  for (int i = 0; i < jobs->n; ++i) max_z = jobs->job[i].split_z > max_z ? jobs->job[i].split_z : max_z;
+  int nz = (max_z + 11) / 12;
+  nz = nz < 1 ? 1 : (nz > 4 ? 4 : nz);
   ++g_cilrs_launches;
-  return cuda_status(launch_pdl(wgrad_reduce_kernel, dim3(jobs->total_blocks), dim3(192), 0, s, *jobs, grads));
+  return cuda_status(launch_pdl(wgrad_reduce_kernel, dim3(jobs->total_blocks), dim3(192 * nz), 0, s, *jobs, grads));
 }
 
 }  // namespace cilrs

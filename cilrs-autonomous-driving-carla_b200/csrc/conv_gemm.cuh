@@ -17,7 +17,7 @@ namespace cilrs {
 
 __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space (LDS/STS)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,34 +105,40 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(CG_BLOCK_M, p.block_n, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // whole warp in uniform control flow (descriptors stay in uniform registers), one elected lane issues; the CTA owns
+    // all 512 TMEM columns, so the allocation starts at column 0 (see conv_flat.cuh)
+    if (tmem_base != 0) __trap();
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(CG_BLOCK_M, p.block_n, 0, 0);
+    const uint64_t descA0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+    const uint64_t descB0 = umma_desc_sw128(smem_u32(smem) + CG_A_BYTES, 16, 1024);
+    const uint32_t stage_units = (uint32_t)(stage_bytes >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = (uint32_t)acc * 256;
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256;
-        for (int k = 0; k < k_iters; ++k) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t b_addr = a_addr + CG_A_BYTES;
+        const uint64_t da = descA0 + (uint64_t)((uint32_t)stage * stage_units);
+        const uint64_t db = descB0 + (uint64_t)((uint32_t)stage * stage_units);
+        if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzled row
-            const uint64_t da = umma_desc_sw128(a_addr + kk * 32, 16, 1024);
-            const uint64_t db = umma_desc_sw128(b_addr + kk * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
-          }
+          for (int kk = 0; kk < 4; ++kk)  // 4 x (K = 16 bf16 = 32 bytes = 2 sixteen-byte units) inside the 128-byte swizzled row
+            umma_bf16(d_tmem, da + kk * 2, db + kk * 2, idesc, (k | kk) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(&tfull_bar[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ================= epilogue (4 warps = 128 TMEM lanes) =================

@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
 // z partial rows (coalesced 768-byte reads), permute through shared memory into the OIHW order ci*9 + tap and add the
 // 576 contiguous floats to the gradient. All flat convolutions of a backward part are served by one launch (job table).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(192) wgrad_reduce_kernel(const __grid_constant__ WgradReduceJobs jobs, float* __restrict__ grads) {
-  __shared__ float s_out[576];
+__global__ void __launch_bounds__(768) wgrad_reduce_kernel(const __grid_constant__ WgradReduceJobs jobs, float* __restrict__ grads) {
+  __shared__ float s_part[4][576];
   pdl_entry();
   int j = 0;
   while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.job[j + 1].first_block) ++j;
@@ -167,20 +167,26 @@ __global__ void __launch_bounds__(192) wgrad_reduce_kernel(const __grid_constant
   const int u = blockIdx.x - jb.first_block;
   const int co = u / jb.ci_chunks, cic = u - co * jb.ci_chunks;
   const int cob = co >> 7, row = co & 127;
-  const int t = threadIdx.x;  // column of the 192-wide tile: tap-in-row (t >> 6), input channel (t & 63)
+  const int t = threadIdx.x % 192;   // column of the 192-wide tile: tap-in-row (t >> 6), input channel (t & 63)
+  const int zs = threadIdx.x / 192;  // this thread sums the K slices z = zs, zs + nz, ... (nz = blockDim.x / 192 chains per column)
+  const int nz = blockDim.x / 192;
 #pragma unroll
   for (int tg = 0; tg < 3; ++tg) {
     const int tile = (cob * jb.ci_chunks + cic) * 3 + tg;
     const float* src = jb.scratch + (((size_t)tile * jb.split_z) * 128 + row) * 192 + t;
     float acc = 0.f;
 #pragma unroll 4
-    for (int z = 0; z < jb.split_z; ++z) acc += __ldcg(src + (size_t)z * 128 * 192);
-    s_out[(t & 63) * 9 + tg * 3 + (t >> 6)] = acc;
+    for (int z = zs; z < jb.split_z; z += nz) acc += __ldcg(src + (size_t)z * 128 * 192);
+    s_part[zs][(t & 63) * 9 + tg * 3 + (t >> 6)] = acc;
   }
   __syncthreads();
+  // 576 contiguous floats of the OIHW gradient: ci*9 + tap
   float* g = grads + jb.grad_off + ((size_t)co * jb.cin + cic * 64) * 9;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) g[k * 192 + t] += s_out[k * 192 + t];
+  for (int o = threadIdx.x; o < 576; o += blockDim.x) {
+    float v = s_part[0][o];
+    for (int k = 1; k < nz; ++k) v += s_part[k][o];
+    g[o] += v;
+  }
 }
 
 }  // namespace cilrs

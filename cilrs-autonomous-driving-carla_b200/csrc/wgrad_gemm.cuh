@@ -16,7 +16,7 @@ namespace cilrs {
 
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space (LDS/STS)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -100,28 +100,33 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, 64 * p.g, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t first = 1;
-      for (int pt = pt_begin; pt < pt_end; ++pt) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t b_addr = a_addr + 2 * WG_SLAB;
+    // whole warp in uniform control flow, one elected lane issues (see conv_flat.cuh); first TMEM allocation of the SM
+    if (tmem_base != 0) __trap();
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(128, 64 * p.g, 1, 1);
+    const uint64_t descA0 = umma_desc_sw128(smem_u32(smem), WG_SLAB, 1024);
+    const uint64_t descB0 = umma_desc_sw128(smem_u32(smem) + 2 * WG_SLAB, WG_SLAB, 1024);
+    const uint32_t stage_units = (uint32_t)(stage_bytes >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t first = 1;
+    for (int pt = pt_begin; pt < pt_end; ++pt) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint64_t da = descA0 + (uint64_t)((uint32_t)stage * stage_units);
+      const uint64_t db = descB0 + (uint64_t)((uint32_t)stage * stage_units);
+      if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {  // 8 x (K = 16 pixels = 16 rows of 128 bytes)
-          const uint64_t da = umma_desc_sw128(a_addr + kk * 2048, WG_SLAB, 1024);
-          const uint64_t db = umma_desc_sw128(b_addr + kk * 2048, WG_SLAB, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (first && kk == 0) ? 0u : 1u);
-        }
-        first = 0;
+        for (int kk = 0; kk < 8; ++kk)  // 8 x (K = 16 pixels = 16 rows of 128 bytes = 128 sixteen-byte units)
+          umma_bf16(0u, da + kk * 128, db + kk * 128, idesc, (first && kk == 0) ? 0u : 1u);
         umma_commit(&empty_bar[stage]);
-        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(done_bar);
+      __syncwarp();
+      first = 0;
+      if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
     }
+    if (leader) umma_commit(done_bar);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
