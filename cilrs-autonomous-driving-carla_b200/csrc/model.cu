@@ -11,6 +11,7 @@
 #include "adam.cuh"
 #include <new>
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace cilrs {
@@ -134,7 +135,14 @@ struct Model {
   float* dcontrols;      // [B,3]
   float* dspeed;         // [B]
   int* err_flag;
-  __nv_bfloat16 *g0, *g1, *ga, *d1, *d2, *dy_stem;
+  __nv_bfloat16 *g0, *g1, *ga, *dy_stem;
+  // dy ring: the weight-gradient kernels run on a side stream concurrently with the dgrad / BatchNorm chain, so the buffer
+  // a wgrad reads must not be overwritten before it finished: block bi uses dyb[bi & 1] (conv_b), dya[bi & 1] (conv_a),
+  // dyd[k & 1] (k-th downsample)
+  __nv_bfloat16 *dyb[2], *dya[2], *dyd[2];
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_ready[6] = {}, ev_done[6] = {}, ev_join = nullptr;  // slot order: dyb0, dyb1, dya0, dya1, dyd0, dyd1
+  bool pending[6] = {false, false, false, false, false, false};      // a side-stream wgrad still reads the slot
   double* sumsq_partial;
   PackJob* pack_jobs;    // device table for the one-launch weight repack
   int pack_njobs = 0, pack_blocks = 0;
@@ -290,8 +298,11 @@ static long long carve(Model& m, char* base) {
   m.g0 = (__nv_bfloat16*)bp.take(gmax);
   m.g1 = (__nv_bfloat16*)bp.take(gmax);
   m.ga = (__nv_bfloat16*)bp.take(gmax);
-  m.d1 = (__nv_bfloat16*)bp.take(gmax);
-  m.d2 = (__nv_bfloat16*)bp.take(gmax);
+  for (int i = 0; i < 2; ++i) {
+    m.dyb[i] = (__nv_bfloat16*)bp.take(gmax);
+    m.dya[i] = (__nv_bfloat16*)bp.take(gmax);
+    m.dyd[i] = (__nv_bfloat16*)bp.take(gmax);
+  }
   m.dy_stem = (__nv_bfloat16*)bp.take(act_elems(B, 44, 100, 64) * 2);
   m.sumsq_partial = (double*)bp.take(1024 * 8);
   m.wscratch = (float*)bp.take(29LL * WF_SCRATCH_BYTES);
@@ -377,6 +388,9 @@ static int build_plans(Model& m, int B, int mode) {
       WgradFlatParams wf;
       // conv_b: dW_b = wgrad(dy_b = d1, act_a);  ga = relu'(act_a) * dgrad_b(d1), + the BN_a backward reductions
       const int part = bi >= 13 ? 0 : (bi >= 7 ? 1 : (bi >= 3 ? 2 : 3));
+      __nv_bfloat16* dyb = m.dyb[bi & 1];
+      __nv_bfloat16* dya = m.dya[bi & 1];
+      __nv_bfloat16* dyd = m.dyd[part & 1];  // one downsample per layer group
       auto add_wflat = [&](const ConvRef& c, const __nv_bfloat16* dy, const __nv_bfloat16* x, int* idx) -> int {
         float* scratch = (float*)((char*)m.wscratch + (long long)m.wflat_plans.size() * WF_SCRATCH_BYTES);
         CK(build_wgrad_flat(&wf, B, c.gin, c.d.in_c, c.d.out_c, dy, x, scratch));
@@ -384,26 +398,26 @@ static int build_plans(Model& m, int B, int mode) {
         *idx = (int)m.wflat_plans.size() - 1;
         return add_wgrad_reduce_job(&m.red_jobs[part], &wf, m.slots[c.w].off);
       };
-      CK(add_wflat(blk.b, m.d1, blk.act_a, &blk.pl.w_b));
-      CK(build_flat_conv(&f, B, blk.b.gin, blk.b.d.out_c, blk.b.d.in_c, 1, m.d1, blk.b.wd, m.ga, CF_MASK | CF_BNBWD));
+      CK(add_wflat(blk.b, dyb, blk.act_a, &blk.pl.w_b));
+      CK(build_flat_conv(&f, B, blk.b.gin, blk.b.d.out_c, blk.b.d.in_c, 1, dyb, blk.b.wd, m.ga, CF_MASK | CF_BNBWD));
       f.mask = blk.act_a; f.y1 = blk.a.y; f.stat1 = blk.a.bn.vec; f.bred1 = blk.a.bn.bred;
       blk.pl.d_b = add_flat(m, f);
       // conv_a: dW_a = wgrad(dy_a = d1, in); downsample: dW_ds = wgrad(dy_ds = d2, in)
       if (blk.a.flat) {
-        CK(add_wflat(blk.a, m.d1, blk.in, &blk.pl.w_a_flat));
+        CK(add_wflat(blk.a, dya, blk.in, &blk.pl.w_a_flat));
       } else {
-        CK(build_wgrad(&wp, &blk.a.d, m.d1, blk.in, nullptr, &blk.a.gin, &blk.a.gout));
+        CK(build_wgrad(&wp, &blk.a.d, dya, blk.in, nullptr, &blk.a.gin, &blk.a.gout));
         m.wold_plans.push_back(wp); blk.pl.w_a_old = (int)m.wold_plans.size() - 1;
       }
       if (blk.has_ds) {
-        CK(build_wgrad(&wp, &blk.ds.d, m.d2, blk.in, nullptr, &blk.ds.gin, &blk.ds.gout));
+        CK(build_wgrad(&wp, &blk.ds.d, dyd, blk.in, nullptr, &blk.ds.gin, &blk.ds.gout));
         m.wold_plans.push_back(wp); blk.pl.w_ds_old = (int)m.wold_plans.size() - 1;
       }
       // gradient of the block input: dgrad_a(d1) + identity path (dz of this block) | + dgrad_ds(d2)
       if (blk.a.flat) {
         int fl = CF_RESIDUAL;
         if (bi > 0) fl |= CF_MASK | CF_BNBWD | (m.blocks[bi - 1].has_ds ? CF_BNBWD2 : 0);
-        CK(build_flat_conv(&f, B, blk.a.gin, blk.a.d.out_c, blk.a.d.in_c, 1, m.d1, blk.a.wd, gnext, fl));
+        CK(build_flat_conv(&f, B, blk.a.gin, blk.a.d.out_c, blk.a.d.in_c, 1, dya, blk.a.wd, gnext, fl));
         f.residual = gcur;
         if (bi > 0) {
           Block& pb = m.blocks[bi - 1];
@@ -416,7 +430,7 @@ static int build_plans(Model& m, int B, int mode) {
         for (int ph = 0; ph < 2; ++ph)
           for (int pw = 0; pw < 2; ++pw) {
             const bool fuse = (ph == 0 && pw == 0);
-            CK(build_dgrad(&p, &blk.a.d, ph, pw, m.d1, blk.a.wd, gnext, nullptr, fuse ? m.d2 : nullptr, fuse ? blk.ds.wd : nullptr,
+            CK(build_dgrad(&p, &blk.a.d, ph, pw, dya, blk.a.wd, gnext, nullptr, fuse ? dyd : nullptr, fuse ? blk.ds.wd : nullptr,
                            &blk.a.gin, &blk.a.gout));
             const int idx = add_old(m, p);
             if (fuse) blk.pl.d_a_old = idx;
@@ -685,19 +699,63 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   static const int part_hi[4] = {15, 12, 6, 2}, part_lo[4] = {13, 7, 3, 0};
   const int b_hi = part < 0 ? 15 : (part < 4 ? part_hi[part] : -1);
   const int b_lo = part < 0 ? 0 : (part < 4 ? part_lo[part] : 0);
+  // Weight gradients (and their split-K reduction) run on the side stream: nothing on the dgrad / BatchNorm chain depends on
+  // them, and their CTAs fill the SMs the chain leaves idle (98-CTA layer3 grids, HBM-bound elementwise kernels).
+  const bool use_side = m.side != nullptr && !m.prof.on;
+  cudaStream_t ws = use_side ? m.side : s;
+  auto slot_write = [&](int slot) -> int {   // main stream is about to overwrite dy slot `slot`
+    if (use_side && m.pending[slot]) {
+      CK(cuda_status(cudaStreamWaitEvent(s, m.ev_done[slot], 0)));
+      m.pending[slot] = false;
+    }
+    return OK;
+  };
+  auto slot_ready = [&](int slot) -> int {   // dy slot `slot` is complete on the main stream: the side stream may read it
+    if (use_side) {
+      CK(cuda_status(cudaEventRecord(m.ev_ready[slot], s)));
+      CK(cuda_status(cudaStreamWaitEvent(m.side, m.ev_ready[slot], 0)));
+    }
+    return OK;
+  };
+  auto slot_read_done = [&](int slot) -> int {  // the side-stream readers of `slot` have been enqueued
+    if (use_side) {
+      CK(cuda_status(cudaEventRecord(m.ev_done[slot], m.side)));
+      m.pending[slot] = true;
+    }
+    return OK;
+  };
   for (int bi = b_hi; bi >= b_lo; --bi) {
     Block& blk = m.blocks[bi];
     const PadGeom& go = blk.b.gout;
     const double cnt = (double)B * blk.b.oh * blk.b.ow;
+    const int sb = bi & 1, sa = 2 + (bi & 1);
+    const int blk_part = bi >= 13 ? 0 : (bi >= 7 ? 1 : (bi >= 3 ? 2 : 3));
+    const int sd = 4 + (blk_part & 1);
+    __nv_bfloat16* dyb = m.dyb[bi & 1];
+    __nv_bfloat16* dya = m.dya[bi & 1];
+    __nv_bfloat16* dyd = m.dyd[blk_part & 1];
     // gcur = dz of this block's output (ReLU-masked), with the reductions of bn_b (and bn_ds) already in their bred
-    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.b.bn, gcur, blk.b.y, cnt, frozen, m.d1, s)));
-    if (blk.has_ds) PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.ds.bn, gcur, blk.ds.y, cnt, frozen, m.d2, s)));
-    PROF(m, PC_WGRAD, s, CK(run_wgrad_flat(m, blk.pl.w_b, s)));            // dW_b
-    PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_b, &blk.a.bn, nullptr, s))); // ga = dz_a (+ BN_a reductions)
-    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.a.bn, m.ga, blk.a.y, cnt, frozen, m.d1, s)));
-    if (blk.pl.w_a_flat >= 0) PROF(m, PC_WGRAD, s, CK(run_wgrad_flat(m, blk.pl.w_a_flat, s)));
-    else PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, blk.pl.w_a_old, blk.a.w, s)));
-    if (blk.has_ds) PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, blk.pl.w_ds_old, blk.ds.w, s)));
+    CK(slot_write(sb));
+    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.b.bn, gcur, blk.b.y, cnt, frozen, dyb, s)));
+    CK(slot_ready(sb));
+    if (blk.has_ds) {
+      CK(slot_write(sd));
+      PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.ds.bn, gcur, blk.ds.y, cnt, frozen, dyd, s)));
+      CK(slot_ready(sd));
+    }
+    PROF(m, PC_WGRAD, ws, CK(run_wgrad_flat(m, blk.pl.w_b, ws)));                     // dW_b
+    CK(slot_read_done(sb));
+    PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_b, &blk.a.bn, nullptr, s)));  // ga = dz_a (+ BN_a reductions)
+    CK(slot_write(sa));
+    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.a.bn, m.ga, blk.a.y, cnt, frozen, dya, s)));
+    CK(slot_ready(sa));
+    if (blk.pl.w_a_flat >= 0) PROF(m, PC_WGRAD, ws, CK(run_wgrad_flat(m, blk.pl.w_a_flat, ws)));
+    else PROF(m, PC_WGRAD, ws, CK(run_wgrad_old(m, blk.pl.w_a_old, blk.a.w, ws)));
+    CK(slot_read_done(sa));
+    if (blk.has_ds) {
+      PROF(m, PC_WGRAD, ws, CK(run_wgrad_old(m, blk.pl.w_ds_old, blk.ds.w, ws)));
+      CK(slot_read_done(sd));
+    }
     if (blk.pl.d_a_flat >= 0) {
       Block* pb = bi > 0 ? &m.blocks[bi - 1] : nullptr;
       PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_a_flat, pb ? &pb->b.bn : nullptr, (pb && pb->has_ds) ? &pb->ds.bn : nullptr, s)));
@@ -711,7 +769,13 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   }
   // fold the split-K partial tiles of this part's flat wgrads into the OIHW gradients (one launch per layer group)
   for (int pt = 0; pt < 4; ++pt)
-    if (part < 0 || part == pt) PROF(m, PC_WGRAD, s, CK(launch_wgrad_reduce(&m.red_jobs[pt], m.grads, s)));
+    if (part < 0 || part == pt) PROF(m, PC_WGRAD, ws, CK(launch_wgrad_reduce(&m.red_jobs[pt], m.grads, ws)));
+  if (use_side) {
+    // join: everything after this call on the caller's stream (allreduce of the part, Adam) sees the finished gradients
+    CK(cuda_status(cudaEventRecord(m.ev_join, m.side)));
+    CK(cuda_status(cudaStreamWaitEvent(s, m.ev_join, 0)));
+    for (int i = 0; i < 6; ++i) m.pending[i] = false;
+  }
   // ---- stem: max-pool backward + ReLU + BN backward, then wgrad ----
   if (part < 0 || part == 4) {
     const BnRef& bn = m.stem.bn;
@@ -815,11 +879,36 @@ int cilrs_model_create(cilrs_model** out, int max_batch, void* workspace, size_t
     delete h;
     return st;
   }
+  if (!getenv("CILRS_NO_SIDE_STREAM")) {
+    // side stream for the weight-gradient kernels (cilrs_model_backward forks and joins it on the caller's stream)
+    // lowest priority: the dgrad / BatchNorm chain on the caller's stream is the critical path and gets the SMs first
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&h->m.side, cudaStreamNonBlocking, prio_lo) != cudaSuccess) h->m.side = nullptr;
+    bool ok = h->m.side != nullptr;
+    for (int i = 0; ok && i < 6; ++i)
+      ok = cudaEventCreateWithFlags(&h->m.ev_ready[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->m.ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->m.ev_join, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok && h->m.side) { cudaStreamDestroy(h->m.side); h->m.side = nullptr; }
+  }
   *out = h;
   return OK;
 }
 
-void cilrs_model_destroy(cilrs_model* h) { delete h; }
+void cilrs_model_destroy(cilrs_model* h) {
+  if (!h) return;
+  if (h->m.side) {
+    cudaStreamSynchronize(h->m.side);
+    for (int i = 0; i < 6; ++i) {
+      if (h->m.ev_ready[i]) cudaEventDestroy(h->m.ev_ready[i]);
+      if (h->m.ev_done[i]) cudaEventDestroy(h->m.ev_done[i]);
+    }
+    if (h->m.ev_join) cudaEventDestroy(h->m.ev_join);
+    cudaStreamDestroy(h->m.side);
+  }
+  delete h;
+}
 
 int cilrs_model_bind(cilrs_model* h, float* params, float* grads, float* buffers, long long* num_batches_tracked) {
   if (!h || !params || !buffers) return ERR_INVALID;
