@@ -273,14 +273,16 @@ def main():
         "gpu_launches": launches_per_step * args.steps,
         "loss_last": loss_last[0],
     }
+    # ---- one profiled eager step (CUDA events around every launch of the plan). With N > 1 the step contains the gradient
+    # allreduce, so EVERY rank runs it (a collective issued by rank 0 alone would hang); only rank 0 collects the timings.
+    torch.cuda.synchronize(dev)
+    if rank == 0:
+        _lib.call("cilrs_model_profile", model._handle, 1)
+    trainer.load_batch(*devb[0])
+    trainer._device_step()
+    torch.cuda.synchronize(dev)
     if rank == 0:
         pk = peaks()
-        # ---- roofline of the dominant kernel (conv_gemm_kernel = fprop + dgrad launches), one profiled eager step ----
-        torch.cuda.synchronize(dev)
-        _lib.call("cilrs_model_profile", model._handle, 1)
-        trainer.load_batch(*devb[0])
-        trainer._device_step()
-        torch.cuda.synchronize(dev)
         out_ms = (ctypes.c_float * 7)()
         out_n = (ctypes.c_int * 7)()
         _lib.call("cilrs_model_profile_collect", model._handle, out_ms, out_n)
