@@ -13,7 +13,9 @@ tensor-core convs with fp32 accumulate, fp32 master weights / heads / optimizer.
   value : frames/s, inputs already in HBM (a rotating pool of device batches), CUDA events over K steps, max over ranks
   e2e   : same steps through the public API with HOST (pinned) uint8 frames: H2D copy + on-device normalise (K0) + step +
           D2H read of the loss scalars every step
-  roofline     : the conv_gemm kernel (fprop+dgrad launches): algorithmic conv FLOPs / time inside those launches
+  roofline     : the implicit-GEMM conv kernels (conv_flat_kernel: 58 of the 77 fprop+dgrad launches, conv_gemm_kernel: stem /
+                 stride-2 / 1x1): algorithmic conv FLOPs / time inside those launches (CUDA events around every launch of
+                 one eager step; the launches also carry the fused BN statistics / ReLU mask / BN-backward reductions)
   cpu_baseline : the oracle port of the reference step (torch fp32 on the host cores), rank 0 / N=1 only
 """
 import argparse
@@ -293,13 +295,24 @@ def main():
         n_gemm = out_n[0] + out_n[1]
         achieved = BATCH * (FLOP_FWD + FLOP_DGRAD) / t_gemm / 1e12 if t_gemm > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
+        traffic, traffic_note = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_flat_traffic.json")))
+            traffic, traffic_note = tj["traffic_bytes_per_launch"], tj["launches"] + " | " + tj["source"]
+        except Exception:
+            pass
         line["roofline"] = {
-            "bound": "tensor", "kernel": "conv_gemm_kernel (implicit-GEMM fprop + dgrad, %d launches/step)" % n_gemm,
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "bound": "tensor",
+            "kernel": "conv_flat_kernel + conv_gemm_kernel (tcgen05 implicit-GEMM fprop + dgrad with fused BN statistics / ReLU mask / "
+                      "BN-backward reductions, %d launches/step)" % n_gemm,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_note": traffic_note,
             "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
             "avg_launch_ms": (out_ms[0] + out_ms[1]) / max(1, n_gemm),
             "wgrad_kernel": {"achieved": BATCH * FLOP_WGRAD / (out_ms[2] * 1e-3) / 1e12 if out_ms[2] > 0 else 0.0,
-                             "frac": (BATCH * FLOP_WGRAD / (out_ms[2] * 1e-3) / 1e12 / peak) if out_ms[2] > 0 else 0.0},
+                             "frac": (BATCH * FLOP_WGRAD / (out_ms[2] * 1e-3) / 1e12 / peak) if out_ms[2] > 0 else 0.0,
+                             "note": "wgrad_flat_kernel + wgrad_reduce_kernel + wgrad_gemm_kernel; in the timed step they run on a side "
+                                     "stream concurrently with the dgrad / BatchNorm chain"},
             "step_level": {"achieved": value / world * FLOP_TRAIN / 1e12, "frac_burst": value / world * FLOP_TRAIN / 1e12 / pk["bf16_tflops"],
                            "frac_sustained": value / world * FLOP_TRAIN / 1e12 / peak,
                            "note": "whole-step frames/s x 8.305 GFLOP conv work per frame (SURVEY.md §8d)"},

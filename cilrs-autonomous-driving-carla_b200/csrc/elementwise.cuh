@@ -297,11 +297,13 @@ CILRS_DEVINL Vec8 stem_gather_grad(const BnBwdReduceParams& p, int n, int h, int
   for (int q = 0; q < 4; ++q) {
     if (ok[q]) {
       const uint32_t gw[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
+      const uint32_t cc = (uint32_t)code[q] * 0x01010101u;
+      const uint32_t m_lo = __vcmpeq4(am[q].x, cc), m_hi = __vcmpeq4(am[q].y, cc);  // 0xFF in every byte whose arg-max is this pixel
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int sel = (int)(((k < 4 ? am[q].x : am[q].y) >> ((k & 3) * 8)) & 0xFF);
+        const uint32_t mk = ((k < 4 ? m_lo : m_hi) >> ((k & 3) * 8)) & 1u;
         const float gv = (k & 1) ? bf16hi(gw[k >> 1]) : bf16lo(gw[k >> 1]);
-        if (sel == code[q]) acc.v[k] += gv;
+        acc.v[k] = fmaf((float)mk, gv, acc.v[k]);
       }
     }
   }

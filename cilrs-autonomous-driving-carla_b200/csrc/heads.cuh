@@ -51,22 +51,26 @@ CILRS_DEVINL void gemv_rows(const float* __restrict__ W, const float* __restrict
                             bool relu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = HD_THREADS / 32;
   const int n4 = in >> 2;
-  // four output rows per warp iteration: 4 independent load/FMA chains per lane hide the L2 latency of the weight rows
-  for (int o0 = warp * 4; o0 < out; o0 += nwarps * 4) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  // eight output rows per warp iteration: 8 independent load/FMA chains per lane hide the L2 latency of the weight rows
+  constexpr int R = 8;
+  for (int o0 = warp * R; o0 < out; o0 += nwarps * R) {
+    float acc[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) acc[q] = 0.f;
     for (int i = lane; i < n4; i += 32) {
       const float4 x4 = *reinterpret_cast<const float4*>(x + 4 * i);
+      float4 w4[R];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (o0 + q < out) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(o0 + q) * in) + i);
-          acc[q] = fmaf(w4.x, x4.x, acc[q]); acc[q] = fmaf(w4.y, x4.y, acc[q]);
-          acc[q] = fmaf(w4.z, x4.z, acc[q]); acc[q] = fmaf(w4.w, x4.w, acc[q]);
-        }
+      for (int q = 0; q < R; ++q)
+        w4[q] = (o0 + q < out) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(o0 + q) * in) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        acc[q] = fmaf(w4[q].x, x4.x, acc[q]); acc[q] = fmaf(w4[q].y, x4.y, acc[q]);
+        acc[q] = fmaf(w4[q].z, x4.z, acc[q]); acc[q] = fmaf(w4[q].w, x4.w, acc[q]);
       }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < R; ++q) {
       const float r = warp_sum(acc[q]);
       if (lane == 0 && o0 + q < out) {
         float v = r + b[o0 + q];
@@ -220,25 +224,38 @@ struct HeadsBwdParams {
   float dropout_p;
 };
 
-// y[i] = sum_o W[o,i] * d[o]  (transposed GEMV; consecutive threads read consecutive i -> coalesced)
-CILRS_DEVINL void gemv_cols(const float* __restrict__ W, const float* d, int in, int out, float* y) {
-  for (int i = threadIdx.x; i < in; i += HD_THREADS) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int o = 0;
-#pragma unroll 4
-    for (; o + 3 < out; o += 4) {  // 4 independent chains x unroll 4 = 16 loads in flight per thread
-      a0 = fmaf(__ldg(W + (size_t)o * in + i), d[o], a0);
-      a1 = fmaf(__ldg(W + (size_t)(o + 1) * in + i), d[o + 1], a1);
-      a2 = fmaf(__ldg(W + (size_t)(o + 2) * in + i), d[o + 2], a2);
-      a3 = fmaf(__ldg(W + (size_t)(o + 3) * in + i), d[o + 3], a3);
+// y[i] = sum_o W[o*ld + i] * d[o], i < in  (transposed GEMV). Threads = (column quad, row slice): float4 loads of four
+// consecutive columns (coalesced across the quad index), `slices` = 256 / (in/4) independent row slices summed through
+// `scratch` (>= 1024 floats of shared memory), so the serial chain per thread is out / slices rows.
+// Contains __syncthreads(): every thread of the CTA must call it; in % 4 == 0, in <= 512.
+CILRS_DEVINL void gemv_cols(const float* __restrict__ W, int ld, const float* d, int in, int out, float* y, float* scratch) {
+  const int ncg = in >> 2;
+  int slices = HD_THREADS / ncg;
+  if (slices > 8) slices = 8;
+  const int cg = threadIdx.x % ncg, sl = threadIdx.x / ncg;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sl < slices) {
+    const float4* wp = reinterpret_cast<const float4*>(W) + cg;
+    const int ld4 = ld >> 2;
+#pragma unroll 8
+    for (int o = sl; o < out; o += slices) {
+      const float4 w = __ldg(wp + (size_t)o * ld4);
+      const float dv = d[o];
+      acc.x = fmaf(w.x, dv, acc.x); acc.y = fmaf(w.y, dv, acc.y); acc.z = fmaf(w.z, dv, acc.z); acc.w = fmaf(w.w, dv, acc.w);
     }
-    for (; o < out; ++o) a0 = fmaf(__ldg(W + (size_t)o * in + i), d[o], a0);
-    y[i] = (a0 + a1) + (a2 + a3);
+    *reinterpret_cast<float4*>(scratch + sl * in + cg * 4) = acc;
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < in; i += HD_THREADS) {
+    float v = scratch[i];
+    for (int k = 1; k < slices; ++k) v += scratch[k * in + i];
+    y[i] = v;
+  }
+  __syncthreads();  // scratch is reused by the next call
 }
 
 __global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const HeadsBwdParams p) {
-  __shared__ float d_a[256], d_b[256], dx[640], dx2[512], d3[4];
+  __shared__ __align__(16) float d_a[256], d_b[256], dx[640], dx2[512], d3[4], scratch[1024];
   const int b = blockIdx.x, t = threadIdx.x;
   long long cmd = p.command[b];
   const int k = cmd < 0 ? 0 : (cmd > 3 ? 3 : (int)cmd);
@@ -250,7 +267,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const HeadsBwdPar
     p.sv.d_br6[(size_t)b * 4 + t] = v;
   }
   __syncthreads();
-  gemv_cols(p.w.br6_w[k], d3, 256, 3, d_a);
+  gemv_cols(p.w.br6_w[k], 256, d3, 256, 3, d_a, scratch);
   __syncthreads();
   {
     const float v = p.sv.b2[(size_t)b * 256 + t] > 0.f ? d_a[t] * ks : 0.f;
@@ -258,7 +275,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const HeadsBwdPar
     p.sv.d_br3[(size_t)b * 256 + t] = v;
   }
   __syncthreads();
-  gemv_cols(p.w.br3_w[k], d_a, 256, 256, d_b);
+  gemv_cols(p.w.br3_w[k], 256, d_a, 256, 256, d_b, scratch);
   __syncthreads();
   {
     const float v = p.sv.b1[(size_t)b * 256 + t] > 0.f ? d_b[t] * ks : 0.f;
@@ -266,7 +283,8 @@ __global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const HeadsBwdPar
     p.sv.d_br0[(size_t)b * 256 + t] = v;
   }
   __syncthreads();
-  gemv_cols(p.w.br0_w[k], d_b, 640, 256, dx);
+  gemv_cols(p.w.br0_w[k], 640, d_b, 512, 256, dx, scratch);
+  gemv_cols(p.w.br0_w[k] + 512, 640, d_b, 128, 256, dx + 512, scratch);
   __syncthreads();
   // ---- speed predictor ----
   if (t == 0) {
@@ -280,7 +298,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const HeadsBwdPar
     p.sv.d_sp3[(size_t)b * 256 + t] = v;
   }
   __syncthreads();
-  gemv_cols(p.w.sp3_w, d_a, 256, 256, d_b);
+  gemv_cols(p.w.sp3_w, 256, d_a, 256, 256, d_b, scratch);
   __syncthreads();
   {
     const float v = p.sv.p1[(size_t)b * 256 + t] > 0.f ? d_b[t] * ks : 0.f;
@@ -288,7 +306,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const HeadsBwdPar
     p.sv.d_sp0[(size_t)b * 256 + t] = v;
   }
   __syncthreads();
-  gemv_cols(p.w.sp0_w, d_b, 512, 256, dx2);
+  gemv_cols(p.w.sp0_w, 512, d_b, 512, 256, dx2, scratch);
   __syncthreads();
   for (int i = t; i < 512; i += HD_THREADS) p.dfeat[(size_t)b * 512 + i] = dx[i] + dx2[i];
   // ---- speed encoder ----
@@ -298,7 +316,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const HeadsBwdPar
     p.sv.d_se3[(size_t)b * 128 + t] = v;
   }
   __syncthreads();
-  gemv_cols(p.w.se3_w, d_a, 128, 128, d_b);
+  gemv_cols(p.w.se3_w, 128, d_a, 128, 128, d_b, scratch);
   __syncthreads();
   if (t < 128) {
     const float v = p.sv.s1[(size_t)b * 128 + t] > 0.f ? d_b[t] * ks : 0.f;
