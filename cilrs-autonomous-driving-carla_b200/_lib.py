@@ -23,7 +23,7 @@ class FlatConvArgs(ctypes.Structure):
     """cilrs_flat_conv_args (include/cilrs_b200.h)"""
     _P, _I, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     _fields_ = [("batch", _I), ("H", _I), ("W", _I), ("in_c", _I), ("out_c", _I), ("dgrad", _I), ("flags", _I),
-                ("x", _P), ("w", _P), ("y", _P), ("scale", _P), ("bias", _P), ("residual", _P), ("mask", _P),
+                ("x", _P), ("w", _P), ("y", _P), ("scale", _P), ("bias", _P), ("residual", _P), ("mask", _P), ("mask_bits", _P),
                 ("gamma", _P), ("beta", _P), ("running_mean", _P), ("running_var", _P), ("num_batches_tracked", _P),
                 ("vec", _P), ("momentum", _F), ("eps", _F), ("update_running", _I),
                 ("y1", _P), ("vec1", _P), ("bred1", _P), ("dgamma1", _P), ("dbeta1", _P),

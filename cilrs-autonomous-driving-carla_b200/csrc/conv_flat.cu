@@ -299,8 +299,9 @@ int cilrs_conv_flat(const cilrs_flat_conv_args* a, void* stream) {
   if ((flags & (CF_STATS | CF_BNBWD)) && (!a->partials_ws || !a->counter_ws)) return ERR_INVALID;
   int st = build_flat_conv(&p, a->batch, g, a->in_c, a->out_c, a->dgrad, a->x, a->w, a->y, flags);
   if (st) return st;
-  p.residual = (const __nv_bfloat16*)a->residual; p.mask = (const __nv_bfloat16*)a->mask; p.scale = a->scale; p.bias = a->bias;
-  p.partials = a->partials_ws; p.counter = a->counter_ws;
+  p.residual = (const __nv_bfloat16*)a->residual; p.mask = (const __nv_bfloat16*)a->mask; p.mask_bits = (const uint8_t*)a->mask_bits;
+  p.scale = a->scale; p.bias = a->bias;
+  p.partials = (double*)a->partials_ws; p.counter = a->counter_ws;
   p.gamma = a->gamma; p.beta = a->beta; p.running_mean = a->running_mean; p.running_var = a->running_var;
   p.nbt = a->num_batches_tracked; p.vec = a->vec; p.count = (double)a->batch * a->H * a->W; p.momentum = a->momentum; p.eps = a->eps;
   p.update_running = a->update_running;

@@ -7,7 +7,7 @@
 // sub-tiles share every weight tile (weights cross 1/mt as often); with 64x64 layers the whole 3x3 filter stays
 // resident in shared memory. Accumulators live in TMEM (acc_sets x mt x block_n columns) so the epilogue of one tile
 // overlaps the MMAs of the next. Persistent CTAs, warp-specialised:
-//   warp 0 : TMA producer     warp 1 : MMA issuer (one lane)     warps 2..9 : two epilogue groups (TMEM -> regs -> smem -> HBM)
+//   warp 0 : TMA producer     warp 1 : MMA issuer     warps 4..11 : two epilogue groups (TMEM -> registers -> HBM)
 // Fused epilogues: folded BN / residual / ReLU (inference), BN batch statistics + finalize (training forward),
 // ReLU mask + BatchNorm-backward reductions + finalize (dgrad). Reductions are deterministic: per-CTA partials in a
 // fixed order, folded by the last CTA to finish.
@@ -114,6 +114,10 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
   const int acc_stride = MT * p.block_n;  // TMEM columns per accumulator set
   const int n_groups = (p.num_taps + p.tap_group - 1) / p.tap_group;
 
+  // 384 threads x 168 registers at launch: warpgroup 0 keeps 64 per thread, the two epilogue warpgroups grow to 216 so that
+  // a unit's operand rows (residual, y) can be prefetched into registers without spilling
+  if (warp < 4) {
+  setmaxnreg_dec<64>();
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
@@ -213,12 +217,14 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
       if (++acc == p.acc_sets) { acc = 0; accph ^= 1; }
       first = false;
     }
+  }
   } else {
+    setmaxnreg_inc<216>();
     // ================= epilogue: 2 groups x 4 warps; a group handles every other 128 x 64 unit =================
     // Register-direct: TMEM -> registers -> (scale/bias, residual, ReLU mask) -> bf16 -> 256-bit global stores; per-channel
     // statistics by a shuffle butterfly into warp-private accumulators. No shared-memory staging and no barriers: the
     // tensor core's operand fetch already saturates the 128 B/clk of shared memory (conv_flat.cu).
-    const int ew = warp - 2;
+    const int ew = warp - 4;
     const int grp = ew >> 2;
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;          // accumulator row
@@ -259,6 +265,16 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
           if (((uc++) & 1u) != (uint32_t)grp) continue;
           const int n_base = n_blk * p.block_n + chunk * 64;
           const long long goff = (long long)f * p.n_total + n_base;
+          // operand loads of this unit are issued first so their latency overlaps the TMEM load; the ReLU mask comes as
+          // 64 bits (two registers) when the producer wrote a bit tensor, which keeps the residual prefetch in registers
+          uint32_t rres[32];
+          uint2 mbits = make_uint2(0xffffffffu, 0xffffffffu);
+          const bool ld_res = (p.flags & CF_RESIDUAL) && valid;
+          const bool use_bits = (p.flags & CF_MASK) && p.mask_bits != nullptr;
+          if (ld_res) load_row64(p.residual + goff, rres);
+          if (use_bits && valid) mbits = __ldg(reinterpret_cast<const uint2*>(p.mask_bits + (goff >> 3)));
+          uint32_t ry[32];
+          if (bwd && valid) load_row64(p.y1 + goff, ry);  // consumed by the second butterfly
           uint32_t v[64];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride + m * p.block_n + chunk * 64);
           tmem_ld_32x32(taddr, v);
@@ -270,16 +286,18 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
             for (int j = 0; j < 64; ++j)
               v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), __ldg(p.scale + n_base + j), __ldg(p.bias + n_base + j)));
           }
-          if ((p.flags & CF_RESIDUAL) && valid) {
-            uint32_t r[32];
-            load_row64(p.residual + goff, r);
+          if (ld_res) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) + bf16lo(r[j]));
-              v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) + bf16hi(r[j]));
+              v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) + bf16lo(rres[j]));
+              v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) + bf16hi(rres[j]));
             }
           }
-          if ((p.flags & CF_MASK) && valid) {
+          if (use_bits) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (!(((j < 32 ? mbits.x : mbits.y) >> (j & 31)) & 1u)) v[j] = 0u;
+          } else if ((p.flags & CF_MASK) && valid) {
             uint32_t r[32];
             load_row64(p.mask + goff, r);
 #pragma unroll
@@ -316,21 +334,19 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
               wa[p.block_n] += s1.x; wa[p.block_n + 1] += s1.y;
             } else {
               // sum dz * y (raw); the finalize turns it into sum dz * xhat = rstd * (sum dz*y - mean * sum dz)
-              uint32_t r[32];
-              if (valid) load_row64(p.y1 + goff, r);
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                x[2 * j] = valid ? bf16lo(u[j]) * bf16lo(r[j]) : 0.f;
-                x[2 * j + 1] = valid ? bf16hi(u[j]) * bf16hi(r[j]) : 0.f;
+                x[2 * j] = valid ? bf16lo(u[j]) * bf16lo(ry[j]) : 0.f;
+                x[2 * j + 1] = valid ? bf16hi(u[j]) * bf16hi(ry[j]) : 0.f;
               }
+              if (bwd2 && valid) load_row64(p.y2 + goff, ry);  // overlaps the second butterfly
               const float2 s1 = warp_colsum64(x, lane);
               wa[p.block_n] += s1.x; wa[p.block_n + 1] += s1.y;
               if (bwd2) {
-                if (valid) load_row64(p.y2 + goff, r);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                  x[2 * j] = valid ? bf16lo(u[j]) * bf16lo(r[j]) : 0.f;
-                  x[2 * j + 1] = valid ? bf16hi(u[j]) * bf16hi(r[j]) : 0.f;
+                  x[2 * j] = valid ? bf16lo(u[j]) * bf16lo(ry[j]) : 0.f;
+                  x[2 * j + 1] = valid ? bf16hi(u[j]) * bf16hi(ry[j]) : 0.f;
                 }
                 const float2 s2 = warp_colsum64(x, lane);
                 wa[2 * p.block_n] += s2.x; wa[2 * p.block_n + 1] += s2.y;
@@ -361,7 +377,9 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
 #pragma unroll
         for (int wv = 0; wv < 8; ++wv) t += s_wacc[wv * 3 * p.block_n + i];
         const int k = i / p.block_n, c = i - k * p.block_n;
-        atomicAdd(p.partials + k * p.n_total + nb * p.block_n + c, t);
+        // fp64 accumulation of fp32 partials is exact unless their exponents span more than 2^22, so the result does not
+        // depend on the order in which the CTAs arrive (reproducible statistics without a serial fold)
+        atomicAdd(p.partials + k * p.n_total + nb * p.block_n + c, (double)t);
       }
       bar_sync_named(3, 256);
       if (tid == 0) {
@@ -399,8 +417,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             if (k < nq) {
-              S[k] = (double)__ldcg(p.partials + k * p.n_total + c);
-              p.partials[k * p.n_total + c] = 0.f;
+              S[k] = __ldcg(p.partials + k * p.n_total + c);
+              p.partials[k * p.n_total + c] = 0.0;
             }
           }
           if (!bwd) {

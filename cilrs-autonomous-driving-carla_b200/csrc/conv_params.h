@@ -88,7 +88,7 @@ struct PadGeom {
   int H, W, Hp, Wp;
 };
 
-constexpr int CF_THREADS = 320;       // warp 0: TMA, warp 1: MMA, warps 2..9: two epilogue groups of 4 warps
+constexpr int CF_THREADS = 384;       // warpgroup 0: TMA (warp 0), MMA (warp 1), two idle warps; warpgroups 1, 2: the two epilogue groups
 constexpr int CF_MAX_A_STAGES = 4;
 constexpr int CF_MAX_B_STAGES = 16;
 constexpr int CF_MAX_ACC = 8;
@@ -123,9 +123,10 @@ struct FlatConvParams {
   __nv_bfloat16* out;
   const __nv_bfloat16* residual;
   const __nv_bfloat16* mask;
+  const uint8_t* mask_bits;    // optional: the same mask as one bit per element ([rows][n_total/8] bytes); used instead of `mask`
   const float* scale;
   const float* bias;
-  float* partials;             // [3][n_total] global accumulators (zero on entry, left zero by the kernel)
+  double* partials;            // [3][n_total] global fp64 accumulators (zero on entry, left zero by the kernel)
   unsigned int* counter;
   // CF_STATS: BatchNorm forward finalize (by the last CTA)
   const float* gamma;

@@ -124,7 +124,10 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
                                                               const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                                                               const __nv_bfloat16* __restrict__ x2, const float* __restrict__ scale2,
                                                               const float* __restrict__ shift2, __nv_bfloat16* __restrict__ out,
-                                                              long long nvec, int C, int relu, const PadGeom g) {
+                                                              long long nvec, int C, int relu, const PadGeom g,
+                                                              uint8_t* __restrict__ bits) {
+  // bits (optional): one byte per 8-channel vector, bit k = (out[channel k] > 0): the ReLU mask the flat dgrad epilogue
+  // applies, 1/16 of the bytes of the activation itself
   pdl_entry();
   const int groups = C >> 3;
   const long long stride = (long long)gridDim.x * EW_THREADS;  // multiple of groups (host guarantees)
@@ -136,7 +139,11 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
   PadWalk walk;
   walk.init(i / groups, stride / groups, g);
   for (; i < nvec; i += stride, walk.next()) {
-    if (!walk.valid()) { store8_zero(out + i * 8); continue; }
+    if (!walk.valid()) {
+      store8_zero(out + i * 8);
+      if (bits) bits[i] = 0;
+      continue;
+    }
     Vec8 a = load8(x + i * 8);
 #pragma unroll
     for (int k = 0; k < 8; ++k) a.v[k] = fmaf(a.v[k], sc.v[k], sh.v[k]);
@@ -155,6 +162,12 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
       for (int k = 0; k < 8; ++k) a.v[k] = fmaxf(a.v[k], 0.f);
     }
     store8(out + i * 8, a);
+    if (bits) {
+      unsigned int m = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m |= (__bfloat162float(__float2bfloat16(a.v[k])) > 0.f ? 1u : 0u) << k;
+      bits[i] = (uint8_t)m;
+    }
   }
 }
 
@@ -250,7 +263,7 @@ struct BnBwdReduceParams {
   const float* rstd;
   long long nvec;
   int C;
-  float* partial;       // [2][C] global accumulators, zero on entry and left zero
+  double* partial;      // [2][C] global fp64 accumulators, zero on entry and left zero
   unsigned int* counter;
   float* bsum;          // [C]
   float* bdot;          // [C]
@@ -395,9 +408,10 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
       for (int k = 0; k < 8; ++k) { t_sum[k] += s_red[t][k]; t_dot[k] += s_red[EW_THREADS + t][k]; }
     }
     // global per-channel accumulators [2][C] (zero on entry, re-zeroed by the last CTA)
-    float* pp = p.partial + threadIdx.x * 8;
+    // (fp64 adds of fp32 partials: exact, hence order-independent, unless their exponents span more than 2^22)
+    double* pp = p.partial + threadIdx.x * 8;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { atomicAdd(pp + k, t_sum[k]); atomicAdd(pp + p.C + k, t_dot[k]); }
+    for (int k = 0; k < 8; ++k) { atomicAdd(pp + k, (double)t_sum[k]); atomicAdd(pp + p.C + k, (double)t_dot[k]); }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -409,9 +423,9 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
   __syncthreads();
   if (s_last) {
     for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
-      const float s = __ldcg(p.partial + c), d = __ldcg(p.partial + p.C + c);
-      p.partial[c] = 0.f;
-      p.partial[p.C + c] = 0.f;
+      const float s = (float)__ldcg(p.partial + c), d = (float)__ldcg(p.partial + p.C + c);
+      p.partial[c] = 0.0;
+      p.partial[p.C + c] = 0.0;
       p.bsum[c] = s;
       p.bdot[c] = d;
       if (p.dgamma) p.dgamma[c] += d;

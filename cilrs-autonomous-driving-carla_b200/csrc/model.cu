@@ -56,6 +56,8 @@ struct Block {
   const __nv_bfloat16* in;
   __nv_bfloat16* act_a;
   __nv_bfloat16* out;
+  uint8_t* bits_a;    // ReLU bits of act_a / out (one bit per element), written by bn_apply, read by the flat dgrad epilogues
+  uint8_t* bits_out;
   int in_h, in_w, in_c;
   BlockPlan pl;
 };
@@ -125,7 +127,7 @@ struct Model {
   uint8_t* pool_arg;
   float* stats;          // shared stats-partials scratch
   float* bwd_partial;    // BN backward partials
-  float* stat_acc;
+  double* stat_acc;
   unsigned int* counters;
   float* unit_vec;       // [2][64]: ones, zeros (max-pool on already-activated stem output)
   float* feat;           // [B,512]
@@ -265,13 +267,15 @@ static long long carve(Model& m, char* base) {
     if (blk.has_ds) carve_conv(bp, blk.ds, B);
     blk.act_a = (__nv_bfloat16*)bp.take(pad_elems(B, blk.a.gout, blk.a.d.out_c) * 2);
     blk.out = (__nv_bfloat16*)bp.take(pad_elems(B, blk.b.gout, blk.b.d.out_c) * 2);
+    blk.bits_a = (uint8_t*)bp.take(pad_elems(B, blk.a.gout, blk.a.d.out_c) / 8);
+    blk.bits_out = (uint8_t*)bp.take(pad_elems(B, blk.b.gout, blk.b.d.out_c) / 8);
     prev = blk.out;
   }
   // stats partial scratch: the stem has the most tiles (<= ceil(B*4400/100) ~ 44*B + slack), 2 x 64 floats each;
   // deeper layers have fewer tiles x more channels; bound by B*44*100/64 tiles * 2 * 64
   m.stats = (float*)bp.take(256LL * 2 * 512 * 4);  // one (sum, sumsq)[C<=512] partial per persistent conv CTA (<= SM count)
   m.bwd_partial = (float*)bp.take((long long)EW_MAX_BLOCKS * 2 * 512 * 4);
-  m.stat_acc = (float*)bp.take(3 * 512 * 4);  // flat kernels: per-channel statistics accumulators (kept zero between launches)
+  m.stat_acc = (double*)bp.take(3 * 512 * 8);  // per-channel fp64 statistics accumulators (kept zero between launches)
   m.counters = (unsigned int*)bp.take(64);
   m.unit_vec = (float*)bp.take(2 * 64 * 4);
   m.feat = (float*)bp.take((long long)B * 512 * 4);
@@ -400,7 +404,7 @@ static int build_plans(Model& m, int B, int mode) {
       };
       CK(add_wflat(blk.b, dyb, blk.act_a, &blk.pl.w_b));
       CK(build_flat_conv(&f, B, blk.b.gin, blk.b.d.out_c, blk.b.d.in_c, 1, dyb, blk.b.wd, m.ga, CF_MASK | CF_BNBWD));
-      f.mask = blk.act_a; f.y1 = blk.a.y; f.stat1 = blk.a.bn.vec; f.bred1 = blk.a.bn.bred;
+      f.mask = blk.act_a; f.mask_bits = blk.bits_a; f.y1 = blk.a.y; f.stat1 = blk.a.bn.vec; f.bred1 = blk.a.bn.bred;
       blk.pl.d_b = add_flat(m, f);
       // conv_a: dW_a = wgrad(dy_a = d1, in); downsample: dW_ds = wgrad(dy_ds = d2, in)
       if (blk.a.flat) {
@@ -422,6 +426,7 @@ static int build_plans(Model& m, int B, int mode) {
         if (bi > 0) {
           Block& pb = m.blocks[bi - 1];
           f.mask = blk.in;  // = output of the previous block
+          f.mask_bits = pb.bits_out;
           f.y1 = pb.b.y; f.stat1 = pb.b.bn.vec; f.bred1 = pb.b.bn.bred;
           if (pb.has_ds) { f.y2 = pb.ds.y; f.stat2 = pb.ds.bn.vec; f.bred2 = pb.ds.bn.bred; }
         }
@@ -458,12 +463,12 @@ static int run_bn_finalize(Model& m, const BnRef& bn, int tiles, double count, i
 
 // out = relu?( bn(x) [+ res] [+ bn2(x2)] ) on padded-flat tensors of geometry g
 static int run_bn_apply(int B, const PadGeom& g, const __nv_bfloat16* x, const BnRef& bn, const __nv_bfloat16* res, const __nv_bfloat16* x2,
-                        const BnRef* bn2, __nv_bfloat16* out, int relu, cudaStream_t s) {
+                        const BnRef* bn2, __nv_bfloat16* out, int relu, uint8_t* bits, cudaStream_t s) {
   const long long nvec = pad_elems(B, g, bn.C) / 8;
   ++g_cilrs_launches;
   return cuda_status(launch_pdl(bn_apply_kernel, dim3(ew_grid(nvec, bn.C)), dim3(EW_THREADS), 0, s, x, (const float*)bn.vec,
                                 (const float*)(bn.vec + bn.C), res, x2, (const float*)(bn2 ? bn2->vec : nullptr),
-                                (const float*)(bn2 ? bn2->vec + bn2->C : nullptr), out, nvec, bn.C, relu, g));
+                                (const float*)(bn2 ? bn2->vec + bn2->C : nullptr), out, nvec, bn.C, relu, g, bits));
 }
 
 // flat conv with the train-mode BatchNorm statistics + finalize fused (pointers bound at launch time)
@@ -561,11 +566,11 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
         return OK;
       };
       CK(conv_bn(blk.a, blk.pl.f_a_flat, blk.pl.f_a_old));
-      PROF(m, PC_BN_FWD, s, CK(run_bn_apply(B, blk.a.gout, blk.a.y, blk.a.bn, nullptr, nullptr, nullptr, blk.act_a, 1, s)));
+      PROF(m, PC_BN_FWD, s, CK(run_bn_apply(B, blk.a.gout, blk.a.y, blk.a.bn, nullptr, nullptr, nullptr, blk.act_a, 1, blk.bits_a, s)));
       if (blk.has_ds) CK(conv_bn(blk.ds, -1, blk.pl.f_ds_old));
       CK(conv_bn(blk.b, blk.pl.f_b_flat, -1));
-      if (blk.has_ds) PROF(m, PC_BN_FWD, s, CK(run_bn_apply(B, blk.b.gout, blk.b.y, blk.b.bn, nullptr, blk.ds.y, &blk.ds.bn, blk.out, 1, s)));
-      else PROF(m, PC_BN_FWD, s, CK(run_bn_apply(B, blk.b.gout, blk.b.y, blk.b.bn, blk.in, nullptr, nullptr, blk.out, 1, s)));
+      if (blk.has_ds) PROF(m, PC_BN_FWD, s, CK(run_bn_apply(B, blk.b.gout, blk.b.y, blk.b.bn, nullptr, blk.ds.y, &blk.ds.bn, blk.out, 1, blk.bits_out, s)));
+      else PROF(m, PC_BN_FWD, s, CK(run_bn_apply(B, blk.b.gout, blk.b.y, blk.b.bn, blk.in, nullptr, nullptr, blk.out, 1, blk.bits_out, s)));
     }
   }
   avgpool_kernel<<<(B * 512 + 255) / 256, 256, 0, s>>>(m.blocks.back().out, m.feat, B, 512, m.blocks.back().b.gout); ++g_cilrs_launches;
@@ -1041,14 +1046,14 @@ static int abi_geom(int pad_h, int pad_w, long long elems, int C, PadGeom* g) {
 }
 
 int cilrs_bn_apply(const void* x, const float* vec, const void* residual, const void* x2, const float* vec2, void* out,
-                   long long elems, int C, int relu, int pad_h, int pad_w, void* stream) {
+                   long long elems, int C, int relu, int pad_h, int pad_w, uint8_t* relu_bits, void* stream) {
   if (!x || !vec || !out || C < 64 || C % 64 || elems % C) return ERR_INVALID;
   PadGeom g;
   CK(abi_geom(pad_h, pad_w, elems, C, &g));
   const long long nvec = elems / 8;
   bn_apply_kernel<<<ew_grid(nvec, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, vec, vec + C, (const __nv_bfloat16*)residual, (const __nv_bfloat16*)x2, vec2, vec2 ? vec2 + C : nullptr,
-      (__nv_bfloat16*)out, nvec, C, relu, g); ++g_cilrs_launches;
+      (__nv_bfloat16*)out, nvec, C, relu, g, relu_bits); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
@@ -1082,7 +1087,7 @@ int cilrs_bn_backward(const void* g, const void* act, const void* y, const float
   float* bred = workspace + (size_t)EW_MAX_BLOCKS * 2 * C;
   BnBwdReduceParams rp{};
   rp.g = (const __nv_bfloat16*)g; rp.act = (const __nv_bfloat16*)act; rp.y = (const __nv_bfloat16*)y;
-  rp.mean = vec + 2 * C; rp.rstd = vec + 3 * C; rp.nvec = nvec; rp.C = C; rp.partial = workspace; rp.counter = counter;
+  rp.mean = vec + 2 * C; rp.rstd = vec + 3 * C; rp.nvec = nvec; rp.C = C; rp.partial = (double*)workspace; rp.counter = counter;
   rp.bsum = bred; rp.bdot = bred + C; rp.dgamma = dgamma; rp.dbeta = dbeta; rp.geom = geom;
   BnBwdApplyParams ap{};
   ap.g = rp.g; ap.act = rp.act; ap.y = rp.y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = gamma; ap.bsum = rp.bsum; ap.bdot = rp.bdot;

@@ -79,8 +79,16 @@ def from_padded(xp, h, w):
     return xp[:, :h, :w].contiguous()
 
 
+def relu_bits(act_pad):
+    """[B,Hp,Wp,C] activation -> uint8 [B,Hp,Wp,C/8], bit k of byte j = (act[..., 8j+k] > 0) (what cilrs_bn_apply emits)."""
+    b, hp, wp, c = act_pad.shape
+    m = (act_pad.float() > 0).view(b, hp, wp, c // 8, 8).to(torch.int32)
+    w = (2 ** torch.arange(8, device=act_pad.device, dtype=torch.int32)).view(1, 1, 1, 1, 8)
+    return (m * w).sum(-1).to(torch.uint8).contiguous()
+
+
 def conv_flat(x_pad, w_pack, out_c, dgrad=False, scale=None, bias=None, residual=None, mask=None, relu=False,
-              bn=None, bnbwd=None, bnbwd2=None):
+              bn=None, bnbwd=None, bnbwd2=None, mask_bits=None):
     """3x3 stride-1 conv (fprop or dgrad) on padded-flat tensors. x_pad [B,H+1,W+1,Cin] bf16 -> [B,H+1,W+1,out_c].
     bn = dict(gamma, beta, running_mean, running_var, nbt, update) -> also returns vec [4,out_c] (fused train-mode BN
     statistics + finalize). bnbwd = dict(y, vec, dgamma, dbeta) -> also returns bred [2,out_c] (fused BN-backward reduce)."""
@@ -103,6 +111,7 @@ def conv_flat(x_pad, w_pack, out_c, dgrad=False, scale=None, bias=None, residual
     if mask is not None:
         flags |= EPI_MASK
         a.mask = ptr(mask)
+        a.mask_bits = ptr(mask_bits)
     if relu:
         flags |= EPI_RELU
     extra = []

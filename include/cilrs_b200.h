@@ -111,6 +111,7 @@ typedef struct cilrs_flat_conv_args {
   const float* bias;
   const void* residual; /* padded-flat [rows][out_c] */
   const void* mask;     /* padded-flat [rows][out_c] */
+  const void* mask_bits; /* optional uint8 [rows][out_c / 8]: the same mask, one bit per element (see cilrs_bn_apply) */
   const float* gamma;
   const float* beta;
   float* running_mean;
@@ -222,13 +223,16 @@ int cilrs_bn_finalize(const float* partials, int tiles, int C, double count, con
                       int training, int update_running, float* vec, void* stream);
 /* pad_h, pad_w > 0 (both): every activation argument is in the padded-flat layout [batch, pad_h+1, pad_w+1, C] (see
  * cilrs_conv_flat) and `elems` counts the padding pixels too; they are written as zeros and never read. 0, 0 = dense NHWC. */
+/* relu_bits (optional): uint8 [elems / 8], bit k of byte i = (out[8 i + k] > 0): the ReLU mask as a bit tensor, which the
+ * flat dgrad epilogue (cilrs_flat_conv_args.mask_bits) reads instead of the bf16 activation */
 int cilrs_bn_apply(const void* x, const float* vec, const void* residual, const void* x2, const float* vec2, void* out,
-                   long long elems, int C, int relu, int pad_h, int pad_w, void* stream);
+                   long long elems, int C, int relu, int pad_h, int pad_w, uint8_t* relu_bits, void* stream);
 /* padded_out != 0: out is padded-flat [batch, (H+1)/2+1, (W+1)/2+1, C] (padding pixels untouched); argmax stays dense */
 int cilrs_bn_relu_maxpool(const void* y, const float* vec, void* out, uint8_t* argmax, int batch, int H, int W, int C,
                           int padded_out, void* stream);
 /* stem variant (argmax != NULL): pad_h > 0 means the pooled gradient g is padded-flat.
- * workspace: cilrs_bn_backward_workspace_floats(C) floats, the first 2*C ZERO on entry (left zero); counter: zeroed uint32 */
+ * workspace: cilrs_bn_backward_workspace_floats(C) floats, 8-byte aligned, the first 4*C ZERO on entry (fp64 accumulators,
+ * left zero); counter: zeroed uint32 */
 int cilrs_bn_backward(const void* g, const void* act, const void* y, const float* vec, const float* gamma, long long elems,
                       int C, double count, int frozen, void* dy, void* dz, float* dgamma, float* dbeta, float* workspace,
                       unsigned int* counter, const uint8_t* argmax, int H, int W, int pad_h, int pad_w, void* stream);

@@ -61,7 +61,7 @@ def test_bn_train_forward_and_running_stats(shape):
     res = torch.randn(B, H, W, C, generator=g, device="cuda").to(torch.bfloat16)
     vec = _finalize(st, C, B * H * W, gamma, beta, rm, rv, nbt, True)
     out = torch.empty_like(y)
-    _lib.call("cilrs_bn_apply", y, vec, res, None, None, out, ctypes.c_longlong(y.numel()), C, 1, 0, 0, _lib.stream_ptr())
+    _lib.call("cilrs_bn_apply", y, vec, res, None, None, out, ctypes.c_longlong(y.numel()), C, 1, 0, 0, None, _lib.stream_ptr())
     torch.cuda.synchronize()
     yf = y.float().permute(0, 3, 1, 2)
     ref = F.batch_norm(yf, rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5)
@@ -71,7 +71,7 @@ def test_bn_train_forward_and_running_stats(shape):
     # frozen (eval) statistics + second BN'd input (downsample branch)
     vec_e = _finalize(None, C, 1.0, gamma, beta, rm, rv, None, False, 0)
     out2 = torch.empty_like(y)
-    _lib.call("cilrs_bn_apply", y, vec_e, None, res, vec, out2, ctypes.c_longlong(y.numel()), C, 0, 0, 0, _lib.stream_ptr())
+    _lib.call("cilrs_bn_apply", y, vec_e, None, res, vec, out2, ctypes.c_longlong(y.numel()), C, 0, 0, 0, None, _lib.stream_ptr())
     torch.cuda.synchronize()
     ref2 = F.batch_norm(yf, rm, rv, gamma, beta, False, 0.1, 1e-5) + F.batch_norm(res.float().permute(0, 3, 1, 2), None, None, gamma, beta, True, 0.1, 1e-5) * 0
     # second input normalised with `vec` (batch statistics of y): restate directly
@@ -92,7 +92,7 @@ def test_bn_relu_backward(shape, frozen):
     rm, rv = 0.1 * torch.randn(C, generator=gen, device="cuda"), torch.rand(C, generator=gen, device="cuda") + 0.5
     vec = _finalize(st, C, B * H * W, gamma, beta, rm.clone(), rv.clone(), None, not frozen, 0)
     act = torch.empty_like(y)
-    _lib.call("cilrs_bn_apply", y, vec, None, None, None, act, ctypes.c_longlong(y.numel()), C, 1, 0, 0, _lib.stream_ptr())
+    _lib.call("cilrs_bn_apply", y, vec, None, None, None, act, ctypes.c_longlong(y.numel()), C, 1, 0, 0, None, _lib.stream_ptr())
     gup = torch.randn(B, H, W, C, generator=gen, device="cuda").to(torch.bfloat16)
     dy, dz = torch.empty_like(y), torch.empty_like(y)
     dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
@@ -164,10 +164,10 @@ def test_padded_flat_layout_bn_apply_and_backward_equal_the_dense_kernels(shape)
     vec = _finalize(st, C, B * H * W, gamma, beta, rm, rv, None, True, 0)
     res = torch.randn(B, H, W, C, generator=gen, device="cuda").to(torch.bfloat16)
     out_d = torch.empty_like(y)
-    _lib.call("cilrs_bn_apply", y, vec, res, None, None, out_d, ctypes.c_longlong(y.numel()), C, 1, 0, 0, _lib.stream_ptr())
+    _lib.call("cilrs_bn_apply", y, vec, res, None, None, out_d, ctypes.c_longlong(y.numel()), C, 1, 0, 0, None, _lib.stream_ptr())
     yp, resp = ops.to_padded(y), ops.to_padded(res)
     out_p = torch.full_like(yp, float("nan"))
-    _lib.call("cilrs_bn_apply", yp, vec, resp, None, None, out_p, ctypes.c_longlong(yp.numel()), C, 1, H, W, _lib.stream_ptr())
+    _lib.call("cilrs_bn_apply", yp, vec, resp, None, None, out_p, ctypes.c_longlong(yp.numel()), C, 1, H, W, None, _lib.stream_ptr())
     torch.cuda.synchronize()
     assert torch.equal(ops.from_padded(out_p, H, W), out_d)
     assert float(out_p[:, H:].float().abs().max()) == 0.0 and float(out_p[:, :, W:].float().abs().max()) == 0.0

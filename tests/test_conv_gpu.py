@@ -357,3 +357,28 @@ def test_flat_dgrad_fused_relu_mask_and_bn_backward_reduce(case):
         _report("bsum2", bred2[0], dzf.sum((0, 1, 2)), 2e-4)
         _report("bdot2", bred2[1], (dzf * xhat2).sum((0, 1, 2)), 2e-4)
         _report("dgamma2", dg2, (dzf * xhat2).sum((0, 1, 2)), 2e-4)
+
+
+def test_flat_dgrad_relu_mask_as_bit_tensor_equals_the_bf16_mask():
+    """the ReLU mask read as one bit per element (written by cilrs_bn_apply) gives the same dz as the bf16 activation"""
+    ops = _ops()
+    from cilrs_b200 import _lib
+    import ctypes
+    _ref_setup()
+    b, h, w, c = 7, 11, 25, 128
+    d = ops.conv_desc(b, h, w, c, c, 3, 1)
+    dy = _mk((b, c, h, w), 50).to(torch.bfloat16)
+    wt = _mk((c, c, 3, 3), 51) * (2.0 / (c * 9)) ** 0.5
+    _, wd = ops.pack_weight(d, wt)
+    ypre = ops.to_padded(_mk((b, h, w, c), 52).to(torch.bfloat16))
+    vec = torch.stack([torch.ones(c), torch.zeros(c), torch.zeros(c), torch.ones(c)]).cuda().contiguous()
+    act = torch.empty_like(ypre)
+    bits = torch.full((b, h + 1, w + 1, c // 8), 255, dtype=torch.uint8, device="cuda")
+    _lib.call("cilrs_bn_apply", ypre, vec, None, None, None, act, ctypes.c_longlong(ypre.numel()), c, 1, h, w, bits, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(bits, ops.relu_bits(act))
+    dyp = ops.to_padded(_nhwc_bf16(dy.float()))
+    a = ops.conv_flat(dyp, wd, c, dgrad=True, mask=act)
+    bb = ops.conv_flat(dyp, wd, c, dgrad=True, mask=act, mask_bits=bits)
+    torch.cuda.synchronize()
+    assert torch.equal(a, bb)

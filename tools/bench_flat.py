@@ -62,7 +62,8 @@ for name, h, w, c, count in layers:
     g = _lib.FlatConvArgs()
     g.batch, g.H, g.W, g.in_c, g.out_c, g.dgrad = B, h, w, c, c, 1
     g.flags = ops.EPI_RESIDUAL | ops.EPI_MASK | ops.EPI_BNBWD
-    g.x, g.w, g.y, g.residual, g.mask = P(dy), P(wd), P(out), P(res), P(act)
+    bits = ops.relu_bits(act)
+    g.x, g.w, g.y, g.residual, g.mask, g.mask_bits = P(dy), P(wd), P(out), P(res), P(act), P(bits)
     g.y1, g.vec1, g.bred1, g.dgamma1, g.dbeta1 = P(y1), P(vec), P(bred), P(dg), P(db)
     g.partials_ws, g.counter_ws = P(ws), P(cnt)
     p = _lib.FlatConvArgs()

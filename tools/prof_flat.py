@@ -32,7 +32,8 @@ if mode in ("plain", "bn"):
     a.momentum, a.eps, a.update_running = 0.1, 1e-5, 1
 elif mode == "dgrad":
     a.dgrad, a.flags = 1, ops.EPI_RESIDUAL | ops.EPI_MASK | ops.EPI_BNBWD
-    a.x, a.w, a.y, a.residual, a.mask = P(dy), P(wd), P(out), P(res), P(act)
+    bits = ops.relu_bits(act)
+    a.x, a.w, a.y, a.residual, a.mask, a.mask_bits = P(dy), P(wd), P(out), P(res), P(act), P(bits)
     a.y1, a.vec1, a.bred1, a.dgamma1, a.dbeta1 = P(y1), P(vec), P(bred), P(dg), P(db)
 sp = _lib.stream_ptr()
 for _ in range(6):

@@ -20,6 +20,16 @@ cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
 gamma, beta, rm, rv = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
 vec = torch.zeros(4, c, device="cuda"); vec[3] = 1
 a.partials_ws, a.counter_ws = P(ws), P(cnt)
+if mode == "dgrad":
+    dy = ops.to_padded(torch.randn(B, h, w, c, device="cuda").to(torch.bfloat16))
+    act = ops.to_padded(torch.relu(torch.randn(B, h, w, c, device="cuda")).to(torch.bfloat16))
+    y1 = ops.to_padded(torch.randn(B, h, w, c, device="cuda").to(torch.bfloat16))
+    res = ops.to_padded(torch.randn(B, h, w, c, device="cuda").to(torch.bfloat16))
+    bred = torch.zeros(2, c, device="cuda"); dg = torch.zeros(c, device="cuda"); db = torch.zeros(c, device="cuda")
+    a.dgrad, a.flags = 1, ops.EPI_RESIDUAL | ops.EPI_MASK | ops.EPI_BNBWD
+    bits = ops.relu_bits(act)
+    a.x, a.w, a.y, a.residual, a.mask, a.mask_bits = P(dy), P(wd), P(out), P(res), P(act), P(bits)
+    a.y1, a.vec1, a.bred1, a.dgamma1, a.dbeta1 = P(y1), P(vec), P(bred), P(dg), P(db)
 if mode == "bn":
     a.flags = ops.EPI_STATS
     a.gamma, a.beta, a.running_mean, a.running_var, a.vec = P(gamma), P(beta), P(rm), P(rv), P(vec)
