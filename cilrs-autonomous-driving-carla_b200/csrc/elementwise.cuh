@@ -377,21 +377,64 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
       }
     }
   } else {
-    for (; i < p.nvec; i += stride) {
-      const Vec8 yv = load8(p.y + i * 8);
-      const long long pix = i / groups;
-      const int w = (int)(pix % p.W);
-      const int h = (int)((pix / p.W) % p.H);
-      const int n = (int)(pix / ((long long)p.W * p.H));
-      Vec8 gv = stem_gather_grad(p, n, h, w, cg);
+    // stem: one thread per 2x2 block of conv1-output pixels (h0 = 2a, w0 = 2b) x 8 channels. The four 3x3/2 pool windows
+    // that can select a pixel of the block are (a, b), (a, b+1), (a+1, b), (a+1, b+1): each is loaded once for the whole
+    // block (the per-pixel form loaded up to four windows per pixel). H and W are even (44 x 100).
+    const int HB = p.H >> 1, WB = p.W >> 1;
+    const long long nblk = (long long)(p.nvec / groups / 4) * groups;  // = batch * HB * WB * groups
+    for (long long bi = (long long)blockIdx.x * EW_THREADS + threadIdx.x; bi < nblk; bi += stride) {
+      const long long blk = bi / groups;
+      const int b = (int)(blk % WB);
+      const int a = (int)((blk / WB) % HB);
+      const int n = (int)(blk / ((long long)WB * HB));
+      uint2 am[4];
+      uint4 gq[4];
+      bool okw[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (!(fmaf(yv.v[k], sc.v[k], sh.v[k]) > 0.f)) gv.v[k] = 0.f;
-      if (p.dz_out) store8(p.dz_out + i * 8, gv);
+      for (int q = 0; q < 4; ++q) {
+        const int oh = a + (q >> 1), ow = b + (q & 1);
+        okw[q] = oh < p.OH && ow < p.OW;
+        if (okw[q]) {
+          am[q] = *reinterpret_cast<const uint2*>(p.argmax + (((long long)n * p.OH + oh) * p.OW + ow) * p.C + cg);  // dense codes
+          gq[q] = *reinterpret_cast<const uint4*>(p.g + (((long long)n * p.OHp + oh) * p.OWp + ow) * p.C + cg);
+        }
+      }
+      Vec8 yv[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        a_sum[k] += gv.v[k];
-        a_dot[k] = fmaf(gv.v[k], (yv.v[k] - mean.v[k]) * rstd.v[k], a_dot[k]);
+      for (int e = 0; e < 4; ++e)
+        yv[e] = load8(p.y + ((((long long)n * p.H + 2 * a + (e >> 1)) * p.W + 2 * b + (e & 1)) * groups) * 8 + cg);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int dh = e >> 1, dw = e & 1;  // pixel (2a + dh, 2b + dw)
+        Vec8 gv;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gv.v[k] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          // window (a + qh, b + qw) covers rows 2(a+qh)-1 .. 2(a+qh)+1: the pixel's row inside it is r = dh + 1 - 2 qh
+          const int r = dh + 1 - 2 * (q >> 1), sx = dw + 1 - 2 * (q & 1);
+          if (r < 0 || sx < 0) continue;  // (compile-time after unrolling)
+          if (okw[q]) {
+            const uint32_t cc = (uint32_t)(r * 3 + sx) * 0x01010101u;
+            const uint32_t m_lo = __vcmpeq4(am[q].x, cc), m_hi = __vcmpeq4(am[q].y, cc);
+            const uint32_t gw[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t mk = ((k < 4 ? m_lo : m_hi) >> ((k & 3) * 8)) & 1u;
+              const float gvk = (k & 1) ? bf16hi(gw[k >> 1]) : bf16lo(gw[k >> 1]);
+              gv.v[k] = fmaf((float)mk, gvk, gv.v[k]);
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (!(fmaf(yv[e].v[k], sc.v[k], sh.v[k]) > 0.f)) gv.v[k] = 0.f;
+        if (p.dz_out) store8(p.dz_out + ((((long long)n * p.H + 2 * a + dh) * p.W + 2 * b + dw) * groups) * 8 + cg, gv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a_sum[k] += gv.v[k];
+          a_dot[k] = fmaf(gv.v[k], (yv[e].v[k] - mean.v[k]) * rstd.v[k], a_dot[k]);
+        }
       }
     }
   }

@@ -49,6 +49,20 @@ def test_matches_oracle_bit_exact(shape, c, reverse):
     assert np.array_equal(O.resize_u8_np(np.ascontiguousarray(src)), u8)  # numpy and C restatements agree
 
 
+@pytest.mark.parametrize("c,reverse", [(3, False), (4, True)])
+def test_already_resized_frames_fast_path_is_bit_identical(c, reverse):
+    """88x200 frames with only the conv1-ready output requested take the no-resize kernel: same bits as the general one"""
+    from cilrs_b200 import _lib
+    frames = torch.from_numpy(np.random.default_rng(8).integers(0, 256, size=(6, 88, 200, c), dtype=np.uint8)).cuda()
+    fast = torch.full((6, 47, 103, 16), 5.0, dtype=torch.bfloat16, device="cuda")
+    gen = torch.full((6, 47, 103, 16), 9.0, dtype=torch.bfloat16, device="cuda")
+    f32 = torch.empty(6, 3, 88, 200, device="cuda")
+    _lib.call("cilrs_preprocess_u8", frames, 6, 88, 200, c, int(reverse), 88, 200, None, None, fast, _lib.stream_ptr())
+    _lib.call("cilrs_preprocess_u8", frames, 6, 88, 200, c, int(reverse), 88, 200, None, f32, gen, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(fast.view(torch.int16), gen.view(torch.int16))
+
+
 def test_golden_odd_size():
     g = np.load(os.path.join(GOLD, "preprocess_ref.npz"))
     odd = np.random.default_rng(13).integers(0, 256, size=(1, 123, 321, 3), dtype=np.uint8)
