@@ -189,7 +189,7 @@ def main():
     torch.manual_seed(0)
     model = CILRS(num_commands=4, dropout=0.0).to(dev)
     trainer = FusedTrainer(model, BATCH, lr=2e-4, weight_decay=1e-4, loss="mse", speed_w=0.05, frames="u8",
-                           use_graph=(world == 1 and not args.no_graph))
+                           use_graph=(not args.no_graph))
 
     # synthetic batches: uint8 200x88 frames (what the reference's dataset stores after prepare_dataset.py), per-rank seed
     g = torch.Generator().manual_seed(100 + rank)
@@ -268,7 +268,7 @@ def main():
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
-                   "cuda_graph": trainer.graph is not None,
+                   "cuda_graph": trainer.graph is not None, "cuda_graph_error": trainer.graph_error,
                    "l2": "no explicit flush: one step touches ~0.9 GB of activations + 0.6 GB of optimizer state, > 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps, "input": "uint8 [128,88,200,3] frames + speed/command/targets from pinned host memory"},
@@ -343,9 +343,14 @@ def main():
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                     "sample": "2 timed full train steps (fwd+MSE loss+bwd+Adam) at batch 128 after 1 warm-up, torch fp32 on the host"}
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: with the allreduces captured in a CUDA graph, destroy_process_group() (and a
+        # barrier issued while rank 0 is still busy with its single-GPU extras) can block on communicator resources the
+        # graph still references. Every rank has finished its collectives at this point; exit code 0.
+        torch.cuda.synchronize(dev)
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

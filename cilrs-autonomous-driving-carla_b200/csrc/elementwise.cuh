@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
     walk.init(i / groups, stride / groups, p.geom);
     for (; i < p.nvec; i += 4 * stride) {
       bool ok[4], in[4];
-      Vec8 yv[4], gv[4], av[4];
+      uint4 yq[4], gq[4], aq[4];  // kept packed (48 registers) until used: two CTAs per SM stay resident
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         in[u] = i + u * stride < p.nvec;
@@ -355,22 +355,34 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdRe
       for (int u = 0; u < 4; ++u) {
         if (ok[u]) {
           const long long o = (i + u * stride) * 8;
-          yv[u] = load8(p.y + o);
-          gv[u] = load8(p.g + o);
-          if (p.act) av[u] = load8(p.act + o);
+          yq[u] = *reinterpret_cast<const uint4*>(p.y + o);
+          gq[u] = *reinterpret_cast<const uint4*>(p.g + o);
+          if (p.act) aq[u] = *reinterpret_cast<const uint4*>(p.act + o);
         }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const long long o = (i + u * stride) * 8;
         if (ok[u]) {
+          const uint32_t yw[4] = {yq[u].x, yq[u].y, yq[u].z, yq[u].w};
+          uint32_t gw[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
+          const uint32_t aw[4] = {aq[u].x, aq[u].y, aq[u].z, aq[u].w};
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            if (p.act && !(av[u].v[k] > 0.f)) gv[u].v[k] = 0.f;
-            a_sum[k] += gv[u].v[k];
-            a_dot[k] = fmaf(gv[u].v[k], (yv[u].v[k] - mean.v[k]) * rstd.v[k], a_dot[k]);
+            const int wi = k >> 1;
+            float gk = (k & 1) ? bf16hi(gw[wi]) : bf16lo(gw[wi]);
+            if (p.act) {
+              const float ak = (k & 1) ? bf16hi(aw[wi]) : bf16lo(aw[wi]);
+              if (!(ak > 0.f)) {
+                gk = 0.f;
+                gw[wi] &= (k & 1) ? 0x0000FFFFu : 0xFFFF0000u;  // dz keeps the bf16 bits of g where the ReLU was active
+              }
+            }
+            const float yk = (k & 1) ? bf16hi(yw[wi]) : bf16lo(yw[wi]);
+            a_sum[k] += gk;
+            a_dot[k] = fmaf(gk, (yk - mean.v[k]) * rstd.v[k], a_dot[k]);
           }
-          if (p.dz_out) store8(p.dz_out + o, gv[u]);
+          if (p.dz_out) *reinterpret_cast<uint4*>(p.dz_out + o) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
         } else if (in[u] && p.dz_out) {
           store8_zero(p.dz_out + o);  // padding pixel: g may hold stale data there; it contributes nothing and dz stays zero
         }

@@ -3,7 +3,7 @@
     H2D -> [K0 normalise] -> forward -> loss -> zero_grad -> backward -> [allreduce] -> [clip] -> Adam -> repack
 
 Everything after the H2D copies is device work launched through the C-ABI with no host synchronisation; with
-`use_graph=True` (single GPU) the whole step is one CUDA-graph replay. Data parallelism shards the batch across ranks
+`use_graph=True` the whole step (with N > 1 including the NCCL allreduces) is one CUDA-graph replay. Data parallelism shards the batch across ranks
 (one process per GPU); the flat gradient arena is all-reduced over NCCL in five ranges that complete back-to-front
 (heads+layer4, layer3, layer2, layer1, stem), each range's allreduce overlapping the backward of the next one.
 BatchNorm statistics stay per rank (plain-DDP semantics; the reference has no SyncBN).
@@ -59,10 +59,19 @@ class FusedTrainer:
         self.part_ranges = backward_part_ranges(model)
         self.graph = None
         self.kernel_launches = None
+        self.graph_error = None
         if use_graph:
             if self.world > 1:
-                raise ValueError("use_graph is for single-GPU steps (NCCL work is enqueued outside the graph)")
-            self._capture()
+                # the NCCL allreduces are captured into the graph with the kernels (PyTorch records them on the process
+                # group's stream, forked from / joined into the capturing stream); any failure falls back to eager launches
+                try:
+                    self._capture()
+                except Exception as ex:  # pragma: no cover - depends on the NCCL / driver combination
+                    self.graph = None
+                    self.graph_error = repr(ex)
+                    torch.cuda.synchronize(self.dev)
+            else:
+                self._capture()
 
     # ------------------------------------------------------------------------------------------
     def _device_step(self):
@@ -120,14 +129,17 @@ class FusedTrainer:
                 self._device_step()
         s.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=s):
-            self._device_step()
-        for t, sv in zip(state, saved):
-            t.copy_(sv)
-        self.opt._step = step0
-        _lib.call("cilrs_model_refresh", m._handle, 1, _lib.stream_ptr())
-        torch.cuda.synchronize(self.dev)
-        self.graph = g
+        try:
+            with torch.cuda.graph(g, stream=s):
+                self._device_step()
+            self.graph = g
+        finally:
+            # the warm-up steps (and a failed capture) must not leave a trace in the training state
+            for t, sv in zip(state, saved):
+                t.copy_(sv)
+            self.opt._step = step0
+            _lib.call("cilrs_model_refresh", m._handle, 1, _lib.stream_ptr())
+            torch.cuda.synchronize(self.dev)
 
     # ------------------------------------------------------------------------------------------
     def load_batch(self, frames_or_image, speed, command, targets):
