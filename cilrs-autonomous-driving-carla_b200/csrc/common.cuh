@@ -94,6 +94,15 @@ CILRS_DEVINL void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, in
       : "memory");
 }
 
+// TMA store of a 2-D box from shared memory (bulk async-group completion); rows past the tensor's end are clipped
+CILRS_DEVINL void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+CILRS_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+CILRS_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // smem reusable
+CILRS_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }        // writes done
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA issue, commit, TMEM loads
 // ----------------------------------------------------------------------------------------------

@@ -29,7 +29,7 @@ static void split_boxes(int rows, int* box_rows, int* boxes) {
 }
 
 static long long flat_smem_fixed(int block_n) {
-  return 1024 /* alignment slack */ + 8LL * 3 * block_n * 4 /* warp-private statistics */ +
+  return 1024 /* alignment slack */ + CF_STAGING_BYTES + 8LL * 3 * block_n * 4 /* warp-private statistics */ +
          (2 * CF_MAX_A_STAGES + 2 * CF_MAX_B_STAGES + 2 * CF_MAX_ACC) * 8 + 64 + 64;
 }
 
@@ -175,6 +175,8 @@ int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channe
   p->flags = flags;
   p->out = (__nv_bfloat16*)out;
   int st = encode_2d_map(&p->tmA, x, k_channels, p->total_rows, 64, p->a_box_rows);
+  if (st) return st;
+  st = encode_2d_map(&p->tmOut, out, n_total, p->total_rows, 64, 32);
   if (st) return st;
   return encode_2d_map(&p->tmB, w, k_channels, 9 * n_total, 64, p->block_n);
 }

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
   const int b_stage_bytes = p.tap_group * b_tap_bytes;  // one stage = the weight tiles of `tap_group` consecutive taps
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)p.a_stages * a_stage_bytes;
-  float* s_wacc = (float*)(sB + (size_t)p.b_stages * b_stage_bytes);  // [8 epilogue warps][3][block_n] running statistics
+  uint8_t* s_out = sB + (size_t)p.b_stages * b_stage_bytes;            // [8 epilogue warps][32 rows][128 B] output staging
+  float* s_wacc = (float*)(s_out + CF_STAGING_BYTES);                  // [8 epilogue warps][3][block_n] running statistics
   uint64_t* bars = (uint64_t*)(s_wacc + 8 * 3 * p.block_n);
   uint64_t* full_a = bars;
   uint64_t* empty_a = full_a + CF_MAX_A_STAGES;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmOut);
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < p.acc_sets; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }  // 8 epilogue warps
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     const bool bwd2 = (p.flags & CF_BNBWD2) != 0;
     const int nq = bwd2 ? 3 : 2;
     float* w_acc = s_wacc + ew * (3 * p.block_n);  // this warp's running sums [3][block_n]
+    uint8_t* w_out = s_out + ew * (32 * 128);      // this warp's output staging (1024-byte aligned, 128B-swizzled rows)
     if (do_stats) {
       for (int i = lane; i < 3 * p.block_n; i += 32) w_acc[i] = 0.f;
       __syncwarp();
@@ -314,9 +317,18 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             u[j] = valid ? pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) : 0u;  // padding pixels stay exact zeros
-          if (in_range) {
+          // Output: the warp's 32 rows x 128 B go through a swizzled staging tile and ONE TMA store (full 128-byte lines).
+          // Per-thread 32-byte stores of a row each cost the LSU 32 sector requests per instruction: 1.5 k clocks per unit.
+          tma_store_wait_read();  // (lane 0 issued the previous store: its shared-memory reads are complete)
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) stg256(p.out + goff + j * 16, u + j * 8);
+          for (int j = 0; j < 8; ++j)
+            *(uint4*)(w_out + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmOut, w_out, n_base, row0 + m * 128 + q * 32);
+            tma_store_commit();
           }
           if (ew == 0 && lane == 0) CF_EVENT(2, 0x605);
           if (do_stats) {
@@ -363,6 +375,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == p.acc_sets) { acc = 0; accph ^= 1; }
     }
+
+    tma_store_wait_all();  // this warp's output stores have been written
 
     if (do_stats) {
       // ---- per-CTA partial (the eight warps' sums in a fixed order), then the last CTA to finish folds all partials ----

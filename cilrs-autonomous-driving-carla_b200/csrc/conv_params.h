@@ -92,7 +92,7 @@ constexpr int CF_THREADS = 384;       // warpgroup 0: TMA (warp 0), MMA (warp 1)
 constexpr int CF_MAX_A_STAGES = 4;
 constexpr int CF_MAX_B_STAGES = 16;
 constexpr int CF_MAX_ACC = 8;
-constexpr int CF_STAGING_BYTES = 2 * 128 * 128;  // one 128 x 64 bf16 chunk per epilogue group
+constexpr int CF_STAGING_BYTES = 8 * 32 * 128;   // 32 rows x 64 bf16 per epilogue warp: staging of the TMA output stores
 
 enum FlatConvFlags : int {
   CF_STATS = 1,       // per-channel sum / sum of squares of the bf16 output; the last CTA folds them into the BN vectors
@@ -107,6 +107,7 @@ enum FlatConvFlags : int {
 struct FlatConvParams {
   CUtensorMap tmA;  // 2-D (channels, flat pixels), box (64, a_box_rows)
   CUtensorMap tmB;  // 2-D (channels, taps * n_total), box (64, block_n)
+  CUtensorMap tmOut;  // 2-D (n_total, flat pixels) view of `out`, box (64, 32): one epilogue warp's 32 rows x 64 channels
   int total_rows;
   PadGeom g;
   int mt;                      // 128-row sub-tiles per tile (they share every weight tile)

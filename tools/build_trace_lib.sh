@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 S=cilrs-autonomous-driving-carla_b200/csrc
 mkdir -p /tmp/cilrs_trace
 for f in api conv conv_flat model preprocess; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DCF_TRACE -c $S/$f.cu -o /tmp/cilrs_trace/$f.o &
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DCF_TRACE $EXTRA -c $S/$f.cu -o /tmp/cilrs_trace/$f.o &
 done
 wait
 nvcc -shared -o tools/libcilrs_trace.so /tmp/cilrs_trace/*.o -gencode arch=compute_100a,code=sm_100a -cudart static
