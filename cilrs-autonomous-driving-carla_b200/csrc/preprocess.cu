@@ -34,84 +34,113 @@ CILRS_DEVINL AxisCoef axis_coef(int d, int ssize, double scale) {
 struct PreParams {
   const uint8_t* src;
   int batch, src_h, src_w, src_c, reverse, dst_h, dst_w;
+  int rows_per_cta;
   double scale_x, scale_y;
   uint8_t* dst_u8;
   float* dst_f32;
   __nv_bfloat16* dst_s2d;
 };
 
+__device__ float g_norm_lut[3 * 256];
+
+__global__ void norm_lut_kernel() {
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  const int i = blockIdx.x * 256 + threadIdx.x, c = blockIdx.x;
+  g_norm_lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.f), mean[c]), stdv[c]);
+}
+
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
-  extern __shared__ __align__(16) uint8_t rows[];  // [2][row_bytes_padded]
-  const int dy = blockIdx.x % p.dst_h;
-  const int n = blockIdx.x / p.dst_h;
+  extern __shared__ __align__(16) uint8_t rows[];  // [rows_per_cta][2][row_bytes_padded]
+  const int R = p.rows_per_cta;
+  const int row_blocks = (p.dst_h + R - 1) / R;
+  const int dy0 = (blockIdx.x % row_blocks) * R;
+  const int n = blockIdx.x / row_blocks;
+  const int nr = min(R, p.dst_h - dy0);
   const int row_bytes = p.src_w * p.src_c;
   const int row_pad = (row_bytes + 15) & ~15;
-  const AxisCoef cy = axis_coef(dy, p.src_h, p.scale_y);
   const uint8_t* img = p.src + (size_t)n * p.src_h * row_bytes;
-  const uint8_t* r0 = img + (size_t)cy.s0 * row_bytes;
-  const uint8_t* r1 = img + (size_t)cy.s1 * row_bytes;
-  if ((row_bytes & 15) == 0 && (((uintptr_t)p.src) & 15) == 0) {
-    const int nv = row_bytes >> 4;
-    for (int i = threadIdx.x; i < 2 * nv; i += blockDim.x) {
-      const int which = i >= nv;
-      const int j = which ? i - nv : i;
-      const uint4 v = __ldg((const uint4*)(which ? r1 : r0) + j);
-      *((uint4*)(rows + which * row_pad) + j) = v;
-    }
-  } else {
-    for (int i = threadIdx.x; i < 2 * row_bytes; i += blockDim.x) {
-      const int which = i >= row_bytes;
-      const int j = which ? i - row_bytes : i;
-      rows[which * row_pad + j] = (which ? r1 : r0)[j];
+  // stage the two source rows of every output row of this CTA (all loads in flight before the first use)
+  const bool vec = (row_bytes & 15) == 0 && (((uintptr_t)p.src) & 15) == 0;
+  __shared__ AxisCoef s_cy[4];  // vertical coefficients of the CTA's rows: computed once (double-precision path), not per thread
+  if (threadIdx.x < nr) s_cy[threadIdx.x] = axis_coef(dy0 + threadIdx.x, p.src_h, p.scale_y);
+  __syncthreads();
+  for (int r = 0; r < nr; ++r) {
+    const AxisCoef cy = s_cy[r];
+    const uint8_t* r0 = img + (size_t)cy.s0 * row_bytes;
+    const uint8_t* r1 = img + (size_t)cy.s1 * row_bytes;
+    uint8_t* dst = rows + (size_t)(2 * r) * row_pad;
+    if (vec) {
+      const int nv = row_bytes >> 4;
+      for (int i = threadIdx.x; i < 2 * nv; i += blockDim.x) {
+        const int which = i >= nv;
+        const int j = which ? i - nv : i;
+        *((uint4*)(dst + which * row_pad) + j) = __ldg((const uint4*)(which ? r1 : r0) + j);
+      }
+    } else {
+      for (int i = threadIdx.x; i < 2 * row_bytes; i += blockDim.x) {
+        const int which = i >= row_bytes;
+        const int j = which ? i - row_bytes : i;
+        dst[which * row_pad + j] = (which ? r1 : r0)[j];
+      }
     }
   }
   __syncthreads();
 
-  const float mean[3] = {0.485f, 0.456f, 0.406f};
-  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  // (v/255 - mean[c]) / std[c] has only 3 x 256 distinct results: g_norm_lut (built once with the exact IEEE operations of the
+  // reference: divide, subtract, divide) replaces two IEEE divisions per output value; the kernel was issue-bound on them
   for (int dx = threadIdx.x; dx < p.dst_w; dx += blockDim.x) {
-    const AxisCoef cx = axis_coef(dx, p.src_w, p.scale_x);
-    uint8_t o[3];
-    float f[3];
+    const AxisCoef cx = axis_coef(dx, p.src_w, p.scale_x);  // once per thread, reused for every row of the CTA
+    for (int r = 0; r < nr; ++r) {
+      const int dy = dy0 + r;
+      const AxisCoef cy = s_cy[r];
+      const uint8_t* ra = rows + (size_t)(2 * r) * row_pad;
+      const uint8_t* rb = ra + row_pad;
+      uint8_t o[3];
+      float f[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const int sc = p.reverse ? 2 - c : c;
-      const int h0 = rows[cx.s0 * p.src_c + sc] * cx.a0 + rows[cx.s1 * p.src_c + sc] * cx.a1;
-      const int h1 = rows[row_pad + cx.s0 * p.src_c + sc] * cx.a0 + rows[row_pad + cx.s1 * p.src_c + sc] * cx.a1;
-      const int v = (((cy.a0 * (h0 >> 4)) >> 16) + ((cy.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
-      o[c] = (uint8_t)v;
-      f[c] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), mean[c]), stdv[c]);
-    }
-    if (p.dst_u8) {
-      uint8_t* d = p.dst_u8 + (((size_t)n * p.dst_h + dy) * p.dst_w + dx) * 3;
-      d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
-    }
-    if (p.dst_f32) {
-      const size_t plane = (size_t)p.dst_h * p.dst_w;
-      float* d = p.dst_f32 + (size_t)n * 3 * plane + (size_t)dy * p.dst_w + dx;
-      d[0] = f[0]; d[plane] = f[1]; d[2 * plane] = f[2];
-    }
-    if (p.dst_s2d) {
-      const int y = dy + 3, x = dx + 3;
-      uint2 v;
-      v.x = pack_bf16x2(f[0], f[1]);
-      v.y = pack_bf16x2(f[2], 0.f);
-      *(uint2*)(p.dst_s2d + (((size_t)n * 47 + (y >> 1)) * 103 + (x >> 1)) * 16 + (y & 1) * 8 + (x & 1) * 4) = v;
+      for (int c = 0; c < 3; ++c) {
+        const int sc = p.reverse ? 2 - c : c;
+        const int h0 = ra[cx.s0 * p.src_c + sc] * cx.a0 + ra[cx.s1 * p.src_c + sc] * cx.a1;
+        const int h1 = rb[cx.s0 * p.src_c + sc] * cx.a0 + rb[cx.s1 * p.src_c + sc] * cx.a1;
+        const int v = (((cy.a0 * (h0 >> 4)) >> 16) + ((cy.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        o[c] = (uint8_t)v;
+        f[c] = __ldg(&g_norm_lut[c * 256 + v]);
+      }
+      if (p.dst_u8) {
+        uint8_t* d = p.dst_u8 + (((size_t)n * p.dst_h + dy) * p.dst_w + dx) * 3;
+        d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
+      }
+      if (p.dst_f32) {
+        const size_t plane = (size_t)p.dst_h * p.dst_w;
+        float* d = p.dst_f32 + (size_t)n * 3 * plane + (size_t)dy * p.dst_w + dx;
+        d[0] = f[0]; d[plane] = f[1]; d[2 * plane] = f[2];
+      }
+      if (p.dst_s2d) {
+        const int y = dy + 3, x = dx + 3;
+        uint2 v;
+        v.x = pack_bf16x2(f[0], f[1]);
+        v.y = pack_bf16x2(f[2], 0.f);
+        *(uint2*)(p.dst_s2d + (((size_t)n * 47 + (y >> 1)) * 103 + (x >> 1)) * 16 + (y & 1) * 8 + (x & 1) * 4) = v;
+      }
     }
   }
   if (p.dst_s2d) {
-    // zero padding of the 94 x 206 padded frame: 3 columns each side of this row, and whole rows 0-2 / 91-93
+    // zero padding of the 94 x 206 padded frame: 3 columns each side of every row, and whole rows 0-2 / 91-93
     const uint2 z = make_uint2(0u, 0u);
-    const int y = dy + 3;
-    if (threadIdx.x < 6) {
-      const int x = threadIdx.x < 3 ? threadIdx.x : 200 + threadIdx.x;
-      *(uint2*)(p.dst_s2d + (((size_t)n * 47 + (y >> 1)) * 103 + (x >> 1)) * 16 + (y & 1) * 8 + (x & 1) * 4) = z;
-    }
-    if (dy == 0 || dy == p.dst_h - 1) {
-      const int ybase = dy == 0 ? 0 : 91;
-      for (int i = threadIdx.x; i < 3 * 206; i += blockDim.x) {
-        const int yy = ybase + i / 206, x = i % 206;
-        *(uint2*)(p.dst_s2d + (((size_t)n * 47 + (yy >> 1)) * 103 + (x >> 1)) * 16 + (yy & 1) * 8 + (x & 1) * 4) = z;
+    for (int r = 0; r < nr; ++r) {
+      const int dy = dy0 + r;
+      const int y = dy + 3;
+      if (threadIdx.x < 6) {
+        const int x = threadIdx.x < 3 ? threadIdx.x : 200 + threadIdx.x;
+        *(uint2*)(p.dst_s2d + (((size_t)n * 47 + (y >> 1)) * 103 + (x >> 1)) * 16 + (y & 1) * 8 + (x & 1) * 4) = z;
+      }
+      if (dy == 0 || dy == p.dst_h - 1) {
+        const int ybase = dy == 0 ? 0 : 91;
+        for (int i = threadIdx.x; i < 3 * 206; i += blockDim.x) {
+          const int yy = ybase + i / 206, x = i % 206;
+          *(uint2*)(p.dst_s2d + (((size_t)n * 47 + (yy >> 1)) * 103 + (x >> 1)) * 16 + (yy & 1) * 8 + (x & 1) * 4) = z;
+        }
       }
     }
   }
@@ -196,14 +225,25 @@ int cilrs_preprocess_u8(const uint8_t* src, int batch, int src_h, int src_w, int
   p.dst_h = dst_h; p.dst_w = dst_w;
   p.scale_x = (double)src_w / dst_w; p.scale_y = (double)src_h / dst_h;
   p.dst_u8 = dst_u8; p.dst_f32 = dst_f32; p.dst_s2d = (__nv_bfloat16*)dst_s2d;
-  const size_t smem = 2 * (size_t)row_pad;
+  static bool lut_ready = false;
+  if (!lut_ready) {  // stream-ordered before the first preprocessing launch of this process (per device in practice)
+    norm_lut_kernel<<<3, 256, 0, (cudaStream_t)stream>>>();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_status(e);
+    lut_ready = true;
+  }
+  // four output rows per CTA when their eight source rows fit in 96 KB of shared memory (more bytes in flight per CTA, the
+  // horizontal coefficients are computed once per thread)
+  p.rows_per_cta = (8 * (size_t)row_pad <= 96 * 1024 && dst_h >= 4) ? 4 : 1;
+  const size_t smem = 2 * (size_t)p.rows_per_cta * (size_t)row_pad;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return cuda_status(e);
     smem_set = 96 * 1024;
   }
-  preprocess_kernel<<<batch * dst_h, 256, smem, (cudaStream_t)stream>>>(p); ++g_cilrs_launches;
+  const int row_blocks = (dst_h + p.rows_per_cta - 1) / p.rows_per_cta;
+  preprocess_kernel<<<batch * row_blocks, 256, smem, (cudaStream_t)stream>>>(p); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 
