@@ -196,7 +196,7 @@ int launch_flat_conv(const FlatConvParams* p, cudaStream_t s) {
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
-  if ((p->flags & (CF_STATS | CF_BNBWD)) && (!p->partials || !p->counter)) return ERR_INVALID;
+  if ((p->flags & (CF_STATS | CF_BNBWD)) && (!p->partials || (!(p->flags & CF_DEFER) && !p->counter))) return ERR_INVALID;
   const int grid = flat_conv_grid(p);
   void (*kernel)(FlatConvParams) = p->mt == 1 ? conv_flat_kernel<1> : (p->mt == 2 ? conv_flat_kernel<2> : (p->mt == 4 ? conv_flat_kernel<4> : nullptr));
   if (!kernel) return ERR_INVALID;

@@ -395,18 +395,22 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
         // depend on the order in which the CTAs arrive (reproducible statistics without a serial fold)
         atomicAdd(p.partials + k * p.n_total + nb * p.block_n + c, (double)t);
       }
-      bar_sync_named(3, 256);
-      if (tid == 0) {
-        // release: the barrier ordered every thread's atomics before this fence (cumulativity); acquire after the count
-        __threadfence();
-        const unsigned int done = atomicAdd(p.counter, 1u);
-        const bool last = (done == gridDim.x - 1);
-        if (last) __threadfence();
-        *s_flag = last ? 1u : 0u;
+      bool last_cta = false;
+      if (!(p.flags & CF_DEFER)) {  // (deferred: the kernel boundary orders the sums before the consumer's reads)
+        bar_sync_named(3, 256);
+        if (tid == 0) {
+          // release: the barrier ordered every thread's atomics before this fence (cumulativity); acquire after the count
+          __threadfence();
+          const unsigned int done = atomicAdd(p.counter, 1u);
+          const bool last = (done == gridDim.x - 1);
+          if (last) __threadfence();
+          *s_flag = last ? 1u : 0u;
+        }
+        bar_sync_named(3, 256);
+        last_cta = *s_flag != 0u;
       }
-      bar_sync_named(3, 256);
       if (tid == 0) CF_EVENT(2, 0x701);
-      if (*s_flag) {
+      if (last_cta) {
         // per-channel inputs of the finalize (loads issued together, one L2 round trip)
         float pre[2][4];
 #pragma unroll

@@ -102,6 +102,9 @@ enum FlatConvFlags : int {
   CF_MASK = 16,       // y = mask[f, n] > 0 ? y : 0          (ReLU backward, fused into the dgrad epilogue)
   CF_BNBWD = 32,      // per-channel sum(y), sum(y * xhat1) with xhat1 = (y1 - mean1) * rstd1   (BatchNorm backward reduce)
   CF_BNBWD2 = 64,     // ... and sum(y * xhat2) for a second BatchNorm fed by the same gradient (downsample branch)
+  CF_DEFER = 128,     // CF_STATS / CF_BNBWD: only add the per-channel sums to `partials` (a per-BatchNorm accumulator that the
+                      // caller zeroed); the elementwise kernel that consumes them finalizes (elementwise.cuh: BnDefer / BnBwdDefer).
+                      // Saves the counter round trip and the last-CTA tail (~6 k clocks per launch).
 };
 
 struct FlatConvParams {

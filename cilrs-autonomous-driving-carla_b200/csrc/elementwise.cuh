@@ -10,12 +10,19 @@ namespace cilrs {
 
 constexpr int EW_THREADS = 256;
 constexpr int EW_MAX_BLOCKS = 148 * 4;
+constexpr int EW_DEFER_MAX_C = 512;  // deferred BatchNorm finalize stages the per-channel values of a CTA in shared memory
 
 struct Vec8 {
   float v[8];
 };
 CILRS_DEVINL Vec8 load8(const __nv_bfloat16* p) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
+  Vec8 r;
+  r.v[0] = bf16lo(u.x); r.v[1] = bf16hi(u.x); r.v[2] = bf16lo(u.y); r.v[3] = bf16hi(u.y);
+  r.v[4] = bf16lo(u.z); r.v[5] = bf16hi(u.z); r.v[6] = bf16lo(u.w); r.v[7] = bf16hi(u.w);
+  return r;
+}
+CILRS_DEVINL Vec8 unpack8(const uint4& u) {
   Vec8 r;
   r.v[0] = bf16lo(u.x); r.v[1] = bf16hi(u.x); r.v[2] = bf16lo(u.y); r.v[3] = bf16hi(u.y);
   r.v[4] = bf16lo(u.z); r.v[5] = bf16hi(u.z); r.v[6] = bf16lo(u.w); r.v[7] = bf16hi(u.w);
@@ -62,6 +69,49 @@ struct BnVectors {
   float* mean;
   float* rstd;
 };
+
+// Deferred finalize (conv_params.h: CF_DEFER). The fused flat-conv epilogues only add their per-channel fp64 sums to a
+// per-BatchNorm accumulator; the elementwise kernel that consumes the statistics derives its own channels' values from the
+// sums in its prologue (every thread runs the same arithmetic, so all copies agree bit for bit), and CTA 0 also writes the
+// vectors / running statistics / parameter gradients that later kernels read. acc == nullptr: nothing is deferred.
+struct BnDefer {
+  const double* acc;  // [2][C]: sum, sum of squares of the conv output
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  long long* nbt;
+  float* vec;         // [4][C] out: scale, shift, mean, rstd
+  double inv_count;
+  double unbias;      // count / (count - 1)
+  float momentum, eps;
+  int update_running;
+};
+struct BnStat {
+  float scale, shift, mean, rstd, unbiased_var;
+};
+CILRS_DEVINL BnStat bn_stat_from_sums(double S0, double S1, double inv_count, double unbias, float eps, float gamma, float beta) {
+  const double mean_d = S0 * inv_count;
+  double var_d = S1 * inv_count - mean_d * mean_d;
+  if (var_d < 0.0) var_d = 0.0;
+  BnStat r;
+  r.mean = (float)mean_d;
+  r.unbiased_var = (float)(var_d * unbias);
+  r.rstd = 1.0f / sqrtf((float)var_d + eps);
+  r.scale = gamma * r.rstd;
+  r.shift = beta - r.mean * r.scale;
+  return r;
+}
+struct BnBwdDefer {
+  const double* acc_sum;  // [C] sum dz
+  const double* acc_dot;  // [C] sum dz * y (raw conv output); bdot = rstd * (acc_dot - mean * acc_sum)
+  float* bred;            // [2][C] out (bsum, bdot)
+  float* dgamma;          // += bdot (may be null)
+  float* dbeta;           // += bsum
+};
+CILRS_DEVINL float bn_bdot_from_sums(double S0, double S1, float mean, float rstd) {
+  return (float)((double)rstd * (S1 - (double)mean * S0));
+}
 
 // ---------------------------------------------------------------------------------------------
 // bn_finalize: per-tile (sum, sumsq) partials -> batch statistics -> scale/shift (+ running stats update)
@@ -125,7 +175,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
                                                               const __nv_bfloat16* __restrict__ x2, const float* __restrict__ scale2,
                                                               const float* __restrict__ shift2, __nv_bfloat16* __restrict__ out,
                                                               long long nvec, int C, int relu, const PadGeom g,
-                                                              uint8_t* __restrict__ bits) {
+                                                              uint8_t* __restrict__ bits, const BnDefer d) {
   // bits (optional): one byte per 8-channel vector, bit k = (out[channel k] > 0): the ReLU mask the flat dgrad epilogue
   // applies, 1/16 of the bytes of the activation itself
   pdl_entry();
@@ -133,40 +183,86 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
   const long long stride = (long long)gridDim.x * EW_THREADS;  // multiple of groups (host guarantees)
   long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
   const int cg = (int)(i % groups) * 8;
-  const Vec8 sc = loadf8(scale + cg), sh = loadf8(shift + cg);
+  Vec8 sc, sh;
+  __shared__ __align__(16) float s_par[2][EW_DEFER_MAX_C];
+  if (d.acc) {
+    // scale / shift straight from the conv epilogue's sums: each CTA derives every channel once (coalesced loads of the
+    // sums; per-thread strided 8-byte loads cost 256 L1 line lookups per warp) and threads pick their channels from shared memory
+    for (int c = threadIdx.x; c < C; c += EW_THREADS) {
+      const BnStat st = bn_stat_from_sums(d.acc[c], d.acc[C + c], d.inv_count, d.unbias, d.eps, d.gamma[c], d.beta[c]);
+      s_par[0][c] = st.scale; s_par[1][c] = st.shift;
+      if (blockIdx.x == 0) {
+        d.vec[c] = st.scale; d.vec[C + c] = st.shift; d.vec[2 * C + c] = st.mean; d.vec[3 * C + c] = st.rstd;
+        if (d.update_running) {
+          d.running_mean[c] = (1.f - d.momentum) * d.running_mean[c] + d.momentum * st.mean;
+          d.running_var[c] = (1.f - d.momentum) * d.running_var[c] + d.momentum * st.unbiased_var;
+        }
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && d.update_running && d.nbt) *d.nbt += 1;
+    __syncthreads();
+    sc = loadf8(&s_par[0][cg]); sh = loadf8(&s_par[1][cg]);
+  } else {
+    sc = loadf8(scale + cg); sh = loadf8(shift + cg);
+  }
   Vec8 sc2, sh2;
   if (x2) { sc2 = loadf8(scale2 + cg); sh2 = loadf8(shift2 + cg); }
   PadWalk walk;
   walk.init(i / groups, stride / groups, g);
-  for (; i < nvec; i += stride, walk.next()) {
-    if (!walk.valid()) {
-      store8_zero(out + i * 8);
-      if (bits) bits[i] = 0;
-      continue;
+  // four vectors per iteration with every load issued before the first use: ~3 CTAs x 256 threads x 4 x (1..2) x 16 B keep
+  // the ~45 KB per SM in flight that HBM latency x bandwidth asks for
+  for (; i < nvec; i += 4 * stride) {
+    bool in[4], ok[4];
+    uint4 xq[4], rq[4], yq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      in[u] = i + u * stride < nvec;
+      ok[u] = in[u] && walk.valid();
+      walk.next();
     }
-    Vec8 a = load8(x + i * 8);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a.v[k] = fmaf(a.v[k], sc.v[k], sh.v[k]);
-    if (res) {
-      const Vec8 r = load8(res + i * 8);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) a.v[k] += r.v[k];
+    for (int u = 0; u < 4; ++u) {
+      if (ok[u]) {
+        const long long o = (i + u * stride) * 8;
+        xq[u] = *reinterpret_cast<const uint4*>(x + o);
+        if (res) rq[u] = *reinterpret_cast<const uint4*>(res + o);
+        if (x2) yq[u] = *reinterpret_cast<const uint4*>(x2 + o);
+      }
     }
-    if (x2) {
-      const Vec8 r = load8(x2 + i * 8);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a.v[k] += fmaf(r.v[k], sc2.v[k], sh2.v[k]);
-    }
-    if (relu) {
+    for (int u = 0; u < 4; ++u) {
+      const long long iv = i + u * stride;
+      if (!ok[u]) {
+        if (in[u]) {
+          store8_zero(out + iv * 8);
+          if (bits) bits[iv] = 0;
+        }
+        continue;
+      }
+      Vec8 a = unpack8(xq[u]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a.v[k] = fmaxf(a.v[k], 0.f);
-    }
-    store8(out + i * 8, a);
-    if (bits) {
-      unsigned int m = 0;
+      for (int k = 0; k < 8; ++k) a.v[k] = fmaf(a.v[k], sc.v[k], sh.v[k]);
+      if (res) {
+        const Vec8 r = unpack8(rq[u]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) m |= (__bfloat162float(__float2bfloat16(a.v[k])) > 0.f ? 1u : 0u) << k;
-      bits[i] = (uint8_t)m;
+        for (int k = 0; k < 8; ++k) a.v[k] += r.v[k];
+      }
+      if (x2) {
+        const Vec8 r = unpack8(yq[u]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.v[k] += fmaf(r.v[k], sc2.v[k], sh2.v[k]);
+      }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.v[k] = fmaxf(a.v[k], 0.f);
+      }
+      store8(out + iv * 8, a);
+      if (bits) {
+        unsigned int m = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m |= (__bfloat162float(__float2bfloat16(a.v[k])) > 0.f ? 1u : 0u) << k;
+        bits[iv] = (uint8_t)m;
+      }
     }
   }
 }
@@ -516,6 +612,7 @@ struct BnBwdApplyParams {
   const float* shift;
   int H, W, OH, OW;
   PadGeom geom;       // padded-flat geometry of g / act / y / dy / dz ({1,1,1,1} = dense)
+  BnBwdDefer defer;   // acc_sum != nullptr: bsum / bdot come from the dgrad epilogue's sums (and CTA 0 accumulates dgamma / dbeta)
 };
 
 template <bool STEM>
@@ -527,7 +624,23 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApp
   const int cg = (int)(i % groups) * 8;
   const Vec8 mean = loadf8(p.mean + cg), rstd = loadf8(p.rstd + cg), gamma = loadf8(p.gamma + cg);
   Vec8 k0, k1, sc, sh;
-  {
+  __shared__ __align__(16) float s_par[2][EW_DEFER_MAX_C];
+  if (p.defer.acc_sum) {
+    // every CTA derives all channels once from the dgrad epilogue's sums (coalesced), threads pick theirs from shared memory
+    for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
+      const double s0 = p.defer.acc_sum[c], s1 = p.defer.acc_dot[c];
+      const float bs = (float)s0, bd = bn_bdot_from_sums(s0, s1, p.mean[c], p.rstd[c]);
+      s_par[0][c] = p.frozen ? 0.f : bs * p.inv_count;
+      s_par[1][c] = p.frozen ? 0.f : bd * p.inv_count;
+      if (blockIdx.x == 0) {
+        p.defer.bred[c] = bs; p.defer.bred[p.C + c] = bd;
+        if (p.defer.dgamma) p.defer.dgamma[c] += bd;
+        if (p.defer.dbeta) p.defer.dbeta[c] += bs;
+      }
+    }
+    __syncthreads();
+    k0 = loadf8(&s_par[0][cg]); k1 = loadf8(&s_par[1][cg]);
+  } else {
     const Vec8 bs = loadf8(p.bsum + cg), bd = loadf8(p.bdot + cg);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -538,46 +651,76 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApp
   if (STEM) { sc = loadf8(p.scale + cg); sh = loadf8(p.shift + cg); }
   BnBwdReduceParams gp;  // only the fields the stem gather reads
   if (STEM) { gp.g = p.g; gp.argmax = p.argmax; gp.OH = p.OH; gp.OW = p.OW; gp.OHp = p.OH; gp.OWp = p.OW; gp.C = p.C; }
-  PadWalk walk;
-  if (!STEM) walk.init(i / groups, stride / groups, p.geom);
-  for (; i < p.nvec; i += stride) {
-    if (!STEM) {
-      const bool ok = walk.valid();
-      walk.next();
-      if (!ok) {
-        store8_zero(p.dy + i * 8);
-        if (p.dz) store8_zero(p.dz + i * 8);
-        continue;
+  if (!STEM) {
+    // four vectors per iteration, all loads issued before the first use (see bn_apply_kernel)
+    PadWalk walk;
+    walk.init(i / groups, stride / groups, p.geom);
+    for (; i < p.nvec; i += 4 * stride) {
+      bool in[4], ok[4];
+      uint4 yq[4], gq[4], aq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        in[u] = i + u * stride < p.nvec;
+        ok[u] = in[u] && walk.valid();
+        walk.next();
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ok[u]) {
+          const long long o = (i + u * stride) * 8;
+          yq[u] = *reinterpret_cast<const uint4*>(p.y + o);
+          gq[u] = *reinterpret_cast<const uint4*>(p.g + o);
+          if (p.act) aq[u] = *reinterpret_cast<const uint4*>(p.act + o);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long o = (i + u * stride) * 8;
+        if (!ok[u]) {
+          if (in[u]) {
+            store8_zero(p.dy + o);
+            if (p.dz) store8_zero(p.dz + o);
+          }
+          continue;
+        }
+        const Vec8 yv = unpack8(yq[u]);
+        Vec8 gv = unpack8(gq[u]);
+        if (p.act) {
+          const Vec8 av = unpack8(aq[u]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (!(av.v[k] > 0.f)) gv.v[k] = 0.f;
+        }
+        if (p.dz) store8(p.dz + o, gv);
+        Vec8 ov;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xhat = (yv.v[k] - mean.v[k]) * rstd.v[k];
+          ov.v[k] = gamma.v[k] * rstd.v[k] * (gv.v[k] - k0.v[k] - xhat * k1.v[k]);
+        }
+        store8(p.dy + o, ov);
       }
     }
-    const Vec8 yv = load8(p.y + i * 8);
-    Vec8 gv;
-    if (STEM) {
+  } else {
+    for (; i < p.nvec; i += stride) {
+      const Vec8 yv = load8(p.y + i * 8);
       const long long pix = i / groups;
       const int w = (int)(pix % p.W);
       const int h = (int)((pix / p.W) % p.H);
       const int n = (int)(pix / ((long long)p.W * p.H));
-      gv = stem_gather_grad(gp, n, h, w, cg);
+      Vec8 gv = stem_gather_grad(gp, n, h, w, cg);
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         if (!(fmaf(yv.v[k], sc.v[k], sh.v[k]) > 0.f)) gv.v[k] = 0.f;
-    } else {
-      gv = load8(p.g + i * 8);
-      if (p.act) {
-        const Vec8 av = load8(p.act + i * 8);
+      if (p.dz) store8(p.dz + i * 8, gv);
+      Vec8 ov;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (!(av.v[k] > 0.f)) gv.v[k] = 0.f;
+      for (int k = 0; k < 8; ++k) {
+        const float xhat = (yv.v[k] - mean.v[k]) * rstd.v[k];
+        ov.v[k] = gamma.v[k] * rstd.v[k] * (gv.v[k] - k0.v[k] - xhat * k1.v[k]);
       }
+      store8(p.dy + i * 8, ov);
     }
-    if (p.dz) store8(p.dz + i * 8, gv);
-    Vec8 o;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float xhat = (yv.v[k] - mean.v[k]) * rstd.v[k];
-      o.v[k] = gamma.v[k] * rstd.v[k] * (gv.v[k] - k0.v[k] - xhat * k1.v[k]);
-    }
-    store8(p.dy + i * 8, o);
   }
 }
 
@@ -597,6 +740,7 @@ inline int ew_grid(long long nvec, int C, int per_thread = 2) {
   (void)C;
   long long blocks = (nvec + (long long)EW_THREADS * per_thread - 1) / ((long long)EW_THREADS * per_thread);
   if (blocks > EW_MAX_BLOCKS) blocks = EW_MAX_BLOCKS;
+  if (per_thread == 4 && blocks > 148 * 3) blocks = 148 * 3;  // the 4-way unrolled streaming kernels: 3 resident CTAs per SM
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }

@@ -30,6 +30,8 @@ struct BnRef {
   int nbt_idx;
   float* vec;   // [4][C] scale, shift, mean, rstd   (workspace)
   float* bred;  // [2][C] bsum, bdot                  (workspace)
+  double* acc;  // [2][C] fp64 sums of the fused forward statistics (zeroed at the start of every training forward)
+  double* bacc; // [3][C] fp64 sums of the fused backward reductions (zeroed at the start of every backward)
 };
 
 struct ConvRef {
@@ -128,6 +130,10 @@ struct Model {
   float* stats;          // shared stats-partials scratch
   float* bwd_partial;    // BN backward partials
   double* stat_acc;
+  double* acc_fwd;       // per-BatchNorm accumulators of the deferred finalize (conv_params.h: CF_DEFER): forward, backward
+  double* acc_bwd;
+  long long acc_fwd_bytes, acc_bwd_bytes;
+  bool bw_deferred = false;  // the reductions of the current block-output gradient sit in bn_b.bacc (fused dgrad) rather than in bred
   unsigned int* counters;
   float* unit_vec;       // [2][64]: ones, zeros (max-pool on already-activated stem output)
   float* feat;           // [B,512]
@@ -276,6 +282,21 @@ static long long carve(Model& m, char* base) {
   m.stats = (float*)bp.take(256LL * 2 * 512 * 4);  // one (sum, sumsq)[C<=512] partial per persistent conv CTA (<= SM count)
   m.bwd_partial = (float*)bp.take((long long)EW_MAX_BLOCKS * 2 * 512 * 4);
   m.stat_acc = (double*)bp.take(3 * 512 * 8);  // per-channel fp64 statistics accumulators (kept zero between launches)
+  {
+    long long ch = m.stem.bn.C;
+    for (auto& blk : m.blocks) ch += blk.a.bn.C + blk.b.bn.C + (blk.has_ds ? blk.ds.bn.C : 0);
+    m.acc_fwd_bytes = ch * 2 * 8; m.acc_bwd_bytes = ch * 3 * 8;
+    m.acc_fwd = (double*)bp.take(m.acc_fwd_bytes);
+    m.acc_bwd = (double*)bp.take(m.acc_bwd_bytes);
+    long long off = 0;
+    auto give = [&](BnRef& bn) {
+      bn.acc = m.acc_fwd ? m.acc_fwd + 2 * off : nullptr;
+      bn.bacc = m.acc_bwd ? m.acc_bwd + 3 * off : nullptr;
+      off += bn.C;
+    };
+    give(m.stem.bn);
+    for (auto& blk : m.blocks) { give(blk.a.bn); give(blk.b.bn); if (blk.has_ds) give(blk.ds.bn); }
+  }
   m.counters = (unsigned int*)bp.take(64);
   m.unit_vec = (float*)bp.take(2 * 64 * 4);
   m.feat = (float*)bp.take((long long)B * 512 * 4);
@@ -462,20 +483,31 @@ static int run_bn_finalize(Model& m, const BnRef& bn, int tiles, double count, i
 }
 
 // out = relu?( bn(x) [+ res] [+ bn2(x2)] ) on padded-flat tensors of geometry g
-static int run_bn_apply(int B, const PadGeom& g, const __nv_bfloat16* x, const BnRef& bn, const __nv_bfloat16* res, const __nv_bfloat16* x2,
-                        const BnRef* bn2, __nv_bfloat16* out, int relu, uint8_t* bits, cudaStream_t s) {
+// deferred != 0: the statistics of `bn` are still the raw sums the fused conv epilogue left in bn.acc (training forward)
+static int run_bn_apply(Model& m, int B, const PadGeom& g, const __nv_bfloat16* x, const BnRef& bn, const __nv_bfloat16* res,
+                        const __nv_bfloat16* x2, const BnRef* bn2, __nv_bfloat16* out, int relu, uint8_t* bits, int deferred,
+                        int update_running, cudaStream_t s) {
   const long long nvec = pad_elems(B, g, bn.C) / 8;
+  BnDefer d{};
+  if (deferred) {
+    const double count = (double)B * g.H * g.W;
+    d.acc = bn.acc; d.gamma = m.params + m.slots[bn.gamma].off; d.beta = m.params + m.slots[bn.beta].off;
+    d.running_mean = m.buffers + bn.rm_off; d.running_var = m.buffers + bn.rv_off; d.nbt = m.nbt ? m.nbt + bn.nbt_idx : nullptr;
+    d.vec = bn.vec; d.inv_count = 1.0 / count; d.unbias = count > 1.0 ? count / (count - 1.0) : 1.0;
+    d.momentum = 0.1f; d.eps = 1e-5f; d.update_running = update_running;
+  }
   ++g_cilrs_launches;
-  return cuda_status(launch_pdl(bn_apply_kernel, dim3(ew_grid(nvec, bn.C)), dim3(EW_THREADS), 0, s, x, (const float*)bn.vec,
+  return cuda_status(launch_pdl(bn_apply_kernel, dim3(ew_grid(nvec, bn.C, 4)), dim3(EW_THREADS), 0, s, x, (const float*)bn.vec,
                                 (const float*)(bn.vec + bn.C), res, x2, (const float*)(bn2 ? bn2->vec : nullptr),
-                                (const float*)(bn2 ? bn2->vec + bn2->C : nullptr), out, nvec, bn.C, relu, g, bits));
+                                (const float*)(bn2 ? bn2->vec + bn2->C : nullptr), out, nvec, bn.C, relu, g, bits, d));
 }
 
 // flat conv with the train-mode BatchNorm statistics + finalize fused (pointers bound at launch time)
 static int launch_flat_fwd(Model& m, int idx, const BnRef& bn, double count, int update_running, cudaStream_t s) {
   FlatConvParams f = m.flat_plans[idx];
   if (f.flags & CF_STATS) {
-    f.partials = m.stat_acc; f.counter = m.counters + 1;
+    f.flags |= CF_DEFER;  // the bn_apply that follows finalizes (run_bn_apply, deferred)
+    f.partials = bn.acc; f.counter = nullptr;
     f.gamma = m.params + m.slots[bn.gamma].off; f.beta = m.params + m.slots[bn.beta].off;
     f.running_mean = m.buffers + bn.rm_off; f.running_var = m.buffers + bn.rv_off;
     f.nbt = m.nbt ? m.nbt + bn.nbt_idx : nullptr;
@@ -534,6 +566,7 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
     return ERR_INVALID;
   }
   const int training = mode == MODE_TRAIN;
+  if (training) CK(cuda_status(cudaMemsetAsync(m.acc_fwd, 0, (size_t)m.acc_fwd_bytes, s)));  // accumulators of the deferred BN finalize
   const long long pool_vec = act_elems(B, 22, 50, 64) / 8;
   PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.old_plans[m.stem_fwd], s)));
   if (mode == MODE_INFER) {
@@ -566,11 +599,15 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
         return OK;
       };
       CK(conv_bn(blk.a, blk.pl.f_a_flat, blk.pl.f_a_old));
-      PROF(m, PC_BN_FWD, s, CK(run_bn_apply(B, blk.a.gout, blk.a.y, blk.a.bn, nullptr, nullptr, nullptr, blk.act_a, 1, blk.bits_a, s)));
+      const int def_a = training && blk.pl.f_a_flat >= 0, def_b = training;
+      PROF(m, PC_BN_FWD, s, CK(run_bn_apply(m, B, blk.a.gout, blk.a.y, blk.a.bn, nullptr, nullptr, nullptr, blk.act_a, 1, blk.bits_a, def_a,
+                                            update_running, s)));
       if (blk.has_ds) CK(conv_bn(blk.ds, -1, blk.pl.f_ds_old));
       CK(conv_bn(blk.b, blk.pl.f_b_flat, -1));
-      if (blk.has_ds) PROF(m, PC_BN_FWD, s, CK(run_bn_apply(B, blk.b.gout, blk.b.y, blk.b.bn, nullptr, blk.ds.y, &blk.ds.bn, blk.out, 1, blk.bits_out, s)));
-      else PROF(m, PC_BN_FWD, s, CK(run_bn_apply(B, blk.b.gout, blk.b.y, blk.b.bn, blk.in, nullptr, nullptr, blk.out, 1, blk.bits_out, s)));
+      if (blk.has_ds) PROF(m, PC_BN_FWD, s, CK(run_bn_apply(m, B, blk.b.gout, blk.b.y, blk.b.bn, nullptr, blk.ds.y, &blk.ds.bn, blk.out, 1,
+                                                            blk.bits_out, def_b, update_running, s)));
+      else PROF(m, PC_BN_FWD, s, CK(run_bn_apply(m, B, blk.b.gout, blk.b.y, blk.b.bn, blk.in, nullptr, nullptr, blk.out, 1, blk.bits_out,
+                                                 def_b, update_running, s)));
     }
   }
   avgpool_kernel<<<(B * 512 + 255) / 256, 256, 0, s>>>(m.blocks.back().out, m.feat, B, 512, m.blocks.back().b.gout); ++g_cilrs_launches;
@@ -602,7 +639,8 @@ static int run_wgrad_flat(Model& m, int idx, cudaStream_t s) { return launch_wgr
 static int launch_flat_bwd(Model& m, int idx, const BnRef* bn1, const BnRef* bn2, cudaStream_t s) {
   FlatConvParams f = m.flat_plans[idx];
   if (f.flags & CF_BNBWD) {
-    f.partials = m.stat_acc; f.counter = m.counters + 1;
+    f.flags |= CF_DEFER;  // the bn_bwd_apply kernels that follow finalize (run_bn_bwd_apply, deferred)
+    f.partials = bn1->bacc; f.counter = nullptr;
     f.dgamma1 = m.grads + m.slots[bn1->gamma].off; f.dbeta1 = m.grads + m.slots[bn1->beta].off;
     if (f.flags & CF_BNBWD2) { f.dgamma2 = m.grads + m.slots[bn2->gamma].off; f.dbeta2 = m.grads + m.slots[bn2->beta].off; }
   }
@@ -624,15 +662,20 @@ static int run_bn_bwd_reduce(Model& m, int B, const PadGeom& g, const BnRef& bn,
 }
 
 // dy = gamma * rstd * (dz - bsum/n - xhat * bdot/n)   (frozen: gamma * rstd * dz); dz is already ReLU-masked
+// acc_sum / acc_dot != nullptr: the reductions are still the raw sums a fused dgrad epilogue left there (deferred finalize)
 static int run_bn_bwd_apply(Model& m, int B, const PadGeom& g, const BnRef& bn, const __nv_bfloat16* dz, const __nv_bfloat16* y,
-                            double count, int frozen, __nv_bfloat16* dy, cudaStream_t s) {
+                            double count, int frozen, __nv_bfloat16* dy, const double* acc_sum, const double* acc_dot, cudaStream_t s) {
   const long long nvec = pad_elems(B, g, bn.C) / 8;
   BnBwdApplyParams ap{};
   ap.g = dz; ap.act = nullptr; ap.y = y; ap.mean = bn.vec + 2 * bn.C; ap.rstd = bn.vec + 3 * bn.C;
   ap.gamma = m.params + m.slots[bn.gamma].off; ap.bsum = bn.bred; ap.bdot = bn.bred + bn.C; ap.inv_count = (float)(1.0 / count);
   ap.frozen = frozen; ap.nvec = nvec; ap.C = bn.C; ap.dy = dy; ap.dz = nullptr; ap.geom = g;
+  if (acc_sum) {
+    ap.defer.acc_sum = acc_sum; ap.defer.acc_dot = acc_dot; ap.defer.bred = bn.bred;
+    ap.defer.dgamma = m.grads + m.slots[bn.gamma].off; ap.defer.dbeta = m.grads + m.slots[bn.beta].off;
+  }
   ++g_cilrs_launches;
-  return cuda_status(launch_pdl(bn_bwd_apply_kernel<false>, dim3(ew_grid(nvec, bn.C)), dim3(EW_THREADS), 0, s, ap));
+  return cuda_status(launch_pdl(bn_bwd_apply_kernel<false>, dim3(ew_grid(nvec, bn.C, 4)), dim3(EW_THREADS), 0, s, ap));
 }
 
 static int heads_backward(Model& m, int B, const float* dcontrols, const float* dspeed, const float* speed,
@@ -690,6 +733,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   const int frozen = mode == MODE_FROZEN;
   if (part < -1 || part > 4) return ERR_INVALID;
   if (part <= 0) {
+    CK(cuda_status(cudaMemsetAsync(m.acc_bwd, 0, (size_t)m.acc_bwd_bytes, s)));  // accumulators of the deferred BN-backward finalize
     PROF(m, PC_HEADS, s, CK(heads_backward(m, B, dcontrols, dspeed, speed, command, dropout_p, s)));
     // ---- trunk: gradient of the last block's output, then its ReLU mask + BN_b reductions ----
     Block& last = m.blocks.back();
@@ -697,6 +741,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     CKL();
     PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_reduce(m, B, last.b.gout, last.b.bn, m.g0, last.out, last.b.y, s)));
     m.bw_gcur = m.g0; m.bw_gnext = m.g1;
+    m.bw_deferred = false;
   }
   __nv_bfloat16*& gcur = m.bw_gcur;
   __nv_bfloat16*& gnext = m.bw_gnext;
@@ -741,18 +786,20 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     __nv_bfloat16* dyd = m.dyd[blk_part & 1];
     // gcur = dz of this block's output (ReLU-masked), with the reductions of bn_b (and bn_ds) already in their bred
     CK(slot_write(sb));
-    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.b.bn, gcur, blk.b.y, cnt, frozen, dyb, s)));
+    const int Cb = blk.b.bn.C;
+    const double* bsum_acc = m.bw_deferred ? blk.b.bn.bacc : nullptr;  // sum dz | sum dz*y_b | sum dz*y_ds
+    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.b.bn, gcur, blk.b.y, cnt, frozen, dyb, bsum_acc, bsum_acc ? bsum_acc + Cb : nullptr, s)));
     CK(slot_ready(sb));
     if (blk.has_ds) {
       CK(slot_write(sd));
-      PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.ds.bn, gcur, blk.ds.y, cnt, frozen, dyd, s)));
+      PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.ds.bn, gcur, blk.ds.y, cnt, frozen, dyd, bsum_acc, bsum_acc ? bsum_acc + 2 * Cb : nullptr, s)));
       CK(slot_ready(sd));
     }
     PROF(m, PC_WGRAD, ws, CK(run_wgrad_flat(m, blk.pl.w_b, ws)));                     // dW_b
     CK(slot_read_done(sb));
     PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_b, &blk.a.bn, nullptr, s)));  // ga = dz_a (+ BN_a reductions)
     CK(slot_write(sa));
-    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.a.bn, m.ga, blk.a.y, cnt, frozen, dya, s)));
+    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.a.bn, m.ga, blk.a.y, cnt, frozen, dya, blk.a.bn.bacc, blk.a.bn.bacc + blk.a.bn.C, s)));
     CK(slot_ready(sa));
     if (blk.pl.w_a_flat >= 0) PROF(m, PC_WGRAD, ws, CK(run_wgrad_flat(m, blk.pl.w_a_flat, ws)));
     else PROF(m, PC_WGRAD, ws, CK(run_wgrad_old(m, blk.pl.w_a_old, blk.a.w, ws)));
@@ -764,11 +811,13 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     if (blk.pl.d_a_flat >= 0) {
       Block* pb = bi > 0 ? &m.blocks[bi - 1] : nullptr;
       PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_a_flat, pb ? &pb->b.bn : nullptr, (pb && pb->has_ds) ? &pb->ds.bn : nullptr, s)));
+      m.bw_deferred = true;
     } else {
       for (int k = 0; k < 4; ++k) PROF(m, PC_DGRAD, s, CK(launch_conv_gemm(&m.old_plans[blk.pl.d_a_old + k], s)));
       // the parity launches write the raw gradient of the previous block's output: mask + reduce it here
       Block& pb = m.blocks[bi - 1];
       PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_reduce(m, B, pb.b.gout, pb.b.bn, gnext, pb.out, pb.b.y, s)));
+      m.bw_deferred = false;
     }
     __nv_bfloat16* t = gcur; gcur = gnext; gnext = t;
   }
@@ -785,7 +834,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   if (part < 0 || part == 4) {
     const BnRef& bn = m.stem.bn;
     const long long nvec = act_elems(B, 44, 100, 64) / 8;
-    const int grid = ew_grid(nvec, 64);
+    const int grid = ew_grid(nvec, 64, 4);
     const int rgrid = ew_grid(nvec, 64, 8);
     BnBwdReduceParams rp{};
     rp.g = gcur; rp.y = m.stem.y; rp.mean = bn.vec + 2 * 64; rp.rstd = bn.vec + 3 * 64; rp.nvec = nvec; rp.C = 64;
@@ -1053,7 +1102,7 @@ int cilrs_bn_apply(const void* x, const float* vec, const void* residual, const 
   const long long nvec = elems / 8;
   bn_apply_kernel<<<ew_grid(nvec, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, vec, vec + C, (const __nv_bfloat16*)residual, (const __nv_bfloat16*)x2, vec2, vec2 ? vec2 + C : nullptr,
-      (__nv_bfloat16*)out, nvec, C, relu, g, relu_bits); ++g_cilrs_launches;
+      (__nv_bfloat16*)out, nvec, C, relu, g, relu_bits, BnDefer{}); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 

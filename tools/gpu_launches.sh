@@ -2,5 +2,5 @@ cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline"
 timeout 600 $CMD > gpurun_out/plain.log 2>&1 &&
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 330 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 420 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1
 tail -2 gpurun_out/ncu1.log
