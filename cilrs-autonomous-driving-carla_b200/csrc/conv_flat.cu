@@ -28,9 +28,10 @@ static void split_boxes(int rows, int* box_rows, int* boxes) {
   *boxes = n;
 }
 
-static long long flat_smem_fixed(int block_n) {
-  return 1024 /* alignment slack */ + CF_STAGING_BYTES + 8LL * 3 * block_n * 4 /* warp-private statistics */ +
-         (2 * CF_MAX_A_STAGES + 2 * CF_MAX_B_STAGES + 2 * CF_MAX_ACC) * 8 + 64 + 64;
+static long long flat_smem_fixed(int block_n, int flags) {
+  return 1024 /* alignment slack */ + CF_STAGING_BYTES + ((flags & CF_BNBWD) ? CF_STAGING_BYTES : 0) /* y tiles */ +
+         8LL * 3 * block_n * 4 /* warp-private statistics */ +
+         (2 * CF_MAX_A_STAGES + 2 * CF_MAX_B_STAGES + 2 * CF_MAX_ACC + 16) * 8 + 64 + 64;
 }
 
 // Tile-shape choice by a small cost model in clocks per CTA, calibrated on B200 traces (tools/trace_flat.py):
@@ -67,7 +68,7 @@ static bool flat_stages(long long budget, int chunks, int n_blocks, int bn, long
   return true;
 }
 
-static FlatShape choose_flat_shape(int total_rows, int k_channels, int n_total, const PadGeom& g) {
+static FlatShape choose_flat_shape(int total_rows, int k_channels, int n_total, const PadGeom& g, int flags) {
   const int sms = sm_count();
   const int chunks = k_channels / 64;
   const int halo = g.Wp + 1;
@@ -80,7 +81,7 @@ static FlatShape choose_flat_shape(int total_rows, int k_channels, int n_total, 
     const int bn = bns[bi];
     if (n_total % bn) continue;
     const int n_blocks = n_total / bn;
-    const long long budget = CG_SMEM_TOTAL - flat_smem_fixed(bn);
+    const long long budget = CG_SMEM_TOTAL - flat_smem_fixed(bn, flags);
     const double mma_clk = bn == 64 ? 48.0 : (bn == 128 ? 64.0 : 128.0);
     for (int mi = 0; mi < 3; ++mi) {
       const int mt = mts[mi];
@@ -126,7 +127,7 @@ static FlatShape choose_flat_shape(int total_rows, int k_channels, int n_total, 
       int box_rows, boxes, a_st, b_st;
       split_boxes(mt * 128 + 2 * halo, &box_rows, &boxes);
       const long long a_stage = (long long)box_rows * boxes * 128;
-      const long long budget = CG_SMEM_TOTAL - flat_smem_fixed(bn);
+      const long long budget = CG_SMEM_TOTAL - flat_smem_fixed(bn, flags);
       if (res) G = 9;
       if (flat_stages(budget, chunks, n_total / bn, bn, a_stage, res, G, &a_st, &b_st))
         best = FlatShape{mt, bn, res, G, a_st, b_st, box_rows, boxes, 0.0};
@@ -161,7 +162,7 @@ int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channe
   memset(p, 0, sizeof(*p));
   p->g = g;
   p->total_rows = flat_total_rows(batch, g);
-  const FlatShape sh = choose_flat_shape(p->total_rows, k_channels, n_total, g);
+  const FlatShape sh = choose_flat_shape(p->total_rows, k_channels, n_total, g, flags);
   if (sh.cost >= 1e30) return ERR_UNSUPPORTED;
   p->mt = sh.mt; p->block_n = sh.block_n; p->n_blocks = n_total / sh.block_n; p->n_total = n_total;
   p->chunks = k_channels / 64;
@@ -181,6 +182,25 @@ int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channe
   return encode_2d_map(&p->tmB, w, k_channels, 9 * n_total, 64, p->block_n);
 }
 
+// tensor maps of the epilogue's operand tiles (residual, y1, y2): call after the pointers are set, before the launch
+int flat_conv_bind_operands(FlatConvParams* p) {
+  p->operand_maps = 0;
+  if ((p->flags & CF_RESIDUAL) && p->residual) {
+    int st = encode_2d_map(&p->tmRes, p->residual, p->n_total, p->total_rows, 64, 32);
+    if (st) return st;
+  }
+  if ((p->flags & CF_BNBWD) && p->y1) {
+    int st = encode_2d_map(&p->tmY1, p->y1, p->n_total, p->total_rows, 64, 32);
+    if (st) return st;
+  }
+  if ((p->flags & CF_BNBWD2) && p->y2) {
+    int st = encode_2d_map(&p->tmY2, p->y2, p->n_total, p->total_rows, 64, 32);
+    if (st) return st;
+  }
+  p->operand_maps = 1;
+  return OK;
+}
+
 int flat_conv_grid(const FlatConvParams* p) {
   const long long total = (long long)p->m_tiles * p->n_blocks;
   int grid = total < sm_count() ? (int)total : sm_count();
@@ -196,6 +216,7 @@ int launch_flat_conv(const FlatConvParams* p, cudaStream_t s) {
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
+  if ((p->flags & CF_BNBWD) && (!p->operand_maps || !p->y1 || ((p->flags & CF_BNBWD2) && !p->y2))) return ERR_INVALID;
   if ((p->flags & (CF_STATS | CF_BNBWD)) && (!p->partials || (!(p->flags & CF_DEFER) && !p->counter))) return ERR_INVALID;
   const int grid = flat_conv_grid(p);
   void (*kernel)(FlatConvParams) = p->mt == 1 ? conv_flat_kernel<1> : (p->mt == 2 ? conv_flat_kernel<2> : (p->mt == 4 ? conv_flat_kernel<4> : nullptr));
@@ -309,6 +330,8 @@ int cilrs_conv_flat(const cilrs_flat_conv_args* a, void* stream) {
   p.update_running = a->update_running;
   p.y1 = (const __nv_bfloat16*)a->y1; p.stat1 = a->vec1; p.bred1 = a->bred1; p.dgamma1 = a->dgamma1; p.dbeta1 = a->dbeta1;
   p.y2 = (const __nv_bfloat16*)a->y2; p.stat2 = a->vec2; p.bred2 = a->bred2; p.dgamma2 = a->dgamma2; p.dbeta2 = a->dbeta2;
+  st = flat_conv_bind_operands(&p);
+  if (st) return st;
   return launch_flat_conv(&p, (cudaStream_t)stream);
 }
 

@@ -8,9 +8,9 @@
 // resident in shared memory. Accumulators live in TMEM (acc_sets x mt x block_n columns) so the epilogue of one tile
 // overlaps the MMAs of the next. Persistent CTAs, warp-specialised:
 //   warp 0 : TMA producer     warp 1 : MMA issuer     warps 4..11 : two epilogue groups (TMEM -> registers -> HBM)
-// Fused epilogues: folded BN / residual / ReLU (inference), BN batch statistics + finalize (training forward),
-// ReLU mask + BatchNorm-backward reductions + finalize (dgrad). Reductions are deterministic: per-CTA partials in a
-// fixed order, folded by the last CTA to finish.
+// Fused epilogues: folded BN / residual / ReLU (inference), BN batch statistics (training forward), ReLU mask +
+// BatchNorm-backward reductions (dgrad). The per-channel sums go to fp64 global accumulators (order-independent); they are
+// finalized either by the last CTA to finish or, with CF_DEFER, by the elementwise kernel that consumes them.
 #pragma once
 #include "common.cuh"
 #include "conv_params.h"
@@ -45,23 +45,6 @@ CILRS_DEVINL void load_row64(const __nv_bfloat16* p, uint32_t* r) {
   for (int j = 0; j < 4; ++j) ldg256(p + j * 16, r + j * 8);
 }
 
-// Column sums across the warp without shared memory: every lane holds one row x[0..63]; after five butterfly steps lane l
-// holds the sums over all 32 rows of columns 2l and 2l+1 (62 shuffles). Destroys x.
-CILRS_DEVINL float2 warp_colsum64(float* x, int lane) {
-#pragma unroll
-  for (int half = 32; half >= 2; half >>= 1) {
-    const int bit = half >> 1;
-    const bool up = (lane & bit) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float send = up ? x[i] : x[i + half];
-      const float keep = up ? x[i + half] : x[i];
-      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-    }
-  }
-  return make_float2(x[0], x[1]);
-}
-
 template <int MT>
 __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_constant__ FlatConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -77,7 +60,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)p.a_stages * a_stage_bytes;
   uint8_t* s_out = sB + (size_t)p.b_stages * b_stage_bytes;            // [8 epilogue warps][32 rows][128 B] output staging
-  float* s_wacc = (float*)(s_out + CF_STAGING_BYTES);                  // [8 epilogue warps][3][block_n] running statistics
+  uint8_t* s_yin = s_out + CF_STAGING_BYTES;                           // [8][32][128 B] y tiles of the BN-backward dot (CF_BNBWD only)
+  float* s_wacc = (float*)(s_yin + ((p.flags & CF_BNBWD) ? CF_STAGING_BYTES : 0));  // [8 epilogue warps][3][block_n] running statistics
   uint64_t* bars = (uint64_t*)(s_wacc + 8 * 3 * p.block_n);
   uint64_t* full_a = bars;
   uint64_t* empty_a = full_a + CF_MAX_A_STAGES;
@@ -85,7 +69,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
   uint64_t* empty_b = full_b + CF_MAX_B_STAGES;
   uint64_t* tfull = empty_b + CF_MAX_B_STAGES;
   uint64_t* tempty = tfull + CF_MAX_ACC;
-  uint32_t* tmem_slot = (uint32_t*)(tempty + CF_MAX_ACC);
+  uint64_t* ebar = tempty + CF_MAX_ACC;                                // [8 epilogue warps][2]: residual tile, y tile landed
+  uint32_t* tmem_slot = (uint32_t*)(ebar + 16);
   uint32_t* s_flag = tmem_slot + 1;
 #ifdef CF_TRACE
   uint32_t* cf_idx = s_flag + 1;  // event counters of the three traced roles (shared memory: cheap to bump)
@@ -97,9 +82,11 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmOut);
+    if (p.operand_maps) { tma_prefetch_desc(&p.tmRes); tma_prefetch_desc(&p.tmY1); }
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < p.acc_sets; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }  // 8 epilogue warps
+    for (int i = 0; i < 16; ++i) mbar_init(&ebar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -223,9 +210,12 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
   } else {
     setmaxnreg_inc<216>();
     // ================= epilogue: 2 groups x 4 warps; a group handles every other 128 x 64 unit =================
-    // Register-direct: TMEM -> registers -> (scale/bias, residual, ReLU mask) -> bf16 -> 256-bit global stores; per-channel
-    // statistics by a shuffle butterfly into warp-private accumulators. No shared-memory staging and no barriers: the
-    // tensor core's operand fetch already saturates the 128 B/clk of shared memory (conv_flat.cu).
+    // TMEM -> registers -> (scale/bias, residual, ReLU / ReLU-mask) -> bf16 -> this warp's swizzled staging tile -> one TMA
+    // store. The operand tiles (residual, y of the BatchNorm-backward dot) come in by TMA as well: per-lane row loads make
+    // every instruction touch 32 different lines. The per-channel sums are a COLUMN pass over the staged tiles: lane l reads
+    // the 4 bytes of columns 2l, 2l+1 of each of the 32 rows (conflict-free, 32 shared-memory cycles) - a third of the
+    // instructions of a shuffle butterfly over the registers, whose 62 shuffles per quantity also each take a cycle of the
+    // shared-memory pipe the tensor core's operand fetch is saturating.
     const int ew = warp - 4;
     const int grp = ew >> 2;
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -234,8 +224,15 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     const bool bwd = (p.flags & CF_BNBWD) != 0;
     const bool bwd2 = (p.flags & CF_BNBWD2) != 0;
     const int nq = bwd2 ? 3 : 2;
+    const bool res_tma = (p.flags & CF_RESIDUAL) && p.operand_maps;
     float* w_acc = s_wacc + ew * (3 * p.block_n);  // this warp's running sums [3][block_n]
     uint8_t* w_out = s_out + ew * (32 * 128);      // this warp's output staging (1024-byte aligned, 128B-swizzled rows)
+    uint8_t* w_y = s_yin + ew * (32 * 128);        // this warp's y tile
+    uint64_t* bar_res = &ebar[ew * 2];
+    uint64_t* bar_y = &ebar[ew * 2 + 1];
+    uint32_t ph_res = 0, ph_y = 0;
+    // byte offset of (row r, columns 2*lane, 2*lane+1) inside a swizzled tile, without the row term
+    const uint32_t col_chunk = (uint32_t)(lane >> 2), col_in = (uint32_t)(lane & 3) * 4u;
     if (do_stats) {
       for (int i = lane; i < 3 * p.block_n; i += 32) w_acc[i] = 0.f;
       __syncwarp();
@@ -268,16 +265,25 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
           if (((uc++) & 1u) != (uint32_t)grp) continue;
           const int n_base = n_blk * p.block_n + chunk * 64;
           const long long goff = (long long)f * p.n_total + n_base;
-          // operand loads of this unit are issued first so their latency overlaps the TMEM load; the ReLU mask comes as
-          // 64 bits (two registers) when the producer wrote a bit tensor, which keeps the residual prefetch in registers
-          uint32_t rres[32];
+          const int row_first = row0 + m * 128 + q * 32;   // first row of this warp's 32 x 64 tile
+          // ---- operand tiles of this unit: issued first so that they land while the accumulator is read ----
+          // (the residual tile lands in the output staging tile: the previous unit's store must have read it; the previous
+          //  unit's column pass over both tiles is complete on every lane)
+          tma_store_wait_read();
+          __syncwarp();
+          if (lane == 0) {
+            if (res_tma) {
+              mbar_arrive_expect_tx(bar_res, 32 * 128);
+              tma_load_2d(&p.tmRes, bar_res, w_out, n_base, row_first);
+            }
+            if (bwd) {
+              mbar_arrive_expect_tx(bar_y, 32 * 128);
+              tma_load_2d(&p.tmY1, bar_y, w_y, n_base, row_first);
+            }
+          }
           uint2 mbits = make_uint2(0xffffffffu, 0xffffffffu);
-          const bool ld_res = (p.flags & CF_RESIDUAL) && valid;
           const bool use_bits = (p.flags & CF_MASK) && p.mask_bits != nullptr;
-          if (ld_res) load_row64(p.residual + goff, rres);
           if (use_bits && valid) mbits = __ldg(reinterpret_cast<const uint2*>(p.mask_bits + (goff >> 3)));
-          uint32_t ry[32];
-          if (bwd && valid) load_row64(p.y1 + goff, ry);  // consumed by the second butterfly
           uint32_t v[64];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride + m * p.block_n + chunk * 64);
           tmem_ld_32x32(taddr, v);
@@ -289,11 +295,25 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
             for (int j = 0; j < 64; ++j)
               v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), __ldg(p.scale + n_base + j), __ldg(p.bias + n_base + j)));
           }
-          if (ld_res) {
+          if (p.flags & CF_RESIDUAL) {
+            uint32_t rres[32];
+            if (res_tma) {
+              mbar_wait(bar_res, ph_res);
+              ph_res ^= 1;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) + bf16lo(rres[j]));
-              v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) + bf16hi(rres[j]));
+              for (int j = 0; j < 8; ++j) {
+                const uint4 t = *(const uint4*)(w_out + lane * 128 + ((j ^ (lane & 7)) << 4));
+                rres[4 * j] = t.x; rres[4 * j + 1] = t.y; rres[4 * j + 2] = t.z; rres[4 * j + 3] = t.w;
+              }
+            } else if (valid) {
+              load_row64(p.residual + goff, rres);
+            }
+            if (res_tma || valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) + bf16lo(rres[j]));
+                v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) + bf16hi(rres[j]));
+              }
             }
           }
           if (use_bits) {
@@ -317,52 +337,65 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             u[j] = valid ? pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) : 0u;  // padding pixels stay exact zeros
-          // Output: the warp's 32 rows x 128 B go through a swizzled staging tile and ONE TMA store (full 128-byte lines).
+          // Output: the warp's 32 rows x 128 B go through the swizzled staging tile and ONE TMA store (full 128-byte lines).
           // Per-thread 32-byte stores of a row each cost the LSU 32 sector requests per instruction: 1.5 k clocks per unit.
-          tma_store_wait_read();  // (lane 0 issued the previous store: its shared-memory reads are complete)
-          __syncwarp();
+          __syncwarp();  // every lane has read its residual row out of the staging tile
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *(uint4*)(w_out + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&p.tmOut, w_out, n_base, row0 + m * 128 + q * 32);
+            tma_store_2d(&p.tmOut, w_out, n_base, row_first);
             tma_store_commit();
           }
           if (ew == 0 && lane == 0) CF_EVENT(2, 0x605);
           if (do_stats) {
-            // statistics of the stored (bf16-rounded) values
+            // column pass over the staged (bf16-rounded, zero on padding rows) tile: lane l owns columns 2l, 2l+1
             float* wa = w_acc + chunk * 64 + 2 * lane;
-            float x[64];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { x[2 * j] = bf16lo(u[j]); x[2 * j + 1] = bf16hi(u[j]); }
-            const float2 s0 = warp_colsum64(x, lane);
-            wa[0] += s0.x; wa[1] += s0.y;
+            float s0x = 0.f, s0y = 0.f, s1x = 0.f, s1y = 0.f;
             if (!bwd) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) { const float a = bf16lo(u[j]), b = bf16hi(u[j]); x[2 * j] = a * a; x[2 * j + 1] = b * b; }
-              const float2 s1 = warp_colsum64(x, lane);
-              wa[p.block_n] += s1.x; wa[p.block_n + 1] += s1.y;
+              for (int r = 0; r < 32; ++r) {
+                const uint32_t t = *(const uint32_t*)(w_out + r * 128 + ((col_chunk ^ (uint32_t)(r & 7)) << 4) + col_in);
+                const float a = bf16lo(t), b = bf16hi(t);
+                s0x += a; s0y += b;
+                s1x = fmaf(a, a, s1x); s1y = fmaf(b, b, s1y);
+              }
             } else {
-              // sum dz * y (raw); the finalize turns it into sum dz * xhat = rstd * (sum dz*y - mean * sum dz)
+              // sum dz and sum dz * y (raw); the finalize turns the latter into sum dz * xhat = rstd * (sum dz*y - mean * sum dz)
+              mbar_wait(bar_y, ph_y);
+              ph_y ^= 1;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                x[2 * j] = valid ? bf16lo(u[j]) * bf16lo(ry[j]) : 0.f;
-                x[2 * j + 1] = valid ? bf16hi(u[j]) * bf16hi(ry[j]) : 0.f;
+              for (int r = 0; r < 32; ++r) {
+                const uint32_t off = (uint32_t)(r * 128) + ((col_chunk ^ (uint32_t)(r & 7)) << 4) + col_in;
+                const uint32_t t = *(const uint32_t*)(w_out + off);
+                const uint32_t y = *(const uint32_t*)(w_y + off);
+                const float a = bf16lo(t), b = bf16hi(t);
+                s0x += a; s0y += b;
+                s1x = fmaf(a, bf16lo(y), s1x); s1y = fmaf(b, bf16hi(y), s1y);
               }
-              if (bwd2 && valid) load_row64(p.y2 + goff, ry);  // overlaps the second butterfly
-              const float2 s1 = warp_colsum64(x, lane);
-              wa[p.block_n] += s1.x; wa[p.block_n + 1] += s1.y;
-              if (bwd2) {
+            }
+            wa[0] += s0x; wa[1] += s0y;
+            wa[p.block_n] += s1x; wa[p.block_n + 1] += s1y;
+            if (bwd2) {
+              // second BatchNorm fed by the same gradient (downsample branch): its y tile replaces the first one
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive_expect_tx(bar_y, 32 * 128);
+                tma_load_2d(&p.tmY2, bar_y, w_y, n_base, row_first);
+              }
+              mbar_wait(bar_y, ph_y);
+              ph_y ^= 1;
+              float s2x = 0.f, s2y = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  x[2 * j] = valid ? bf16lo(u[j]) * bf16lo(ry[j]) : 0.f;
-                  x[2 * j + 1] = valid ? bf16hi(u[j]) * bf16hi(ry[j]) : 0.f;
-                }
-                const float2 s2 = warp_colsum64(x, lane);
-                wa[2 * p.block_n] += s2.x; wa[2 * p.block_n + 1] += s2.y;
+              for (int r = 0; r < 32; ++r) {
+                const uint32_t off = (uint32_t)(r * 128) + ((col_chunk ^ (uint32_t)(r & 7)) << 4) + col_in;
+                const uint32_t t = *(const uint32_t*)(w_out + off);
+                const uint32_t y = *(const uint32_t*)(w_y + off);
+                s2x = fmaf(bf16lo(t), bf16lo(y), s2x); s2y = fmaf(bf16hi(t), bf16hi(y), s2y);
               }
+              wa[2 * p.block_n] += s2x; wa[2 * p.block_n + 1] += s2y;
             }
           }
           if (ew == 0 && lane == 0) CF_EVENT(2, 0x606);

@@ -55,6 +55,7 @@ int flat_total_rows(int batch, const PadGeom& g);
 // dgrad: the same call with dy as x, the dgrad weight pack and dgrad = 1. Epilogue pointers are filled in by the caller.
 int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channels, int n_total, int dgrad, const void* x,
                     const void* w, void* out, int flags);
+int flat_conv_bind_operands(FlatConvParams* p);  // after residual / y1 / y2 are set
 int flat_conv_grid(const FlatConvParams* p);
 int launch_flat_conv(const FlatConvParams* p, cudaStream_t s);
 struct WgradReduceJobs;

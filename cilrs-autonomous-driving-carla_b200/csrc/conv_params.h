@@ -111,6 +111,10 @@ struct FlatConvParams {
   CUtensorMap tmA;  // 2-D (channels, flat pixels), box (64, a_box_rows)
   CUtensorMap tmB;  // 2-D (channels, taps * n_total), box (64, block_n)
   CUtensorMap tmOut;  // 2-D (n_total, flat pixels) view of `out`, box (64, 32): one epilogue warp's 32 rows x 64 channels
+  CUtensorMap tmRes;  // the same view of `residual`, `y1`, `y2` (operand tiles of the epilogue; conv_flat.cu: flat_conv_bind_operands)
+  CUtensorMap tmY1;
+  CUtensorMap tmY2;
+  int operand_maps;   // tmRes / tmY1 / tmY2 are valid for the current residual / y1 / y2 pointers
   int total_rows;
   PadGeom g;
   int mt;                      // 128-row sub-tiles per tile (they share every weight tile)

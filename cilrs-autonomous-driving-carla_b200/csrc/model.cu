@@ -397,6 +397,7 @@ static int build_plans(Model& m, int B, int mode) {
       if (infer) {
         f.scale = blk.b.bn.vec; f.bias = blk.b.bn.vec + blk.b.bn.C;
         f.residual = blk.has_ds ? blk.ds.y : blk.in;
+        CK(flat_conv_bind_operands(&f));
       }
       blk.pl.f_b_flat = add_flat(m, f);
     }
@@ -426,6 +427,7 @@ static int build_plans(Model& m, int B, int mode) {
       CK(add_wflat(blk.b, dyb, blk.act_a, &blk.pl.w_b));
       CK(build_flat_conv(&f, B, blk.b.gin, blk.b.d.out_c, blk.b.d.in_c, 1, dyb, blk.b.wd, m.ga, CF_MASK | CF_BNBWD));
       f.mask = blk.act_a; f.mask_bits = blk.bits_a; f.y1 = blk.a.y; f.stat1 = blk.a.bn.vec; f.bred1 = blk.a.bn.bred;
+      CK(flat_conv_bind_operands(&f));
       blk.pl.d_b = add_flat(m, f);
       // conv_a: dW_a = wgrad(dy_a = d1, in); downsample: dW_ds = wgrad(dy_ds = d2, in)
       if (blk.a.flat) {
@@ -451,6 +453,7 @@ static int build_plans(Model& m, int B, int mode) {
           f.y1 = pb.b.y; f.stat1 = pb.b.bn.vec; f.bred1 = pb.b.bn.bred;
           if (pb.has_ds) { f.y2 = pb.ds.y; f.stat2 = pb.ds.bn.vec; f.bred2 = pb.ds.bn.bred; }
         }
+        CK(flat_conv_bind_operands(&f));
         blk.pl.d_a_flat = add_flat(m, f);
       } else {
         for (int ph = 0; ph < 2; ++ph)
