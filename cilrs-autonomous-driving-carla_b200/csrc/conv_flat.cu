@@ -39,6 +39,8 @@ static long long flat_smem_fixed(int block_n, int flags) {
 //    48 / 64 / 128 for N = 64 / 128 / 256;
 //  * every mbarrier round trip of the issuing warp (one per weight stage = `tap_group` taps) costs ~550 clocks of which the
 //    tensor-core queue hides ~3.3 MMAs;
+//  * a weight stage comes around every b_stages groups and is busy for its MMAs + ~700 clocks of TMA latency + its transfer:
+//    two big stages stall the issuing warp where four small ones do not (layer3: tap_group 1 x 4 stages beats 2 x 2);
 //  * a 128 x 64 epilogue unit costs ~2000 clocks and is only hidden behind the MMAs of a following tile;
 //  * activations + weights cross L2->SMEM at ~min(64, 6300 / active CTAs) bytes per clock.
 struct FlatShape {
@@ -104,7 +106,15 @@ static FlatShape choose_flat_shape(int total_rows, int k_channels, int n_total, 
         double chunk_clk = 0.0;
         for (int t0 = 0; t0 < 9; t0 += G) {
           const int cnt = 9 - t0 < G ? 9 - t0 : G;
-          chunk_clk += cnt * mt * 4 * mma_clk + exposed;
+          double group = cnt * mt * 4 * mma_clk + exposed;
+          if (!res) {
+            // weight-stage pipeline: a stage is busy for its own MMAs plus its refill (~700 clocks of TMA latency + the
+            // transfer at ~64 B/clk), and comes around every b_st groups
+            const double refill = 700.0 + cnt * bn * 128.0 / 64.0;
+            const double ring = (refill + cnt * mt * 4 * mma_clk) / b_st;
+            if (ring > group) group = ring;
+          }
+          chunk_clk += group;
         }
         const double mma = chunks * chunk_clk;
         const double bytes = (double)chunks * a_stage + (res ? 0.0 : 9.0 * chunks * bn * 128.0);
@@ -131,6 +141,10 @@ static FlatShape choose_flat_shape(int total_rows, int k_channels, int n_total, 
       if (res) G = 9;
       if (flat_stages(budget, chunks, n_total / bn, bn, a_stage, res, G, &a_st, &b_st))
         best = FlatShape{mt, bn, res, G, a_st, b_st, box_rows, boxes, 0.0};
+      else
+        best.cost = 1e30;  // the requested shape does not fit: fail instead of silently measuring the model's choice
+    } else {
+      best.cost = 1e30;
     }
   }
   if (getenv("CILRS_FLAT_DEBUG"))
@@ -312,14 +326,15 @@ int cilrs_conv_flat(const cilrs_flat_conv_args* a, void* stream) {
   if (a->flags & CILRS_EPI_MASK) flags |= CF_MASK;
   if (a->flags & CILRS_EPI_BNBWD) flags |= CF_BNBWD;
   if (a->flags & CILRS_EPI_BNBWD2) flags |= CF_BNBWD | CF_BNBWD2;
+  if ((a->flags & CILRS_EPI_DEFER) && (flags & (CF_STATS | CF_BNBWD))) flags |= CF_DEFER;
   if ((flags & CF_STATS) && (flags & CF_BNBWD)) return ERR_INVALID;
   if ((flags & CF_SCALE_BIAS) && (!a->scale || !a->bias)) return ERR_INVALID;
   if ((flags & CF_RESIDUAL) && !a->residual) return ERR_INVALID;
   if ((flags & CF_MASK) && !a->mask) return ERR_INVALID;
-  if ((flags & CF_STATS) && (!a->gamma || !a->beta || !a->running_mean || !a->running_var || !a->vec)) return ERR_INVALID;
-  if ((flags & CF_BNBWD) && (!a->y1 || !a->vec1 || !a->bred1)) return ERR_INVALID;
-  if ((flags & CF_BNBWD2) && (!a->y2 || !a->vec2 || !a->bred2)) return ERR_INVALID;
-  if ((flags & (CF_STATS | CF_BNBWD)) && (!a->partials_ws || !a->counter_ws)) return ERR_INVALID;
+  if ((flags & CF_STATS) && !(flags & CF_DEFER) && (!a->gamma || !a->beta || !a->running_mean || !a->running_var || !a->vec)) return ERR_INVALID;
+  if ((flags & CF_BNBWD) && (!a->y1 || (!(flags & CF_DEFER) && (!a->vec1 || !a->bred1)))) return ERR_INVALID;
+  if ((flags & CF_BNBWD2) && (!a->y2 || (!(flags & CF_DEFER) && (!a->vec2 || !a->bred2)))) return ERR_INVALID;
+  if ((flags & (CF_STATS | CF_BNBWD)) && (!a->partials_ws || (!(flags & CF_DEFER) && !a->counter_ws))) return ERR_INVALID;
   int st = build_flat_conv(&p, a->batch, g, a->in_c, a->out_c, a->dgrad, a->x, a->w, a->y, flags);
   if (st) return st;
   p.residual = (const __nv_bfloat16*)a->residual; p.mask = (const __nv_bfloat16*)a->mask; p.mask_bits = (const uint8_t*)a->mask_bits;

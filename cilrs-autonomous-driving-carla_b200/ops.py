@@ -6,7 +6,7 @@ from . import _lib
 from ._lib import ConvDesc
 
 EPI_STATS, EPI_SCALE_BIAS, EPI_RESIDUAL, EPI_RELU = 1, 2, 4, 8
-EPI_MASK, EPI_BNBWD, EPI_BNBWD2 = 16, 32, 64
+EPI_MASK, EPI_BNBWD, EPI_BNBWD2, EPI_DEFER = 16, 32, 64, 128
 
 
 def _need_cuda(*ts):
@@ -88,10 +88,12 @@ def relu_bits(act_pad):
 
 
 def conv_flat(x_pad, w_pack, out_c, dgrad=False, scale=None, bias=None, residual=None, mask=None, relu=False,
-              bn=None, bnbwd=None, bnbwd2=None, mask_bits=None):
+              bn=None, bnbwd=None, bnbwd2=None, mask_bits=None, defer_sums=None):
     """3x3 stride-1 conv (fprop or dgrad) on padded-flat tensors. x_pad [B,H+1,W+1,Cin] bf16 -> [B,H+1,W+1,out_c].
     bn = dict(gamma, beta, running_mean, running_var, nbt, update) -> also returns vec [4,out_c] (fused train-mode BN
-    statistics + finalize). bnbwd = dict(y, vec, dgamma, dbeta) -> also returns bred [2,out_c] (fused BN-backward reduce)."""
+    statistics + finalize). bnbwd = dict(y, vec, dgamma, dbeta) -> also returns bred [2,out_c] (fused BN-backward reduce).
+    defer_sums = "stats" | "bnbwd" (with bnbwd=dict(y=...), bnbwd2=dict(y=...)): deferred finalize - only the raw per-channel
+    fp64 sums [3,out_c] are produced (CILRS_EPI_DEFER) and returned instead of vec / bred."""
     _need_cuda(x_pad, w_pack)
     b, hp, wp, cin = x_pad.shape
     dev = x_pad.device
@@ -115,6 +117,19 @@ def conv_flat(x_pad, w_pack, out_c, dgrad=False, scale=None, bias=None, residual
     if relu:
         flags |= EPI_RELU
     extra = []
+    if defer_sums is not None:
+        acc = torch.zeros(3, out_c, dtype=torch.float64, device=dev)
+        a.partials_ws = ptr(acc)
+        keep.append(acc)
+        flags |= EPI_DEFER | (EPI_STATS if defer_sums == "stats" else EPI_BNBWD)
+        if defer_sums != "stats":
+            a.y1 = ptr(bnbwd["y"])
+            if bnbwd2 is not None:
+                flags |= EPI_BNBWD2
+                a.y2 = ptr(bnbwd2["y"])
+        a.flags = flags
+        _lib.call("cilrs_conv_flat", a, _lib.stream_ptr())
+        return y, acc
     if bn is not None or bnbwd is not None:
         ws = torch.zeros(_lib.query("cilrs_conv_flat_workspace_floats", out_c), dtype=torch.float32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int32, device=dev)

@@ -73,7 +73,10 @@ enum {
   /* padded-flat kernels only (cilrs_conv_flat): */
   CILRS_EPI_MASK = 16,      /* y = mask > 0 ? y : 0  (ReLU backward fused into the dgrad epilogue) */
   CILRS_EPI_BNBWD = 32,     /* also reduce sum(y), sum(y * xhat1) per channel = the BatchNorm-backward reductions */
-  CILRS_EPI_BNBWD2 = 64     /* ... and sum(y * xhat2) for a second BatchNorm fed by the same gradient */
+  CILRS_EPI_BNBWD2 = 64,    /* ... and sum(y * xhat2) for a second BatchNorm fed by the same gradient */
+  CILRS_EPI_DEFER = 128     /* with STATS / BNBWD: only ADD the per-channel fp64 sums to partials_ws ([3][out_c] doubles, zeroed by the
+                               caller: sum, sum of squares | sum dz, sum dz*y1, sum dz*y2) and leave the finalize to the consumer -
+                               what the network plan does (the BatchNorm apply kernels finalize in their prologue) */
 };
 
 /* bytes of packed bf16 weights for fprop / dgrad, and of the stats scratch for a given desc */

@@ -359,6 +359,39 @@ def test_flat_dgrad_fused_relu_mask_and_bn_backward_reduce(case):
         _report("dgamma2", dg2, (dzf * xhat2).sum((0, 1, 2)), 2e-4)
 
 
+@pytest.mark.parametrize("case", [(9, 11, 25, 128), (128, 22, 50, 64), (40, 3, 7, 512)])
+def test_flat_deferred_finalize_sums(case):
+    """CILRS_EPI_DEFER: the kernel only adds the per-channel fp64 sums (what the network plan uses; the BatchNorm apply
+    kernels finalize them) - forward: sum y, sum y^2; backward: sum dz, sum dz*y1, sum dz*y2 of the stored bf16 values"""
+    ops = _ops()
+    _ref_setup()
+    b, h, w, c = case
+    d = ops.conv_desc(b, h, w, c, c, 3, 1)
+    x = _mk((b, c, h, w), 60).to(torch.bfloat16)
+    wt = _mk((c, c, 3, 3), 61) * (2.0 / (c * 9)) ** 0.5
+    wf, wd = ops.pack_weight(d, wt)
+    xp = ops.to_padded(_nhwc_bf16(x.float()))
+    yp, acc = ops.conv_flat(xp, wf, c, defer_sums="stats")
+    yp_ref = ops.conv_flat(xp, wf, c)
+    torch.cuda.synchronize()
+    assert torch.equal(yp, yp_ref)
+    y = ops.from_padded(yp, h, w).double()
+    _report("sum y", acc[0], y.sum((0, 1, 2)), 1e-5)
+    _report("sum y^2", acc[1], (y * y).sum((0, 1, 2)), 1e-5)
+    res = ops.to_padded(_mk((b, h, w, c), 62).to(torch.bfloat16))
+    act = ops.to_padded(torch.relu(_mk((b, h, w, c), 63)).to(torch.bfloat16))
+    y1 = _mk((b, h, w, c), 64).to(torch.bfloat16)
+    y2 = _mk((b, h, w, c), 65).to(torch.bfloat16)
+    dzp, acc = ops.conv_flat(xp, wd, c, dgrad=True, residual=res, mask=act, mask_bits=ops.relu_bits(act),
+                             bnbwd=dict(y=ops.to_padded(y1)), bnbwd2=dict(y=ops.to_padded(y2)), defer_sums="bnbwd")
+    torch.cuda.synchronize()
+    assert _pads_are_zero(dzp, h, w)
+    dz = ops.from_padded(dzp, h, w).double()
+    _report("sum dz", acc[0], dz.sum((0, 1, 2)), 1e-5)
+    _report("sum dz*y1", acc[1], (dz * y1.double()).sum((0, 1, 2)), 1e-5)
+    _report("sum dz*y2", acc[2], (dz * y2.double()).sum((0, 1, 2)), 1e-5)
+
+
 def test_flat_dgrad_relu_mask_as_bit_tensor_equals_the_bf16_mask():
     """the ReLU mask read as one bit per element (written by cilrs_bn_apply) gives the same dz as the bf16 activation"""
     ops = _ops()

@@ -31,8 +31,15 @@ for name, h, w, c in layers:
     gamma, beta, rm, rv = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
     vec = torch.zeros(4, c, device="cuda")
     a = _lib.FlatConvArgs()
-    a.batch, a.H, a.W, a.in_c, a.out_c, a.dgrad, a.flags = B, h, w, c, c, 0, (ops.EPI_STATS if mode == "bn" else 0)
+    a.batch, a.H, a.W, a.in_c, a.out_c, a.dgrad, a.flags = B, h, w, c, c, 0, ((ops.EPI_STATS | ops.EPI_DEFER) if mode == "bn" else 0)
     a.x, a.w, a.y = P(x), P(wf), P(out)
+    if mode == "dgrad":  # what the network's backward launches: residual + ReLU mask bits + BN-backward sums, deferred finalize
+        act = ops.to_padded(torch.relu(torch.randn(B, h, w, c, device="cuda")).to(torch.bfloat16))
+        y1 = ops.to_padded(torch.randn(B, h, w, c, device="cuda").to(torch.bfloat16))
+        resid = ops.to_padded(torch.randn(B, h, w, c, device="cuda").to(torch.bfloat16))
+        bits = ops.relu_bits(act)
+        a.dgrad, a.flags = 1, ops.EPI_RESIDUAL | ops.EPI_MASK | ops.EPI_BNBWD | ops.EPI_DEFER
+        a.w, a.residual, a.mask, a.mask_bits, a.y1 = P(wd), P(resid), P(act), P(bits), P(y1)
     a.gamma, a.beta, a.running_mean, a.running_var, a.vec = P(gamma), P(beta), P(rm), P(rv), P(vec)
     a.momentum, a.eps, a.update_running = 0.1, 1e-5, 1
     a.partials_ws, a.counter_ws = P(ws), P(cnt)
