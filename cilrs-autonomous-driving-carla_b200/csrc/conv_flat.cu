@@ -46,12 +46,53 @@ static long long flat_smem_fixed(int block_n, int flags) {
 struct FlatShape {
   int mt, block_n, resident, tap_group, a_stages, b_stages, a_box_rows, a_boxes;
   double cost;
+  int pair;
 };
 
-static bool flat_stages(long long budget, int chunks, int n_blocks, int bn, long long a_stage, int resident, int G, int* a_st, int* b_st) {
-  const long long b_stage = (long long)G * bn * 128;
+template <int MT, bool PAIR> static void (*flat_kernel_ptr())(FlatConvParams) { return conv_flat_kernel<MT, PAIR>; }
+static void (*flat_kernel(int mt, int pair))(FlatConvParams) {
+  if (pair) return mt == 1 ? flat_kernel_ptr<1, true>() : (mt == 2 ? flat_kernel_ptr<2, true>() : (mt == 4 ? flat_kernel_ptr<4, true>() : nullptr));
+  return mt == 1 ? flat_kernel_ptr<1, false>() : (mt == 2 ? flat_kernel_ptr<2, false>() : (mt == 4 ? flat_kernel_ptr<4, false>() : nullptr));
+}
+static int flat_kernel_attrs() {
+  static bool done = false;
+  if (done) return OK;
+  const int mts[3] = {1, 2, 4};
+  for (int pr = 0; pr < 2; ++pr)
+    for (int i = 0; i < 3; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(flat_kernel(mts[i], pr), cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL);
+      if (e != cudaSuccess) return cuda_status(e);
+    }
+  done = true;
+  return OK;
+}
+// CTA pairs (clusters of 2) that can be resident at once; 0 = pairs unavailable / switched off (CILRS_FLAT_PAIR=0)
+static int max_pairs() {
+  static int n = -1;
+  if (n >= 0) return n;
+  n = 0;
+  const char* env = getenv("CILRS_FLAT_PAIR");
+  if (env && env[0] == '0') return n;
+  if (flat_kernel_attrs() != OK) return n;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * sm_count()); cfg.blockDim = dim3(CF_THREADS); cfg.dynamicSmemBytes = CG_SMEM_TOTAL;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&clusters, flat_kernel(1, 1), &cfg) == cudaSuccess && clusters > 0) n = clusters;
+  else cudaGetLastError();
+  if (n > sm_count() / 2) n = sm_count() / 2;
+  return n;
+}
+
+// bn_cta = weight-tile rows held by one CTA (block_n, or block_n / 2 for a CTA pair)
+static bool flat_stages(long long budget, int chunks, int n_blocks, int bn_cta, long long a_stage, int resident, int G, int* a_st, int* b_st) {
+  const long long b_stage = (long long)G * bn_cta * 128;
   if (resident) {
-    if (n_blocks != 1 || G != 9 || chunks > CF_MAX_B_STAGES) return false;
+    (void)n_blocks;
+    if (G != 9 || chunks > CF_MAX_B_STAGES) return false;
     const long long left = budget - chunks * b_stage;
     if (left < 2 * a_stage) return false;
     *b_st = chunks;
@@ -79,68 +120,79 @@ static FlatShape choose_flat_shape(int total_rows, int k_channels, int n_total, 
   const int bns[3] = {256, 128, 64};
   const int mts[3] = {1, 2, 4};
   const int groups[4] = {9, 3, 2, 1};
-  for (int bi = 0; bi < 3; ++bi) {
-    const int bn = bns[bi];
-    if (n_total % bn) continue;
-    const int n_blocks = n_total / bn;
-    const long long budget = CG_SMEM_TOTAL - flat_smem_fixed(bn, flags);
-    const double mma_clk = bn == 64 ? 48.0 : (bn == 128 ? 64.0 : 128.0);
-    for (int mi = 0; mi < 3; ++mi) {
-      const int mt = mts[mi];
-      if (mt * bn > 512) continue;
-      int box_rows, boxes;
-      split_boxes(mt * 128 + 2 * halo, &box_rows, &boxes);
-      const long long a_stage = (long long)box_rows * boxes * 128;
-      for (int gi = 0; gi < 4; ++gi) {
-        const int res = gi == 0;
-        const int G = res ? 9 : groups[gi];
-        int a_st, b_st;
-        if (!flat_stages(budget, chunks, n_blocks, bn, a_stage, res, G, &a_st, &b_st)) continue;
-        const int m_tiles = (total_rows + mt * 128 - 1) / (mt * 128);
-        const long long tiles = (long long)m_tiles * n_blocks;
-        int active = tiles < sms ? (int)tiles : sms;
-        active -= active % n_blocks;  // the grid is a multiple of n_blocks (one channel block per CTA)
-        if (active < 1) continue;
-        const double bw = 6300.0 / active < 64.0 ? 6300.0 / active : 64.0;
-        const double exposed = 550.0 - 3.3 * mma_clk > 60.0 ? 550.0 - 3.3 * mma_clk : 60.0;
-        double chunk_clk = 0.0;
-        for (int t0 = 0; t0 < 9; t0 += G) {
-          const int cnt = 9 - t0 < G ? 9 - t0 : G;
-          double group = cnt * mt * 4 * mma_clk + exposed;
-          if (!res) {
-            // weight-stage pipeline: a stage is busy for its own MMAs plus its refill (~700 clocks of TMA latency + the
-            // transfer at ~64 B/clk), and comes around every b_st groups
-            const double refill = 700.0 + cnt * bn * 128.0 / 64.0;
-            const double ring = (refill + cnt * mt * 4 * mma_clk) / b_st;
-            if (ring > group) group = ring;
+  const int pairs_avail = max_pairs();
+  for (int pr = 0; pr < 2; ++pr) {
+    if (pr && pairs_avail < 1) continue;
+    for (int bi = 0; bi < 3; ++bi) {
+      const int bn = bns[bi];
+      if (n_total % bn) continue;
+      const int n_blocks = n_total / bn;
+      const int bn_cta = pr ? bn / 2 : bn;  // weight-tile rows per CTA
+      const long long budget = CG_SMEM_TOTAL - flat_smem_fixed(bn, flags);
+      // tcgen05.mma 128(x2) x N x 16: max(N/2, shared-memory operand fetch per CTA at 128 B/clk)
+      const double fetch = (4096.0 + 32.0 * bn_cta) / 128.0;
+      const double mma_clk = bn / 2.0 > fetch ? bn / 2.0 : fetch;
+      for (int mi = 0; mi < 3; ++mi) {
+        const int mt = mts[mi];
+        if (mt * bn > 512) continue;
+        int box_rows, boxes;
+        split_boxes(mt * 128 + 2 * halo, &box_rows, &boxes);
+        const long long a_stage = (long long)box_rows * boxes * 128;
+        for (int gi = 0; gi < 4; ++gi) {
+          const int res = gi == 0;
+          const int G = res ? 9 : groups[gi];
+          int a_st, b_st;
+          if (!flat_stages(budget, chunks, n_blocks, bn_cta, a_stage, res, G, &a_st, &b_st)) continue;
+          const int tile_rows = (pr ? 2 : 1) * mt * 128;
+          const int m_tiles = (total_rows + tile_rows - 1) / tile_rows;
+          const long long tiles = (long long)m_tiles * n_blocks;
+          const int slots = pr ? pairs_avail : sms;          // CTAs or CTA pairs that work on tiles concurrently
+          int active = tiles < slots ? (int)tiles : slots;
+          active -= active % n_blocks;  // the grid is a multiple of n_blocks (one channel block per CTA)
+          if (active < 1) continue;
+          const int ctas = active * (pr ? 2 : 1);
+          const double bw = 6300.0 / ctas < 64.0 ? 6300.0 / ctas : 64.0;
+          const double exposed = 550.0 - 3.3 * mma_clk > 60.0 ? 550.0 - 3.3 * mma_clk : 60.0;
+          double chunk_clk = 0.0;
+          for (int t0 = 0; t0 < 9; t0 += G) {
+            const int cnt = 9 - t0 < G ? 9 - t0 : G;
+            double group = cnt * mt * 4 * mma_clk + exposed;
+            if (!res) {
+              // weight-stage pipeline: a stage is busy for its own MMAs plus its refill (~700 clocks of TMA latency + the
+              // transfer at ~64 B/clk), and comes around every b_st groups
+              const double refill = 700.0 + cnt * bn_cta * 128.0 / 64.0;
+              const double ring = (refill + cnt * mt * 4 * mma_clk) / b_st;
+              if (ring > group) group = ring;
+            }
+            chunk_clk += group;
           }
-          chunk_clk += group;
+          const double mma = chunks * chunk_clk;
+          const double bytes = (double)chunks * a_stage + (res ? 0.0 : 9.0 * chunks * bn_cta * 128.0);
+          const double tile_clk = mma > bytes / bw ? mma : bytes / bw;
+          const long long rounds = (tiles + active - 1) / active;
+          const double units = mt * (bn / 64) * 0.5;                      // per epilogue group (and CTA)
+          const int acc_sets = 512 / (mt * bn);
+          // the epilogue of a tile hides behind the next tile's MMAs only with >= 2 accumulator sets and a next tile
+          const double epi_tail = units * 2000.0 * (acc_sets >= 2 ? 1.0 : (double)rounds);
+          const double cost = rounds * tile_clk + 1500.0 + epi_tail;
+          if (cost < best.cost * 0.99) best = FlatShape{mt, bn, res, G, a_st, b_st, box_rows, boxes, cost, pr};
         }
-        const double mma = chunks * chunk_clk;
-        const double bytes = (double)chunks * a_stage + (res ? 0.0 : 9.0 * chunks * bn * 128.0);
-        const double tile_clk = mma > bytes / bw ? mma : bytes / bw;
-        const long long rounds = (tiles + active - 1) / active;
-        const double units = mt * (bn / 64) * 0.5;                      // per epilogue group
-        const int acc_sets = 512 / (mt * bn);
-        // the epilogue of a tile hides behind the next tile's MMAs only with >= 2 accumulator sets and a next tile
-        const double epi_tail = units * 2000.0 * (acc_sets >= 2 ? 1.0 : (double)rounds);
-        const double cost = rounds * tile_clk + 1500.0 + epi_tail;
-        if (cost < best.cost * 0.99) best = FlatShape{mt, bn, res, G, a_st, b_st, box_rows, boxes, cost};
       }
     }
   }
-  // measurement aid: CILRS_FLAT_SHAPE="mt,block_n,resident,tap_group" overrides the model
+  // measurement aid: CILRS_FLAT_SHAPE="mt,block_n,resident,tap_group[,pair]" overrides the model
   if (const char* env = getenv("CILRS_FLAT_SHAPE")) {
-    int mt = 0, bn = 0, res = 0, G = 0;
-    if (sscanf(env, "%d,%d,%d,%d", &mt, &bn, &res, &G) == 4 && (mt == 1 || mt == 2 || mt == 4) && bn >= 64 && n_total % bn == 0 &&
-        mt * bn <= 512 && G >= 1 && G <= 9) {
+    int mt = 0, bn = 0, res = 0, G = 0, pr = 0;
+    const int nf = sscanf(env, "%d,%d,%d,%d,%d", &mt, &bn, &res, &G, &pr);
+    if (nf >= 4 && (mt == 1 || mt == 2 || mt == 4) && bn >= 64 && n_total % bn == 0 && mt * bn <= 512 && G >= 1 && G <= 9 &&
+        (!pr || pairs_avail > 0)) {
       int box_rows, boxes, a_st, b_st;
       split_boxes(mt * 128 + 2 * halo, &box_rows, &boxes);
       const long long a_stage = (long long)box_rows * boxes * 128;
       const long long budget = CG_SMEM_TOTAL - flat_smem_fixed(bn, flags);
       if (res) G = 9;
-      if (flat_stages(budget, chunks, n_total / bn, bn, a_stage, res, G, &a_st, &b_st))
-        best = FlatShape{mt, bn, res, G, a_st, b_st, box_rows, boxes, 0.0};
+      if (flat_stages(budget, chunks, n_total / bn, pr ? bn / 2 : bn, a_stage, res, G, &a_st, &b_st))
+        best = FlatShape{mt, bn, res, G, a_st, b_st, box_rows, boxes, 0.0, pr ? 1 : 0};
       else
         best.cost = 1e30;  // the requested shape does not fit: fail instead of silently measuring the model's choice
     } else {
@@ -148,9 +200,9 @@ static FlatShape choose_flat_shape(int total_rows, int k_channels, int n_total, 
     }
   }
   if (getenv("CILRS_FLAT_DEBUG"))
-    fprintf(stderr, "[cilrs flat] rows=%d K=%d N=%d Wp=%d -> mt=%d block_n=%d resident=%d tap_group=%d a_stages=%d b_stages=%d a_box=%dx%d cost=%.0f\n",
-            total_rows, k_channels, n_total, g.Wp, best.mt, best.block_n, best.resident, best.tap_group, best.a_stages, best.b_stages,
-            best.a_boxes, best.a_box_rows, best.cost);
+    fprintf(stderr, "[cilrs flat] rows=%d K=%d N=%d Wp=%d flags=%d -> pair=%d mt=%d block_n=%d resident=%d tap_group=%d a_stages=%d b_stages=%d a_box=%dx%d cost=%.0f\n",
+            total_rows, k_channels, n_total, g.Wp, flags, best.pair, best.mt, best.block_n, best.resident, best.tap_group, best.a_stages,
+            best.b_stages, best.a_boxes, best.a_box_rows, best.cost);
   return best;
 }
 
@@ -178,6 +230,7 @@ int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channe
   p->total_rows = flat_total_rows(batch, g);
   const FlatShape sh = choose_flat_shape(p->total_rows, k_channels, n_total, g, flags);
   if (sh.cost >= 1e30) return ERR_UNSUPPORTED;
+  p->pair = sh.pair;
   p->mt = sh.mt; p->block_n = sh.block_n; p->n_blocks = n_total / sh.block_n; p->n_total = n_total;
   p->chunks = k_channels / 64;
   p->halo = g.Wp + 1;
@@ -185,7 +238,8 @@ int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channe
   p->a_stages = sh.a_stages; p->b_stages = sh.b_stages; p->b_resident = sh.resident; p->tap_group = sh.tap_group;
   int sets = 512 / (sh.mt * sh.block_n);
   p->acc_sets = sets > CF_MAX_ACC ? CF_MAX_ACC : sets;
-  p->m_tiles = (p->total_rows + sh.mt * 128 - 1) / (sh.mt * 128);
+  const int tile_rows = (sh.pair ? 2 : 1) * sh.mt * 128;
+  p->m_tiles = (p->total_rows + tile_rows - 1) / tile_rows;
   flat_taps(p, dgrad);
   p->flags = flags;
   p->out = (__nv_bfloat16*)out;
@@ -193,7 +247,7 @@ int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channe
   if (st) return st;
   st = encode_2d_map(&p->tmOut, out, n_total, p->total_rows, 64, 32);
   if (st) return st;
-  return encode_2d_map(&p->tmB, w, k_channels, 9 * n_total, 64, p->block_n);
+  return encode_2d_map(&p->tmB, w, k_channels, 9 * n_total, 64, sh.pair ? p->block_n / 2 : p->block_n);
 }
 
 // tensor maps of the epilogue's operand tiles (residual, y1, y2): call after the pointers are set, before the launch
@@ -215,27 +269,26 @@ int flat_conv_bind_operands(FlatConvParams* p) {
   return OK;
 }
 
+// CTAs of the launch: one per tile up to the SM count (pairs: two per tile up to the resident pair count), a multiple of
+// n_blocks tiles wide so that every CTA only ever sees one channel block
 int flat_conv_grid(const FlatConvParams* p) {
   const long long total = (long long)p->m_tiles * p->n_blocks;
-  int grid = total < sm_count() ? (int)total : sm_count();
-  return grid - grid % p->n_blocks;  // a multiple of n_blocks: every CTA then only ever sees one channel block
+  const int slots = p->pair ? max_pairs() : sm_count();
+  int n = total < slots ? (int)total : slots;
+  n -= n % p->n_blocks;
+  return p->pair ? 2 * n : n;
 }
 
 int launch_flat_conv(const FlatConvParams* p, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_flat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_flat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL);
-    if (e != cudaSuccess) return cuda_status(e);
-    attr_set = true;
-  }
+  int st = flat_kernel_attrs();
+  if (st) return st;
   if ((p->flags & CF_BNBWD) && (!p->operand_maps || !p->y1 || ((p->flags & CF_BNBWD2) && !p->y2))) return ERR_INVALID;
   if ((p->flags & (CF_STATS | CF_BNBWD)) && (!p->partials || (!(p->flags & CF_DEFER) && !p->counter))) return ERR_INVALID;
   const int grid = flat_conv_grid(p);
-  void (*kernel)(FlatConvParams) = p->mt == 1 ? conv_flat_kernel<1> : (p->mt == 2 ? conv_flat_kernel<2> : (p->mt == 4 ? conv_flat_kernel<4> : nullptr));
-  if (!kernel) return ERR_INVALID;
+  void (*kernel)(FlatConvParams) = flat_kernel(p->mt, p->pair);
+  if (!kernel || grid < 1) return ERR_INVALID;
   ++g_cilrs_launches;
+  if (p->pair) return cuda_status(launch_pdl_cluster(kernel, dim3(grid), dim3(CF_THREADS), CG_SMEM_TOTAL, s, 2, *p));
   return cuda_status(launch_pdl(kernel, dim3(grid), dim3(CF_THREADS), CG_SMEM_TOTAL, s, *p));
 }
 

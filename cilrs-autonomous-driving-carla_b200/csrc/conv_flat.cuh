@@ -13,6 +13,7 @@
 // finalized either by the last CTA to finish or, with CF_DEFER, by the elementwise kernel that consumes them.
 #pragma once
 #include "common.cuh"
+#include "pair.cuh"
 #include "conv_params.h"
 
 namespace cilrs {
@@ -45,7 +46,13 @@ CILRS_DEVINL void load_row64(const __nv_bfloat16* p, uint32_t* r) {
   for (int j = 0; j < 4; ++j) ldg256(p + j * 16, r + j * 8);
 }
 
-template <int MT>
+// PAIR: the grid is made of clusters of two CTAs that share every tcgen05.mma (cta_group::2, M = 256): CTA `rank` of a pair
+// owns the rows [(2*m_tile + rank) * MT*128, +MT*128) of a pair tile - its own activation slab, its own 128-row accumulators
+// in its own TMEM, its own epilogue - and HALF of every weight tile (block_n/2 rows), so each weight byte crosses L2->SMEM
+// once per pair and the tensor core fetches 4096 + 16 N instead of 4096 + 32 N bytes of shared memory per instruction and
+// CTA (the single-CTA form is bound by exactly that: conv_flat.cu). The leader (rank 0) issues all MMAs; both CTAs' TMA
+// loads complete on the leader's `full` barriers, the leader's commits arrive on the `empty` / `tfull` barriers of both.
+template <int MT, bool PAIR>
 __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_constant__ FlatConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // aligned by pointer arithmetic on the __shared__ array (not through an integer cast) so that the compiler keeps the
@@ -54,8 +61,12 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int pair_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile iterator of this CTA (pair)
+  const int n_pairs = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int a_stage_bytes = p.a_boxes * p.a_box_rows * 128;
-  const int b_tap_bytes = p.block_n * 128;
+  const int b_rows = PAIR ? (p.block_n >> 1) : p.block_n;       // weight-tile rows held by this CTA
+  const int b_tap_bytes = b_rows * 128;
   const int b_stage_bytes = p.tap_group * b_tap_bytes;  // one stage = the weight tiles of `tap_group` consecutive taps
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)p.a_stages * a_stage_bytes;
@@ -85,16 +96,17 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     if (p.operand_maps) { tma_prefetch_desc(&p.tmRes); tma_prefetch_desc(&p.tmY1); }
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
-    for (int i = 0; i < p.acc_sets; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }  // 8 epilogue warps
+    for (int i = 0; i < p.acc_sets; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 16 : 8); }  // 8 epilogue warps (per CTA)
     for (int i = 0; i < 16; ++i) mbar_init(&ebar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above is local to the CTA; from here on the predecessor's results are read
@@ -113,17 +125,20 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       bool first = true;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = pair_id; tile < total_tiles; tile += n_pairs) {
         const int m_tile = tile / p.n_blocks;
         const int n_blk = tile - m_tile * p.n_blocks;
-        const int row0 = m_tile * MT * 128;
+        const int row0 = (m_tile * (PAIR ? 2 : 1) + (int)rank) * MT * 128;
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(&empty_a[as], aph ^ 1);
           CF_EVENT(0, 0x100 + c);
-          mbar_arrive_expect_tx(&full_a[as], (uint32_t)a_stage_bytes);
+          // (pair: the leader's barrier counts the bytes of both CTAs; the peer only issues its loads)
+          if (rank == 0) mbar_arrive_expect_tx(&full_a[as], (uint32_t)a_stage_bytes * (PAIR ? 2u : 1u));
           uint8_t* dst = sA + (size_t)as * a_stage_bytes;
-          for (int bx = 0; bx < p.a_boxes; ++bx)
-            tma_load_2d(&p.tmA, &full_a[as], dst + (size_t)bx * p.a_box_rows * 128, c * 64, row0 - p.halo + bx * p.a_box_rows);
+          for (int bx = 0; bx < p.a_boxes; ++bx) {
+            if (PAIR) tma_load_2d_pair(&p.tmA, &full_a[as], dst + (size_t)bx * p.a_box_rows * 128, c * 64, row0 - p.halo + bx * p.a_box_rows);
+            else tma_load_2d(&p.tmA, &full_a[as], dst + (size_t)bx * p.a_box_rows * 128, c * 64, row0 - p.halo + bx * p.a_box_rows);
+          }
           if (++as == p.a_stages) { as = 0; aph ^= 1; }
           for (int gi = 0; gi < n_groups; ++gi) {
             const int t0 = gi * p.tap_group;
@@ -131,10 +146,13 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
             if (!p.b_resident || first) {
               if (!p.b_resident) mbar_wait(&empty_b[bs], bph ^ 1);
               CF_EVENT(0, 0x200 + gi);
-              mbar_arrive_expect_tx(&full_b[bs], (uint32_t)(cnt * b_tap_bytes));
-              for (int j = 0; j < cnt; ++j)
-                tma_load_2d(&p.tmB, &full_b[bs], sB + (size_t)bs * b_stage_bytes + (size_t)j * b_tap_bytes, c * 64,
-                            p.tap_slab[t0 + j] * p.n_total + n_blk * p.block_n);
+              if (rank == 0) mbar_arrive_expect_tx(&full_b[bs], (uint32_t)(cnt * b_tap_bytes) * (PAIR ? 2u : 1u));
+              for (int j = 0; j < cnt; ++j) {
+                uint8_t* dstb = sB + (size_t)bs * b_stage_bytes + (size_t)j * b_tap_bytes;
+                const int wrow = p.tap_slab[t0 + j] * p.n_total + n_blk * p.block_n + (int)rank * b_rows;
+                if (PAIR) tma_load_2d_pair(&p.tmB, &full_b[bs], dstb, c * 64, wrow);
+                else tma_load_2d(&p.tmB, &full_b[bs], dstb, c * 64, wrow);
+              }
             }
             if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
           }
@@ -142,15 +160,15 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
         first = false;
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
+  } else if (warp == 1 && rank == 0) {
+    // ================= MMA issuer (pair: the leader CTA only) =================
     // The whole warp runs the loop so every address / descriptor stays in uniform registers and an MMA costs ~8
     // instructions; one elected lane issues. (With a lone lane inside a divergent branch each tcgen05.mma cost ~90
     // clocks of instruction issue - more than the 32..64 clocks the tensor core needs for N = 64..128;
     // tools/umma_rate_test2.cu.) The CTA owns all 512 TMEM columns, so the allocation starts at column 0.
     if (tmem_base != 0) __trap();
     const bool leader = elect_one();
-    const uint32_t idesc = umma_idesc_bf16(128, p.block_n, 0, 0);
+    const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, p.block_n, 0, 0);
     const uint64_t descA0 = umma_desc_sw128(smem_u32(sA), 16, 1024);
     const uint64_t descB0 = umma_desc_sw128(smem_u32(sB), 16, 1024);
     const uint32_t a_stage_units = (uint32_t)(a_stage_bytes >> 4), b_stage_units = (uint32_t)(b_stage_bytes >> 4);
@@ -158,8 +176,9 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     int as = 0, bs = 0, acc = 0;
     uint32_t aph = 0, bph = 0, accph = 0;
     bool first = true;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty[acc], accph ^ 1);
+    for (int tile = pair_id; tile < total_tiles; tile += n_pairs) {
+      if (PAIR) mbar_wait_cluster(&tempty[acc], accph ^ 1);  // (the peer's epilogue warps arrive remotely)
+      else mbar_wait(&tempty[acc], accph ^ 1);
       tc_fence_after();
       if (leader) CF_EVENT(1, 0x300);
       const uint32_t d_base = (uint32_t)(acc * acc_stride);
@@ -186,20 +205,23 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
                 const uint64_t da = da_tap + (uint64_t)((uint32_t)m * 1024u);
                 const uint32_t d = d_base + (uint32_t)(m * p.block_n);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) umma_bf16(d, da + kk * 2, db + kk * 2, idesc, (c | (t0 + j) | kk) != 0 ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk) {
+                  if (PAIR) umma_bf16_pair(d, da + kk * 2, db + kk * 2, idesc, (c | (t0 + j) | kk) != 0 ? 1u : 0u);
+                  else umma_bf16(d, da + kk * 2, db + kk * 2, idesc, (c | (t0 + j) | kk) != 0 ? 1u : 0u);
+                }
               }
             }
-            if (!p.b_resident) umma_commit(&empty_b[bs]);
+            if (!p.b_resident) { if (PAIR) umma_commit_pair(&empty_b[bs], 3); else umma_commit(&empty_b[bs]); }
           }
           __syncwarp();
           if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
         }
-        if (leader) umma_commit(&empty_a[as]);
+        if (leader) { if (PAIR) umma_commit_pair(&empty_a[as], 3); else umma_commit(&empty_a[as]); }
         __syncwarp();
         if (++as == p.a_stages) { as = 0; aph ^= 1; }
       }
       if (leader) {
-        umma_commit(&tfull[acc]);
+        if (PAIR) umma_commit_pair(&tfull[acc], 3); else umma_commit(&tfull[acc]);
         CF_EVENT(1, 0x400);
       }
       __syncwarp();
@@ -241,10 +263,10 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     uint32_t accph = 0;
     uint32_t uc = 0;
     const int n_chunks = p.block_n >> 6;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = pair_id; tile < total_tiles; tile += n_pairs) {
       const int m_tile = tile / p.n_blocks;
       const int n_blk = tile - m_tile * p.n_blocks;
-      const int row0 = m_tile * MT * 128;
+      const int row0 = (m_tile * (PAIR ? 2 : 1) + (int)rank) * MT * 128;
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
       if (ew == 0 && lane == 0) CF_EVENT(2, 0x500);
@@ -405,7 +427,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
       // all of this warp's reads of the accumulator set are complete: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) { if (PAIR) mbar_arrive_remote(&tempty[acc], 0); else mbar_arrive(&tempty[acc]); }
       if (++acc == p.acc_sets) { acc = 0; accph ^= 1; }
     }
 
@@ -418,7 +440,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
       bar_sync_named(3, 256);
       // this CTA's sums (the eight warps in a fixed order) go into the global per-channel accumulators [3][n_total] with
       // red.global.add; the last CTA to arrive reads them, finalizes and re-zeroes them for the next launch
-      const int nb = blockIdx.x % p.n_blocks;  // gridDim.x is a multiple of n_blocks: one channel block per CTA
+      const int nb = pair_id % p.n_blocks;  // the number of CTAs (pairs) is a multiple of n_blocks: one channel block per CTA
       for (int i = tid; i < nq * p.block_n; i += 256) {
         float t = 0.f;
 #pragma unroll
@@ -515,13 +537,14 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // nobody leaves while the peer may still signal its barriers or the pair's MMAs run
+  else __syncthreads();
 #ifdef CF_TRACE
   if (blockIdx.x == 0 && threadIdx.x < 3) g_cf_trace_n[threadIdx.x] = (int)cf_idx[threadIdx.x];
 #endif
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 

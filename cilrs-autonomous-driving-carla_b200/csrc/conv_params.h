@@ -117,7 +117,8 @@ struct FlatConvParams {
   int operand_maps;   // tmRes / tmY1 / tmY2 are valid for the current residual / y1 / y2 pointers
   int total_rows;
   PadGeom g;
-  int mt;                      // 128-row sub-tiles per tile (they share every weight tile)
+  int mt;                      // 128-row sub-tiles per tile and CTA (they share every weight tile)
+  int pair;                    // 1: clusters of two CTAs share every MMA (cta_group::2); a tile then covers 2*mt*128 rows
   int block_n, n_blocks, n_total;
   int chunks, num_taps;
   int tap_shift[9];

@@ -51,16 +51,17 @@ for name, h, w, c in layers:
             if c % bn or mt * bn > 512:
                 continue
             for r, G in ((1, 9), (0, 3), (0, 2), (0, 1)):
-                os.environ["CILRS_FLAT_SHAPE"] = "%d,%d,%d,%d" % (mt, bn, r, G)
+              for pr in (0, 1):
+                os.environ["CILRS_FLAT_SHAPE"] = "%d,%d,%d,%d,%d" % (mt, bn, r, G, pr)
                 os.environ["CILRS_FLAT_DEBUG"] = "1"
                 try:
                     t = timeit_hot(lambda: _lib.call("cilrs_conv_flat", a, sp))
                 except RuntimeError as e:
                     continue
-                res.append((t, mt, bn, r, G))
+                res.append((t, mt, bn, r, G, pr))
     del os.environ["CILRS_FLAT_SHAPE"]
     del os.environ["CILRS_FLAT_DEBUG"]
     t_auto = timeit_hot(lambda: _lib.call("cilrs_conv_flat", a, sp))
     res.sort()
     print("%s %s auto %.1f us (%.0f TF) | best:" % (name, mode, t_auto * 1e3, flops / t_auto / 1e9),
-          "  ".join("%.1fus mt%d bn%d r%d G%d" % (t * 1e3, mt, bn, r, G) for t, mt, bn, r, G in res[:10]))
+          "  ".join("%.1fus %smt%d bn%d r%d G%d" % (t * 1e3, "PAIR " if pr else "", mt, bn, r, G) for t, mt, bn, r, G, pr in res[:12]))
