@@ -183,6 +183,32 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
   const long long stride = (long long)gridDim.x * EW_THREADS;  // multiple of groups (host guarantees)
   long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
   const int cg = (int)(i % groups) * 8;
+  Vec8 sc2, sh2;
+  if (x2) { sc2 = loadf8(scale2 + cg); sh2 = loadf8(shift2 + cg); }
+  PadWalk walk;
+  walk.init(i / groups, stride / groups, g);
+  // Four vectors per iteration with every load issued before the first use: ~3 CTAs x 256 threads x 4 x (1..2) x 16 B keep
+  // the ~45 KB per SM in flight that HBM latency x bandwidth asks for. The first batch is requested BEFORE the deferred
+  // finalize below, whose chain (sums from L2 -> fp64 arithmetic -> shared memory -> barrier) then overlaps its latency.
+  bool in[4], ok[4];
+  uint4 xq[4], rq[4], yq[4];
+#define CILRS_BN_APPLY_LOAD()                                                     \
+  {                                                                               \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                               \
+      in[u] = i + u * stride < nvec;                                              \
+      ok[u] = in[u] && walk.valid();                                              \
+      walk.next();                                                                \
+    }                                                                             \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                               \
+      if (ok[u]) {                                                                \
+        const long long o = (i + u * stride) * 8;                                 \
+        xq[u] = *reinterpret_cast<const uint4*>(x + o);                           \
+        if (res) rq[u] = *reinterpret_cast<const uint4*>(res + o);                \
+        if (x2) yq[u] = *reinterpret_cast<const uint4*>(x2 + o);                  \
+      }                                                                           \
+    }                                                                             \
+  }
+  CILRS_BN_APPLY_LOAD()
   Vec8 sc, sh;
   __shared__ __align__(16) float s_par[2][EW_DEFER_MAX_C];
   if (d.acc) {
@@ -205,30 +231,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
   } else {
     sc = loadf8(scale + cg); sh = loadf8(shift + cg);
   }
-  Vec8 sc2, sh2;
-  if (x2) { sc2 = loadf8(scale2 + cg); sh2 = loadf8(shift2 + cg); }
-  PadWalk walk;
-  walk.init(i / groups, stride / groups, g);
-  // four vectors per iteration with every load issued before the first use: ~3 CTAs x 256 threads x 4 x (1..2) x 16 B keep
-  // the ~45 KB per SM in flight that HBM latency x bandwidth asks for
-  for (; i < nvec; i += 4 * stride) {
-    bool in[4], ok[4];
-    uint4 xq[4], rq[4], yq[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      in[u] = i + u * stride < nvec;
-      ok[u] = in[u] && walk.valid();
-      walk.next();
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (ok[u]) {
-        const long long o = (i + u * stride) * 8;
-        xq[u] = *reinterpret_cast<const uint4*>(x + o);
-        if (res) rq[u] = *reinterpret_cast<const uint4*>(res + o);
-        if (x2) yq[u] = *reinterpret_cast<const uint4*>(x2 + o);
-      }
-    }
+  for (;;) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long iv = i + u * stride;
@@ -264,7 +267,11 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
         bits[iv] = (uint8_t)m;
       }
     }
+    i += 4 * stride;
+    if (i >= nvec) break;
+    CILRS_BN_APPLY_LOAD()
   }
+#undef CILRS_BN_APPLY_LOAD
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -622,6 +629,30 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApp
   const long long stride = (long long)gridDim.x * EW_THREADS;
   long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
   const int cg = (int)(i % groups) * 8;
+  // (the first batch of the main loop is requested before the deferred finalize, whose latency chain it overlaps)
+  PadWalk walk;
+  bool in[4], ok[4];
+  uint4 yq[4], gq[4], aq[4];
+#define CILRS_BN_BWD_LOAD()                                                       \
+  {                                                                               \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                               \
+      in[u] = i + u * stride < p.nvec;                                            \
+      ok[u] = in[u] && walk.valid();                                              \
+      walk.next();                                                                \
+    }                                                                             \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                               \
+      if (ok[u]) {                                                                \
+        const long long o = (i + u * stride) * 8;                                 \
+        yq[u] = *reinterpret_cast<const uint4*>(p.y + o);                         \
+        gq[u] = *reinterpret_cast<const uint4*>(p.g + o);                         \
+        if (p.act) aq[u] = *reinterpret_cast<const uint4*>(p.act + o);            \
+      }                                                                           \
+    }                                                                             \
+  }
+  if (!STEM) {
+    walk.init(i / groups, stride / groups, p.geom);
+    CILRS_BN_BWD_LOAD()
+  }
   const Vec8 mean = loadf8(p.mean + cg), rstd = loadf8(p.rstd + cg), gamma = loadf8(p.gamma + cg);
   Vec8 k0, k1, sc, sh;
   __shared__ __align__(16) float s_par[2][EW_DEFER_MAX_C];
@@ -653,26 +684,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApp
   if (STEM) { gp.g = p.g; gp.argmax = p.argmax; gp.OH = p.OH; gp.OW = p.OW; gp.OHp = p.OH; gp.OWp = p.OW; gp.C = p.C; }
   if (!STEM) {
     // four vectors per iteration, all loads issued before the first use (see bn_apply_kernel)
-    PadWalk walk;
-    walk.init(i / groups, stride / groups, p.geom);
-    for (; i < p.nvec; i += 4 * stride) {
-      bool in[4], ok[4];
-      uint4 yq[4], gq[4], aq[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        in[u] = i + u * stride < p.nvec;
-        ok[u] = in[u] && walk.valid();
-        walk.next();
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (ok[u]) {
-          const long long o = (i + u * stride) * 8;
-          yq[u] = *reinterpret_cast<const uint4*>(p.y + o);
-          gq[u] = *reinterpret_cast<const uint4*>(p.g + o);
-          if (p.act) aq[u] = *reinterpret_cast<const uint4*>(p.act + o);
-        }
-      }
+    for (;;) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const long long o = (i + u * stride) * 8;
@@ -700,6 +712,9 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApp
         }
         store8(p.dy + o, ov);
       }
+      i += 4 * stride;
+      if (i >= p.nvec) break;
+      CILRS_BN_BWD_LOAD()
     }
   } else {
     for (; i < p.nvec; i += stride) {
@@ -723,6 +738,8 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApp
     }
   }
 }
+
+#undef CILRS_BN_BWD_LOAD
 
 // grid size for the vector kernels: a multiple of the channel-group count keeps every thread on one channel group
 // reductions: ~1 CTA per SM is enough with the 4-way unrolled loop, and keeps the partials the last CTA folds small
