@@ -365,6 +365,32 @@ int launch_conv_gemm(const ConvGemmParams* p, cudaStream_t s) {
   return cuda_status(launch_pdl(conv_gemm_kernel, dim3(grid), dim3(CG_THREADS), CG_SMEM_TOTAL, s, *p));
 }
 
+// `count` (<= 4) independent problems in one launch (conv_gemm_multi_kernel): the parity plans of a stride-2 dgrad
+int launch_conv_gemm_multi(const ConvGemmParams* plans, int count, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL);
+    if (e != cudaSuccess) return cuda_status(e);
+    attr_set = true;
+  }
+  if (count < 1 || count > 4) return ERR_INVALID;
+  ConvGemmParams4 pp;
+  int most = 1;
+  for (int i = 0; i < 4; ++i) {
+    pp.p[i] = plans[i < count ? i : 0];
+    if (i < count) {
+      if (plans[i].flags & CG_STATS) return ERR_INVALID;  // the per-CTA statistics slots are indexed by blockIdx.x alone
+      const int total = plans[i].tiles_w * plans[i].tiles_h * plans[i].tiles_n * plans[i].n_blocks;
+      most = total > most ? total : most;
+    }
+  }
+  int per = num_sms() / count;
+  if (per < 1) per = 1;
+  const int gx = most < per ? most : per;
+  ++g_cilrs_launches;
+  return cuda_status(launch_pdl(conv_gemm_multi_kernel, dim3(gx, count), dim3(CG_THREADS), CG_SMEM_TOTAL, s, pp));
+}
+
 int launch_wgrad(const WgradParams* p, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {

@@ -15,7 +15,7 @@
 
 namespace cilrs {
 
-__global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+CILRS_DEVINL void conv_gemm_body(const ConvGemmParams& p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space (LDS/STS)
 
@@ -285,6 +285,17 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_c
     __syncwarp();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+__global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) { conv_gemm_body(p); }
+
+// The four output-parity problems of a stride-2 dgrad in ONE launch: blockIdx.y selects the problem, every problem gets
+// gridDim.x persistent CTAs. (Four separate launches of ~40..100 tiles each left most of the SMs idle four times in a row.)
+struct ConvGemmParams4 {
+  ConvGemmParams p[4];
+};
+__global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_multi_kernel(const __grid_constant__ ConvGemmParams4 pp) {
+  conv_gemm_body(pp.p[blockIdx.y]);
 }
 
 }  // namespace cilrs

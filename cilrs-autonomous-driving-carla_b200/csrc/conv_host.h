@@ -66,6 +66,7 @@ int add_wgrad_reduce_job(WgradReduceJobs* jobs, const WgradFlatParams* p, long l
 int launch_wgrad_reduce(const WgradReduceJobs* jobs, float* grads, cudaStream_t s);
 
 int launch_conv_gemm(const ConvGemmParams* p, cudaStream_t s);
+int launch_conv_gemm_multi(const ConvGemmParams* plans, int count, cudaStream_t s);  // <= 4 independent problems, one launch
 int conv_gemm_grid(const ConvGemmParams* p);  // CTAs launched = number of stats partials
 int launch_wgrad(const WgradParams* p, cudaStream_t s);
 int conv_out_dim(int in, int k, int stride, int pad);

@@ -816,7 +816,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
       PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_a_flat, pb ? &pb->b.bn : nullptr, (pb && pb->has_ds) ? &pb->ds.bn : nullptr, s)));
       m.bw_deferred = true;
     } else {
-      for (int k = 0; k < 4; ++k) PROF(m, PC_DGRAD, s, CK(launch_conv_gemm(&m.old_plans[blk.pl.d_a_old + k], s)));
+      PROF(m, PC_DGRAD, s, CK(launch_conv_gemm_multi(&m.old_plans[blk.pl.d_a_old], 4, s)));  // the four output parities
       // the parity launches write the raw gradient of the previous block's output: mask + reduce it here
       Block& pb = m.blocks[bi - 1];
       PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_reduce(m, B, pb.b.gout, pb.b.bn, gnext, pb.out, pb.b.y, s)));
