@@ -337,7 +337,9 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __res
   feat[i] = s / (float)(g.H * g.W);
 }
 // backward: g padded-flat [B,Hp,Wp,C] bf16 = dfeat[b,c] / (H*W) on real pixels, 0 on padding
-__global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, __nv_bfloat16* __restrict__ gout, int B, int C, const PadGeom g) {
+// (dfeat2: optional second addend - the heads backward produces the feature gradient in two parts)
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ dfeat2, __nv_bfloat16* __restrict__ gout, int B,
+                                   int C, const PadGeom g) {
   pdl_entry();
   const int PP = g.Hp * g.Wp;
   const long long total = (long long)B * PP * C;
@@ -348,7 +350,9 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, __nv_bfloat1
     const int n = (int)(pix / PP);
     const int q = (int)(pix - (long long)n * PP);
     const bool valid = (q % g.Wp) < g.W && (q / g.Wp) < g.H;
-    gout[i] = __float2bfloat16(valid ? dfeat[(long long)n * C + c] * inv : 0.f);
+    float d = 0.f;
+    if (valid) d = dfeat[(long long)n * C + c] + (dfeat2 ? dfeat2[(long long)n * C + c] : 0.f);
+    gout[i] = __float2bfloat16(d * inv);
   }
 }
 
@@ -740,6 +744,11 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApp
 }
 
 #undef CILRS_BN_BWD_LOAD
+
+// out = a + b (fp32; the two parts of the feature gradient for callers that want it as one tensor)
+__global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = a[i] + b[i];
+}
 
 // grid size for the vector kernels: a multiple of the channel-group count keeps every thread on one channel group
 // reductions: ~1 CTA per SM is enough with the 4-way unrolled loop, and keeps the partials the last CTA folds small

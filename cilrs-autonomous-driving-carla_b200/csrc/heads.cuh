@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(HD_THREADS) heads_fwd_kernel(const HeadsFwdPar
   __shared__ __align__(16) float h1[256];
   __shared__ __align__(16) float h2[256];
   __shared__ __align__(16) float o3[4];
-  const int b = blockIdx.x;
+  // two CTAs per sample: role 0 = speed encoder + command branch -> controls, role 1 = speed predictor -> pred_speed
+  // (the two chains are independent; one CTA per sample ran seven dependent GEMVs back to back)
+  const int b = blockIdx.x >> 1;
+  const int role = blockIdx.x & 1;
   const int t = threadIdx.x;
   long long cmd = p.command[b];
   if (cmd < 0 || cmd > 3) {
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_fwd_kernel(const HeadsFwdPar
   const int k = (int)cmd;
   const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
   for (int i = t; i < 512; i += HD_THREADS) x[i] = p.feat[(size_t)b * 512 + i];
+  if (role == 0) {
   // speed encoder: Linear(1,128) + ReLU + Dropout, Linear(128,128) + ReLU
   if (t < 128) {
     float v = fmaxf(fmaf(p.w.se0_w[t], p.speed[b], p.w.se0_b[t]), 0.f);
@@ -135,7 +139,10 @@ __global__ void __launch_bounds__(HD_THREADS) heads_fwd_kernel(const HeadsFwdPar
   gemv_rows(p.w.br6_w[k], p.w.br6_b[k], h2, 256, 3, o3, false);
   __syncthreads();
   if (t < 3) p.controls[(size_t)b * 3 + t] = o3[t];
+  return;
+  }
   // speed predictor on the visual features only: Linear(512,256)+ReLU+Drop, Linear(256,256)+ReLU, Linear(256,1)
+  __syncthreads();
   gemv_rows(p.w.sp0_w, p.w.sp0_b, x, 512, 256, h1, true);
   __syncthreads();
   if (p.dropout_p > 0.f) h1[t] = drop_keep(p.seed, b, 3, t, p.dropout_p) ? h1[t] * keep_scale : 0.f;
@@ -219,7 +226,8 @@ struct HeadsBwdParams {
   const float* dcontrols;  // [B,3]
   const float* dspeed;     // [B]
   const long long* command;
-  float* dfeat;            // [B,512]
+  float* dfeat;            // [B,512]  gradient of the features through the command branch
+  float* dfeat2;           // [B,512]  ... through the speed predictor (the consumer adds the two)
   int batch;
   float dropout_p;
 };
@@ -256,10 +264,37 @@ CILRS_DEVINL void gemv_cols(const float* __restrict__ W, int ld, const float* d,
 
 __global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const HeadsBwdParams p) {
   __shared__ __align__(16) float d_a[256], d_b[256], dx[640], dx2[512], d3[4], scratch[1024];
-  const int b = blockIdx.x, t = threadIdx.x;
+  // two CTAs per sample (see heads_fwd_kernel): role 0 = command branch + speed encoder, role 1 = speed predictor
+  const int b = blockIdx.x >> 1, role = blockIdx.x & 1, t = threadIdx.x;
   long long cmd = p.command[b];
   const int k = cmd < 0 ? 0 : (cmd > 3 ? 3 : (int)cmd);
   const float ks = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+  if (role == 1) {
+    // ---- speed predictor ----
+    if (t == 0) {
+      d3[0] = p.dspeed[b];
+      p.sv.d_sp5[b] = d3[0];
+    }
+    __syncthreads();
+    {
+      const float v = p.sv.p2[(size_t)b * 256 + t] > 0.f ? p.w.sp5_w[t] * d3[0] : 0.f;
+      d_a[t] = v;
+      p.sv.d_sp3[(size_t)b * 256 + t] = v;
+    }
+    __syncthreads();
+    gemv_cols(p.w.sp3_w, 256, d_a, 256, 256, d_b, scratch);
+    __syncthreads();
+    {
+      const float v = p.sv.p1[(size_t)b * 256 + t] > 0.f ? d_b[t] * ks : 0.f;
+      d_b[t] = v;
+      p.sv.d_sp0[(size_t)b * 256 + t] = v;
+    }
+    __syncthreads();
+    gemv_cols(p.w.sp0_w, 512, d_b, 512, 256, dx2, scratch);
+    __syncthreads();
+    for (int i = t; i < 512; i += HD_THREADS) p.dfeat2[(size_t)b * 512 + i] = dx2[i];
+    return;
+  }
   // ---- control branch ----
   if (t < 4) {
     const float v = t < 3 ? p.dcontrols[(size_t)b * 3 + t] : 0.f;
@@ -286,29 +321,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const HeadsBwdPar
   gemv_cols(p.w.br0_w[k], 640, d_b, 512, 256, dx, scratch);
   gemv_cols(p.w.br0_w[k] + 512, 640, d_b, 128, 256, dx + 512, scratch);
   __syncthreads();
-  // ---- speed predictor ----
-  if (t == 0) {
-    d3[0] = p.dspeed[b];
-    p.sv.d_sp5[b] = d3[0];
-  }
-  __syncthreads();
-  {
-    const float v = p.sv.p2[(size_t)b * 256 + t] > 0.f ? p.w.sp5_w[t] * d3[0] : 0.f;
-    d_a[t] = v;
-    p.sv.d_sp3[(size_t)b * 256 + t] = v;
-  }
-  __syncthreads();
-  gemv_cols(p.w.sp3_w, 256, d_a, 256, 256, d_b, scratch);
-  __syncthreads();
-  {
-    const float v = p.sv.p1[(size_t)b * 256 + t] > 0.f ? d_b[t] * ks : 0.f;
-    d_b[t] = v;
-    p.sv.d_sp0[(size_t)b * 256 + t] = v;
-  }
-  __syncthreads();
-  gemv_cols(p.w.sp0_w, 512, d_b, 512, 256, dx2, scratch);
-  __syncthreads();
-  for (int i = t; i < 512; i += HD_THREADS) p.dfeat[(size_t)b * 512 + i] = dx[i] + dx2[i];
+  for (int i = t; i < 512; i += HD_THREADS) p.dfeat[(size_t)b * 512 + i] = dx[i];
   // ---- speed encoder ----
   if (t < 128) {
     const float v = p.sv.sfeat[(size_t)b * 128 + t] > 0.f ? dx[512 + t] : 0.f;

@@ -138,6 +138,8 @@ struct Model {
   float* unit_vec;       // [2][64]: ones, zeros (max-pool on already-activated stem output)
   float* feat;           // [B,512]
   float* dfeat;
+  float* dfeat2;         // feature gradient through the speed predictor (dfeat: through the command branch)
+  float* head_comb;      // [B,640] = [feat | sfeat]: input of the first branch layer, staged for its weight gradient
   HeadsSaved hs;
   float* loss_out;       // [8]
   float* dcontrols;      // [B,3]
@@ -149,6 +151,7 @@ struct Model {
   // dyd[k & 1] (k-th downsample)
   __nv_bfloat16 *dyb[2], *dya[2], *dyd[2];
   cudaStream_t side = nullptr;
+  cudaEvent_t ev_heads = nullptr;  // head deltas ready: the head weight gradients run on the side stream
   cudaEvent_t ev_ready[6] = {}, ev_done[6] = {}, ev_join = nullptr;  // slot order: dyb0, dyb1, dya0, dya1, dyd0, dyd1
   bool pending[6] = {false, false, false, false, false, false};      // a side-stream wgrad still reads the slot
   double* sumsq_partial;
@@ -301,6 +304,8 @@ static long long carve(Model& m, char* base) {
   m.unit_vec = (float*)bp.take(2 * 64 * 4);
   m.feat = (float*)bp.take((long long)B * 512 * 4);
   m.dfeat = (float*)bp.take((long long)B * 512 * 4);
+  m.dfeat2 = (float*)bp.take((long long)B * 512 * 4);
+  m.head_comb = (float*)bp.take((long long)B * 640 * 4);
   m.hs.s1 = (float*)bp.take((long long)B * 128 * 4);
   m.hs.sfeat = (float*)bp.take((long long)B * 128 * 4);
   m.hs.b1 = (float*)bp.take((long long)B * 256 * 4);
@@ -626,7 +631,7 @@ static int heads_forward(Model& m, int B, const float* speed, const long long* c
   if (keep_for_backward) hp.sv = m.hs; else memset(&hp.sv, 0, sizeof(hp.sv));
   hp.feat = m.feat; hp.speed = speed; hp.command = command; hp.controls = controls; hp.pred_speed = pred_speed;
   hp.batch = B; hp.dropout_p = dropout_p; hp.seed = seed; hp.error_flag = m.err_flag;
-  heads_fwd_kernel<<<B, HD_THREADS, 0, s>>>(hp); ++g_cilrs_launches;
+  heads_fwd_kernel<<<2 * B, HD_THREADS, 0, s>>>(hp); ++g_cilrs_launches;  // two CTAs per sample
   CKL();
   return OK;
 }
@@ -681,14 +686,20 @@ static int run_bn_bwd_apply(Model& m, int B, const PadGeom& g, const BnRef& bn, 
   return cuda_status(launch_pdl(bn_bwd_apply_kernel<false>, dim3(ew_grid(nvec, bn.C, 4)), dim3(EW_THREADS), 0, s, ap));
 }
 
+// deltas + d(features) on stream s; the weight / bias gradients on stream ws (the side stream of the backward when it is in
+// use: nothing on the trunk's chain depends on them)
 static int heads_backward(Model& m, int B, const float* dcontrols, const float* dspeed, const float* speed,
-                          const long long* command, float dropout_p, cudaStream_t s) {
+                          const long long* command, float dropout_p, cudaStream_t s, cudaStream_t ws) {
   // ---- heads ----
   HeadsBwdParams bp;
   bp.w = head_weights(m, m.params); bp.sv = m.hs; bp.dcontrols = dcontrols; bp.dspeed = dspeed; bp.command = command;
-  bp.dfeat = m.dfeat; bp.batch = B; bp.dropout_p = dropout_p;
-  heads_bwd_kernel<<<B, HD_THREADS, 0, s>>>(bp); ++g_cilrs_launches;
+  bp.dfeat = m.dfeat; bp.dfeat2 = m.dfeat2; bp.batch = B; bp.dropout_p = dropout_p;
+  heads_bwd_kernel<<<2 * B, HD_THREADS, 0, s>>>(bp); ++g_cilrs_launches;  // two CTAs per sample
   CKL();
+  if (ws != s) {
+    CK(cuda_status(cudaEventRecord(m.ev_heads, s)));
+    CK(cuda_status(cudaStreamWaitEvent(ws, m.ev_heads, 0)));
+  }
   {
     HeadsWgradParams wp;
     memset(&wp, 0, sizeof(wp));
@@ -716,12 +727,12 @@ static int heads_backward(Model& m, int B, const float* dcontrols, const float* 
     add(m.hs.d_sp5, 1, m.hs.p2, 256, 1, 256, sidx + 4, -1);
     wp.num_jobs = nj;
     // combined input [B,640] = [feat(512) | sfeat(128)] lives in dfeat-sized scratch: build it once
-    float* comb = (float*)m.ga;  // ga is free until the trunk backward starts (needs B*640*4 bytes)
-    CK(cuda_status(cudaMemcpy2DAsync(comb, 640 * 4, m.feat, 512 * 4, 512 * 4, B, cudaMemcpyDeviceToDevice, s)));
-    CK(cuda_status(cudaMemcpy2DAsync(comb + 512, 640 * 4, m.hs.sfeat, 128 * 4, 128 * 4, B, cudaMemcpyDeviceToDevice, s)));
+    float* comb = m.head_comb;
+    CK(cuda_status(cudaMemcpy2DAsync(comb, 640 * 4, m.feat, 512 * 4, 512 * 4, B, cudaMemcpyDeviceToDevice, ws)));
+    CK(cuda_status(cudaMemcpy2DAsync(comb + 512, 640 * 4, m.hs.sfeat, 128 * 4, 128 * 4, B, cudaMemcpyDeviceToDevice, ws)));
     for (int j = 0; j < nj; ++j)
       if (!wp.job[j].x) { wp.job[j].x = comb; wp.job[j].ld_x = 640; }
-    heads_wgrad_kernel<<<tiles, 256, 0, s>>>(wp); ++g_cilrs_launches;
+    heads_wgrad_kernel<<<tiles, 256, 0, ws>>>(wp); ++g_cilrs_launches;
     CKL();
   }
   return OK;
@@ -737,10 +748,13 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   if (part < -1 || part > 4) return ERR_INVALID;
   if (part <= 0) {
     CK(cuda_status(cudaMemsetAsync(m.acc_bwd, 0, (size_t)m.acc_bwd_bytes, s)));  // accumulators of the deferred BN-backward finalize
-    PROF(m, PC_HEADS, s, CK(heads_backward(m, B, dcontrols, dspeed, speed, command, dropout_p, s)));
+    {
+      cudaStream_t hws = (m.side != nullptr && !m.prof.on) ? m.side : s;
+      PROF(m, PC_HEADS, s, CK(heads_backward(m, B, dcontrols, dspeed, speed, command, dropout_p, s, hws)));
+    }
     // ---- trunk: gradient of the last block's output, then its ReLU mask + BN_b reductions ----
     Block& last = m.blocks.back();
-    avgpool_bwd_kernel<<<(int)((pad_elems(B, last.b.gout, 512) + 255) / 256), 256, 0, s>>>(m.dfeat, m.g0, B, 512, last.b.gout); ++g_cilrs_launches;
+    avgpool_bwd_kernel<<<(int)((pad_elems(B, last.b.gout, 512) + 255) / 256), 256, 0, s>>>(m.dfeat, m.dfeat2, m.g0, B, 512, last.b.gout); ++g_cilrs_launches;
     CKL();
     PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_reduce(m, B, last.b.gout, last.b.bn, m.g0, last.out, last.b.y, s)));
     m.bw_gcur = m.g0; m.bw_gnext = m.g1;
@@ -947,6 +961,7 @@ int cilrs_model_create(cilrs_model** out, int max_batch, void* workspace, size_t
       ok = cudaEventCreateWithFlags(&h->m.ev_ready[i], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&h->m.ev_done[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->m.ev_join, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->m.ev_heads, cudaEventDisableTiming) == cudaSuccess;
     if (!ok && h->m.side) { cudaStreamDestroy(h->m.side); h->m.side = nullptr; }
   }
   *out = h;
@@ -962,6 +977,7 @@ void cilrs_model_destroy(cilrs_model* h) {
       if (h->m.ev_done[i]) cudaEventDestroy(h->m.ev_done[i]);
     }
     if (h->m.ev_join) cudaEventDestroy(h->m.ev_join);
+    if (h->m.ev_heads) cudaEventDestroy(h->m.ev_heads);
     cudaStreamDestroy(h->m.side);
   }
   delete h;
@@ -1049,8 +1065,11 @@ int cilrs_model_heads_backward(cilrs_model* h, int batch, const float* dcontrols
   Model& m = h->m;
   if (batch < 1 || batch > m.maxB || !m.params || !m.grads) return ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  CK(heads_backward(m, batch, dcontrols, dspeed, speed, command, dropout_p, s));
-  if (dfeat_out) CK(cuda_status(cudaMemcpyAsync(dfeat_out, m.dfeat, (size_t)batch * 512 * 4, cudaMemcpyDeviceToDevice, s)));
+  CK(heads_backward(m, batch, dcontrols, dspeed, speed, command, dropout_p, s, s));
+  if (dfeat_out) {
+    add2_kernel<<<(batch * 512 + 255) / 256, 256, 0, s>>>(m.dfeat, m.dfeat2, dfeat_out, (long long)batch * 512); ++g_cilrs_launches;
+    CKL();
+  }
   return OK;
 }
 

@@ -392,6 +392,38 @@ def test_flat_deferred_finalize_sums(case):
     _report("sum dz*y2", acc[2], (dz * y2.double()).sum((0, 1, 2)), 1e-5)
 
 
+@pytest.mark.parametrize("case", [(128, 11, 25, 128, "1,128,0,3,1"), (37, 22, 50, 64, "2,64,1,9,1"), (128, 6, 13, 256, "1,256,0,1,1"),
+                                  (5, 3, 7, 512, "1,128,0,3,1"), (64, 3, 7, 512, "2,256,0,1,1")])
+def test_flat_cta_pair_kernel_is_bit_identical_to_the_single_cta_kernel(case, monkeypatch):
+    """conv_flat_kernel<MT, PAIR>: clusters of two CTAs sharing tcgen05.mma.cta_group::2 (M = 256, weight tiles split between
+    the CTAs) accumulate in the same order as the single-CTA kernel: outputs equal bit for bit, fused sums to fp32 rounding.
+    Tile shapes are forced through CILRS_FLAT_SHAPE = "mt,block_n,resident,tap_group,pair"."""
+    ops = _ops()
+    _ref_setup()
+    b, h, w, c, shape = case
+    d = ops.conv_desc(b, h, w, c, c, 3, 1)
+    x = ops.to_padded(_nhwc_bf16(_mk((b, c, h, w), 70)))
+    wf, wd = ops.pack_weight(d, _mk((c, c, 3, 3), 71) * (2.0 / (c * 9)) ** 0.5)
+    act = ops.to_padded(torch.relu(_mk((b, h, w, c), 72)).to(torch.bfloat16))
+    y1 = ops.to_padded(_mk((b, h, w, c), 73).to(torch.bfloat16))
+    res = ops.to_padded(_mk((b, h, w, c), 74).to(torch.bfloat16))
+    bits = ops.relu_bits(act)
+
+    def run():
+        f, sf = ops.conv_flat(x, wf, c, defer_sums="stats")
+        g, sg = ops.conv_flat(x, wd, c, dgrad=True, residual=res, mask=act, mask_bits=bits, bnbwd=dict(y=y1), defer_sums="bnbwd")
+        torch.cuda.synchronize()
+        return f, sf, g, sg
+
+    monkeypatch.setenv("CILRS_FLAT_SHAPE", "1,64,0,3,0")
+    ref = run()
+    monkeypatch.setenv("CILRS_FLAT_SHAPE", shape)
+    got = run()
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[2], ref[2])
+    _report("pair: forward sums", got[1], ref[1].double(), 1e-5)
+    _report("pair: backward sums", got[3], ref[3].double(), 1e-5)
+
+
 def test_flat_dgrad_relu_mask_as_bit_tensor_equals_the_bf16_mask():
     """the ReLU mask read as one bit per element (written by cilrs_bn_apply) gives the same dz as the bf16 activation"""
     ops = _ops()
