@@ -298,15 +298,25 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_maxpool_kernel(const __nv_
     int bi[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { best.v[k] = -INFINITY; bi[k] = 0; }
+    // all nine window loads are issued before the first comparison
+    uint4 q[9];
+    bool okq[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int h = oh * 2 - 1 + r;
-      if (h < 0 || h >= H) continue;
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         const int w = ow * 2 - 1 + s;
-        if (w < 0 || w >= W) continue;
-        const Vec8 a = load8(y + (((long long)n * H + h) * W + w) * C + cg);
+        okq[r * 3 + s] = h >= 0 && h < H && w >= 0 && w < W;
+        if (okq[r * 3 + s]) q[r * 3 + s] = *reinterpret_cast<const uint4*>(y + (((long long)n * H + h) * W + w) * C + cg);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        if (!okq[r * 3 + s]) continue;
+        const Vec8 a = unpack8(q[r * 3 + s]);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // round to bf16 first: the comparison must see exactly the values a separate BN+ReLU pass would store
@@ -431,7 +441,7 @@ CILRS_DEVINL Vec8 stem_gather_grad(const BnBwdReduceParams& p, int n, int h, int
 }
 
 template <bool STEM>
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(const BnBwdReduceParams p) {
+__global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(const BnBwdReduceParams p) {
   __shared__ float s_red[2 * EW_THREADS][8];  // 16 KB: per-thread partial (sum | dot) vectors
   __shared__ bool s_last;
   pdl_entry();
@@ -627,7 +637,7 @@ struct BnBwdApplyParams {
 };
 
 template <bool STEM>
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnBwdApplyParams p) {
+__global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(const BnBwdApplyParams p) {
   pdl_entry();
   const int groups = p.C >> 3;
   const long long stride = (long long)gridDim.x * EW_THREADS;
@@ -762,11 +772,12 @@ inline int ew_reduce_grid(long long nvec, int C) {
 
 // (EW_THREADS = 256 is a multiple of every group count 8..64, so any block count keeps that property.)
 // `per_thread` = vectors each thread should get at least: streaming kernels use 2, reductions 8 (fewer partials to fold).
-inline int ew_grid(long long nvec, int C, int per_thread = 2) {
+inline int ew_grid(long long nvec, int C, int per_thread = 2, int ctas_per_sm = 3) {
   (void)C;
   long long blocks = (nvec + (long long)EW_THREADS * per_thread - 1) / ((long long)EW_THREADS * per_thread);
   if (blocks > EW_MAX_BLOCKS) blocks = EW_MAX_BLOCKS;
-  if (per_thread == 4 && blocks > 148 * 3) blocks = 148 * 3;  // the 4-way unrolled streaming kernels: 3 resident CTAs per SM
+  // the 4-way unrolled streaming kernels: exactly the resident CTAs (bn_apply: 70 registers -> 3 per SM, bn_bwd_apply: 123 -> 2)
+  if (per_thread == 4 && blocks > 148 * ctas_per_sm) blocks = 148 * ctas_per_sm;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }

@@ -683,7 +683,7 @@ static int run_bn_bwd_apply(Model& m, int B, const PadGeom& g, const BnRef& bn, 
     ap.defer.dgamma = m.grads + m.slots[bn.gamma].off; ap.defer.dbeta = m.grads + m.slots[bn.beta].off;
   }
   ++g_cilrs_launches;
-  return cuda_status(launch_pdl(bn_bwd_apply_kernel<false>, dim3(ew_grid(nvec, bn.C, 4)), dim3(EW_THREADS), 0, s, ap));
+  return cuda_status(launch_pdl(bn_bwd_apply_kernel<false>, dim3(ew_grid(nvec, bn.C, 4, 2)), dim3(EW_THREADS), 0, s, ap));
 }
 
 // deltas + d(features) on stream s; the weight / bias gradients on stream ws (the side stream of the backward when it is in
@@ -851,8 +851,8 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   if (part < 0 || part == 4) {
     const BnRef& bn = m.stem.bn;
     const long long nvec = act_elems(B, 44, 100, 64) / 8;
-    const int grid = ew_grid(nvec, 64, 4);
-    const int rgrid = ew_grid(nvec, 64, 8);
+    const int grid = ew_grid(nvec, 64, 4, 2);
+    const int rgrid = 148 * 2;  // 128 registers: two resident CTAs per SM, one wave
     BnBwdReduceParams rp{};
     rp.g = gcur; rp.y = m.stem.y; rp.mean = bn.vec + 2 * 64; rp.rstd = bn.vec + 3 * 64; rp.nvec = nvec; rp.C = 64;
     rp.partial = m.stat_acc; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + 64;
