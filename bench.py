@@ -53,49 +53,89 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML every ~2 ms from a thread (the timed region of the
+    default run is ~0.1 s - an `nvidia-smi -lms 200` child would not deliver a single sample); nvidia-smi as the fallback."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.sm, self.mask = [], 0
+        self.max_mhz = None
+        self.handle = None
+        self.stop_flag = False
+        self.thread = None
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _sample_nvml(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        try:
+            self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                self._sample_nvml()
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.nv, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nv.nvmlDeviceGetMaxClockInfo(self.handle, self.nv.NVML_CLOCK_SM))
+            self._sample_nvml()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.handle = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+        r = [c.strip() for c in out.split(",")]
+        self.sm.append(float(r[0]))
+        self.max_mhz = float(r[1])
+        for (bit, _), v in zip(self.REASONS, r[2:6]):
+            if v.lower().startswith("active"):
+                self.mask |= bit
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1)
+        if self.handle is None:
+            # fallback: one nvidia-smi reading right after the timed region (the GPU is still under load from the e2e leg)
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
+                self._smi_once()
+                self.source = "nvidia-smi (single reading after the timed region)"
             except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [name for bit, name in self.REASONS if self.mask & bit], "samples": len(sm), "source": self.source}
 
 
 def cpu_reference_step_rate(batch, steps, warmup):
