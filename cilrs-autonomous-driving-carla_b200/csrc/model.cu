@@ -151,6 +151,7 @@ struct Model {
   // dyd[k & 1] (k-th downsample)
   __nv_bfloat16 *dyb[2], *dya[2], *dyd[2];
   cudaStream_t side = nullptr;
+  cudaEvent_t ev_part = nullptr;   // end of an asynchronous backward part on the caller's stream
   cudaEvent_t ev_heads = nullptr;  // head deltas ready: the head weight gradients run on the side stream
   cudaEvent_t ev_ready[6] = {}, ev_done[6] = {}, ev_join = nullptr;  // slot order: dyb0, dyb1, dya0, dya1, dyd0, dyd1
   bool pending[6] = {false, false, false, false, false, false};      // a side-stream wgrad still reads the slot
@@ -739,8 +740,11 @@ static int heads_backward(Model& m, int B, const float* dcontrols, const float* 
 }
 
 // part: -1 = whole backward; 0 = heads + layer4, 1 = layer3, 2 = layer2, 3 = layer1, 4 = stem (must be called in order)
+// async_part: do not make the caller's stream wait for the weight-gradient stream at the end of the part; instead the
+// weight-gradient stream waits for the caller's stream, so that "everything this part wrote" is complete in THAT stream's order
+// (the host enqueues the part's allreduce there and joins once, after the last part: cilrs_model_backward_join)
 static int backward(Model& m, int B, int mode, int part, const float* dcontrols, const float* dspeed, const float* speed,
-                    const long long* command, float dropout_p, cudaStream_t s) {
+                    const long long* command, float dropout_p, cudaStream_t s, bool async_part = false) {
   if (mode == MODE_INFER) return ERR_INVALID;
   if (B != m.planB || mode != m.planMode) return ERR_INVALID;  // must follow a forward with keep_for_backward
   if (!m.grads) return ERR_INVALID;
@@ -841,7 +845,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   // fold the split-K partial tiles of this part's flat wgrads into the OIHW gradients (one launch per layer group)
   for (int pt = 0; pt < 4; ++pt)
     if (part < 0 || part == pt) PROF(m, PC_WGRAD, ws, CK(launch_wgrad_reduce(&m.red_jobs[pt], m.grads, ws)));
-  if (use_side) {
+  if (use_side && !async_part) {
     // join: everything after this call on the caller's stream (allreduce of the part, Adam) sees the finished gradients
     CK(cuda_status(cudaEventRecord(m.ev_join, m.side)));
     CK(cuda_status(cudaStreamWaitEvent(s, m.ev_join, 0)));
@@ -867,6 +871,10 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     ap.C = 64; ap.dy = m.dy_stem; ap.geom = kDense;
     PROF(m, PC_BN_BWD, s, { ++g_cilrs_launches; CK(cuda_status(launch_pdl(bn_bwd_apply_kernel<false>, dim3(grid), dim3(EW_THREADS), 0, s, ap))); });
     PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, m.stem_wgrad, m.stem.w, s)));
+  }
+  if (use_side && async_part) {
+    CK(cuda_status(cudaEventRecord(m.ev_part, s)));
+    CK(cuda_status(cudaStreamWaitEvent(m.side, m.ev_part, 0)));
   }
   return OK;
 }
@@ -962,6 +970,7 @@ int cilrs_model_create(cilrs_model** out, int max_batch, void* workspace, size_t
            cudaEventCreateWithFlags(&h->m.ev_done[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->m.ev_join, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->m.ev_heads, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->m.ev_part, cudaEventDisableTiming) == cudaSuccess;
     if (!ok && h->m.side) { cudaStreamDestroy(h->m.side); h->m.side = nullptr; }
   }
   *out = h;
@@ -978,6 +987,7 @@ void cilrs_model_destroy(cilrs_model* h) {
     }
     if (h->m.ev_join) cudaEventDestroy(h->m.ev_join);
     if (h->m.ev_heads) cudaEventDestroy(h->m.ev_heads);
+    if (h->m.ev_part) cudaEventDestroy(h->m.ev_part);
     cudaStreamDestroy(h->m.side);
   }
   delete h;
@@ -1010,6 +1020,23 @@ int cilrs_model_backward(cilrs_model* h, int batch, int mode, int part, const fl
                          const float* speed, const long long* command, float dropout_p, void* stream) {
   if (!h || !dcontrols || !dspeed || !speed || !command) return ERR_INVALID;
   return backward(h->m, batch, mode, part, dcontrols, dspeed, speed, command, dropout_p, (cudaStream_t)stream);
+}
+
+int cilrs_model_backward_part_async(cilrs_model* h, int batch, int mode, int part, const float* dcontrols, const float* dspeed,
+                                    const float* speed, const long long* command, float dropout_p, void* stream) {
+  if (!h || !dcontrols || !dspeed || !speed || !command || part < 0) return ERR_INVALID;
+  return backward(h->m, batch, mode, part, dcontrols, dspeed, speed, command, dropout_p, (cudaStream_t)stream, true);
+}
+void* cilrs_model_gradient_stream(cilrs_model* h) { return (h && h->m.side && !h->m.prof.on) ? (void*)h->m.side : nullptr; }
+int cilrs_model_backward_join(cilrs_model* h, void* stream) {
+  if (!h) return ERR_INVALID;
+  Model& m = h->m;
+  if (m.side && !m.prof.on) {
+    CK(cuda_status(cudaEventRecord(m.ev_join, m.side)));
+    CK(cuda_status(cudaStreamWaitEvent((cudaStream_t)stream, m.ev_join, 0)));
+    for (int i = 0; i < 6; ++i) m.pending[i] = false;
+  }
+  return OK;
 }
 
 int cilrs_model_backward_part_first_tensor(int part) {

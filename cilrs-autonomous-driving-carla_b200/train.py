@@ -93,10 +93,26 @@ class FusedTrainer:
         g.zero_()
         works = []
         if self.world > 1:
+            # The backward runs in five parts; the allreduce of a part's gradient range is enqueued behind the model's
+            # gradient stream (where the part's weight gradients finish) while the caller's stream already runs the next
+            # part: the dgrad / BatchNorm chain never waits for a weight gradient or a collective. One join at the end.
+            lib = _lib.lib()
+            lib.cilrs_model_gradient_stream.restype = ctypes.c_void_p
+            lib.cilrs_model_gradient_stream.argtypes = [ctypes.c_void_p]
+            gs_ptr = lib.cilrs_model_gradient_stream(m._handle)
+            gstream = torch.cuda.ExternalStream(gs_ptr, device=self.dev) if gs_ptr else None
             for part in range(5):
-                _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, part, self.dcontrols, self.dspeed, self.d_speed,
-                          self.d_command, ctypes.c_float(m.dropout), sp)
-                works.extend(allreduce_ranges(g, [self.part_ranges[part]], self.pg))
+                if gstream is not None:
+                    _lib.call("cilrs_model_backward_part_async", m._handle, b, MODE_TRAIN, part, self.dcontrols, self.dspeed,
+                              self.d_speed, self.d_command, ctypes.c_float(m.dropout), sp)
+                    with torch.cuda.stream(gstream):
+                        works.extend(allreduce_ranges(g, [self.part_ranges[part]], self.pg))
+                else:
+                    _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, part, self.dcontrols, self.dspeed, self.d_speed,
+                              self.d_command, ctypes.c_float(m.dropout), sp)
+                    works.extend(allreduce_ranges(g, [self.part_ranges[part]], self.pg))
+            if gstream is not None:
+                _lib.call("cilrs_model_backward_join", m._handle, sp)
             for w in works:
                 w.wait()
         else:

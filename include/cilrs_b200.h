@@ -197,6 +197,16 @@ int cilrs_model_backward(cilrs_model* m, int batch, int mode, int part, const fl
 /* first parameter-tensor index (into cilrs_model_param_layout) whose gradient backward part `part` completes;
  * part p completes tensors [first(p), first(p-1)) with first(-1) = number of tensors */
 int cilrs_model_backward_part_first_tensor(int part);
+/* Asynchronous form of a backward part (part = 0..4): the caller's stream is NOT made to wait for the part's weight
+ * gradients (they run on the model's internal gradient stream). Instead everything the part wrote is complete in the ORDER OF
+ * cilrs_model_gradient_stream(): enqueue the part's allreduce there (or behind an event recorded there), call the next
+ * part right away, and join once after the last part with cilrs_model_backward_join(m, stream) before the optimizer.
+ * gradient_stream returns NULL when the model runs everything on the caller's stream (then the three calls degrade to the
+ * synchronous behaviour). */
+int cilrs_model_backward_part_async(cilrs_model* m, int batch, int mode, int part, const float* dcontrols, const float* dspeed,
+                                    const float* speed, const long long* command, float dropout_p, void* stream);
+void* cilrs_model_gradient_stream(cilrs_model* m);
+int cilrs_model_backward_join(cilrs_model* m, void* stream);
 /* measurement aid (bench.py roofline): CUDA events around every launch of the plan, summed per kernel class
  * {conv fprop, conv dgrad, conv wgrad, BN forward + pooling, BN backward, heads, other}. collect() synchronises. */
 int cilrs_model_profile(cilrs_model* m, int enable);
