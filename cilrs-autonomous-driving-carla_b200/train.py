@@ -20,7 +20,8 @@ from .optim import FusedAdam
 
 class FusedTrainer:
     def __init__(self, model, batch, lr=2e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, loss="mse", steer_w=5.0,
-                 throttle_w=1.0, brake_w=1.0, speed_w=0.05, grad_clip=0.0, process_group=None, use_graph=False, frames="f32"):
+                 throttle_w=1.0, brake_w=1.0, speed_w=0.05, grad_clip=0.0, process_group=None, use_graph=False, frames="f32",
+                 async_parts=False):
         if frames not in ("f32", "u8"):
             raise ValueError("frames: 'f32' ([B,3,88,200] normalised, as the reference's loader yields) or 'u8' ([B,88,200,3])")
         self.model = model
@@ -57,6 +58,10 @@ class FusedTrainer:
         self.norm_out = torch.zeros(2, dtype=torch.float32, device=dev)
         self.s2d = model.input_s2d_buffer(batch)
         self.part_ranges = backward_part_ranges(model)
+        # async_parts: enqueue each part's allreduce behind the model's gradient stream instead of joining that stream into the
+        # caller's after every part (cilrs_model_backward_part_async). Measured on 2 GPUs: 3.38 ms/step when the host reads the
+        # loss every step (3.52 joined) but 3.63 ms for back-to-back graph replays (3.41 joined) - hence off by default.
+        self.async_parts = bool(async_parts)
         self.graph = None
         self.kernel_launches = None
         self.graph_error = None
@@ -100,7 +105,7 @@ class FusedTrainer:
             lib.cilrs_model_gradient_stream.restype = ctypes.c_void_p
             lib.cilrs_model_gradient_stream.argtypes = [ctypes.c_void_p]
             gs_ptr = lib.cilrs_model_gradient_stream(m._handle)
-            gstream = torch.cuda.ExternalStream(gs_ptr, device=self.dev) if gs_ptr else None
+            gstream = torch.cuda.ExternalStream(gs_ptr, device=self.dev) if (gs_ptr and self.async_parts) else None
             for part in range(5):
                 if gstream is not None:
                     _lib.call("cilrs_model_backward_part_async", m._handle, b, MODE_TRAIN, part, self.dcontrols, self.dspeed,
