@@ -53,7 +53,7 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region: NVML every ~2 ms from a thread (the timed region of the
+    """SM clock / throttle reasons sampled DURING the timed region: NVML every ~20 ms from a thread (the timed region of the
     default run is ~0.1 s - an `nvidia-smi -lms 200` child would not deliver a single sample); nvidia-smi as the fallback."""
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
@@ -97,7 +97,7 @@ class ClockSampler:
                 self._sample_nvml()
             except Exception:
                 break
-            time.sleep(0.002)
+            time.sleep(0.02)   # (a 2 ms loop measurably slowed the multi-rank step: it competes with the launch / NCCL threads)
 
     def start(self):
         try:
@@ -258,14 +258,16 @@ def main():
         trainer.opt._step += 0
     torch.cuda.synchronize(dev)
 
-    for i in range(args.warmup):
+    # W warm-up steps as asked, plus (multi-rank only) a few settle steps: the first replays after start-up pay NCCL's lazy
+    # channel / buffer set-up and showed up as +0.3 ms/step in 20-step runs on 2 GPUs
+    settle = 10 if world > 1 else 0
+    for i in range(args.warmup + settle):
         trainer.load_batch(*devb[i % POOL])
         trainer.step()
     # ---------------- device-resident timing ----------------
     sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.start()   # every rank samples its own GPU; rank 0 reports the slowest one and the union of the throttle reasons
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -277,7 +279,17 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    if world > 1:
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        if rank == 0:
+            ok = [c for c in allc if c and c.get("sm_mhz") is not None]
+            if ok:
+                slow = min(ok, key=lambda c: c["sm_mhz"])
+                clocks = dict(slow)
+                clocks["reasons"] = sorted(set(r for c in allc if c for r in c.get("reasons", [])))
+                clocks["per_rank_sm_mhz"] = [c.get("sm_mhz") if c else None for c in allc]
     loss_last = trainer.loss6.tolist()
 
     # ---------------- end-to-end timing: host frames in, loss out, every step ----------------
@@ -308,7 +320,7 @@ def main():
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
-                   "cuda_graph": trainer.graph is not None, "cuda_graph_error": trainer.graph_error,
+                   "cuda_graph": trainer.graph is not None, "cuda_graph_error": trainer.graph_error, "settle_steps": settle,
                    "l2": "no explicit flush: one step touches ~0.9 GB of activations + 0.6 GB of optimizer state, > 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps, "input": "uint8 [128,88,200,3] frames + speed/command/targets from pinned host memory"},
