@@ -131,6 +131,12 @@ class FusedTrainer:
             scale_dev = self.norm_out[1:]
         self.opt.step(grad_scale=1.0 / self.world, grad_scale_dev=scale_dev, grads_in_arena=True)
         _lib.call("cilrs_model_refresh", m._handle, 1, sp)
+        self._after_step()
+
+    def _after_step(self):
+        # parameters and BatchNorm buffers changed through raw pointers (also on every graph replay): the bf16 operands were
+        # repacked on the stream, but the next eval forward of the module must re-fold its BatchNorm
+        m = self.model
         m.mark_parameters_changed(repacked=True)
         m._extra_b += 1
         m._fwd_gen += 1
@@ -177,6 +183,7 @@ class FusedTrainer:
         if self.graph is not None:
             self.graph.replay()
             self.opt._step += 1
+            self._after_step()
         else:
             self._device_step()
         return self.loss6

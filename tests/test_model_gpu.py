@@ -273,6 +273,34 @@ def test_reference_style_training_loop_runs():
     assert c.shape == (8, 3) and p.shape == (8,) and torch.isfinite(c).all()
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_trainer_steps_then_eval_sees_the_new_weights_and_statistics(use_graph):
+    """FusedTrainer updates parameters and BatchNorm buffers through raw pointers (on every CUDA-graph replay too): an eval
+    forward afterwards must use the refreshed bf16 operands and re-folded BatchNorm, i.e. equal a fresh module that loads the
+    trained state_dict."""
+    from cilrs_b200.train import FusedTrainer
+    O, sd, image, speed, command, targets = _setup(B=8, seed=9)
+    m = _model(sd, train=True)
+    tr = FusedTrainer(m, 8, lr=1e-3, use_graph=use_graph)
+    m.eval()
+    with torch.no_grad():
+        c0, p0 = m(image.cuda(), speed.cuda(), command.cuda())   # folds BatchNorm for the initial weights
+    m.train()
+    tr.load_batch(image.cuda(), speed.cuda(), command.cuda(), targets.cuda())
+    for _ in range(3):
+        loss6 = tr.step()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss6).all()
+    m.eval()
+    with torch.no_grad():
+        c1, p1 = m(image.cuda(), speed.cuda(), command.cuda())
+    fresh = _model({k: v.detach().cpu().clone() for k, v in m.state_dict().items()}, train=False)
+    with torch.no_grad():
+        c2, p2 = fresh(image.cuda(), speed.cuda(), command.cuda())
+    assert torch.equal(c1, c2) and torch.equal(p1, p2)
+    assert not torch.equal(c1, c0)
+
+
 def test_fails_loudly_without_cuda_tensors():
     from cilrs_b200.model import CILRS
     m = CILRS()
