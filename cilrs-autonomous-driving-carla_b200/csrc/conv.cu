@@ -437,12 +437,14 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const float* __restrict__
     tile[co][r] = w[((long long)(co0 + co) * jb.cin + ci0) * kk + r];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 32 * run; idx += 256) {
-    const int a = idx & 31, b = (idx >> 5) & 31, t = idx >> 10;  // t < kk
+  for (int idx = threadIdx.x; idx < 16 * run; idx += 256) {
+    const int a = (idx & 15) * 2, b = (idx >> 4) & 31, t = idx >> 9;  // t < kk; two consecutive elements per 4-byte store
     // fprop layout [t][co][ci]: a = ci (fastest), b = co
-    jb.wf[((long long)t * jb.cout + co0 + b) * jb.cin + ci0 + a] = __float2bfloat16(tile[b][a * kk + t]);
+    *reinterpret_cast<uint32_t*>(jb.wf + ((long long)t * jb.cout + co0 + b) * jb.cin + ci0 + a) =
+        pack_bf16x2(tile[b][a * kk + t], tile[b][(a + 1) * kk + t]);
     // dgrad layout [t][ci][co]: a = co (fastest), b = ci
-    jb.wd[((long long)t * jb.cin + ci0 + b) * jb.cout + co0 + a] = __float2bfloat16(tile[a][b * kk + t]);
+    *reinterpret_cast<uint32_t*>(jb.wd + ((long long)t * jb.cin + ci0 + b) * jb.cout + co0 + a) =
+        pack_bf16x2(tile[a][b * kk + t], tile[a + 1][b * kk + t]);
   }
 }
 
