@@ -128,7 +128,6 @@ struct Model {
   __nv_bfloat16* pool_out;
   uint8_t* pool_arg;
   float* stats;          // shared stats-partials scratch
-  float* bwd_partial;    // BN backward partials
   double* stat_acc;
   double* acc_fwd;       // per-BatchNorm accumulators of the deferred finalize (conv_params.h: CF_DEFER): forward, backward
   double* acc_bwd;
@@ -284,7 +283,6 @@ static long long carve(Model& m, char* base) {
   // stats partial scratch: the stem has the most tiles (<= ceil(B*4400/100) ~ 44*B + slack), 2 x 64 floats each;
   // deeper layers have fewer tiles x more channels; bound by B*44*100/64 tiles * 2 * 64
   m.stats = (float*)bp.take(256LL * 2 * 512 * 4);  // one (sum, sumsq)[C<=512] partial per persistent conv CTA (<= SM count)
-  m.bwd_partial = (float*)bp.take((long long)EW_MAX_BLOCKS * 2 * 512 * 4);
   m.stat_acc = (double*)bp.take(3 * 512 * 8);  // per-channel fp64 statistics accumulators (kept zero between launches)
   {
     long long ch = m.stem.bn.C;
