@@ -229,7 +229,9 @@ def main():
     torch.manual_seed(0)
     model = CILRS(num_commands=4, dropout=0.0).to(dev)
     trainer = FusedTrainer(model, BATCH, lr=2e-4, weight_decay=1e-4, loss="mse", speed_w=0.05, frames="u8",
-                           use_graph=(not args.no_graph))
+                           use_graph=(not args.no_graph),
+                           overlap_allreduce={"tail": False, "all": True}.get(os.environ.get("CILRS_BENCH_ALLREDUCE", "first"), "first"),  # measurement aids
+                           async_parts=os.environ.get("CILRS_BENCH_ASYNC_PARTS", "0") == "1")
 
     # synthetic batches: uint8 200x88 frames (what the reference's dataset stores after prepare_dataset.py), per-rank seed
     g = torch.Generator().manual_seed(100 + rank)

@@ -21,7 +21,10 @@ from .optim import FusedAdam
 class FusedTrainer:
     def __init__(self, model, batch, lr=2e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, loss="mse", steer_w=5.0,
                  throttle_w=1.0, brake_w=1.0, speed_w=0.05, grad_clip=0.0, process_group=None, use_graph=False, frames="f32",
-                 async_parts=False):
+                 async_parts=False, overlap_allreduce="first"):
+        # overlap_allreduce: True = every backward part's range as soon as it is complete; False = one allreduce after the
+        # backward; "first" = only the first part (heads + layer4, 64 % of the bytes) overlapped - it runs under layer3's
+        # backward, whose 98-CTA conv grids leave SMs free for NCCL's CTAs - and one allreduce for the rest at the end
         if frames not in ("f32", "u8"):
             raise ValueError("frames: 'f32' ([B,3,88,200] normalised, as the reference's loader yields) or 'u8' ([B,88,200,3])")
         self.model = model
@@ -62,6 +65,9 @@ class FusedTrainer:
         # caller's after every part (cilrs_model_backward_part_async). Measured on 2 GPUs: 3.38 ms/step when the host reads the
         # loss every step (3.52 joined) but 3.63 ms for back-to-back graph replays (3.41 joined) - hence off by default.
         self.async_parts = bool(async_parts)
+        # overlap_allreduce=False: one allreduce of the whole gradient arena after the backward (no NCCL CTAs competing with the
+        # convolutions for SMs, but the collective is fully exposed)
+        self.overlap_allreduce = overlap_allreduce if overlap_allreduce == "first" else bool(overlap_allreduce)
         self.graph = None
         self.kernel_launches = None
         self.graph_error = None
@@ -97,7 +103,22 @@ class FusedTrainer:
         g = m.flat_gradients()
         g.zero_()
         works = []
-        if self.world > 1:
+        if self.world > 1 and self.overlap_allreduce == "first":
+            args = (self.dcontrols, self.dspeed, self.d_speed, self.d_command, ctypes.c_float(m.dropout), sp)
+            _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, 0, *args)
+            works.extend(allreduce_ranges(g, [self.part_ranges[0]], self.pg))
+            for part in range(1, 5):
+                _lib.call("cilrs_model_backward_part_async", m._handle, b, MODE_TRAIN, part, *args)
+            _lib.call("cilrs_model_backward_join", m._handle, sp)
+            works.extend(allreduce_ranges(g, [(0, self.part_ranges[0][0])], self.pg))
+            for w in works:
+                w.wait()
+        elif self.world > 1 and not self.overlap_allreduce:
+            _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, -1, self.dcontrols, self.dspeed, self.d_speed,
+                      self.d_command, ctypes.c_float(m.dropout), sp)
+            for w in allreduce_ranges(g, [(0, g.numel())], self.pg):
+                w.wait()
+        elif self.world > 1:
             # The backward runs in five parts; the allreduce of a part's gradient range is enqueued behind the model's
             # gradient stream (where the part's weight gradients finish) while the caller's stream already runs the next
             # part: the dgrad / BatchNorm chain never waits for a weight gradient or a collective. One join at the end.
