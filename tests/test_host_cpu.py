@@ -63,6 +63,19 @@ def test_param_layout_matches_reference_order():
                                            "visual_encoder.5.0.conv1.weight", "visual_encoder.4.0.conv1.weight", "visual_encoder.0.weight"]
 
 
+def test_backward_part_ranges_tile_the_gradient_arena():
+    """FusedTrainer's default data-parallel schedule allreduces part 0's range early and [0, lo(part 0)) in one collective at
+    the end: the five part ranges must be contiguous, back to front, and cover the arena exactly once."""
+    from cilrs_b200.model import CILRS
+    from cilrs_b200.ddp import backward_part_ranges
+    m = CILRS(num_commands=4, dropout=0.0)
+    r = backward_part_ranges(m)
+    assert len(r) == 5 and r[0][1] == m._total and r[4][0] == 0
+    for p in range(4):
+        assert r[p][0] == r[p + 1][1] and r[p][0] < r[p][1]
+    assert r[0][1] - r[0][0] > 0.6 * m._total   # heads + layer4: most of the bytes go out first
+
+
 def test_dropin_module_state_dict_and_cpu_refusal():
     from cilrs_b200.model import CILRS
     from oracle import cilrs_oracle as O
