@@ -393,9 +393,9 @@ def main():
             line["infer_b1"] = {"error": repr(ex)}
         # ---- CPU baseline (oracle port), bounded sample ----
         if world == 1 and not args.no_cpu_baseline:
-            fps, sec, cores = cpu_reference_step_rate(BATCH, 2, 1)
+            fps, sec, cores = cpu_reference_step_rate(BATCH, 12, 1)   # ~10 s of host work
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                    "sample": "2 timed full train steps (fwd+MSE loss+bwd+Adam) at batch 128 after 1 warm-up, torch fp32 on the host"}
+                                    "sample": "12 timed full train steps (fwd+MSE loss+bwd+Adam) at batch 128 after 1 warm-up, torch fp32 on the host"}
         print(json.dumps(line))
         sys.stdout.flush()
     if world > 1:
