@@ -135,6 +135,12 @@ def _ddp_worker(rank, world, port, q):
         for x in w:
             x.wait()
     g.mul_(1.0 / world)
+    # FusedTrainer's default schedule: part 0's range early, everything below it in one collective at the end
+    h = torch.full((total,), float(rank + 1))
+    for x in allreduce_ranges(h, [ranges[0]], None) + allreduce_ranges(h, [(0, ranges[0][0])], None):
+        x.wait()
+    h.mul_(1.0 / world)
+    assert torch.equal(g, h)
     q.put((rank, float(g.min()), float(g.max())))
     dist.destroy_process_group()
 
