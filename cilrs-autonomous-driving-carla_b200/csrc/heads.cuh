@@ -92,6 +92,7 @@ struct HeadsFwdParams {
   int batch;
   float dropout_p;
   unsigned long long seed;
+  const long long* seed_counter;  // optional device counter mixed into the seed (a new mask on every CUDA-graph replay)
   int* error_flag;     // set to 1 if a command is outside [0,4)
 };
 
@@ -112,12 +113,13 @@ __global__ void __launch_bounds__(HD_THREADS) heads_fwd_kernel(const HeadsFwdPar
   }
   const int k = (int)cmd;
   const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+  const unsigned long long seed = p.seed + (p.seed_counter ? 0x9E3779B97F4A7C15ull * (unsigned long long)(*p.seed_counter + 1) : 0ull);
   for (int i = t; i < 512; i += HD_THREADS) x[i] = p.feat[(size_t)b * 512 + i];
   if (role == 0) {
   // speed encoder: Linear(1,128) + ReLU + Dropout, Linear(128,128) + ReLU
   if (t < 128) {
     float v = fmaxf(fmaf(p.w.se0_w[t], p.speed[b], p.w.se0_b[t]), 0.f);
-    if (p.dropout_p > 0.f) v = drop_keep(p.seed, b, 0, t, p.dropout_p) ? v * keep_scale : 0.f;
+    if (p.dropout_p > 0.f) v = drop_keep(seed, b, 0, t, p.dropout_p) ? v * keep_scale : 0.f;
     h1[t] = v;
     if (p.sv.s1) p.sv.s1[(size_t)b * 128 + t] = v;
   }
@@ -128,12 +130,12 @@ __global__ void __launch_bounds__(HD_THREADS) heads_fwd_kernel(const HeadsFwdPar
   // control branch k: Linear(640,256)+ReLU+Drop, Linear(256,256)+ReLU+Drop, Linear(256,3)
   gemv_rows(p.w.br0_w[k], p.w.br0_b[k], x, 640, 256, h1, true);
   __syncthreads();
-  if (p.dropout_p > 0.f) h1[t] = drop_keep(p.seed, b, 1, t, p.dropout_p) ? h1[t] * keep_scale : 0.f;
+  if (p.dropout_p > 0.f) h1[t] = drop_keep(seed, b, 1, t, p.dropout_p) ? h1[t] * keep_scale : 0.f;
   if (p.sv.b1) p.sv.b1[(size_t)b * 256 + t] = h1[t];
   __syncthreads();
   gemv_rows(p.w.br3_w[k], p.w.br3_b[k], h1, 256, 256, h2, true);
   __syncthreads();
-  if (p.dropout_p > 0.f) h2[t] = drop_keep(p.seed, b, 2, t, p.dropout_p) ? h2[t] * keep_scale : 0.f;
+  if (p.dropout_p > 0.f) h2[t] = drop_keep(seed, b, 2, t, p.dropout_p) ? h2[t] * keep_scale : 0.f;
   if (p.sv.b2) p.sv.b2[(size_t)b * 256 + t] = h2[t];
   __syncthreads();
   gemv_rows(p.w.br6_w[k], p.w.br6_b[k], h2, 256, 3, o3, false);
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_fwd_kernel(const HeadsFwdPar
   __syncthreads();
   gemv_rows(p.w.sp0_w, p.w.sp0_b, x, 512, 256, h1, true);
   __syncthreads();
-  if (p.dropout_p > 0.f) h1[t] = drop_keep(p.seed, b, 3, t, p.dropout_p) ? h1[t] * keep_scale : 0.f;
+  if (p.dropout_p > 0.f) h1[t] = drop_keep(seed, b, 3, t, p.dropout_p) ? h1[t] * keep_scale : 0.f;
   if (p.sv.p1) p.sv.p1[(size_t)b * 256 + t] = h1[t];
   __syncthreads();
   gemv_rows(p.w.sp3_w, p.w.sp3_b, h1, 256, 256, h2, true);
@@ -214,6 +216,68 @@ __global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
     else control = p.w_steer * steer + p.w_throttle * thr + p.w_brake * brk;
     p.out[0] = control + p.w_speed * spd;
     p.out[1] = control; p.out[2] = steer; p.out[3] = thr; p.out[4] = brk; p.out[5] = spd;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// validate() on the device (notebook/notebook.ipynb:563-585): per batch the six loss scalars (as loss_kernel) and the
+// per-command steer absolute error, ACCUMULATED into acc[16] (fp64):
+//   acc[0..5]  += total, control, steer, throttle, brake, speed of this batch      (the reference sums .item()s per batch)
+//   acc[6..9]  += sum over samples with command k of |pred_steer - target_steer|    (the reference extends per-command lists)
+//   acc[10..13] += number of samples with command k;   acc[14] += 1 (batches)
+// One CTA, fixed-order tree reduction: deterministic. The host reads acc once per validation pass instead of
+// (6 + up to 4) synchronising copies per batch.
+// ---------------------------------------------------------------------------------------------
+struct ValidateParams {
+  const float* controls;
+  const float* pred_speed;
+  const float* targets;
+  const float* speed_target;
+  const long long* command;
+  int batch, mode;
+  float w_steer, w_throttle, w_brake, w_speed;
+  double* acc;
+};
+
+__global__ void __launch_bounds__(256) validate_kernel(const ValidateParams p) {
+  __shared__ float red[12][256];
+  float a[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) a[j] = 0.f;
+  for (int b = threadIdx.x; b < p.batch; b += 256) {
+    const float ds = p.pred_speed[b] - p.speed_target[b];
+    a[3] += ds * ds;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float d = p.controls[b * 3 + j] - p.targets[b * 3 + j];
+      a[j] += p.mode == 0 ? d * d : fabsf(d);
+    }
+    const long long c = p.command[b];
+    const float se = fabsf(p.controls[b * 3] - p.targets[b * 3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (c == k) { a[4 + k] += se; a[8 + k] += 1.f; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 12; ++j) red[j][threadIdx.x] = a[j];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) red[j][threadIdx.x] += red[j][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float invB = 1.f / (float)p.batch;
+    const float steer = red[0][0] * invB, thr = red[1][0] * invB, brk = red[2][0] * invB, spd = red[3][0] * invB;
+    const float control = p.mode == 0 ? (steer + thr + brk) * (1.f / 3.f) : p.w_steer * steer + p.w_throttle * thr + p.w_brake * brk;
+    p.acc[0] += (double)(control + p.w_speed * spd);
+    p.acc[1] += (double)control; p.acc[2] += (double)steer; p.acc[3] += (double)thr; p.acc[4] += (double)brk; p.acc[5] += (double)spd;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { p.acc[6 + k] += (double)red[4 + k][0]; p.acc[10 + k] += (double)red[8 + k][0]; }
+    p.acc[14] += 1.0;
   }
 }
 

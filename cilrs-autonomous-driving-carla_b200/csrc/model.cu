@@ -144,6 +144,7 @@ struct Model {
   float* dcontrols;      // [B,3]
   float* dspeed;         // [B]
   int* err_flag;
+  const long long* drop_counter = nullptr;  // optional device counter mixed into the dropout seed (CUDA-graph replays)
   __nv_bfloat16 *g0, *g1, *ga, *dy_stem;
   // dy ring: the weight-gradient kernels run on a side stream concurrently with the dgrad / BatchNorm chain, so the buffer
   // a wgrad reads must not be overwritten before it finished: block bi uses dyb[bi & 1] (conv_b), dya[bi & 1] (conv_a),
@@ -629,7 +630,7 @@ static int heads_forward(Model& m, int B, const float* speed, const long long* c
   hp.w = head_weights(m, m.params);
   if (keep_for_backward) hp.sv = m.hs; else memset(&hp.sv, 0, sizeof(hp.sv));
   hp.feat = m.feat; hp.speed = speed; hp.command = command; hp.controls = controls; hp.pred_speed = pred_speed;
-  hp.batch = B; hp.dropout_p = dropout_p; hp.seed = seed; hp.error_flag = m.err_flag;
+  hp.batch = B; hp.dropout_p = dropout_p; hp.seed = seed; hp.seed_counter = m.drop_counter; hp.error_flag = m.err_flag;
   heads_fwd_kernel<<<2 * B, HD_THREADS, 0, s>>>(hp); ++g_cilrs_launches;  // two CTAs per sample
   CKL();
   return OK;
@@ -741,14 +742,38 @@ static int heads_backward(Model& m, int B, const float* dcontrols, const float* 
 // async_part: do not make the caller's stream wait for the weight-gradient stream at the end of the part; instead the
 // weight-gradient stream waits for the caller's stream, so that "everything this part wrote" is complete in THAT stream's order
 // (the host enqueues the part's allreduce there and joins once, after the last part: cilrs_model_backward_join)
+// dbg_hi / dbg_lo (test hook, cilrs_model_debug_backward): run only blocks dbg_hi..max(dbg_lo,0) (none if dbg_hi < 0) from the
+// gradient the caller placed in m.g0, plus the stem if dbg_lo < 0; the heads are skipped
 static int backward(Model& m, int B, int mode, int part, const float* dcontrols, const float* dspeed, const float* speed,
-                    const long long* command, float dropout_p, cudaStream_t s, bool async_part = false) {
+                    const long long* command, float dropout_p, cudaStream_t s, bool async_part = false, int dbg_hi = -2,
+                    int dbg_lo = -2) {
+  const bool dbg = dbg_hi != -2;
   if (mode == MODE_INFER) return ERR_INVALID;
   if (B != m.planB || mode != m.planMode) return ERR_INVALID;  // must follow a forward with keep_for_backward
   if (!m.grads) return ERR_INVALID;
   const int frozen = mode == MODE_FROZEN;
   if (part < -1 || part > 4) return ERR_INVALID;
-  if (part <= 0) {
+  if (dbg) {
+    CK(cuda_status(cudaMemsetAsync(m.acc_bwd, 0, (size_t)m.acc_bwd_bytes, s)));
+    if (dbg_hi >= 0) {
+      Block& top = m.blocks[dbg_hi];
+      PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_reduce(m, B, top.b.gout, top.b.bn, m.g0, top.out, top.b.y, s)));
+      if (top.has_ds) {
+        // the downsample BatchNorm is fed by the same masked gradient: its reductions (the regular path gets them from the
+        // fused dgrad of the next block)
+        BnBwdReduceParams rp{};
+        const long long nvec = pad_elems(B, top.b.gout, top.ds.bn.C) / 8;
+        rp.g = m.g0; rp.act = nullptr; rp.y = top.ds.y; rp.mean = top.ds.bn.vec + 2 * top.ds.bn.C; rp.rstd = top.ds.bn.vec + 3 * top.ds.bn.C;
+        rp.nvec = nvec; rp.C = top.ds.bn.C; rp.partial = m.stat_acc; rp.counter = m.counters; rp.bsum = top.ds.bn.bred;
+        rp.bdot = top.ds.bn.bred + top.ds.bn.C; rp.dgamma = m.grads + m.slots[top.ds.bn.gamma].off;
+        rp.dbeta = m.grads + m.slots[top.ds.bn.beta].off; rp.dz_out = nullptr; rp.geom = top.b.gout;
+        ++g_cilrs_launches;
+        CK(cuda_status(launch_pdl(bn_bwd_reduce_kernel<false>, dim3(ew_reduce_grid(nvec, rp.C)), dim3(EW_THREADS), 0, s, rp)));
+      }
+    }
+    m.bw_gcur = m.g0; m.bw_gnext = m.g1;
+    m.bw_deferred = false;
+  } else if (part <= 0) {
     CK(cuda_status(cudaMemsetAsync(m.acc_bwd, 0, (size_t)m.acc_bwd_bytes, s)));  // accumulators of the deferred BN-backward finalize
     {
       cudaStream_t hws = (m.side != nullptr && !m.prof.on) ? m.side : s;
@@ -766,8 +791,8 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   __nv_bfloat16*& gnext = m.bw_gnext;
   // blocks 15..13 = layer4, 12..7 = layer3, 6..3 = layer2, 2..0 = layer1
   static const int part_hi[4] = {15, 12, 6, 2}, part_lo[4] = {13, 7, 3, 0};
-  const int b_hi = part < 0 ? 15 : (part < 4 ? part_hi[part] : -1);
-  const int b_lo = part < 0 ? 0 : (part < 4 ? part_lo[part] : 0);
+  const int b_hi = dbg ? dbg_hi : (part < 0 ? 15 : (part < 4 ? part_hi[part] : -1));
+  const int b_lo = dbg ? (dbg_lo < 0 ? 0 : dbg_lo) : (part < 0 ? 0 : (part < 4 ? part_lo[part] : 0));
   // Weight gradients (and their split-K reduction) run on the side stream: nothing on the dgrad / BatchNorm chain depends on
   // them, and their CTAs fill the SMs the chain leaves idle (98-CTA layer3 grids, HBM-bound elementwise kernels).
   const bool use_side = m.side != nullptr && !m.prof.on;
@@ -850,7 +875,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     for (int i = 0; i < 6; ++i) m.pending[i] = false;
   }
   // ---- stem: max-pool backward + ReLU + BN backward, then wgrad ----
-  if (part < 0 || part == 4) {
+  if (dbg ? dbg_lo < 0 : (part < 0 || part == 4)) {
     const BnRef& bn = m.stem.bn;
     const long long nvec = act_elems(B, 44, 100, 64) / 8;
     const int grid = ew_grid(nvec, 64, 4, 2);
@@ -1114,6 +1139,31 @@ void* cilrs_model_debug_activation(cilrs_model* h, int which, int* dims) {
   return nullptr;
 }
 
+// test hook: backward of blocks hi..max(lo,0) only (hi < 0: none), plus the stem when lo < 0, from a given gradient.
+// g_out: bf16 padded-flat gradient w.r.t. the OUTPUT of block hi (before that block's final ReLU mask is applied), or - stem only -
+// w.r.t. the max-pool output [batch,23,51,64]; its padding pixels must be zero. Must follow a forward(keep_for_backward) of the
+// same batch / mode. Parameter gradients are accumulated into the bound arena as usual; the gradient w.r.t. the input of block
+// max(lo,0) is left in cilrs_model_debug_gradient() (same padded-flat geometry as that input; masked by the previous block's ReLU
+// when lo > 0, exactly as the full backward does).
+int cilrs_model_debug_backward(cilrs_model* h, int batch, int mode, int hi, int lo, const void* g_out, void* stream) {
+  if (!h || !g_out || hi > 15 || lo > hi + 1 || lo < -1 || hi < -1) return ERR_INVALID;
+  Model& m = h->m;
+  if (hi < 0 && lo >= 0) return ERR_INVALID;
+  const PadGeom g = hi >= 0 ? m.blocks[hi].b.gout : kGeom0;
+  const int C = hi >= 0 ? m.blocks[hi].b.d.out_c : 64;
+  CK(cuda_status(cudaMemcpyAsync(m.g0, g_out, (size_t)pad_elems(batch, g, C) * 2, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)));
+  return backward(m, batch, mode, -1, nullptr, nullptr, nullptr, nullptr, 0.f, (cudaStream_t)stream, false, hi, lo);
+}
+void* cilrs_model_debug_gradient(cilrs_model* h) { return h ? (void*)h->m.bw_gcur : nullptr; }
+
+// dropout under a captured CUDA graph: the mask seed of every forward becomes seed + golden * (*counter + 1), with `counter` a
+// device int64 that changes between replays (FusedTrainer passes the optimizer's device step counter). NULL switches it off.
+int cilrs_model_set_dropout_counter(cilrs_model* h, const long long* counter_dev) {
+  if (!h) return ERR_INVALID;
+  h->m.drop_counter = counter_dev;
+  return OK;
+}
+
 void* cilrs_model_input_s2d(cilrs_model* h) { return h ? (void*)h->m.x_s2d : nullptr; }
 int* cilrs_model_error_flag(cilrs_model* h) { return h ? h->m.err_flag : nullptr; }
 
@@ -1219,35 +1269,86 @@ int cilrs_loss(const float* controls, const float* pred_speed, const float* targ
   return cuda_status(cudaGetLastError());
 }
 
+int cilrs_validate_accumulate(const float* controls, const float* pred_speed, const float* targets, const float* speed_target,
+                              const long long* command, int batch, int mode, float w_steer, float w_throttle, float w_brake,
+                              float w_speed, double* acc16, void* stream) {
+  if (!controls || !pred_speed || !targets || !speed_target || !command || !acc16 || batch < 1) return ERR_INVALID;
+  if (mode != 0 && mode != 1) return ERR_INVALID;
+  ValidateParams p;
+  p.controls = controls; p.pred_speed = pred_speed; p.targets = targets; p.speed_target = speed_target; p.command = command;
+  p.batch = batch; p.mode = mode; p.w_steer = w_steer; p.w_throttle = w_throttle; p.w_brake = w_brake; p.w_speed = w_speed; p.acc = acc16;
+  validate_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p); ++g_cilrs_launches;
+  return cuda_status(cudaGetLastError());
+}
+
+static int adam_launch(AdamParams& a, long long* step_dev, cudaStream_t s) {
+  if (step_dev) {
+    step_increment_kernel<<<1, 1, 0, s>>>(step_dev); ++g_cilrs_launches;
+    int st = cuda_status(cudaGetLastError());
+    if (st) return st;
+  }
+  long long blocks = (a.n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_kernel<<<(int)blocks, 256, 0, s>>>(a); ++g_cilrs_launches;
+  return cuda_status(cudaGetLastError());
+}
+
 int cilrs_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, long long step, long long* step_dev, float grad_scale, const float* grad_scale_dev,
                     void* stream) {
   if (!p || !g || !m || !v || n < 0 || (n & 3) || (step < 1 && !step_dev)) return ERR_INVALID;
   if ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) return ERR_INVALID;
   if (n == 0) return OK;
-  AdamParams a;
-  a.p = p; a.g = g; a.m = m; a.v = v; a.n = n; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  AdamParams a{};
+  a.p = p; a.g = const_cast<float*>(g); a.m = m; a.v = v; a.n = n; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
   a.bias_correction1 = step >= 1 ? (float)(1.0 - pow((double)beta1, (double)step)) : 1.f;
   a.bias_correction2_sqrt = step >= 1 ? (float)sqrt(1.0 - pow((double)beta2, (double)step)) : 1.f;
   a.grad_scale = grad_scale; a.grad_scale_dev = grad_scale_dev; a.step_dev = step_dev;
-  if (step_dev) {
-    step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev); ++g_cilrs_launches;
-    int st = cuda_status(cudaGetLastError());
-    if (st) return st;
-  }
-  long long blocks = (n / 4 + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a); ++g_cilrs_launches;
-  return cuda_status(cudaGetLastError());
+  return adam_launch(a, step_dev, (cudaStream_t)stream);
 }
 
-int cilrs_grad_sumsq(const float* g, long long n, double* partial_ws /* >= 1024 doubles */, unsigned int* counter_ws /* zeroed */,
-                     float max_norm, float* out2, void* stream) {
-  if (!g || !partial_ws || !counter_ws || !out2 || n < 0 || (n & 3)) return ERR_INVALID;
+// The CUDA-graph form: every hyper-parameter lives in device memory (hyper_dev float[8] = lr, beta1, beta2, eps, weight_decay,
+// grad_scale, -, -; step_dev int64 incremented on the stream first), so one captured graph follows an LR schedule and resumes
+// from a loaded optimizer state. g_bf16 (optional) replaces g as the gradient source (all-reduced bf16 exchange buffer);
+// zero_grad also clears the fp32 arena g (the next step's optimizer.zero_grad()).
+int cilrs_adam_step_ex(float* p, float* g, const void* g_bf16, float* m, float* v, long long n, const float* hyper_dev,
+                       long long* step_dev, const float* grad_scale_dev, int zero_grad, void* stream) {
+  if (!p || !m || !v || n < 0 || (n & 3) || !hyper_dev || !step_dev) return ERR_INVALID;
+  if (!g && (!g_bf16 || zero_grad)) return ERR_INVALID;
+  if ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v) | ((uintptr_t)hyper_dev)) & 15) return ERR_INVALID;
+  if (((uintptr_t)g_bf16) & 7) return ERR_INVALID;
+  if (n == 0) return OK;
+  AdamParams a{};
+  a.p = p; a.g = g; a.g16 = (const __nv_bfloat16*)g_bf16; a.m = m; a.v = v; a.n = n;
+  a.bias_correction1 = 1.f; a.bias_correction2_sqrt = 1.f; a.grad_scale = 1.f;
+  a.grad_scale_dev = grad_scale_dev; a.step_dev = step_dev; a.hyper_dev = hyper_dev; a.zero_grad = zero_grad;
+  return adam_launch(a, step_dev, (cudaStream_t)stream);
+}
+
+static int sumsq_launch(const float* g, const void* g16, long long n, double* partial_ws, unsigned int* counter_ws, float max_norm,
+                        float* out2, void* stream) {
+  if ((!g && !g16) || !partial_ws || !counter_ws || !out2 || n < 0 || (n & 3)) return ERR_INVALID;
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 592) blocks = 592;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, n, partial_ws, counter_ws, out2, max_norm); ++g_cilrs_launches;
+  sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)g16, n, partial_ws, counter_ws, out2, max_norm); ++g_cilrs_launches;
+  return cuda_status(cudaGetLastError());
+}
+int cilrs_grad_sumsq(const float* g, long long n, double* partial_ws /* >= 1024 doubles */, unsigned int* counter_ws /* zeroed */,
+                     float max_norm, float* out2, void* stream) {
+  return sumsq_launch(g, nullptr, n, partial_ws, counter_ws, max_norm, out2, stream);
+}
+int cilrs_grad_sumsq_bf16(const void* g_bf16, long long n, double* partial_ws, unsigned int* counter_ws, float max_norm, float* out2,
+                          void* stream) {
+  return sumsq_launch(nullptr, g_bf16, n, partial_ws, counter_ws, max_norm, out2, stream);
+}
+
+int cilrs_grad_to_bf16(float* g, void* out_bf16, long long n, int zero_source, void* stream) {
+  if (!g || !out_bf16 || n < 0 || (n & 3) || (((uintptr_t)g) & 15) || (((uintptr_t)out_bf16) & 7)) return ERR_INVALID;
+  if (n == 0) return OK;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  grad_to_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, (__nv_bfloat16*)out_bf16, n, zero_source); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 

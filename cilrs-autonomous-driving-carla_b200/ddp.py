@@ -12,6 +12,21 @@ import torch.distributed as dist
 from . import _lib
 
 
+# which backward parts (0 = heads + layer4, 1 = layer3, 2 = layer2, 3 = layer1, 4 = stem; completed in this order) share one
+# allreduce: a group's collective starts when its LAST part is complete and covers [lo(last part), hi(first part))
+SCHEDULES = {
+    "all": ((0,), (1,), (2,), (3,), (4,)),
+    "two": ((0,), (1,), (2, 3, 4)),
+    "first": ((0,), (1, 2, 3, 4)),
+    "tail": ((0, 1, 2, 3, 4),),
+}
+
+
+def schedule_ranges(part_ranges, schedule):
+    """[(lo, hi)] element range each group of `schedule` exchanges (contiguous because the parts complete back to front)."""
+    return [(part_ranges[g[-1]][0], part_ranges[g[0]][1]) for g in schedule]
+
+
 def backward_part_ranges(model):
     """[(lo, hi)] element ranges of the flat gradient arena completed by backward part 0..4."""
     lib = _lib.lib()

@@ -57,3 +57,49 @@ class CILRSLoss(nn.Module):
             vals = out.tolist()  # one D2H copy / sync instead of six
             return total, dict(zip(_NAMES, vals))
         return total, {n: out[i] for i, n in enumerate(_NAMES)}
+
+
+CMD_NAMES = {0: "FOLLOW", 1: "LEFT", 2: "RIGHT", 3: "STRAIGHT"}   # notebook/notebook.ipynb:583
+
+
+class Validator:
+    """Device-side accumulator behind `validate()` (notebook/notebook.ipynb:563-585): per batch ONE kernel adds the six loss
+    scalars and the per-command steer absolute errors / counts to a 16-double device buffer; `result()` does the only D2H copy
+    of the pass. The reference reads 6 `.item()`s and up to 4 masked `.cpu()` tensors per batch."""
+
+    def __init__(self, criterion, device="cuda"):
+        self.criterion = criterion
+        self.acc = torch.zeros(16, dtype=torch.float64, device=device)
+
+    def reset(self):
+        self.acc.zero_()
+
+    def update(self, pred_controls, target_controls, pred_speed, target_speed, command):
+        c = self.criterion
+        _lib.call("cilrs_validate_accumulate", pred_controls.contiguous().float(), pred_speed.contiguous().float(),
+                  target_controls.contiguous().float(), target_speed.contiguous().float(), command.contiguous(),
+                  int(pred_controls.shape[0]), 1 if c.mode == "l1" else 0, ctypes.c_float(c.steer_w), ctypes.c_float(c.throttle_w),
+                  ctypes.c_float(c.brake_w), ctypes.c_float(c.speed_w), self.acc, _lib.stream_ptr())
+
+    def result(self):
+        """({total, control, steer, throttle, brake, speed} averaged over batches, {FOLLOW, LEFT, RIGHT, STRAIGHT} mean steer
+        error, nan where a command never occurred) — the pair the reference's validate() returns."""
+        a = self.acc.tolist()
+        n = max(a[14], 1.0)
+        losses = {k: a[i] / n for i, k in enumerate(_NAMES)}
+        cmd_avg = {CMD_NAMES[k]: (a[6 + k] / a[10 + k] if a[10 + k] > 0 else float("nan")) for k in range(4)}
+        return losses, cmd_avg
+
+
+def validate(model, loader, criterion, device):
+    """Drop-in for the notebook's validate(model, loader, criterion, device) (notebook/notebook.ipynb:563-585): eval-mode
+    forward over the loader, mean losses and per-command steer MAE — with no host synchronisation inside the loop."""
+    model.eval()
+    v = Validator(criterion, device)
+    with torch.no_grad():
+        for imgs, speeds, cmds, tgts in loader:
+            imgs, speeds, cmds, tgts = (imgs.to(device, non_blocking=True), speeds.to(device, non_blocking=True),
+                                        cmds.to(device, non_blocking=True), tgts.to(device, non_blocking=True))
+            pred_ctrl, pred_spd = model(imgs, speeds, cmds)
+            v.update(pred_ctrl, tgts, pred_spd, speeds, cmds)
+    return v.result()

@@ -166,7 +166,14 @@ class CILRS(nn.Module):
         self._fkey = None         # (parameter, buffer) version the folded eval-mode BN vectors were made from
         self._extra_w = 0         # bumped by code that writes the parameter arena through raw pointers (FusedAdam)
         self._extra_b = 0         # same for the BN running statistics (train-mode forward)
-        self._seed = 0x5EED
+        # dropout mask stream: follows torch.manual_seed and differs per data-parallel rank (identical masks on every rank
+        # for the same local sample index would correlate the replicas)
+        rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank = torch.distributed.get_rank()
+        self._seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + 0x5EED + (rank << 40)) & 0xFFFFFFFFFFFFFFFF
+        self._plan_gen = 0        # bumped whenever the C plan / workspace is rebuilt: FusedTrainer / InferenceSession check it
+        self._plist = None
         self._flatten()
 
     # ------------------------------------------------------------------------------------------
@@ -200,6 +207,7 @@ class CILRS(nn.Module):
             o += 2 * c
         self._flat, self._flat_buf, self._flat_nbt = flat, fbuf, nbt
         self._flat_grad = None
+        self._plist = plist
         self._destroy_handle()
 
     def _apply(self, fn, *args, **kwargs):
@@ -215,6 +223,7 @@ class CILRS(nn.Module):
         self._max_batch = 0
         self._wkey = None
         self._fkey = None
+        self._plan_gen = getattr(self, "_plan_gen", 0) + 1
 
     def __del__(self):
         try:
@@ -274,8 +283,13 @@ class CILRS(nn.Module):
         if self._handle is not None:
             _lib.call("cilrs_model_bind", self._handle, self._flat, self._flat_grad, self._flat_buf, self._flat_nbt)
 
+    def _param_version(self):
+        # `p.data = flat[...]` (see _flatten) leaves every parameter with its OWN version counter: in-place updates made through
+        # the parameters (torch.optim.Adam.step(), load_state_dict(), p.mul_()) bump p._version, not flat._version
+        return sum(p._version for p in self._plist) + self._flat._version
+
     def _refresh_if_needed(self, infer):
-        wkey = (self._flat._version, self._extra_w)
+        wkey = (self._param_version(), self._extra_w)
         what = 0
         if wkey != self._wkey:
             what |= 1
@@ -293,7 +307,7 @@ class CILRS(nn.Module):
         operands were already refreshed on the stream (so the next forward need not do it again)."""
         self._extra_w += 1
         if repacked:
-            self._wkey = (self._flat._version, self._extra_w)
+            self._wkey = (self._param_version(), self._extra_w)
 
     def _check_inputs(self, image, speed, command):
         if image.dim() != 4 or tuple(image.shape[1:]) != (3, IMG_H, IMG_W):
@@ -334,6 +348,47 @@ class CILRS(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return _Function.apply(self, image, speed, command, *self.parameters())
         return self._launch_forward(image, speed, command, keep=False)
+
+    def _workspace_view(self, ptr, nbytes):
+        start = ptr - self._workspace.data_ptr()
+        if start < 0 or start + nbytes > self._workspace.numel():
+            raise RuntimeError("cilrs_b200: pointer outside the model workspace")
+        return self._workspace[start:start + nbytes]
+
+    def error_flag(self):
+        """int32[1] device tensor the kernels set to 1 when a command outside {0,1,2,3} was seen (the reference's gather
+        would raise, model/autonomous_drive.py:395-398; here the command is clamped and the flag raised)."""
+        self._ensure(max(1, self._max_batch))
+        lib = _lib.lib()
+        lib.cilrs_model_error_flag.restype = ctypes.c_void_p
+        return self._workspace_view(lib.cilrs_model_error_flag(self._handle), 4).view(torch.int32)
+
+    def check_errors(self):
+        """Synchronising check of the device error flag; raises like the reference's out-of-range gather would."""
+        if self._handle is None:
+            return
+        flag = self.error_flag()
+        if int(flag.item()) != 0:
+            flag.zero_()
+            raise IndexError("cilrs_b200: a command index outside [0, %d) reached the model" % self.num_commands)
+
+    def debug_backward(self, batch, hi, lo, g_out):
+        """Test hook (cilrs_model_debug_backward): backward of blocks hi..max(lo,0) (+ the stem when lo < 0) from `g_out`, a bf16
+        padded-flat gradient w.r.t. block hi's output; returns the bf16 padded-flat gradient w.r.t. the input of block max(lo,0)."""
+        lib = _lib.lib()
+        _lib.call("cilrs_model_debug_backward", self._handle, int(batch), self._last_mode, int(hi), int(lo), g_out.contiguous(),
+                  _lib.stream_ptr())
+        lib.cilrs_model_debug_gradient.restype = ctypes.c_void_p
+        ptr = lib.cilrs_model_debug_gradient(self._handle)
+        first = max(lo, 0)
+        if hi < 0:
+            return None  # stem only: the gradient w.r.t. the image is not computed (the input needs none)
+        dims = (ctypes.c_int * 5)()
+        lib.cilrs_model_debug_activation.restype = ctypes.c_void_p
+        lib.cilrs_model_debug_activation(self._handle, int(first), dims)   # activation `first` is the input of block `first`
+        h, w, c, hp, wp = dims[0], dims[1], dims[2], dims[3], dims[4]
+        n = batch * hp * wp * c * 2
+        return self._workspace_view(ptr, n).view(torch.bfloat16).view(batch, hp, wp, c)
 
     def input_s2d_buffer(self, batch):
         """bf16 [batch,47,103,16] view of the plan's conv1 input: the preprocessing kernel can write frames there directly."""

@@ -2,8 +2,12 @@
 
 `FusedAdam(model.parameters(), lr, weight_decay=...)` is a `torch.optim.Optimizer` with torch.optim.Adam's semantics
 (L2-coupled weight decay, bias correction, eps outside the sqrt — notebook/notebook.ipynb:533-534,555) and state layout
-(`state[p] = {step, exp_avg, exp_avg_sq}`, so `optimizer.state_dict()` stays interchangeable), but one kernel launch
-updates every parameter: p, g, m, v are single contiguous fp32 buffers.
+(`state[p] = {step, exp_avg, exp_avg_sq}`, so `optimizer.state_dict()` / `load_state_dict()` stay interchangeable with
+torch.optim.Adam's), but one kernel launch updates every parameter: p, g, m, v are single contiguous fp32 buffers.
+
+Every hyper-parameter the kernel uses (lr, betas, eps, weight_decay, the 1/world gradient scale) and the step number live in
+DEVICE memory, so a CUDA graph captured around `step()` keeps following `param_groups[0]["lr"]` — the reference halves the rate
+every 8 epochs with `StepLR` (notebook/notebook.ipynb:535-536,604) — and resumes correctly from a loaded optimizer state.
 """
 import ctypes
 
@@ -25,12 +29,33 @@ class FusedAdam(torch.optim.Optimizer):
         if len(plist) != len(params) or any(a is not b for a, b in zip(plist, params)):
             raise ValueError("FusedAdam must be given exactly model.parameters()")
         flat = model.flat_parameters()
+        if not flat.is_cuda:
+            raise RuntimeError("FusedAdam: create the optimizer after model.to('cuda') (there is no CPU path)")
         self._m = torch.zeros_like(flat)
         self._v = torch.zeros_like(flat)
-        self._step = 0
-        self._step_dev = torch.zeros(1, dtype=torch.long, device=flat.device) if flat.is_cuda else None
-        for p, mv, vv in zip(plist, model._views(self._m), model._views(self._v)):
-            self.state[p] = {"step": torch.tensor(0.0), "exp_avg": mv, "exp_avg_sq": vv}
+        self._step = 0                      # host mirror of the device step counter
+        self._step_dev = torch.zeros(1, dtype=torch.long, device=flat.device)
+        self._hyper = torch.zeros(8, dtype=torch.float32, device=flat.device)
+        self._hyper_host = None             # the values last uploaded
+        self._point_state_at_views()
+
+    # ------------------------------------------------------------------------------------------
+    def _point_state_at_views(self):
+        model = self.model
+        for p, mv, vv in zip(model.parameters(), model._views(self._m), model._views(self._v)):
+            self.state[p] = {"step": torch.tensor(float(self._step)), "exp_avg": mv, "exp_avg_sq": vv}
+
+    def _sync_hyper(self, grad_scale=1.0):
+        """Upload (lr, betas, eps, weight_decay, grad_scale) when they differ from what the device holds. Stream-ordered, so a
+        change made between two graph replays applies to the later one."""
+        grp = self.param_groups[0]
+        vals = (float(grp["lr"]), float(grp["betas"][0]), float(grp["betas"][1]), float(grp["eps"]), float(grp["weight_decay"]),
+                float(grad_scale), 0.0, 0.0)
+        if vals != self._hyper_host:
+            staging = torch.tensor(vals, dtype=torch.float32).pin_memory()
+            self._hyper.copy_(staging, non_blocking=True)
+            self._staging = staging  # keep the pinned buffer alive until the copy has run
+            self._hyper_host = vals
 
     def _gather_grads(self):
         """Gradients normally already live in the model's flat arena (autograd hands out views of it); anything else
@@ -45,25 +70,57 @@ class FusedAdam(torch.optim.Optimizer):
         return g
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale=1.0, grad_scale_dev=None, grads_in_arena=False):
+    def step(self, closure=None, grad_scale=1.0, grad_scale_dev=None, grads_in_arena=False, grads_bf16=None, zero_grad=False):
+        """grad_scale / grad_scale_dev: host / device factors applied to the gradient first (1/world, clip coefficient).
+        grads_bf16: bf16 gradient buffer (arena layout) used instead of the fp32 arena. zero_grad: also clear the fp32 arena
+        (the next step's optimizer.zero_grad())."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        grp = self.param_groups[0]
         model = self.model
         flat = model.flat_parameters()
-        if self._m.device != flat.device or self._m.data_ptr() == 0:
+        if self._m.device != flat.device:
             raise RuntimeError("FusedAdam: the model moved to another device after the optimizer was created")
-        g = model.flat_gradients() if grads_in_arena else self._gather_grads()
+        g = model.flat_gradients() if (grads_in_arena or grads_bf16 is not None) else self._gather_grads()
+        self._sync_hyper(grad_scale)
         self._step += 1
-        if self._step_dev is None:
-            raise RuntimeError("FusedAdam: create the optimizer after model.to('cuda')")
-        _lib.call("cilrs_adam_step", flat, g, self._m, self._v, ctypes.c_longlong(flat.numel()), ctypes.c_float(grp["lr"]),
-                  ctypes.c_float(grp["betas"][0]), ctypes.c_float(grp["betas"][1]), ctypes.c_float(grp["eps"]),
-                  ctypes.c_float(grp["weight_decay"]), ctypes.c_longlong(0), self._step_dev, ctypes.c_float(grad_scale),
-                  grad_scale_dev, _lib.stream_ptr())
+        _lib.call("cilrs_adam_step_ex", flat, g, grads_bf16, self._m, self._v, ctypes.c_longlong(flat.numel()), self._hyper,
+                  self._step_dev, grad_scale_dev, int(bool(zero_grad)), _lib.stream_ptr())
         model.mark_parameters_changed()
-        for st in self.state.values():
-            st["step"] = torch.tensor(float(self._step))
         return loss
+
+    # ------------------------------------------------------------------------------------------
+    # checkpoint interchange with torch.optim.Adam (notebook/notebook.ipynb:642-646 saves optimizer.state_dict())
+    # ------------------------------------------------------------------------------------------
+    def state_dict(self):
+        step = torch.tensor(float(self._step))
+        for st in self.state.values():
+            st["step"] = step.clone()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """Accepts FusedAdam's own and torch.optim.Adam's state dicts: the loaded moments are copied into the flat m / v arenas
+        the kernel reads, and the device step counter is set from the loaded step."""
+        super().load_state_dict(state_dict)
+        model = self.model
+        plist = list(model.parameters())
+        steps = set()
+        with torch.no_grad():
+            for p, mv, vv in zip(plist, model._views(self._m), model._views(self._v)):
+                st = self.state.get(p)
+                if not st:
+                    mv.zero_()
+                    vv.zero_()
+                    steps.add(0)
+                    continue
+                mv.copy_(st["exp_avg"])
+                vv.copy_(st["exp_avg_sq"])
+                steps.add(int(float(st["step"])))
+        if len(steps) != 1:
+            raise ValueError("FusedAdam.load_state_dict: parameters have different step counts (%s); one shared step is "
+                             "supported (the whole model is one parameter group)" % sorted(steps))
+        self._step = steps.pop()
+        self._step_dev.fill_(self._step)
+        self._hyper_host = None  # param_groups may have been replaced: upload again
+        self._point_state_at_views()

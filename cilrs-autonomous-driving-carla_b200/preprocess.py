@@ -56,6 +56,7 @@ class InferenceSession:
         self.batch = batch
         self.reverse = reverse
         dev = model.flat_parameters().device
+        model._ensure(batch)
         self.h_frames = torch.empty(batch, src_hw[0], src_hw[1], src_c, dtype=torch.uint8).pin_memory()
         self.h_speed = torch.empty(batch, dtype=torch.float32).pin_memory()
         self.h_command = torch.empty(batch, dtype=torch.long).pin_memory()
@@ -65,6 +66,9 @@ class InferenceSession:
         self.d_command = torch.zeros(batch, dtype=torch.long, device=dev)
         self.d_out = torch.empty(batch, 4, dtype=torch.float32, device=dev)
         self.s2d = model.input_s2d_buffer(batch)
+        self.err = model.error_flag()
+        self.h_err = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._plan_gen = model._plan_gen
         self.graph = None
         self.stream = torch.cuda.Stream(device=dev)
         with torch.no_grad():
@@ -93,6 +97,9 @@ class InferenceSession:
     @torch.no_grad()
     def run(self):
         """h_frames / h_speed / h_command (pinned) -> h_out (pinned): H2D, kernels, D2H on the session stream, then sync."""
+        if self.model._plan_gen != self._plan_gen:
+            raise RuntimeError("cilrs_b200.InferenceSession: the model's plan was rebuilt (a larger batch went through the module, "
+                               "or it moved device) after this session was created; create a new InferenceSession")
         with torch.cuda.stream(self.stream):
             self.d_frames.copy_(self.h_frames, non_blocking=True)
             self.d_speed.copy_(self.h_speed, non_blocking=True)
@@ -102,7 +109,11 @@ class InferenceSession:
             else:
                 self._body()
             self.h_out.copy_(self.d_out, non_blocking=True)
+            self.h_err.copy_(self.err, non_blocking=True)
         self.stream.synchronize()
+        if int(self.h_err[0]) != 0:   # the reference's gather(0, command) raises on an out-of-range command
+            self.err.zero_()
+            raise IndexError("cilrs_b200: a command index outside [0, 4) reached the model")
         return self.h_out
 
     def predict(self, image, speed_kmh, command_idx):
@@ -111,3 +122,48 @@ class InferenceSession:
         self.h_command[0] = int(command_idx)
         o = self.run()[0]
         return float(o[0]), float(o[1]), float(o[2]), float(o[3]) * SPEED_NORM_FACTOR
+
+
+class ShardedInference:
+    """BASELINE.json configs[4]: batched CILRS inference (multi-agent rollout) sharded across the GPUs of one box. The batch
+    dimension shards with no data-path collective: rank r owns frames [r*per_rank, (r+1)*per_rank); every rank runs its own
+    `InferenceSession(batch=per_rank)` (one CUDA graph: H2D, K0, forward, D2H). `gather()` collects the [B,4] results on every
+    rank (16 bytes per frame) when one host wants them; it is the only communication. World size 1 works without
+    torch.distributed."""
+
+    def __init__(self, model, global_batch, src_hw=(600, 800), src_c=3, reverse=False, process_group=None, use_graph=True):
+        import torch.distributed as dist
+        self.pg = process_group
+        self.world, self.rank = 1, 0
+        if dist.is_available() and dist.is_initialized():
+            self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        if global_batch % self.world:
+            raise ValueError("global_batch must be a multiple of the world size")
+        self.global_batch = global_batch
+        self.per_rank = global_batch // self.world
+        self.session = InferenceSession(model, batch=self.per_rank, src_hw=src_hw, src_c=src_c, reverse=reverse, use_graph=use_graph)
+
+    def shard(self):
+        """(lo, hi) global frame indices this rank owns."""
+        return self.rank * self.per_rank, (self.rank + 1) * self.per_rank
+
+    def predict_batch(self, frames_u8, speed_kmh, command_idx):
+        """frames_u8 uint8 [per_rank,H,W,C], speed_kmh float [per_rank], command_idx int [per_rank] (this rank's shard, host
+        tensors / arrays) -> pinned float [per_rank,4] = (steer, throttle, brake, speed_kmh)."""
+        s = self.session
+        s.h_frames.copy_(torch.as_tensor(frames_u8))
+        s.h_speed.copy_(torch.clamp(torch.as_tensor(speed_kmh, dtype=torch.float32) / SPEED_NORM_FACTOR, max=1.0))
+        s.h_command.copy_(torch.as_tensor(command_idx, dtype=torch.long))
+        out = s.run()
+        out[:, 3] *= SPEED_NORM_FACTOR
+        return out
+
+    def gather(self, local_out):
+        """[per_rank,4] of every rank -> [global_batch,4] on every rank (a 16 B/frame all_gather; identity at world size 1)."""
+        if self.world == 1:
+            return local_out.clone()
+        import torch.distributed as dist
+        dev = self.session.d_out.device
+        full = torch.empty(self.global_batch, 4, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(full, local_out.to(dev, non_blocking=True), group=self.pg)
+        return full.cpu()

@@ -1,19 +1,24 @@
 """The fused training step (reference: train_one_epoch body, notebook/notebook.ipynb:545-555) and its data-parallel form.
 
-    H2D -> [K0 normalise] -> forward -> loss -> zero_grad -> backward -> [allreduce] -> [clip] -> Adam -> repack
+    H2D -> [K0 normalise] -> forward -> loss -> backward -> [allreduce] -> [clip] -> Adam (+ zero_grad) -> repack
 
 Everything after the H2D copies is device work launched through the C-ABI with no host synchronisation; with
-`use_graph=True` the whole step (with N > 1 including the NCCL allreduces) is one CUDA-graph replay. Data parallelism shards the batch across ranks
-(one process per GPU); the flat gradient arena is all-reduced over NCCL in five ranges that complete back-to-front
-(heads+layer4, layer3, layer2, layer1, stem), each range's allreduce overlapping the backward of the next one.
-BatchNorm statistics stay per rank (plain-DDP semantics; the reference has no SyncBN).
+`use_graph=True` the whole step (with N > 1 including the NCCL allreduces) is one CUDA-graph replay. Everything that varies
+from step to step lives in device memory — the Adam step number and hyper-parameters (so `StepLR`, notebook.ipynb:535-536,604,
+keeps working on the captured graph), the clip coefficient (`clip_grad_norm_(…, 1.0)`, :553-554) and the dropout mask counter
+(`dropout=0.5`, :480) — so the reference's executed recipe runs on the replayed graph unchanged.
+
+Data parallelism shards the batch across ranks (one process per GPU); the gradient arena is all-reduced over NCCL in groups
+of the five ranges the backward completes back-to-front (heads+layer4, layer3, layer2, layer1, stem), each group's allreduce
+overlapping the backward of the next one; `grad_comm="bf16"` exchanges bf16 gradients (half the bytes; Adam's moments and the
+master weights stay fp32). BatchNorm statistics stay per rank (plain-DDP semantics; the reference has no SyncBN).
 """
 import ctypes
 
 import torch
 
 from . import _lib
-from .ddp import allreduce_ranges, backward_part_ranges, broadcast_parameters
+from .ddp import SCHEDULES, allreduce_ranges, backward_part_ranges, broadcast_parameters
 from .model import MODE_TRAIN
 from .optim import FusedAdam
 
@@ -21,12 +26,21 @@ from .optim import FusedAdam
 class FusedTrainer:
     def __init__(self, model, batch, lr=2e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, loss="mse", steer_w=5.0,
                  throttle_w=1.0, brake_w=1.0, speed_w=0.05, grad_clip=0.0, process_group=None, use_graph=False, frames="f32",
-                 async_parts=False, overlap_allreduce="first"):
-        # overlap_allreduce: True = every backward part's range as soon as it is complete; False = one allreduce after the
-        # backward; "first" = only the first part (heads + layer4, 64 % of the bytes) overlapped - it runs under layer3's
-        # backward, whose 98-CTA conv grids leave SMs free for NCCL's CTAs - and one allreduce for the rest at the end
+                 async_parts=False, overlap_allreduce="two", grad_comm="bf16"):
+        # overlap_allreduce: a key of ddp.SCHEDULES (or True = "all", False = "tail"): which backward parts share an allreduce
+        #   "all"   every part's range as soon as it is complete
+        #   "two"   heads+layer4 | layer3 | layer2+layer1+stem  (the default: the exposed tail is 1.35 M of 22.4 M gradients)
+        #   "first" heads+layer4 early, the rest after the backward    "tail" one allreduce after the backward
         if frames not in ("f32", "u8"):
             raise ValueError("frames: 'f32' ([B,3,88,200] normalised, as the reference's loader yields) or 'u8' ([B,88,200,3])")
+        if grad_comm not in ("bf16", "fp32"):
+            raise ValueError("grad_comm: 'bf16' or 'fp32'")
+        if overlap_allreduce is True:
+            overlap_allreduce = "all"
+        elif overlap_allreduce is False:
+            overlap_allreduce = "tail"
+        if overlap_allreduce not in SCHEDULES:
+            raise ValueError("overlap_allreduce: one of %s" % sorted(SCHEDULES))
         self.model = model
         self.batch = batch
         self.opt = FusedAdam(model.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, model=model)
@@ -40,10 +54,11 @@ class FusedTrainer:
         self.frames = frames
         dev = model.flat_parameters().device
         self.dev = dev
-        if use_graph and model.dropout > 0:
-            raise ValueError("use_graph replays one dropout mask; train with dropout through the eager step")
         model.train()
         model._ensure(batch)
+        self._plan_gen = model._plan_gen
+        # dropout masks follow the optimizer's DEVICE step counter, so a replayed graph draws a new mask every step
+        _lib.call("cilrs_model_set_dropout_counter", model._handle, self.opt._step_dev)
         if self.world > 1:
             broadcast_parameters(model, 0, process_group)
         self.d_image = torch.zeros(batch, 3, 88, 200, dtype=torch.float32, device=dev) if frames == "f32" else None
@@ -58,18 +73,19 @@ class FusedTrainer:
         self.loss6 = torch.zeros(6, dtype=torch.float32, device=dev)
         self.norm_ws = torch.zeros(1024, dtype=torch.float64, device=dev)
         self.norm_cnt = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.norm_out = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.norm_out = torch.zeros(2, dtype=torch.float32, device=dev)   # [sum of squares, clip coefficient]
         self.s2d = model.input_s2d_buffer(batch)
+        self.err = model.error_flag()
         self.part_ranges = backward_part_ranges(model)
-        # async_parts: enqueue each part's allreduce behind the model's gradient stream instead of joining that stream into the
-        # caller's after every part (cilrs_model_backward_part_async). Measured on 2 GPUs: 3.38 ms/step when the host reads the
-        # loss every step (3.52 joined) but 3.63 ms for back-to-back graph replays (3.41 joined) - hence off by default.
+        self.schedule = SCHEDULES[overlap_allreduce]
+        self.overlap_allreduce = overlap_allreduce
+        # async_parts: enqueue each group's (conversion and) allreduce behind the model's gradient stream instead of joining
+        # that stream into the caller's after every group: the dgrad / BatchNorm chain never waits for a weight gradient
         self.async_parts = bool(async_parts)
-        # overlap_allreduce=False: one allreduce of the whole gradient arena after the backward (no NCCL CTAs competing with the
-        # convolutions for SMs, but the collective is fully exposed)
-        self.overlap_allreduce = overlap_allreduce if overlap_allreduce == "first" else bool(overlap_allreduce)
+        self.grad_comm = grad_comm if self.world > 1 else "fp32"
+        self.g16 = torch.zeros(model.flat_parameters().numel(), dtype=torch.bfloat16, device=dev) if self.grad_comm == "bf16" else None
+        model.flat_gradients().zero_()   # from here on Adam / the bf16 conversion leave the arena zeroed for the next step
         self.graph = None
-        self.kernel_launches = None
         self.graph_error = None
         if use_graph:
             if self.world > 1:
@@ -85,6 +101,16 @@ class FusedTrainer:
                 self._capture()
 
     # ------------------------------------------------------------------------------------------
+    def _backward_args(self):
+        return (self.dcontrols, self.dspeed, self.d_speed, self.d_command, ctypes.c_float(self.model.dropout), _lib.stream_ptr())
+
+    def _exchange(self, g, lo, hi):
+        """Start the allreduce of gradient range [lo, hi) on the current stream's order; returns work handles."""
+        if self.grad_comm == "bf16":
+            _lib.call("cilrs_grad_to_bf16", g[lo:hi], self.g16[lo:hi], ctypes.c_longlong(hi - lo), 1, _lib.stream_ptr())
+            return allreduce_ranges(self.g16, [(lo, hi)], self.pg)
+        return allreduce_ranges(g, [(lo, hi)], self.pg)
+
     def _device_step(self):
         m = self.model
         b = self.batch
@@ -100,57 +126,45 @@ class FusedTrainer:
         _lib.call("cilrs_loss", self.controls, self.pred_speed, self.d_targets, self.d_speed, b, self.loss_mode,
                   ctypes.c_float(self.ws[0]), ctypes.c_float(self.ws[1]), ctypes.c_float(self.ws[2]), ctypes.c_float(self.ws[3]),
                   ctypes.c_float(1.0), self.loss6, self.dcontrols, self.dspeed, sp)
-        g = m.flat_gradients()
-        g.zero_()
-        works = []
-        if self.world > 1 and self.overlap_allreduce == "first":
-            args = (self.dcontrols, self.dspeed, self.d_speed, self.d_command, ctypes.c_float(m.dropout), sp)
-            _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, 0, *args)
-            works.extend(allreduce_ranges(g, [self.part_ranges[0]], self.pg))
-            for part in range(1, 5):
-                _lib.call("cilrs_model_backward_part_async", m._handle, b, MODE_TRAIN, part, *args)
-            _lib.call("cilrs_model_backward_join", m._handle, sp)
-            works.extend(allreduce_ranges(g, [(0, self.part_ranges[0][0])], self.pg))
-            for w in works:
-                w.wait()
-        elif self.world > 1 and not self.overlap_allreduce:
-            _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, -1, self.dcontrols, self.dspeed, self.d_speed,
-                      self.d_command, ctypes.c_float(m.dropout), sp)
-            for w in allreduce_ranges(g, [(0, g.numel())], self.pg):
-                w.wait()
-        elif self.world > 1:
-            # The backward runs in five parts; the allreduce of a part's gradient range is enqueued behind the model's
-            # gradient stream (where the part's weight gradients finish) while the caller's stream already runs the next
-            # part: the dgrad / BatchNorm chain never waits for a weight gradient or a collective. One join at the end.
+        g = m.flat_gradients()   # zero on entry: the previous step's Adam / bf16 conversion cleared it (optimizer.zero_grad())
+        if self.world > 1:
+            works = []
             lib = _lib.lib()
             lib.cilrs_model_gradient_stream.restype = ctypes.c_void_p
             lib.cilrs_model_gradient_stream.argtypes = [ctypes.c_void_p]
-            gs_ptr = lib.cilrs_model_gradient_stream(m._handle)
-            gstream = torch.cuda.ExternalStream(gs_ptr, device=self.dev) if (gs_ptr and self.async_parts) else None
-            for part in range(5):
+            gs_ptr = lib.cilrs_model_gradient_stream(m._handle) if self.async_parts else None
+            gstream = torch.cuda.ExternalStream(gs_ptr, device=self.dev) if gs_ptr else None
+            for group in self.schedule:
+                lo, hi = self.part_ranges[group[-1]][0], self.part_ranges[group[0]][1]
                 if gstream is not None:
-                    _lib.call("cilrs_model_backward_part_async", m._handle, b, MODE_TRAIN, part, self.dcontrols, self.dspeed,
-                              self.d_speed, self.d_command, ctypes.c_float(m.dropout), sp)
+                    # everything the group wrote is complete in the ORDER OF the gradient stream: exchange it there
+                    for part in group:
+                        _lib.call("cilrs_model_backward_part_async", m._handle, b, MODE_TRAIN, part, *self._backward_args())
                     with torch.cuda.stream(gstream):
-                        works.extend(allreduce_ranges(g, [self.part_ranges[part]], self.pg))
+                        works.extend(self._exchange(g, lo, hi))
                 else:
-                    _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, part, self.dcontrols, self.dspeed, self.d_speed,
-                              self.d_command, ctypes.c_float(m.dropout), sp)
-                    works.extend(allreduce_ranges(g, [self.part_ranges[part]], self.pg))
+                    for part in group[:-1]:
+                        _lib.call("cilrs_model_backward_part_async", m._handle, b, MODE_TRAIN, part, *self._backward_args())
+                    _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, group[-1], *self._backward_args())  # joins the gradient stream
+                    works.extend(self._exchange(g, lo, hi))
             if gstream is not None:
                 _lib.call("cilrs_model_backward_join", m._handle, sp)
             for w in works:
                 w.wait()
         else:
-            _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, -1, self.dcontrols, self.dspeed, self.d_speed,
-                      self.d_command, ctypes.c_float(m.dropout), sp)
+            _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, -1, *self._backward_args())
         scale_dev = None
         if self.grad_clip > 0:
-            # norm of the averaged gradient = norm of the summed one / world
-            _lib.call("cilrs_grad_sumsq", g, ctypes.c_longlong(g.numel()), self.norm_ws, self.norm_cnt,
-                      ctypes.c_float(self.grad_clip * self.world), self.norm_out, sp)
+            # clip_grad_norm_ on the AVERAGED gradient: norm(avg) = norm(sum) / world, so the bound is scaled instead
+            if self.g16 is not None:
+                _lib.call("cilrs_grad_sumsq_bf16", self.g16, ctypes.c_longlong(g.numel()), self.norm_ws, self.norm_cnt,
+                          ctypes.c_float(self.grad_clip * self.world), self.norm_out, sp)
+            else:
+                _lib.call("cilrs_grad_sumsq", g, ctypes.c_longlong(g.numel()), self.norm_ws, self.norm_cnt,
+                          ctypes.c_float(self.grad_clip * self.world), self.norm_out, sp)
             scale_dev = self.norm_out[1:]
-        self.opt.step(grad_scale=1.0 / self.world, grad_scale_dev=scale_dev, grads_in_arena=True)
+        self.opt.step(grad_scale=1.0 / self.world, grad_scale_dev=scale_dev, grads_in_arena=True, grads_bf16=self.g16,
+                      zero_grad=self.g16 is None)
         _lib.call("cilrs_model_refresh", m._handle, 1, sp)
         self._after_step()
 
@@ -164,13 +178,14 @@ class FusedTrainer:
 
     def _capture(self):
         """Warm up on a side stream, restore the state the warm-up mutated, then capture one step into a CUDA graph.
-        (The Adam step number lives in device memory, so the same graph is valid for every step.)"""
+        (Step number, hyper-parameters, clip coefficient and dropout counter live in device memory, so the same graph is valid
+        for every step.)"""
         s = torch.cuda.Stream(device=self.dev)
         m = self.model
         m._refresh_if_needed(infer=False)
         state = (m.flat_parameters(), self.opt._m, self.opt._v, m._flat_buf, m._flat_nbt, self.opt._step_dev)
         saved = [t.clone() for t in state]
-        step0 = self.opt._step
+        step0, seed0 = self.opt._step, m._seed
         torch.cuda.synchronize(self.dev)
         with torch.cuda.stream(s):
             for _ in range(2):
@@ -186,6 +201,8 @@ class FusedTrainer:
             for t, sv in zip(state, saved):
                 t.copy_(sv)
             self.opt._step = step0
+            m._seed = seed0
+            m.flat_gradients().zero_()
             _lib.call("cilrs_model_refresh", m._handle, 1, _lib.stream_ptr())
             torch.cuda.synchronize(self.dev)
 
@@ -201,10 +218,30 @@ class FusedTrainer:
     def step(self):
         """One optimisation step on the loaded batch. Returns the device tensor of the 6 loss scalars
         (total, control, steer, throttle, brake, speed) — no host sync."""
+        if self.model._plan_gen != self._plan_gen:
+            raise RuntimeError("cilrs_b200.FusedTrainer: the model's plan was rebuilt (a larger batch went through the module, or it "
+                               "moved device) after this trainer was created; create a new FusedTrainer")
         if self.graph is not None:
+            self.opt._sync_hyper(1.0 / self.world)   # lr / weight-decay changes (StepLR) reach the captured kernels here
             self.graph.replay()
             self.opt._step += 1
             self._after_step()
         else:
             self._device_step()
         return self.loss6
+
+    def read_loss(self):
+        """Host copy of the 6 loss scalars (one D2H sync) — also the point where an out-of-range command raises, like the
+        reference's gather would."""
+        vals = torch.cat([self.loss6, self.err.float()]).tolist()
+        if vals[6] != 0:
+            self.err.zero_()
+            raise IndexError("cilrs_b200: a command index outside [0, 4) reached the model")
+        return dict(zip(("total", "control", "steer", "throttle", "brake", "speed"), vals[:6]))
+
+    def close(self):
+        """Drop the captured graph (it references the process group's communicator) before the process group is destroyed."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.dev)
+            self.graph.reset()
+            self.graph = None

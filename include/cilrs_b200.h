@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CILRS_ABI_VERSION 2
+#define CILRS_ABI_VERSION 3
 
 int cilrs_abi_version(void);
 /* human-readable text for a status code returned by any entry point (static storage) */
@@ -217,6 +217,16 @@ void* cilrs_model_input_s2d(cilrs_model* m); /* where K0 may write the conv1-rea
  * [:, :H, :W] (padded-flat layout; the stem output is dense, Hp = H, Wp = W) */
 void* cilrs_model_debug_activation(cilrs_model* m, int which, int* dims);
 int* cilrs_model_error_flag(cilrs_model* m); /* device int, set to 1 when a command was outside [0,4) */
+/* test hook: backward of BasicBlocks hi..max(lo,0) only (hi < 0: none; blocks are numbered 0..15 in forward order), plus the stem
+ * (max-pool / BN / conv1 backward) when lo < 0, from a given gradient. g_out: bf16 padded-flat gradient w.r.t. the OUTPUT of block
+ * hi before its final ReLU mask (stem only: w.r.t. the max-pool output [batch,23,51,64]); padding pixels zero. Must follow a
+ * forward(keep_for_backward) of the same batch / mode. Parameter gradients accumulate into the bound arena; the gradient w.r.t.
+ * the input of block max(lo,0) is left in cilrs_model_debug_gradient() (padded-flat, geometry of that input). */
+int cilrs_model_debug_backward(cilrs_model* m, int batch, int mode, int hi, int lo, const void* g_out, void* stream);
+void* cilrs_model_debug_gradient(cilrs_model* m);
+/* Dropout(p) of the heads under a captured CUDA graph (notebook/notebook.ipynb:480 trains with dropout=0.5): the mask seed of a
+ * forward becomes seed + c * (*counter_dev + 1); counter_dev is a device int64 that changes between replays. NULL = off. */
+int cilrs_model_set_dropout_counter(cilrs_model* m, const long long* counter_dev);
 
 /* heads only (speed encoder + selected branch + speed predictor; model/autonomous_drive.py:371-398) on given
  * features f32 [batch,512]; the backward also accumulates the head parameter gradients and returns d(features) */
@@ -260,6 +270,14 @@ int cilrs_loss(const float* controls, const float* pred_speed, const float* targ
                int batch, int mode, float w_steer, float w_throttle, float w_brake, float w_speed, float grad_scale,
                float* out6, float* dcontrols, float* dspeed, void* stream);
 
+/* validate() on the device (notebook/notebook.ipynb:563-585): ACCUMULATES into acc16 (device double[16], zeroed by the caller
+ * before a validation pass): [0..5] the six loss scalars of this batch (same order as cilrs_loss), [6..9] sum of
+ * |pred_steer - target_steer| over the samples of command 0..3, [10..13] their counts, [14] += 1 (batches). One read of acc16 at
+ * the end of the pass replaces the reference's 6 .item() + up to 4 masked .cpu() copies per batch. */
+int cilrs_validate_accumulate(const float* controls, const float* pred_speed, const float* targets, const float* speed_target,
+                              const long long* command, int batch, int mode, float w_steer, float w_throttle, float w_brake,
+                              float w_speed, double* acc16, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * O1/O2  optimiser.  torch.optim.Adam(lr, weight_decay) single step over a flat arena (notebook/notebook.ipynb:533-534,555)
  *        and the squared gradient norm + clip coefficient of clip_grad_norm_ (notebook/notebook.ipynb:553-554).
@@ -271,6 +289,17 @@ int cilrs_adam_step(float* p, const float* g, float* m, float* v, long long n, f
                     const float* grad_scale_dev, void* stream);
 int cilrs_grad_sumsq(const float* g, long long n, double* partial_ws, unsigned int* counter_ws, float max_norm,
                      float* out2, void* stream);
+/* CUDA-graph form of the step: hyper_dev = device float[8] {lr, beta1, beta2, eps, weight_decay, grad_scale, -, -} read by the
+ * kernel at run time (StepLR, notebook/notebook.ipynb:535-536,604, reaches a captured graph through a 32-byte copy);
+ * step_dev (device int64, required) is incremented on the stream first. g_bf16 (optional): bf16 gradients used instead of g
+ * (the all-reduced exchange buffer of data-parallel training); zero_grad != 0 also clears the fp32 arena g
+ * (optimizer.zero_grad(), notebook/notebook.ipynb:551, of the next step). */
+int cilrs_adam_step_ex(float* p, float* g, const void* g_bf16, float* m, float* v, long long n, const float* hyper_dev,
+                       long long* step_dev, const float* grad_scale_dev, int zero_grad, void* stream);
+int cilrs_grad_sumsq_bf16(const void* g_bf16, long long n, double* partial_ws, unsigned int* counter_ws, float max_norm,
+                          float* out2, void* stream);
+/* fp32 gradient range -> bf16 exchange buffer (round to nearest even); zero_source != 0 also clears the fp32 range */
+int cilrs_grad_to_bf16(float* g, void* out_bf16, long long n, int zero_source, void* stream);
 
 #ifdef __cplusplus
 }
