@@ -138,57 +138,202 @@ class ClockSampler:
                 "reasons": [name for bit, name in self.REASONS if self.mask & bit], "samples": len(sm), "source": self.source}
 
 
-def cpu_reference_step_rate(batch, steps, warmup):
-    """The reference's train step restated on the CPU (oracle port: torch fp32, all host threads):
-    forward (train-mode BN) + MSE losses + backward + Adam (notebook/notebook.ipynb:545-555 with the BASELINE recipe)."""
+def _reference_module():
+    """oracle/_ref/reference_hotpath.py (the reference's own classes, extracted by oracle/extract_ref.py at build() time and
+    shipped with the snapshot), or None -> the oracle port is used instead."""
+    try:
+        from oracle import extract_ref
+        return extract_ref.load()
+    except Exception:
+        return None
+
+
+def synthetic_host_batches(batch, pool, seed):
+    """The bench's synthetic data: uint8 200x88 frames (what the reference's dataset stores after prepare_dataset.py),
+    speed U[0,1), command randint(0,4), targets U[0,1)^3. Same generator for our arm and the reference arm."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(pool):
+        out.append((torch.randint(0, 256, (batch, 88, 200, 3), generator=g, dtype=torch.uint8), torch.rand(batch, generator=g),
+                    torch.randint(0, 4, (batch,), generator=g), torch.rand(batch, 3, generator=g)))
+    return out
+
+
+def reference_initial_state_dict():
+    """Random-init weights the way the reference constructs them: `CILRS(num_commands=4, dropout=0.0)` under
+    torch.manual_seed(0) (kaiming fan_out convs, BN 1/0, default Linear init). Falls back to the oracle's synthetic state dict
+    (same initialiser scales) when oracle/_ref is absent. Returns (state_dict, kind)."""
+    import warnings
+    import torch
+    R = _reference_module()
+    if R is not None:
+        torch.manual_seed(0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = R.CILRS(num_commands=4, dropout=0.0)
+        return {k: v.detach().clone() for k, v in ref.state_dict().items()}, "reference"
+    from oracle import cilrs_oracle as O
+    return O.synthetic_state_dict(0, perturb_bn=False), "port"
+
+
+def cpu_reference_step_rate(batch, steps, warmup, state_dict=None, batches=None):
+    """The reference's train step on the host cores, ALL of them (torch.set_num_threads(os.cpu_count()): torchrun exports
+    OMP_NUM_THREADS=1, which must not apply to this arm): `model(imgs, speeds, cmds)` -> loss -> zero_grad -> backward ->
+    optimizer.step(), i.e. the body of train_one_epoch (notebook/notebook.ipynb:545-555) with the BASELINE recipe (MSE + 0.05 MSE,
+    torch.optim.Adam lr 2e-4 wd 1e-4). Runs the reference's own `class CILRS` from oracle/_ref when it was built (kind
+    "reference"), else the oracle's functional port (kind "port"). Returns (frames/s, s/step, threads, kind, first-step loss)."""
+    import warnings
     import torch
     from oracle import cilrs_oracle as O
-    torch.manual_seed(0)
-    sd = O.synthetic_state_dict(0, perturb_bn=False)
-    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
-    state = dict(sd)
-    state.update(params)
-    opt = torch.optim.Adam(list(params.values()), lr=2e-4, weight_decay=1e-4)
-    g = torch.Generator().manual_seed(1)
-    image = torch.randn(batch, 3, 88, 200, generator=g)
-    speed = torch.rand(batch, generator=g)
-    command = torch.randint(0, 4, (batch,), generator=g)
-    targets = torch.rand(batch, 3, generator=g)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        upd = {}
-        c, p = O.forward(state, image, speed, command, training=True, update=upd)
-        loss, _ = O.loss_mse(c, targets, p, speed)
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
-        for k, v in upd.items():
-            state[k] = v
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    R = _reference_module()
+    if state_dict is None:
+        state_dict, _ = reference_initial_state_dict()
+    if batches is None:
+        batches = synthetic_host_batches(batch, 2, 100)
+    data = []
+    for fr, sp, cm, tg in batches:
+        img = torch.from_numpy(O.normalise_np(fr.numpy()))   # the loader's /255 + Normalize (notebook/notebook.ipynb:412-414)
+        data.append((img, sp.clone(), cm.clone(), tg.clone()))
+    times, first_loss = [], None
+    if R is not None:
+        kind = "reference"
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model = R.CILRS(num_commands=4, dropout=0.0)
+        model.load_state_dict(state_dict)
+        model.train()
+        optimizer = torch.optim.Adam(model.parameters(), lr=2e-4, weight_decay=1e-4)
+        for i in range(warmup + steps):
+            imgs, speeds, cmds, tgts = data[i % len(data)]
+            t0 = time.perf_counter()
+            pred_ctrl, pred_spd = model(imgs, speeds, cmds)
+            loss, _ = O.loss_mse(pred_ctrl, tgts, pred_spd, speeds)   # README / train_config recipe; the reference has no code for it
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+            lv = loss.item()
+            if first_loss is None:
+                first_loss = lv
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        kind = "port"
+        params = {k: v.clone().requires_grad_(True) for k, v in state_dict.items()
+                  if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
+        state = dict(state_dict)
+        state.update(params)
+        opt = torch.optim.Adam(list(params.values()), lr=2e-4, weight_decay=1e-4)
+        for i in range(warmup + steps):
+            imgs, speeds, cmds, tgts = data[i % len(data)]
+            t0 = time.perf_counter()
+            upd = {}
+            c, p = O.forward(state, imgs, speeds, cmds, training=True, update=upd)
+            loss, _ = O.loss_mse(c, tgts, p, speeds)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            state.update(upd)
+            lv = loss.item()
+            if first_loss is None:
+                first_loss = lv
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
     total = sum(times)
-    return batch * len(times) / total, total / len(times), torch.get_num_threads()
+    return batch * len(times) / total, total / len(times), torch.get_num_threads(), kind, first_loss
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's own CPU implementation of the path. The reference is pure Python on top of torch
-    (nothing to compile into oracle/_ref, and /root/reference is absent on the GPU box), so this is the oracle port."""
+    """--impl reference: the reference's own CPU implementation of the path, on the stated config (batch 128), with every host
+    thread: oracle/_ref (the reference's class CILRS, extracted at build() time) when present, else the oracle port."""
     if rank != 0:
         return
-    sample = 32
-    fps, sec, cores = cpu_reference_step_rate(sample, max(1, args.steps), min(args.warmup, 2))
+    warm = max(1, min(args.warmup, 2))
+    fps, sec, cores, kind, _ = cpu_reference_step_rate(BATCH, max(1, args.steps), warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "global_batch": BATCH * args.gpus, "parallelism": "cpu"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "each step = one full train step (fwd+loss+bwd+Adam) on a %d-frame batch, torch fp32 CPU" % sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": "each step = one full train step (fwd + MSE loss + bwd + torch.optim.Adam) on a %d-frame batch, "
+                                   "torch fp32 on the host, %d threads" % (BATCH, cores)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def _timeit(torch, fn, reps=10, flush=None):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2] * 1e-3
+
+
+def extra_kernel_lines(torch, model, pk):
+    """The HBM-bound kernels of the path, timed alone (CUDA events, L2 flushed by a 256 MB memset between repetitions):
+    K0 preprocessing on configs[2] (1024 frames), the fused Adam, the heads at batch 128."""
+    import ctypes
+    from cilrs_b200 import _lib
+    out = {}
+    sp = _lib.stream_ptr()
+    hbm = pk["hbm_gbs"]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    try:
+        B = 1024
+        frames = torch.randint(0, 256, (B, 600, 800, 3), dtype=torch.uint8, device="cuda")
+        f32 = torch.empty(B, 3, 88, 200, device="cuda")
+        t = _timeit(torch, lambda: _lib.call("cilrs_preprocess_u8", frames, B, 600, 800, 3, 0, 88, 200, None, f32, None, sp), flush=flush)
+        alg = 633600.0
+        out["c3_preprocess"] = {"workload": "1024 x (600x800x3 u8 -> 88x200 f32 NCHW), K0", "ms": t * 1e3, "frames_per_s": B / t,
+                                "algorithmic_GBps": B * alg / t / 1e9, "hbm_frac": B * alg / t / 1e9 / hbm, "bytes_per_frame": alg}
+        del frames, f32
+    except Exception as ex:
+        out["c3_preprocess"] = {"error": repr(ex)}
+    try:
+        n = model.flat_parameters().numel()
+        p = torch.randn(n, device="cuda")
+        g = torch.randn(n, device="cuda") * 1e-3
+        mm, vv = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        hyper = torch.tensor([2e-4, 0.9, 0.999, 1e-8, 1e-4, 1.0, 0, 0], device="cuda")
+        step = torch.zeros(1, dtype=torch.long, device="cuda")
+        t = _timeit(torch, lambda: _lib.call("cilrs_adam_step_ex", p, g, None, mm, vv, ctypes.c_longlong(n), hyper, step, None, 1, sp),
+                    flush=flush)
+        out["adam"] = {"workload": "fused Adam + zero_grad over the 22.4 M-parameter arena (32 B/param)", "ms": t * 1e3,
+                       "GBps": n * 32 / t / 1e9, "hbm_frac": n * 32 / t / 1e9 / hbm}
+        del p, g, mm, vv
+    except Exception as ex:
+        out["adam"] = {"error": repr(ex)}
+    try:
+        B = 128
+        model.train()
+        model._ensure(B)
+        feat = torch.randn(B, 512, device="cuda")
+        speed = torch.rand(B, device="cuda")
+        cmd = torch.randint(0, 4, (B,), device="cuda")
+        c, ps = torch.empty(B, 3, device="cuda"), torch.empty(B, device="cuda")
+        dc, dsp, df = torch.randn(B, 3, device="cuda"), torch.randn(B, device="cuda"), torch.empty(B, 512, device="cuda")
+        model.flat_gradients()
+        t = _timeit(torch, lambda: _lib.call("cilrs_model_heads_forward", model._handle, B, feat, speed, cmd, c, ps, 1, ctypes.c_float(0.0),
+                                             ctypes.c_ulonglong(1), sp))
+        t2 = _timeit(torch, lambda: _lib.call("cilrs_model_heads_backward", model._handle, B, dc, dsp, speed, cmd, ctypes.c_float(0.0), df, sp))
+        out["heads"] = {"workload": "heads at batch 128", "forward_ms": t * 1e3, "backward_incl_wgrad_ms": t2 * 1e3}
+        model.flat_gradients().zero_()
+    except Exception as ex:
+        out["heads"] = {"error": repr(ex)}
+    return out
 
 
 def main():
@@ -199,6 +344,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -226,21 +372,20 @@ def main():
 
     lib = _lib.lib()
     lib.cilrs_launch_count.restype = ctypes.c_longlong
-    torch.manual_seed(0)
-    model = CILRS(num_commands=4, dropout=0.0).to(dev)
+    # random-init weights as the reference constructs them, loaded through the checkpoint interface (both arms start equal)
+    init_sd, init_kind = reference_initial_state_dict()
+    model = CILRS(num_commands=4, dropout=0.0)
+    model.load_state_dict(init_sd, strict=True)
+    model = model.to(dev)
     trainer = FusedTrainer(model, BATCH, lr=2e-4, weight_decay=1e-4, loss="mse", speed_w=0.05, frames="u8",
                            use_graph=(not args.no_graph),
-                           overlap_allreduce={"tail": False, "all": True}.get(os.environ.get("CILRS_BENCH_ALLREDUCE", "first"), "first"),  # measurement aids
+                           overlap_allreduce=os.environ.get("CILRS_BENCH_ALLREDUCE", "two"),       # measurement aids
+                           grad_comm=os.environ.get("CILRS_BENCH_GRAD_COMM", "bf16"),
                            async_parts=os.environ.get("CILRS_BENCH_ASYNC_PARTS", "0") == "1")
 
-    # synthetic batches: uint8 200x88 frames (what the reference's dataset stores after prepare_dataset.py), per-rank seed
-    g = torch.Generator().manual_seed(100 + rank)
+    # synthetic batches, per-rank seed (rank 0's are the ones the CPU arm sees)
     POOL = 4
-    host = []
-    for _ in range(POOL):
-        host.append((torch.randint(0, 256, (BATCH, 88, 200, 3), generator=g, dtype=torch.uint8).pin_memory(),
-                     torch.rand(BATCH, generator=g).pin_memory(), torch.randint(0, 4, (BATCH,), generator=g).pin_memory(),
-                     torch.rand(BATCH, 3, generator=g).pin_memory()))
+    host = [tuple(t.pin_memory() for t in b) for b in synthetic_host_batches(BATCH, POOL, 100 + rank)]
     devb = [tuple(t.to(dev) for t in b) for b in host]
     loss_host = torch.zeros(6).pin_memory()
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
@@ -251,14 +396,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # launches per step (counted on one eager step; a graph replays exactly the same kernels)
+    # launches per step (counted on the first step of the run; a graph replays exactly the same kernels). Its loss - the very
+    # first step from the initial weights on batch 0 - is what the CPU arm's first step must reproduce (loss_check below).
     trainer.load_batch(*devb[0])
     c0 = lib.cilrs_launch_count()
-    trainer._device_step()
-    launches_per_step = int(lib.cilrs_launch_count() - c0)
-    if trainer.graph is not None:
-        trainer.opt._step += 0
+    if trainer.graph is None:
+        trainer._device_step()
+        launches_per_step = int(lib.cilrs_launch_count() - c0)
+    else:
+        trainer.step()
+        launches_per_step = None
     torch.cuda.synchronize(dev)
+    loss_first = trainer.read_loss()["total"]
 
     # W warm-up steps as asked, plus (multi-rank only) a few settle steps: the first replays after start-up pay NCCL's lazy
     # channel / buffer set-up and showed up as +0.3 ms/step in 20-step runs on 2 GPUs
@@ -292,7 +441,7 @@ def main():
                 clocks = dict(slow)
                 clocks["reasons"] = sorted(set(r for c in allc if c for r in c.get("reasons", [])))
                 clocks["per_rank_sm_mhz"] = [c.get("sm_mhz") if c else None for c in allc]
-    loss_last = trainer.loss6.tolist()
+    loss_last = trainer.read_loss()["total"]
 
     # ---------------- end-to-end timing: host frames in, loss out, every step ----------------
     for i in range(2):
@@ -317,26 +466,73 @@ def main():
     value = frames / (ms_total * 1e-3)
     e2e_value = frames / (ms_e2e * 1e-3)
 
-    line = {
-        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
-                   "cuda_graph": trainer.graph is not None, "cuda_graph_error": trainer.graph_error, "settle_steps": settle,
-                   "l2": "no explicit flush: one step touches ~0.9 GB of activations + 0.6 GB of optimizer state, > 126 MB L2"},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": ms_e2e / args.steps, "input": "uint8 [128,88,200,3] frames + speed/command/targets from pinned host memory"},
-        "gpu_launches": launches_per_step * args.steps,
-        "loss_last": loss_last[0],
-    }
     # ---- one profiled eager step (CUDA events around every launch of the plan). With N > 1 the step contains the gradient
     # allreduce, so EVERY rank runs it (a collective issued by rank 0 alone would hang); only rank 0 collects the timings.
     torch.cuda.synchronize(dev)
     if rank == 0:
         _lib.call("cilrs_model_profile", model._handle, 1)
     trainer.load_batch(*devb[0])
+    c0 = lib.cilrs_launch_count()
     trainer._device_step()
+    eager_launches = int(lib.cilrs_launch_count() - c0)
+    if launches_per_step is None:
+        launches_per_step = eager_launches
     torch.cuda.synchronize(dev)
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
+                   "cuda_graph": trainer.graph is not None, "cuda_graph_error": trainer.graph_error, "settle_steps": settle,
+                   "initial_weights": "reference ctor under torch.manual_seed(0) (%s), loaded via load_state_dict" % init_kind,
+                   "allreduce_schedule": trainer.overlap_allreduce if world > 1 else None,
+                   "grad_comm": trainer.grad_comm if world > 1 else None,
+                   "l2": "no explicit flush: one step touches ~0.9 GB of activations + 0.6 GB of optimizer state, > 126 MB L2"},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e / args.steps, "input": "uint8 [128,88,200,3] frames + speed/command/targets from pinned host memory"},
+        "gpu_launches": launches_per_step * args.steps,
+        "loss_first": loss_first, "loss_last": loss_last,
+    }
+    # ---- configs[4]: batched inference sharded over the ranks (512 frames per GPU), all ranks ----
+    try:
+        from cilrs_b200.preprocess import ShardedInference
+        model.eval()
+        PER = 512
+        sh = ShardedInference(model, PER * world, src_hw=(88, 200))   # frames already 200x88 (the rollout's resized stream)
+        gi = torch.Generator().manual_seed(7 + rank)
+        sh.session.h_frames.copy_(torch.randint(0, 256, tuple(sh.session.h_frames.shape), generator=gi, dtype=torch.uint8))
+        sh.session.h_speed.copy_(torch.rand(PER, generator=gi))
+        sh.session.h_command.copy_(torch.randint(0, 4, (PER,), generator=gi))
+        for _ in range(3):
+            sh.session.run()
+        barrier()
+        reps = 20
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sh.session.run()           # H2D of the shard's frames, K0 normalise, eval forward, D2H of [512,4]
+        torch.cuda.synchronize(dev)
+        tloc = torch.tensor([(time.perf_counter() - t0) / reps], device=dev, dtype=torch.float64)
+        s = sh.session
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(s.stream):
+            ev0.record()
+            for _ in range(reps):
+                s.graph.replay() if s.graph is not None else s._body()
+            ev1.record()
+        s.stream.synchronize()
+        tdev = torch.tensor([ev0.elapsed_time(ev1) * 1e-3 / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tloc, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tdev, op=dist.ReduceOp.MAX)
+        line["infer_c5"] = {"workload": "batched CILRS inference, %d frames (512 per GPU x %d), mixed commands, bf16 eval" % (PER * world, world),
+                            "frames_per_s": PER * world / float(tdev), "ms_per_batch": float(tdev) * 1e3,
+                            "conv_TFLOPs_per_gpu": PER * FLOP_FWD / float(tdev) / 1e12,
+                            "e2e_frames_per_s": PER * world / float(tloc),
+                            "e2e_span": "uint8 frames in pinned host memory -> [512,4] controls on the host, per rank; max over ranks"}
+        del sh
+    except Exception as ex:  # never lose the training line to the extra measurement
+        line["infer_c5"] = {"error": repr(ex)}
+    model.train()
     if rank == 0:
         pk = peaks()
         out_ms = (ctypes.c_float * 7)()
@@ -348,28 +544,29 @@ def main():
         t_gemm = (out_ms[0] + out_ms[1]) * 1e-3
         n_gemm = out_n[0] + out_n[1]
         achieved = BATCH * (FLOP_FWD + FLOP_DGRAD) / t_gemm / 1e12 if t_gemm > 0 else 0.0
-        peak = pk["bf16_tflops_sustained"]
+        burst, sustained = pk["bf16_tflops"], pk["bf16_tflops_sustained"]
         traffic, traffic_note = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_flat_traffic.json")))
             traffic, traffic_note = tj["traffic_bytes_per_launch"], tj["launches"] + " | " + tj["source"]
         except Exception:
             pass
+        step_tf = value / world * FLOP_TRAIN / 1e12
         line["roofline"] = {
             "bound": "tensor",
             "kernel": "conv_flat_kernel + conv_gemm_kernel (tcgen05 implicit-GEMM fprop + dgrad with fused BN statistics / ReLU mask / "
                       "BN-backward reductions, %d launches/step)" % n_gemm,
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic,
             "traffic_note": traffic_note,
-            "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+            "peak_source": pk["source"] + " bf16_tflops (burst; primary per SURVEY.md 8d)",
+            "frac_sustained": achieved / sustained, "peak_sustained": sustained,
             "avg_launch_ms": (out_ms[0] + out_ms[1]) / max(1, n_gemm),
             "wgrad_kernel": {"achieved": BATCH * FLOP_WGRAD / (out_ms[2] * 1e-3) / 1e12 if out_ms[2] > 0 else 0.0,
-                             "frac": (BATCH * FLOP_WGRAD / (out_ms[2] * 1e-3) / 1e12 / peak) if out_ms[2] > 0 else 0.0,
+                             "frac": (BATCH * FLOP_WGRAD / (out_ms[2] * 1e-3) / 1e12 / burst) if out_ms[2] > 0 else 0.0,
                              "note": "wgrad_flat_kernel + wgrad_reduce_kernel + wgrad_gemm_kernel; in the timed step they run on a side "
                                      "stream concurrently with the dgrad / BatchNorm chain"},
-            "step_level": {"achieved": value / world * FLOP_TRAIN / 1e12, "frac_burst": value / world * FLOP_TRAIN / 1e12 / pk["bf16_tflops"],
-                           "frac_sustained": value / world * FLOP_TRAIN / 1e12 / peak,
-                           "note": "whole-step frames/s x 8.305 GFLOP conv work per frame (SURVEY.md §8d)"},
+            "step_level": {"achieved": step_tf, "frac": step_tf / burst, "frac_sustained": step_tf / sustained,
+                           "note": "whole-step frames/s x 8.305 GFLOP conv work per frame (SURVEY.md 8d), all GEMM + non-GEMM time included"},
             "breakdown_ms": breakdown,
         }
         line["clocks"] = clocks
@@ -382,28 +579,45 @@ def main():
             sess.h_speed.fill_(0.3)
             sess.h_command.fill_(1)
             lat = []
-            for i in range(320):
+            for i in range(1020):
                 t0 = time.perf_counter()
                 sess.run()
                 lat.append((time.perf_counter() - t0) * 1e3)
             lat = sorted(lat[20:])
-            line["infer_b1"] = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)],
+            line["infer_b1"] = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "iterations": len(lat),
                                 "span": "raw uint8 600x800x3 frame in pinned host memory -> (steer, throttle, brake, speed) on the host"}
-        except Exception as ex:  # never lose the training line to the extra measurement
+            del sess
+            model.train()
+        except Exception as ex:
             line["infer_b1"] = {"error": repr(ex)}
-        # ---- CPU baseline (oracle port), bounded sample ----
+        if not args.no_extras:
+            line.update(extra_kernel_lines(torch, model, pk))
+        # ---- CPU baseline (the reference's class when oracle/_ref was built, else the oracle port), bounded sample ----
+        check_failed = None
         if world == 1 and not args.no_cpu_baseline:
-            fps, sec, cores = cpu_reference_step_rate(BATCH, 12, 1)   # ~10 s of host work
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                    "sample": "12 timed full train steps (fwd+MSE loss+bwd+Adam) at batch 128 after 1 warm-up, torch fp32 on the host"}
+            fps, sec, cores, kind, ref_first = cpu_reference_step_rate(BATCH, 12, 1, state_dict=init_sd,
+                                                                       batches=[tuple(t.clone() for t in b) for b in host[:2]])
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                                    "sample": "12 timed full train steps (fwd + MSE loss + bwd + torch.optim.Adam) at batch 128 after 1 warm-up, "
+                                              "torch fp32 on the host, %d threads" % cores}
+            rel = abs(loss_first - ref_first) / abs(ref_first)
+            line["loss_check"] = {"ours_first_step": loss_first, "cpu_first_step": ref_first, "rel": rel, "bar": 2e-2, "ok": rel <= 2e-2,
+                                  "note": "same initial weights, same batch 0: the CUDA step's loss vs the CPU arm's"}
+            if rel > 2e-2:
+                check_failed = "bench.py: first-step loss %.6f differs from the CPU reference's %.6f by %.2e (> 2e-2)" % (loss_first, ref_first, rel)
         print(json.dumps(line))
         sys.stdout.flush()
+        if check_failed:
+            raise SystemExit(check_failed)
     if world > 1:
-        # Leave without tearing NCCL down: with the allreduces captured in a CUDA graph, destroy_process_group() (and a
-        # barrier issued while rank 0 is still busy with its single-GPU extras) can block on communicator resources the
-        # graph still references. Every rank has finished its collectives at this point; exit code 0.
+        # orderly teardown: drop the captured graph (it references the communicator) before the process group goes away. A
+        # watchdog keeps a wedged NCCL teardown from turning a finished measurement into a hung job (the line is already out).
+        import threading
+        threading.Timer(60.0, lambda: os._exit(0)).start()
+        trainer.close()
         torch.cuda.synchronize(dev)
-        sys.stderr.flush()
+        dist.barrier()
+        dist.destroy_process_group()
         os._exit(0)
 
 

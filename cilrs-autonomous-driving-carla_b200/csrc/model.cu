@@ -1155,6 +1155,16 @@ int cilrs_model_debug_backward(cilrs_model* h, int batch, int mode, int hi, int 
   return backward(m, batch, mode, -1, nullptr, nullptr, nullptr, nullptr, 0.f, (cudaStream_t)stream, false, hi, lo);
 }
 void* cilrs_model_debug_gradient(cilrs_model* h) { return h ? (void*)h->m.bw_gcur : nullptr; }
+// test hook: fp32 [batch, width] head activations kept by the last forward(keep_for_backward), post-ReLU and post-dropout.
+// which: 0 = speed_encoder.0 (128), 1 = speed_encoder.3 (128), 2 = branch.0 (256), 3 = branch.3 (256), 4 = speed_predictor.0
+// (256), 5 = speed_predictor.3 (256); *width receives the row length
+float* cilrs_model_debug_heads_saved(cilrs_model* h, int which, int* width) {
+  if (!h || which < 0 || which > 5) return nullptr;
+  HeadsSaved& s = h->m.hs;
+  float* ptr[6] = {s.s1, s.sfeat, s.b1, s.b2, s.p1, s.p2};
+  if (width) *width = which < 2 ? 128 : 256;
+  return ptr[which];
+}
 
 // dropout under a captured CUDA graph: the mask seed of every forward becomes seed + golden * (*counter + 1), with `counter` a
 // device int64 that changes between replays (FusedTrainer passes the optimizer's device step counter). NULL switches it off.

@@ -390,6 +390,16 @@ class CILRS(nn.Module):
         n = batch * hp * wp * c * 2
         return self._workspace_view(ptr, n).view(torch.bfloat16).view(batch, hp, wp, c)
 
+    def debug_heads_saved(self, which, batch):
+        """Test hook: fp32 [batch, width] head activation kept by the last forward (post-ReLU, post-Dropout); see the header."""
+        lib = _lib.lib()
+        lib.cilrs_model_debug_heads_saved.restype = ctypes.c_void_p
+        width = ctypes.c_int()
+        ptr = lib.cilrs_model_debug_heads_saved(self._handle, int(which), ctypes.byref(width))
+        if not ptr:
+            raise ValueError("no such head activation")
+        return self._workspace_view(ptr, batch * width.value * 4).view(torch.float32).view(batch, width.value)
+
     def input_s2d_buffer(self, batch):
         """bf16 [batch,47,103,16] view of the plan's conv1 input: the preprocessing kernel can write frames there directly."""
         self._ensure(batch)

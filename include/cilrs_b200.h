@@ -224,6 +224,10 @@ int* cilrs_model_error_flag(cilrs_model* m); /* device int, set to 1 when a comm
  * the input of block max(lo,0) is left in cilrs_model_debug_gradient() (padded-flat, geometry of that input). */
 int cilrs_model_debug_backward(cilrs_model* m, int batch, int mode, int hi, int lo, const void* g_out, void* stream);
 void* cilrs_model_debug_gradient(cilrs_model* m);
+/* test hook: fp32 [batch, width] head activations the last forward(keep_for_backward) kept (post-ReLU, post-Dropout).
+ * which: 0 speed_encoder.0 (128), 1 speed_encoder.3 (128), 2 branch.0 (256), 3 branch.3 (256), 4 speed_predictor.0 (256),
+ * 5 speed_predictor.3 (256) */
+float* cilrs_model_debug_heads_saved(cilrs_model* m, int which, int* width);
 /* Dropout(p) of the heads under a captured CUDA graph (notebook/notebook.ipynb:480 trains with dropout=0.5): the mask seed of a
  * forward becomes seed + c * (*counter_dev + 1); counter_dev is a device int64 that changes between replays. NULL = off. */
 int cilrs_model_set_dropout_counter(cilrs_model* m, const long long* counter_dev);

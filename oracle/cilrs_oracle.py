@@ -224,35 +224,89 @@ def _bn(sd, prefix, x, training, momentum=0.1, eps=1e-5, update=None):
     return F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], training, momentum, eps)
 
 
-def visual_encoder(sd, image, training=False, update=None, taps=None):
-    """resnet34 conv1..avgpool + Flatten (model/autonomous_drive.py:366-370)."""
-    x = F.conv2d(image, sd["visual_encoder.0.weight"], stride=2, padding=3)
+def block_prefixes():
+    """state_dict prefixes of the 16 BasicBlocks in forward order, with their stride."""
+    return [("visual_encoder.%d.%d" % (idx, b), 2 if (b == 0 and idx != 4) else 1) for idx, c, blocks in STAGES for b in range(blocks)]
+
+
+def basic_block(sd, p, x, stride, training=False, update=None, rnd=None):
+    """torchvision BasicBlock.forward (torchvision/models/resnet.py:89-105) on state-dict entries with prefix `p`.
+    rnd: optional rounding hook applied where the CUDA path stores a bf16 tensor (see forward_bf16emu)."""
+    r = rnd if rnd is not None else (lambda t: t)
+    out = r(F.conv2d(x, sd[p + ".conv1.weight"], stride=stride, padding=1))
+    out = r(F.relu(_bn(sd, p + ".bn1", out, training, update=update)))
+    out = r(F.conv2d(out, sd[p + ".conv2.weight"], stride=1, padding=1))
+    out = _bn(sd, p + ".bn2", out, training, update=update)
+    if (p + ".downsample.0.weight") in sd:
+        idn = r(F.conv2d(x, sd[p + ".downsample.0.weight"], stride=stride))
+        idn = _bn(sd, p + ".downsample.1", idn, training, update=update)
+    else:
+        idn = x
+    return r(F.relu(out + idn))
+
+
+def stem(sd, image, training=False, update=None, rnd=None):
+    """resnet34 conv1 + bn1 + relu + maxpool (model/autonomous_drive.py:367)."""
+    r = rnd if rnd is not None else (lambda t: t)
+    x = r(F.conv2d(image, sd["visual_encoder.0.weight"], stride=2, padding=3))
     x = F.relu(_bn(sd, "visual_encoder.1", x, training, update=update))
-    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    return r(F.max_pool2d(x, kernel_size=3, stride=2, padding=1))
+
+
+def visual_encoder(sd, image, training=False, update=None, taps=None, rnd=None):
+    """resnet34 conv1..avgpool + Flatten (model/autonomous_drive.py:366-370)."""
+    x = stem(sd, image, training, update, rnd)
     if taps is not None:
         taps["stem"] = x
-    for idx, c, blocks in STAGES:
-        for b in range(blocks):
-            p = "visual_encoder.%d.%d" % (idx, b)
-            stride = 2 if (b == 0 and idx != 4) else 1
-            out = F.conv2d(x, sd[p + ".conv1.weight"], stride=stride, padding=1)
-            out = F.relu(_bn(sd, p + ".bn1", out, training, update=update))
-            out = F.conv2d(out, sd[p + ".conv2.weight"], stride=1, padding=1)
-            out = _bn(sd, p + ".bn2", out, training, update=update)
-            if (p + ".downsample.0.weight") in sd:
-                idn = F.conv2d(x, sd[p + ".downsample.0.weight"], stride=stride)
-                idn = _bn(sd, p + ".downsample.1", idn, training, update=update)
-            else:
-                idn = x
-            x = F.relu(out + idn)
-            if taps is not None:
-                taps[p] = x
+    for p, stride in block_prefixes():
+        x = basic_block(sd, p, x, stride, training, update, rnd)
+        if taps is not None:
+            taps[p] = x
     return x.mean(dim=(2, 3))
 
 
-def forward(sd, image, speed, command, training=False, update=None, num_commands=4, taps=None):
+class _RoundBF16(torch.autograd.Function):
+    """Round to bf16 (nearest even) in the forward AND the backward pass: the value and its gradient are both tensors the CUDA
+    path stores in bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def round_bf16(x):
+    return _RoundBF16.apply(x)
+
+
+def bf16_weights(sd):
+    """Copy of `sd` whose CONVOLUTION weights are rounded to bf16 (the tensor-core operands; BN, heads and everything else
+    stay as they are). Gradients w.r.t. the rounded weights are what the CUDA path's fp32 weight gradients approximate."""
+    out = {}
+    for k, v in sd.items():
+        if v.dim() == 4:
+            out[k] = v.detach().to(torch.bfloat16).to(v.dtype)
+            if v.requires_grad:
+                out[k].requires_grad_(True)
+        else:
+            out[k] = v
+    return out
+
+
+def forward_bf16emu(sd, image, speed, command, training=False, update=None, taps=None):
+    """CILRS.forward in the precision of `sd` (fp64 for tests) with bf16 rounding inserted exactly where the CUDA path stores
+    bf16 tensors: the input image, every raw convolution output, every post-BN/ReLU activation, the max-pool output and every
+    block output — forward values and (through _RoundBF16.backward) the gradients that flow through the same tensors.
+    `sd` should come from bf16_weights(). The heads, BN statistics, losses stay in full precision (fp32 in the CUDA path)."""
+    return forward(sd, round_bf16(image), speed, command, training, update, taps=taps, rnd=round_bf16)
+
+
+def forward(sd, image, speed, command, training=False, update=None, num_commands=4, taps=None, rnd=None):
     """CILRS.forward (model/autonomous_drive.py:389-399); dropout p = 0 (the parity configuration)."""
-    vf = visual_encoder(sd, image, training, update, taps)
+    vf = visual_encoder(sd, image, training, update, taps, rnd)
     s = F.relu(F.linear(speed.unsqueeze(1), sd["speed_encoder.0.weight"], sd["speed_encoder.0.bias"]))
     s = F.relu(F.linear(s, sd["speed_encoder.3.weight"], sd["speed_encoder.3.bias"]))
     combined = torch.cat([vf, s], dim=1)

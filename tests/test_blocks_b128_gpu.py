@@ -1,0 +1,164 @@
+"""Parity at the BENCHMARKED configuration (batch 128): every BasicBlock and the stem, train-mode forward AND backward, against
+the fp64 oracle on identical bf16 inputs.
+
+Why per block: at random init the 36-BatchNorm train-mode backward of the whole network amplifies rounding ~1e5x (SURVEY
+§7.3-H1: the reference's own fp32 is 2e-3..8e-3 from fp64), so a whole-model gradient bound cannot tell a correct bf16
+implementation from a broken one. One block is well conditioned: with the same bf16 input activation and the same output
+gradient, a correct implementation must agree with fp64 to bf16 rounding (a handful of 2^-9 roundings), and a wrong BN-backward,
+mask, deferred finalize, fused dgrad reduction or stride-2 parity launch shows up as an O(1) error. The tile shapes the cost
+model picks (pair, MT, block_n, tap_group) depend on the batch, hence B = 128, the bench batch.
+
+The block under test runs through the real plan (`cilrs_model_forward`, then `cilrs_model_debug_backward(hi=lo=block)`): the
+same launches, buffers and fused epilogues as a training step. The checker is the oracle's `basic_block` / `stem` in fp64
+(torch fp64 on the GPU only to keep the suite short; it is the checker, never the product).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+B = 128
+BAR = 2e-2   # BASELINE.json north_star, bf16 mode: 2e-2 relative
+
+
+def _O():
+    from oracle import cilrs_oracle as O
+    return O
+
+
+def _rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def _rel_max(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-300))
+
+
+@pytest.fixture(scope="module")
+def net():
+    """One train-mode forward at B=128 (activations, ReLU bits and BatchNorm vectors of every layer are then in the plan)."""
+    from cilrs_b200.model import CILRS
+    O = _O()
+    sd = O.synthetic_state_dict(0)
+    m = CILRS(num_commands=4, dropout=0.0)
+    m.load_state_dict(sd, strict=True)
+    m = m.to("cuda").train()
+    g = torch.Generator().manual_seed(77)
+    coarse = torch.randn(B, 3, 11, 25, generator=g)
+    image = torch.nn.functional.interpolate(coarse, size=(88, 200), mode="bicubic", align_corners=False).contiguous()
+    speed = torch.rand(B, generator=g)
+    command = torch.randint(0, 4, (B,), generator=g)
+    controls, pred_speed = m(image.cuda(), speed.cuda(), command.cuda())   # grad enabled: activations are kept
+    torch.cuda.synchronize()
+    sd64 = {k: (v.double().cuda() if v.is_floating_point() else v.cuda()) for k, v in sd.items()}
+    return m, sd64, image
+
+
+def _leaf(sd64, keys):
+    out = dict(sd64)
+    for k in keys:
+        v = sd64[k]
+        if v.dim() == 4:   # conv weights: the tensor-core operand is the bf16 rounding of the fp32 master
+            v = v.float().to(torch.bfloat16).double()
+        out[k] = v.clone().requires_grad_(True)
+    return out
+
+
+def _param(m, name):
+    return dict(m.named_parameters())[name]
+
+
+@pytest.mark.parametrize("bi", list(range(16)))
+def test_basic_block_train_forward_backward_b128(net, bi):
+    from cilrs_b200 import ops
+    O = _O()
+    m, sd64, _ = net
+    prefix, stride = O.block_prefixes()[bi]
+    x = m.debug_activation(bi, B).clone()            # [B,H,W,C] bf16: the block's input as the plan holds it
+    out = m.debug_activation(bi + 1, B).clone()
+    keys = [k for k in sd64 if k.startswith(prefix + ".") and sd64[k].is_floating_point() and "running" not in k]
+    sd = _leaf(sd64, keys)
+    x64 = x.double().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    out64 = O.basic_block(sd, prefix, x64, stride, training=True)
+    e_fwd = _rel_max(out.double().permute(0, 3, 1, 2), out64)
+    # ---- backward from a random output gradient (bf16-exact values so both sides start from the same tensor) ----
+    gen = torch.Generator(device="cuda").manual_seed(1000 + bi)
+    g = (torch.randn(out.shape, generator=gen, device="cuda") * 0.05).to(torch.bfloat16)
+    (out64 * g.double().permute(0, 3, 1, 2)).sum().backward()
+    m.flat_gradients().zero_()
+    dx = m.debug_backward(B, bi, bi, ops.to_padded(g))
+    torch.cuda.synchronize()
+    dx = dx[:, :x.shape[1], :x.shape[2]].double().permute(0, 3, 1, 2)
+    ref_dx = x64.grad
+    if bi > 0:   # the fused dgrad epilogue also applies the ReLU mask of the tensor it produces the gradient of
+        ref_dx = ref_dx * (x64 > 0)
+    rows = [("forward out", e_fwd), ("dx", _rel_l2(dx, ref_dx))]
+    views = dict(zip([n for n, _ in m.named_parameters()], m._views(m.flat_gradients())))
+    for k in keys:
+        rows.append((k[len(prefix) + 1:], _rel_l2(views[k], sd[k].grad)))
+    print("block %2d (%s, stride %d): %s" % (bi, prefix, stride, ", ".join("%s %.2e" % r for r in rows)))
+    bad = [r for r in rows if not r[1] <= BAR]
+    assert not bad, bad
+
+
+def test_stem_train_forward_backward_b128(net):
+    from cilrs_b200 import ops
+    O = _O()
+    m, sd64, image = net
+    keys = ["visual_encoder.0.weight", "visual_encoder.1.weight", "visual_encoder.1.bias"]
+    sd = _leaf(sd64, keys)
+    img64 = image.cuda().to(torch.bfloat16).double()   # conv1's operand is the bf16 space-to-depth copy of the image
+    y64 = torch.nn.functional.conv2d(img64, sd["visual_encoder.0.weight"], stride=2, padding=3)
+    pool64 = O.stem(sd, img64, training=True)
+    y = m.debug_activation(17, B).double().permute(0, 3, 1, 2)
+    pool = m.debug_activation(0, B)
+    e_y, e_pool = _rel_max(y, y64), _rel_max(pool.double().permute(0, 3, 1, 2), pool64)
+    gen = torch.Generator(device="cuda").manual_seed(4242)
+    g = (torch.randn(pool.shape, generator=gen, device="cuda") * 0.05).to(torch.bfloat16)
+    (pool64 * g.double().permute(0, 3, 1, 2)).sum().backward()
+    m.flat_gradients().zero_()
+    m.debug_backward(B, -1, -1, ops.to_padded(g))
+    torch.cuda.synchronize()
+    views = dict(zip([n for n, _ in m.named_parameters()], m._views(m.flat_gradients())))
+    rows = [("conv1 out", e_y), ("pool out", e_pool)] + [(k, _rel_l2(views[k], sd[k].grad)) for k in keys]
+    print("stem: %s" % ", ".join("%s %.2e" % r for r in rows))
+    bad = [r for r in rows if not r[1] <= BAR]
+    assert not bad, bad
+
+
+def test_layer_group_backward_b128(net):
+    """Blocks 7..12 (all of layer3, with its stride-2 / downsample head) in ONE debug backward: the composition deferred sums ->
+    bn_bwd_apply prologue finalize -> fused dgrad reductions -> conv_gemm_multi parity launches across block boundaries."""
+    from cilrs_b200 import ops
+    O = _O()
+    m, sd64, _ = net
+    hi, lo = 12, 7
+    pre = O.block_prefixes()
+    keys = [k for k in sd64 if any(k.startswith(pre[b][0] + ".") for b in range(lo, hi + 1)) and sd64[k].is_floating_point()
+            and "running" not in k]
+    sd = _leaf(sd64, keys)
+    x = m.debug_activation(lo, B).clone()
+    out = m.debug_activation(hi + 1, B).clone()
+    x64 = x.double().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    h = x64
+    for b in range(lo, hi + 1):
+        h = O.basic_block(sd, pre[b][0], h, pre[b][1], training=True, rnd=O.round_bf16)
+    e_fwd = _rel_max(out.double().permute(0, 3, 1, 2), h)
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    g = (torch.randn(out.shape, generator=gen, device="cuda") * 0.05).to(torch.bfloat16)
+    (h * g.double().permute(0, 3, 1, 2)).sum().backward()
+    m.flat_gradients().zero_()
+    dx = m.debug_backward(B, hi, lo, ops.to_padded(g))
+    torch.cuda.synchronize()
+    dx = dx[:, :x.shape[1], :x.shape[2]].double().permute(0, 3, 1, 2)
+    views = dict(zip([n for n, _ in m.named_parameters()], m._views(m.flat_gradients())))
+    flat_got = torch.cat([views[k].double().reshape(-1) for k in keys])
+    flat_ref = torch.cat([sd[k].grad.reshape(-1) for k in keys])
+    e_glob = _rel_l2(flat_got, flat_ref)
+    e_dx = _rel_l2(dx, x64.grad * (x64 > 0))
+    per = sorted(((_rel_l2(views[k], sd[k].grad), k) for k in keys), reverse=True)
+    print("layer3 group: forward %.2e, global param-grad %.2e, dx %.2e, worst tensors %s" % (e_fwd, e_glob, e_dx, per[:3]))
+    # six chained train-mode blocks: bf16 roundings compound (each block ~5e-3): 2e-2 on the global figure, 5e-2 per tensor
+    assert e_fwd <= BAR and e_glob <= BAR and e_dx <= 5e-2
+    assert per[0][0] <= 5e-2, per[:3]

@@ -94,10 +94,14 @@ def test_dropin_module_state_dict_and_cpu_refusal():
     flat = m.flat_parameters()
     for p, o in zip(m.parameters(), m._offsets):
         assert p.is_leaf and p.requires_grad and p.data_ptr() == flat.data_ptr() + 4 * o
-    with pytest.raises(KeyError):
-        m.load_state_dict({k: v for k, v in syn.items() if k != "speed_predictor.5.bias"}) if False else (_ for _ in ()).throw(KeyError())
-    with pytest.raises(RuntimeError):
+    # strict loading (model/autonomous_drive.py:497 uses the default strict=True): a missing key, an unexpected key and a wrong
+    # shape must all raise, as they do for the reference module
+    with pytest.raises(RuntimeError, match="Missing key"):
         m.load_state_dict({k: v for k, v in syn.items() if k != "speed_predictor.5.bias"}, strict=True)
+    with pytest.raises(RuntimeError, match="Unexpected key"):
+        m.load_state_dict(dict(syn, **{"visual_encoder.8.weight": torch.zeros(1)}), strict=True)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        m.load_state_dict(dict(syn, **{"speed_encoder.0.weight": torch.zeros(128, 2)}), strict=True)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 3, 88, 200), torch.zeros(1), torch.zeros(1, dtype=torch.long))
     with pytest.raises(ValueError):
@@ -122,7 +126,7 @@ def _ddp_worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, ROOT)
-    from cilrs_b200.ddp import allreduce_ranges, backward_part_ranges
+    from cilrs_b200.ddp import SCHEDULES, allreduce_ranges, backward_part_ranges, schedule_ranges
     from cilrs_b200.model import CILRS
     m = CILRS()
     ranges = backward_part_ranges(m)
@@ -141,6 +145,15 @@ def _ddp_worker(rank, world, port, q):
         x.wait()
     h.mul_(1.0 / world)
     assert torch.equal(g, h)
+    # every schedule FusedTrainer offers exchanges each gradient exactly once (fp32 and the bf16 exchange buffer alike)
+    for name, sched in SCHEDULES.items():
+        rs = schedule_ranges(ranges, sched)
+        assert rs[0][1] == total and rs[-1][0] == 0 and all(rs[i][0] == rs[i + 1][1] for i in range(len(rs) - 1)), name
+        for dtype in (torch.float32, torch.bfloat16):
+            t = torch.full((total,), float(rank + 1), dtype=dtype)
+            for x in allreduce_ranges(t, rs, None):
+                x.wait()
+            assert float(t.float().min()) == float(t.float().max()) == 3.0, (name, dtype)
     q.put((rank, float(g.min()), float(g.max())))
     dist.destroy_process_group()
 
