@@ -478,6 +478,16 @@ def main():
     if launches_per_step is None:
         launches_per_step = eager_launches
     torch.cuda.synchronize(dev)
+    out_ms = (ctypes.c_float * 7)()
+    out_n = (ctypes.c_int * 7)()
+    if rank == 0:
+        _lib.call("cilrs_model_profile_collect", model._handle, out_ms, out_n)
+        _lib.call("cilrs_model_profile", model._handle, 0)
+    # the inference measurements below use their OWN module, loaded from the trained state_dict like a rollout worker would
+    # (a 512-frame session on the training module would rebuild its plan under the trainer's feet)
+    infer_model = CILRS(num_commands=4, dropout=0.0)
+    infer_model.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
+    infer_model = infer_model.to(dev).eval()
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -496,9 +506,8 @@ def main():
     # ---- configs[4]: batched inference sharded over the ranks (512 frames per GPU), all ranks ----
     try:
         from cilrs_b200.preprocess import ShardedInference
-        model.eval()
         PER = 512
-        sh = ShardedInference(model, PER * world, src_hw=(88, 200))   # frames already 200x88 (the rollout's resized stream)
+        sh = ShardedInference(infer_model, PER * world, src_hw=(88, 200))   # frames already 200x88 (the rollout's resized stream)
         gi = torch.Generator().manual_seed(7 + rank)
         sh.session.h_frames.copy_(torch.randint(0, 256, tuple(sh.session.h_frames.shape), generator=gi, dtype=torch.uint8))
         sh.session.h_speed.copy_(torch.rand(PER, generator=gi))
@@ -532,13 +541,8 @@ def main():
         del sh
     except Exception as ex:  # never lose the training line to the extra measurement
         line["infer_c5"] = {"error": repr(ex)}
-    model.train()
     if rank == 0:
         pk = peaks()
-        out_ms = (ctypes.c_float * 7)()
-        out_n = (ctypes.c_int * 7)()
-        _lib.call("cilrs_model_profile_collect", model._handle, out_ms, out_n)
-        _lib.call("cilrs_model_profile", model._handle, 0)
         names = ["conv_fprop", "conv_dgrad", "conv_wgrad", "bn_forward_pool", "bn_backward", "heads", "other"]
         breakdown = {n: {"ms": round(float(out_ms[i]), 4), "launches": int(out_n[i])} for i, n in enumerate(names)}
         t_gemm = (out_ms[0] + out_ms[1]) * 1e-3
@@ -573,8 +577,7 @@ def main():
         # ---- batch-1 inference latency (the other half of BASELINE.json's metric) ----
         try:
             from cilrs_b200.preprocess import InferenceSession
-            model.eval()
-            sess = InferenceSession(model, batch=1)
+            sess = InferenceSession(infer_model, batch=1)
             sess.h_frames.random_(0, 256)
             sess.h_speed.fill_(0.3)
             sess.h_command.fill_(1)
@@ -587,11 +590,10 @@ def main():
             line["infer_b1"] = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "iterations": len(lat),
                                 "span": "raw uint8 600x800x3 frame in pinned host memory -> (steer, throttle, brake, speed) on the host"}
             del sess
-            model.train()
         except Exception as ex:
             line["infer_b1"] = {"error": repr(ex)}
         if not args.no_extras:
-            line.update(extra_kernel_lines(torch, model, pk))
+            line.update(extra_kernel_lines(torch, infer_model, pk))
         # ---- CPU baseline (the reference's class when oracle/_ref was built, else the oracle port), bounded sample ----
         check_failed = None
         if world == 1 and not args.no_cpu_baseline:

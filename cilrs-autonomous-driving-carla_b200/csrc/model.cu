@@ -742,6 +742,8 @@ static int heads_backward(Model& m, int B, const float* dcontrols, const float* 
 // async_part: do not make the caller's stream wait for the weight-gradient stream at the end of the part; instead the
 // weight-gradient stream waits for the caller's stream, so that "everything this part wrote" is complete in THAT stream's order
 // (the host enqueues the part's allreduce there and joins once, after the last part: cilrs_model_backward_join)
+static __nv_bfloat16* debug_gradient_buffer(Model& m, int hi) { return (hi >= 0 && ((15 - hi) & 1)) ? m.g1 : m.g0; }
+
 // dbg_hi / dbg_lo (test hook, cilrs_model_debug_backward): run only blocks dbg_hi..max(dbg_lo,0) (none if dbg_hi < 0) from the
 // gradient the caller placed in m.g0, plus the stem if dbg_lo < 0; the heads are skipped
 static int backward(Model& m, int B, int mode, int part, const float* dcontrols, const float* dspeed, const float* speed,
@@ -755,15 +757,17 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   if (part < -1 || part > 4) return ERR_INVALID;
   if (dbg) {
     CK(cuda_status(cudaMemsetAsync(m.acc_bwd, 0, (size_t)m.acc_bwd_bytes, s)));
+    // the plans bake the ping-pong buffers in: block 15 reads g0 and writes g1, block 14 reads g1, ...
+    __nv_bfloat16* gin = debug_gradient_buffer(m, dbg_hi);
     if (dbg_hi >= 0) {
       Block& top = m.blocks[dbg_hi];
-      PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_reduce(m, B, top.b.gout, top.b.bn, m.g0, top.out, top.b.y, s)));
+      PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_reduce(m, B, top.b.gout, top.b.bn, gin, top.out, top.b.y, s)));
       if (top.has_ds) {
         // the downsample BatchNorm is fed by the same masked gradient: its reductions (the regular path gets them from the
         // fused dgrad of the next block)
         BnBwdReduceParams rp{};
         const long long nvec = pad_elems(B, top.b.gout, top.ds.bn.C) / 8;
-        rp.g = m.g0; rp.act = nullptr; rp.y = top.ds.y; rp.mean = top.ds.bn.vec + 2 * top.ds.bn.C; rp.rstd = top.ds.bn.vec + 3 * top.ds.bn.C;
+        rp.g = gin; rp.act = nullptr; rp.y = top.ds.y; rp.mean = top.ds.bn.vec + 2 * top.ds.bn.C; rp.rstd = top.ds.bn.vec + 3 * top.ds.bn.C;
         rp.nvec = nvec; rp.C = top.ds.bn.C; rp.partial = m.stat_acc; rp.counter = m.counters; rp.bsum = top.ds.bn.bred;
         rp.bdot = top.ds.bn.bred + top.ds.bn.C; rp.dgamma = m.grads + m.slots[top.ds.bn.gamma].off;
         rp.dbeta = m.grads + m.slots[top.ds.bn.beta].off; rp.dz_out = nullptr; rp.geom = top.b.gout;
@@ -771,7 +775,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
         CK(cuda_status(launch_pdl(bn_bwd_reduce_kernel<false>, dim3(ew_reduce_grid(nvec, rp.C)), dim3(EW_THREADS), 0, s, rp)));
       }
     }
-    m.bw_gcur = m.g0; m.bw_gnext = m.g1;
+    m.bw_gcur = gin; m.bw_gnext = gin == m.g0 ? m.g1 : m.g0;
     m.bw_deferred = false;
   } else if (part <= 0) {
     CK(cuda_status(cudaMemsetAsync(m.acc_bwd, 0, (size_t)m.acc_bwd_bytes, s)));  // accumulators of the deferred BN-backward finalize
@@ -1151,7 +1155,8 @@ int cilrs_model_debug_backward(cilrs_model* h, int batch, int mode, int hi, int 
   if (hi < 0 && lo >= 0) return ERR_INVALID;
   const PadGeom g = hi >= 0 ? m.blocks[hi].b.gout : kGeom0;
   const int C = hi >= 0 ? m.blocks[hi].b.d.out_c : 64;
-  CK(cuda_status(cudaMemcpyAsync(m.g0, g_out, (size_t)pad_elems(batch, g, C) * 2, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)));
+  CK(cuda_status(cudaMemcpyAsync(debug_gradient_buffer(m, hi), g_out, (size_t)pad_elems(batch, g, C) * 2, cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream)));
   return backward(m, batch, mode, -1, nullptr, nullptr, nullptr, nullptr, 0.f, (cudaStream_t)stream, false, hi, lo);
 }
 void* cilrs_model_debug_gradient(cilrs_model* h) { return h ? (void*)h->m.bw_gcur : nullptr; }

@@ -56,6 +56,7 @@ class FusedTrainer:
         self.dev = dev
         model.train()
         model._ensure(batch)
+        model._refresh_if_needed(infer=False)   # the bf16 operands must exist before the first (eager) step
         self._plan_gen = model._plan_gen
         # dropout masks follow the optimizer's DEVICE step counter, so a replayed graph draws a new mask every step
         _lib.call("cilrs_model_set_dropout_counter", model._handle, self.opt._step_dev)
