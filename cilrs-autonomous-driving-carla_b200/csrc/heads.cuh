@@ -1,24 +1,31 @@
-// K3: the CILRS heads in fp32 on CUDA cores (they are < 0.1 % of the model FLOPs and latency-bound):
+// K3: the CILRS heads in fp32 on CUDA cores (< 0.1 % of the model FLOPs, latency-bound):
 //   speed encoder 1->128->128, command-selected control branch 640->256->256->3, speed predictor 512->256->256->1,
-//   the two training losses and their gradients, and the head backward pass.
+//   the two training losses and their gradients (fused into the forward), and the head backward pass.
 // Reference: CILRS.forward model/autonomous_drive.py:389-399 (all 4 branches evaluated then gather(0, command));
-// only the selected branch is computed here — the others receive exactly zero gradient.
+// only the selected branch is computed here - the others receive exactly zero gradient.
+//
+// Batched form (round 2): a thread-block CLUSTER of 8 CTAs owns a group of up to 32 samples that share their weights (the
+// samples of one command for the branch role, 32 consecutive samples for the speed-predictor role). Every CTA computes a
+// 1/8 column slice of each layer for all 32 samples, so each weight byte is read ONCE per sample group (round 1: once per
+// sample - 228 MB of L2->SM traffic per forward at B = 128), and hands its slice of the activations to the other seven CTAs
+// through distributed shared memory (st.shared::cluster) before a cluster barrier starts the next layer. One launch per
+// direction, no global-memory round trips between layers.
 #pragma once
 #include "common.cuh"
+#include "pair.cuh"
 
 namespace cilrs {
 
 constexpr int HD_THREADS = 256;
+constexpr int HD_G = 32;    // samples per cluster
+constexpr int HD_CL = 8;    // CTAs per cluster
+constexpr int HD_SMEM_FLOATS = HD_G * 640 + 2 * HD_G * 256;   // X | H1 | H2  (forward)  /  dA | dB | dC (backward)
+constexpr int HD_SMEM_BYTES = HD_SMEM_FLOATS * 4;
 
 struct HeadsWeights {
   const float *se0_w, *se0_b, *se3_w, *se3_b;
   const float *br0_w[4], *br0_b[4], *br3_w[4], *br3_b[4], *br6_w[4], *br6_b[4];
   const float *sp0_w, *sp0_b, *sp3_w, *sp3_b, *sp5_w, *sp5_b;
-};
-struct HeadsGrads {
-  float *se0_w, *se0_b, *se3_w, *se3_b;
-  float *br0_w[4], *br0_b[4], *br3_w[4], *br3_b[4], *br6_w[4], *br6_b[4];
-  float *sp0_w, *sp0_b, *sp3_w, *sp3_b, *sp5_w, *sp5_b;
 };
 // activations kept for the backward pass (post-ReLU, post-dropout), all fp32 row-major [B, width]
 struct HeadsSaved {
@@ -46,118 +53,6 @@ CILRS_DEVINL bool drop_keep(unsigned long long seed, int sample, int site, int j
   return (float)(z >> 40) * (1.0f / 16777216.0f) >= p;
 }
 
-// y[o] = act( W[o,:] . x + b[o] ),  W row-major [out, in], in % 128 == 0 or in == 1; x and y in shared memory
-CILRS_DEVINL void gemv_rows(const float* __restrict__ W, const float* __restrict__ b, const float* x, int in, int out, float* y,
-                            bool relu) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = HD_THREADS / 32;
-  const int n4 = in >> 2;
-  // eight output rows per warp iteration: 8 independent load/FMA chains per lane hide the L2 latency of the weight rows
-  constexpr int R = 8;
-  for (int o0 = warp * R; o0 < out; o0 += nwarps * R) {
-    float acc[R];
-#pragma unroll
-    for (int q = 0; q < R; ++q) acc[q] = 0.f;
-    for (int i = lane; i < n4; i += 32) {
-      const float4 x4 = *reinterpret_cast<const float4*>(x + 4 * i);
-      float4 w4[R];
-#pragma unroll
-      for (int q = 0; q < R; ++q)
-        w4[q] = (o0 + q < out) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(o0 + q) * in) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        acc[q] = fmaf(w4[q].x, x4.x, acc[q]); acc[q] = fmaf(w4[q].y, x4.y, acc[q]);
-        acc[q] = fmaf(w4[q].z, x4.z, acc[q]); acc[q] = fmaf(w4[q].w, x4.w, acc[q]);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < R; ++q) {
-      const float r = warp_sum(acc[q]);
-      if (lane == 0 && o0 + q < out) {
-        float v = r + b[o0 + q];
-        if (relu) v = fmaxf(v, 0.f);
-        y[o0 + q] = v;
-      }
-    }
-  }
-}
-
-struct HeadsFwdParams {
-  HeadsWeights w;
-  HeadsSaved sv;       // pointers may be null when nothing has to be kept (inference)
-  const float* feat;   // [B,512]
-  const float* speed;  // [B]
-  const long long* command;  // [B] int64
-  float* controls;     // [B,3]
-  float* pred_speed;   // [B]
-  int batch;
-  float dropout_p;
-  unsigned long long seed;
-  const long long* seed_counter;  // optional device counter mixed into the seed (a new mask on every CUDA-graph replay)
-  int* error_flag;     // set to 1 if a command is outside [0,4)
-};
-
-__global__ void __launch_bounds__(HD_THREADS) heads_fwd_kernel(const HeadsFwdParams p) {
-  __shared__ __align__(16) float x[640];
-  __shared__ __align__(16) float h1[256];
-  __shared__ __align__(16) float h2[256];
-  __shared__ __align__(16) float o3[4];
-  // two CTAs per sample: role 0 = speed encoder + command branch -> controls, role 1 = speed predictor -> pred_speed
-  // (the two chains are independent; one CTA per sample ran seven dependent GEMVs back to back)
-  const int b = blockIdx.x >> 1;
-  const int role = blockIdx.x & 1;
-  const int t = threadIdx.x;
-  long long cmd = p.command[b];
-  if (cmd < 0 || cmd > 3) {
-    if (t == 0 && p.error_flag) *p.error_flag = 1;
-    cmd = cmd < 0 ? 0 : 3;
-  }
-  const int k = (int)cmd;
-  const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
-  const unsigned long long seed = p.seed + (p.seed_counter ? 0x9E3779B97F4A7C15ull * (unsigned long long)(*p.seed_counter + 1) : 0ull);
-  for (int i = t; i < 512; i += HD_THREADS) x[i] = p.feat[(size_t)b * 512 + i];
-  if (role == 0) {
-  // speed encoder: Linear(1,128) + ReLU + Dropout, Linear(128,128) + ReLU
-  if (t < 128) {
-    float v = fmaxf(fmaf(p.w.se0_w[t], p.speed[b], p.w.se0_b[t]), 0.f);
-    if (p.dropout_p > 0.f) v = drop_keep(seed, b, 0, t, p.dropout_p) ? v * keep_scale : 0.f;
-    h1[t] = v;
-    if (p.sv.s1) p.sv.s1[(size_t)b * 128 + t] = v;
-  }
-  __syncthreads();
-  gemv_rows(p.w.se3_w, p.w.se3_b, h1, 128, 128, x + 512, true);
-  __syncthreads();
-  if (p.sv.sfeat && t < 128) p.sv.sfeat[(size_t)b * 128 + t] = x[512 + t];
-  // control branch k: Linear(640,256)+ReLU+Drop, Linear(256,256)+ReLU+Drop, Linear(256,3)
-  gemv_rows(p.w.br0_w[k], p.w.br0_b[k], x, 640, 256, h1, true);
-  __syncthreads();
-  if (p.dropout_p > 0.f) h1[t] = drop_keep(seed, b, 1, t, p.dropout_p) ? h1[t] * keep_scale : 0.f;
-  if (p.sv.b1) p.sv.b1[(size_t)b * 256 + t] = h1[t];
-  __syncthreads();
-  gemv_rows(p.w.br3_w[k], p.w.br3_b[k], h1, 256, 256, h2, true);
-  __syncthreads();
-  if (p.dropout_p > 0.f) h2[t] = drop_keep(seed, b, 2, t, p.dropout_p) ? h2[t] * keep_scale : 0.f;
-  if (p.sv.b2) p.sv.b2[(size_t)b * 256 + t] = h2[t];
-  __syncthreads();
-  gemv_rows(p.w.br6_w[k], p.w.br6_b[k], h2, 256, 3, o3, false);
-  __syncthreads();
-  if (t < 3) p.controls[(size_t)b * 3 + t] = o3[t];
-  return;
-  }
-  // speed predictor on the visual features only: Linear(512,256)+ReLU+Drop, Linear(256,256)+ReLU, Linear(256,1)
-  __syncthreads();
-  gemv_rows(p.w.sp0_w, p.w.sp0_b, x, 512, 256, h1, true);
-  __syncthreads();
-  if (p.dropout_p > 0.f) h1[t] = drop_keep(seed, b, 3, t, p.dropout_p) ? h1[t] * keep_scale : 0.f;
-  if (p.sv.p1) p.sv.p1[(size_t)b * 256 + t] = h1[t];
-  __syncthreads();
-  gemv_rows(p.w.sp3_w, p.w.sp3_b, h1, 256, 256, h2, true);
-  __syncthreads();
-  if (p.sv.p2) p.sv.p2[(size_t)b * 256 + t] = h2[t];
-  gemv_rows(p.w.sp5_w, p.w.sp5_b, h2, 256, 1, o3, false);
-  __syncthreads();
-  if (t == 0) p.pred_speed[b] = o3[0];
-}
-
 // ---------------------------------------------------------------------------------------------
 // losses (+ gradients w.r.t. the predictions). mode 0: MSE(controls) + w_speed*MSE(speed)  (README/config recipe)
 //                                               mode 1: w0*L1(steer)+w1*L1(thr)+w2*L1(brk) + w_speed*MSE(speed)  (notebook)
@@ -178,8 +73,8 @@ struct LossParams {
   float* dspeed;          // [B]   may be null
 };
 
-__global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
-  __shared__ float red[4][256];
+// the whole CTA (256 threads) calls this; red = 4 x 256 floats of shared memory
+CILRS_DEVINL void loss_body(const LossParams& p, float (*red)[256]) {
   float a[4] = {0.f, 0.f, 0.f, 0.f};
   const float invB = 1.f / (float)p.batch;
   for (int b = threadIdx.x; b < p.batch; b += 256) {
@@ -219,6 +114,11 @@ __global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
   }
 }
 
+static __global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
+  __shared__ float red[4][256];
+  loss_body(p, red);
+}
+
 // ---------------------------------------------------------------------------------------------
 // validate() on the device (notebook/notebook.ipynb:563-585): per batch the six loss scalars (as loss_kernel) and the
 // per-command steer absolute error, ACCUMULATED into acc[16] (fp64):
@@ -239,7 +139,7 @@ struct ValidateParams {
   double* acc;
 };
 
-__global__ void __launch_bounds__(256) validate_kernel(const ValidateParams p) {
+static __global__ void __launch_bounds__(256) validate_kernel(const ValidateParams p) {
   __shared__ float red[12][256];
   float a[12];
 #pragma unroll
@@ -282,7 +182,260 @@ __global__ void __launch_bounds__(256) validate_kernel(const ValidateParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// heads backward, part 1: per-sample deltas (one CTA per sample) and d(features)
+// cluster helpers
+// ---------------------------------------------------------------------------------------------
+CILRS_DEVINL void st_cluster_f32(uint32_t addr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+CILRS_DEVINL void st_cluster_v4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// The sample list of a cluster. Branch role (k in 0..3): the samples whose (clamped) command is k, ranks [j*32, j*32+32) in
+// batch order; speed-predictor role (k < 0): samples [j*32, j*32+32). Every CTA of the cluster computes the same list.
+// Returns the number of samples (0 = nothing to do; uniform over the cluster). Contains __syncthreads().
+CILRS_DEVINL int heads_sample_list(const long long* __restrict__ command, int batch, int k, int j, int* s_list, int* s_wcnt,
+                                   int* error_flag) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t < HD_G) s_list[t] = -1;
+  __syncthreads();
+  if (k < 0) {
+    const int b = j * HD_G + t;
+    if (t < HD_G && b < batch) s_list[t] = b;
+    __syncthreads();
+    return min(HD_G, batch - j * HD_G);
+  }
+  int base = 0;
+  const int lo = j * HD_G, hi = lo + HD_G;
+  for (int b0 = 0; b0 < batch; b0 += HD_THREADS) {
+    const int b = b0 + t;
+    bool match = false;
+    if (b < batch) {
+      long long c = command[b];
+      if (c < 0 || c > 3) {
+        if (error_flag) *error_flag = 1;   // the reference's gather(0, command) would raise; clamp and flag
+        c = c < 0 ? 0 : 3;
+      }
+      match = (int)c == k;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, match);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = base, tot = 0;
+#pragma unroll
+    for (int w = 0; w < HD_THREADS / 32; ++w) {
+      if (w < warp) off += s_wcnt[w];
+      tot += s_wcnt[w];
+    }
+    const int r = off + __popc(bal & ((1u << lane) - 1u));
+    if (match && r >= lo && r < hi) s_list[r - lo] = b;
+    base += tot;
+    __syncthreads();
+    if (base >= hi) break;
+  }
+  return max(0, min(HD_G, base - lo));
+}
+
+// v[32] per lane -> v[0] = sum over the 32 lanes of their v[lane] (recursive halving: 31 shuffles instead of 160)
+CILRS_DEVINL void reduce_transpose32(float (&v)[HD_G], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
+// One layer slice, forward: this warp computes output rows o0..o0+3 of W [out, in] (row-major, in % 128 == 0) for the 32
+// samples x[32][ldx] (shared memory). Lanes split K (float4 per lane and step); afterwards lane l holds the four sums of
+// sample l in r[0..3].
+CILRS_DEVINL void rows_dot4(const float* __restrict__ W, int in, int o0, int out, const float* x, int ldx, int lane, float (&r)[4]) {
+  float acc[4][HD_G];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int t = 0; t < HD_G; ++t) acc[q][t] = 0.f;
+  const int n4 = in >> 2;
+  for (int i = lane; i < n4; i += 32) {
+    float4 w4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      w4[q] = (o0 + q < out) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(o0 + q) * in) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < HD_G; ++t) {
+      const float4 x4 = *reinterpret_cast<const float4*>(x + t * ldx + 4 * i);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc[q][t] = fmaf(w4[q].x, x4.x, acc[q][t]); acc[q][t] = fmaf(w4[q].y, x4.y, acc[q][t]);
+        acc[q][t] = fmaf(w4[q].z, x4.z, acc[q][t]); acc[q][t] = fmaf(w4[q].w, x4.w, acc[q][t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    reduce_transpose32(acc[q], lane);
+    r[q] = acc[q][0];
+  }
+}
+
+// write this lane's (sample = lane) four consecutive outputs [col, col+4) into row `lane` of the buffer `dst` (row length ld)
+// of EVERY CTA of the cluster
+CILRS_DEVINL void bcast_row4(float* dst, int ld, int lane, int col, float4 v) {
+  float* p = dst + lane * ld + col;
+#pragma unroll
+  for (int rk = 0; rk < HD_CL; ++rk) st_cluster_v4(mapa_u32(p, (uint32_t)rk), v);
+}
+
+struct HeadsLossFuse {
+  int enabled;             // 0: the forward only produces controls / pred_speed
+  LossParams lp;           // controls / pred_speed / batch are filled from the forward's own arguments
+  unsigned int* counter;   // zeroed device counter, left zero
+};
+
+struct HeadsFwdParams {
+  HeadsWeights w;
+  HeadsSaved sv;       // pointers may be null when nothing has to be kept (inference)
+  const float* feat;   // [B,512]
+  const float* speed;  // [B]
+  const long long* command;  // [B] int64
+  float* controls;     // [B,3]
+  float* pred_speed;   // [B]
+  int batch;
+  float dropout_p;
+  unsigned long long seed;
+  const long long* seed_counter;  // optional device counter mixed into the seed (a new mask on every CUDA-graph replay)
+  int* error_flag;     // set to 1 if a command is outside [0,4)
+  HeadsLossFuse loss;
+};
+
+__host__ __device__ inline int heads_groups(int batch) { return (batch + HD_G - 1) / HD_G; }
+inline int heads_grid(int batch) { return 5 * heads_groups(batch) * HD_CL; }   // 4 branch roles + the speed predictor
+
+// generic hidden layer of a role: out columns [32*rank + 4*warp, +4) (or 16 per CTA when out == 128), ReLU, optional dropout,
+// broadcast into `dst` of every CTA, optional global save
+CILRS_DEVINL void heads_layer(const float* __restrict__ W, const float* __restrict__ bias, int in, int out, const float* x, int ldx,
+                              float* dst, int ldd, int dst_col0, float* save, int save_ld, const int* s_list, int cnt, uint32_t rank,
+                              float dropout_p, float keep_scale, unsigned long long seed, int site) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_cta = out / HD_CL;           // 32 or 16
+  if (warp * 4 >= per_cta) return;
+  const int o0 = (int)rank * per_cta + warp * 4;
+  float r[4];
+  rows_dot4(W, in, o0, out, x, ldx, lane, r);
+  const int b = s_list[lane];
+  float v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float u = fmaxf(r[q] + __ldg(bias + o0 + q), 0.f);
+    if (dropout_p > 0.f && b >= 0) u = drop_keep(seed, b, site, o0 + q, dropout_p) ? u * keep_scale : 0.f;
+    v[q] = (lane < cnt) ? u : 0.f;
+  }
+  const float4 v4 = make_float4(v[0], v[1], v[2], v[3]);
+  bcast_row4(dst, ldd, lane, dst_col0 + o0, v4);
+  if (save && lane < cnt) *reinterpret_cast<float4*>(save + (size_t)b * save_ld + o0) = v4;
+}
+
+static __global__ void __launch_bounds__(HD_THREADS, 1) heads_fwd_kernel(const HeadsFwdParams p) {
+  extern __shared__ __align__(16) float hd_smem[];
+  __shared__ int s_list[HD_G];
+  __shared__ int s_wcnt[HD_THREADS / 32];
+  __shared__ float s_red[4][256];
+  __shared__ int s_last;
+  float* X = hd_smem;                    // [32][640]  features | speed features
+  float* H1 = X + HD_G * 640;            // [32][256]
+  float* H2 = H1 + HD_G * 256;           // [32][256]  (its first half doubles as the speed encoder's hidden layer [32][128])
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = blockIdx.x / HD_CL;
+  const int ngrp = heads_groups(p.batch);
+  const bool branch_role = cluster < 4 * ngrp;
+  const int k = branch_role ? cluster / ngrp : -1;
+  const int j = branch_role ? cluster % ngrp : cluster - 4 * ngrp;
+  const int cnt = heads_sample_list(p.command, p.batch, k, j, s_list, s_wcnt, p.error_flag);
+  const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+  const unsigned long long seed = p.seed + (p.seed_counter ? 0x9E3779B97F4A7C15ull * (unsigned long long)(*p.seed_counter + 1) : 0ull);
+  if (cnt > 0) {   // (uniform over the cluster: empty clusters skip every cluster barrier together)
+    // features of the group's samples (rows of absent samples are zero)
+    for (int e = t; e < HD_G * 128; e += HD_THREADS) {
+      const int g = e >> 7, c4 = e & 127;
+      const int b = s_list[g];
+      const float4 v = b >= 0 ? __ldg(reinterpret_cast<const float4*>(p.feat + (size_t)b * 512) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(X + g * 640 + 4 * c4) = v;
+    }
+    if (branch_role) {
+      // speed encoder layer 0: Linear(1,128) + ReLU + Dropout - cheap, every CTA computes all of it
+      for (int e = t; e < HD_G * 128; e += HD_THREADS) {
+        const int g = e >> 7, c = e & 127;
+        const int b = s_list[g];
+        float v = 0.f;
+        if (b >= 0) {
+          v = fmaxf(fmaf(__ldg(p.w.se0_w + c), __ldg(p.speed + b), __ldg(p.w.se0_b + c)), 0.f);
+          if (p.dropout_p > 0.f) v = drop_keep(seed, b, 0, c, p.dropout_p) ? v * keep_scale : 0.f;
+          if (p.sv.s1 && rank == 0) p.sv.s1[(size_t)b * 128 + c] = v;
+        }
+        H2[g * 128 + c] = v;
+      }
+      __syncthreads();
+      cluster_sync_all();   // every CTA's X / H2 are written before peers start to store speed features into them
+      // speed encoder layer 3: Linear(128,128) + ReLU -> X[:, 512:640] of every CTA
+      heads_layer(p.w.se3_w, p.w.se3_b, 128, 128, H2, 128, X, 640, 512, p.sv.sfeat, 128, s_list, cnt, rank, 0.f, 1.f, seed, 0);
+      cluster_sync_all();
+      // branch k: Linear(640,256)+ReLU+Drop, Linear(256,256)+ReLU+Drop, Linear(256,3)
+      heads_layer(p.w.br0_w[k], p.w.br0_b[k], 640, 256, X, 640, H1, 256, 0, p.sv.b1, 256, s_list, cnt, rank, p.dropout_p, keep_scale, seed, 1);
+      cluster_sync_all();
+      heads_layer(p.w.br3_w[k], p.w.br3_b[k], 256, 256, H1, 256, H2, 256, 0, p.sv.b2, 256, s_list, cnt, rank, p.dropout_p, keep_scale, seed, 2);
+      cluster_sync_all();
+      if (rank == 0 && warp == 0) {
+        float r[4];
+        rows_dot4(p.w.br6_w[k], 256, 0, 3, H2, 256, lane, r);
+        if (lane < cnt) {
+          const int b = s_list[lane];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) p.controls[(size_t)b * 3 + q] = r[q] + __ldg(p.w.br6_b[k] + q);
+        }
+      }
+    } else {
+      __syncthreads();
+      cluster_sync_all();
+      // speed predictor on the visual features only: Linear(512,256)+ReLU+Drop, Linear(256,256)+ReLU, Linear(256,1)
+      heads_layer(p.w.sp0_w, p.w.sp0_b, 512, 256, X, 640, H1, 256, 0, p.sv.p1, 256, s_list, cnt, rank, p.dropout_p, keep_scale, seed, 3);
+      cluster_sync_all();
+      heads_layer(p.w.sp3_w, p.w.sp3_b, 256, 256, H1, 256, H2, 256, 0, p.sv.p2, 256, s_list, cnt, rank, 0.f, 1.f, seed, 0);
+      cluster_sync_all();
+      if (rank == 0 && warp == 0) {
+        float r[4];
+        rows_dot4(p.w.sp5_w, 256, 0, 1, H2, 256, lane, r);
+        if (lane < cnt) p.pred_speed[s_list[lane]] = r[0] + __ldg(p.w.sp5_b);
+      }
+    }
+    cluster_sync_all();   // nobody leaves while a peer may still write into its shared memory
+  }
+  // ---- fused loss: the last cluster to finish (rank 0 CTAs count) reduces over the whole batch ----
+  if (p.loss.enabled && rank == 0) {
+    __syncthreads();
+    if (t == 0) {
+      __threadfence();
+      const unsigned int done = atomicAdd(p.loss.counter, 1u);
+      const int last = done == gridDim.x / HD_CL - 1;
+      if (last) __threadfence();
+      s_last = last;
+    }
+    __syncthreads();
+    if (s_last) {
+      LossParams lp = p.loss.lp;
+      lp.controls = p.controls; lp.pred_speed = p.pred_speed; lp.batch = p.batch;
+      loss_body(lp, s_red);
+      if (t == 0) *p.loss.counter = 0u;   // ready for the next launch / graph replay
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// heads backward, part 1: per-sample deltas and d(features), same cluster decomposition.
+// A transposed layer y[g][c] = sum_o W[o][c] d[g][o] is split by COLUMNS c over the CTAs; thread = (column, sample subgroup),
+// so the weight loads of a warp are contiguous and every output is one thread's fixed-order sum (deterministic).
 // ---------------------------------------------------------------------------------------------
 struct HeadsBwdParams {
   HeadsWeights w;
@@ -296,109 +449,162 @@ struct HeadsBwdParams {
   float dropout_p;
 };
 
-// y[i] = sum_o W[o*ld + i] * d[o], i < in  (transposed GEMV). Threads = (column quad, row slice): float4 loads of four
-// consecutive columns (coalesced across the quad index), `slices` = 256 / (in/4) independent row slices summed through
-// `scratch` (>= 1024 floats of shared memory), so the serial chain per thread is out / slices rows.
-// Contains __syncthreads(): every thread of the CTA must call it; in % 4 == 0, in <= 512.
-CILRS_DEVINL void gemv_cols(const float* __restrict__ W, int ld, const float* d, int in, int out, float* y, float* scratch) {
-  const int ncg = in >> 2;
-  int slices = HD_THREADS / ncg;
-  if (slices > 8) slices = 8;
-  const int cg = threadIdx.x % ncg, sl = threadIdx.x / ncg;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (sl < slices) {
-    const float4* wp = reinterpret_cast<const float4*>(W) + cg;
-    const int ld4 = ld >> 2;
+// acc[s] = sum_{o < K} W[o*ld + col] * d[(sg*SPT + s)*ldd + o]   with col = c0 + (t % WD), sg = t / WD, SPT = 32 / (256 / WD)
+template <int WD>
+CILRS_DEVINL void cols_dot(const float* __restrict__ W, int ld, int c0, int K, const float* d, int ldd, float (&acc)[HD_G * WD / HD_THREADS]) {
+  constexpr int SPT = HD_G * WD / HD_THREADS;
+  const int c = threadIdx.x % WD, sg = threadIdx.x / WD;
+  const float* wp = W + c0 + c;
+  const float* dp = d + (sg * SPT) * ldd;
+#pragma unroll
+  for (int s = 0; s < SPT; ++s) acc[s] = 0.f;
 #pragma unroll 8
-    for (int o = sl; o < out; o += slices) {
-      const float4 w = __ldg(wp + (size_t)o * ld4);
-      const float dv = d[o];
-      acc.x = fmaf(w.x, dv, acc.x); acc.y = fmaf(w.y, dv, acc.y); acc.z = fmaf(w.z, dv, acc.z); acc.w = fmaf(w.w, dv, acc.w);
-    }
-    *reinterpret_cast<float4*>(scratch + sl * in + cg * 4) = acc;
+  for (int o = 0; o < K; ++o) {
+    const float w = __ldg(wp + (size_t)o * ld);
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) acc[s] = fmaf(w, dp[s * ldd + o], acc[s]);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < in; i += HD_THREADS) {
-    float v = scratch[i];
-    for (int k = 1; k < slices; ++k) v += scratch[k * in + i];
-    y[i] = v;
-  }
-  __syncthreads();  // scratch is reused by the next call
 }
 
-__global__ void __launch_bounds__(HD_THREADS) heads_bwd_kernel(const HeadsBwdParams p) {
-  __shared__ __align__(16) float d_a[256], d_b[256], dx[640], dx2[512], d3[4], scratch[1024];
-  // two CTAs per sample (see heads_fwd_kernel): role 0 = command branch + speed encoder, role 1 = speed predictor
-  const int b = blockIdx.x >> 1, role = blockIdx.x & 1, t = threadIdx.x;
-  long long cmd = p.command[b];
-  const int k = cmd < 0 ? 0 : (cmd > 3 ? 3 : (int)cmd);
+// store value v of (sample g, column col) into `dst[g*ld + col]` of every CTA of the cluster
+CILRS_DEVINL void bcast_f32(float* dst, int ld, int g, int col, float v) {
+  float* p = dst + g * ld + col;
+#pragma unroll
+  for (int rk = 0; rk < HD_CL; ++rk) st_cluster_f32(mapa_u32(p, (uint32_t)rk), v);
+}
+
+static __global__ void __launch_bounds__(HD_THREADS, 1) heads_bwd_kernel(const HeadsBwdParams p) {
+  extern __shared__ __align__(16) float hd_smem[];
+  __shared__ int s_list[HD_G];
+  __shared__ int s_wcnt[HD_THREADS / 32];
+  __shared__ float s_d3[HD_G][4];
+  float* dA = hd_smem;                 // [32][256]
+  float* dB = dA + HD_G * 256;         // [32][256]
+  float* dC = dB + HD_G * 256;         // [32][128]
+  const int t = threadIdx.x;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = blockIdx.x / HD_CL;
+  const int ngrp = heads_groups(p.batch);
+  const bool branch_role = cluster < 4 * ngrp;
+  const int k = branch_role ? cluster / ngrp : -1;
+  const int j = branch_role ? cluster % ngrp : cluster - 4 * ngrp;
+  const int cnt = heads_sample_list(p.command, p.batch, k, j, s_list, s_wcnt, nullptr);
+  if (cnt == 0) return;   // uniform over the cluster
   const float ks = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
-  if (role == 1) {
+  if (branch_role) {
+    // ---- control branch ----
+    if (t < HD_G * 4) {
+      const int g = t >> 2, q = t & 3;
+      const int b = s_list[g];
+      const float v = (b >= 0 && q < 3) ? p.dcontrols[(size_t)b * 3 + q] : 0.f;
+      s_d3[g][q] = v;
+      if (b >= 0 && rank == 0) p.sv.d_br6[(size_t)b * 4 + q] = v;
+    }
+    __syncthreads();
+    {  // delta of layer .3's output: every CTA needs all 256 columns, three terms each - computed redundantly
+      const float w0 = __ldg(p.w.br6_w[k] + t), w1 = __ldg(p.w.br6_w[k] + 256 + t), w2 = __ldg(p.w.br6_w[k] + 512 + t);
+      for (int g = 0; g < HD_G; ++g) {
+        const int b = s_list[g];
+        float v = 0.f;
+        if (b >= 0 && p.sv.b2[(size_t)b * 256 + t] > 0.f) v = (w0 * s_d3[g][0] + w1 * s_d3[g][1] + w2 * s_d3[g][2]) * ks;
+        dA[g * 256 + t] = v;
+        if (b >= 0 && (t >> 5) == (int)rank) p.sv.d_br3[(size_t)b * 256 + t] = v;
+      }
+    }
+    __syncthreads();
+    cluster_sync_all();   // peers' dB / dC are free to be written
+    {  // delta of layer .0's output, this CTA's 32 columns
+      float acc[4];
+      cols_dot<32>(p.w.br3_w[k], 256, 32 * (int)rank, 256, dA, 256, acc);
+      const int col = 32 * (int)rank + (t & 31), sg = t >> 5;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int g = sg * 4 + s, b = s_list[g];
+        const float v = (b >= 0 && p.sv.b1[(size_t)b * 256 + col] > 0.f) ? acc[s] * ks : 0.f;
+        bcast_f32(dB, 256, g, col, v);
+        if (b >= 0) p.sv.d_br0[(size_t)b * 256 + col] = v;
+      }
+    }
+    cluster_sync_all();
+    {  // d(features): 64 of the 512 feature columns of W0
+      float acc[8];
+      cols_dot<64>(p.w.br0_w[k], 640, 64 * (int)rank, 256, dB, 256, acc);
+      const int col = 64 * (int)rank + (t & 63), sg = t >> 6;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const int b = s_list[sg * 8 + s];
+        if (b >= 0) p.dfeat[(size_t)b * 512 + col] = acc[s];
+      }
+    }
+    {  // d(speed features): 16 of the 128 columns 512..639 of W0, through the speed encoder's last ReLU
+      float acc[2];
+      cols_dot<16>(p.w.br0_w[k], 640, 512 + 16 * (int)rank, 256, dB, 256, acc);
+      const int col = 16 * (int)rank + (t & 15), sg = t >> 4;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int g = sg * 2 + s, b = s_list[g];
+        const float v = (b >= 0 && p.sv.sfeat[(size_t)b * 128 + col] > 0.f) ? acc[s] : 0.f;
+        bcast_f32(dC, 128, g, col, v);
+        if (b >= 0) p.sv.d_se3[(size_t)b * 128 + col] = v;
+      }
+    }
+    cluster_sync_all();
+    {  // speed encoder layer 0 delta
+      float acc[2];
+      cols_dot<16>(p.w.se3_w, 128, 16 * (int)rank, 128, dC, 128, acc);
+      const int col = 16 * (int)rank + (t & 15), sg = t >> 4;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int b = s_list[sg * 2 + s];
+        if (b >= 0) p.sv.d_se0[(size_t)b * 128 + col] = p.sv.s1[(size_t)b * 128 + col] > 0.f ? acc[s] * ks : 0.f;
+      }
+    }
+  } else {
     // ---- speed predictor ----
-    if (t == 0) {
-      d3[0] = p.dspeed[b];
-      p.sv.d_sp5[b] = d3[0];
+    if (t < HD_G) {
+      const int b = s_list[t];
+      const float v = b >= 0 ? p.dspeed[b] : 0.f;
+      s_d3[t][0] = v;
+      if (b >= 0 && rank == 0) p.sv.d_sp5[b] = v;
     }
     __syncthreads();
     {
-      const float v = p.sv.p2[(size_t)b * 256 + t] > 0.f ? p.w.sp5_w[t] * d3[0] : 0.f;
-      d_a[t] = v;
-      p.sv.d_sp3[(size_t)b * 256 + t] = v;
+      const float w = __ldg(p.w.sp5_w + t);
+      for (int g = 0; g < HD_G; ++g) {
+        const int b = s_list[g];
+        float v = 0.f;
+        if (b >= 0 && p.sv.p2[(size_t)b * 256 + t] > 0.f) v = w * s_d3[g][0];
+        dA[g * 256 + t] = v;
+        if (b >= 0 && (t >> 5) == (int)rank) p.sv.d_sp3[(size_t)b * 256 + t] = v;
+      }
     }
     __syncthreads();
-    gemv_cols(p.w.sp3_w, 256, d_a, 256, 256, d_b, scratch);
-    __syncthreads();
+    cluster_sync_all();
     {
-      const float v = p.sv.p1[(size_t)b * 256 + t] > 0.f ? d_b[t] * ks : 0.f;
-      d_b[t] = v;
-      p.sv.d_sp0[(size_t)b * 256 + t] = v;
+      float acc[4];
+      cols_dot<32>(p.w.sp3_w, 256, 32 * (int)rank, 256, dA, 256, acc);
+      const int col = 32 * (int)rank + (t & 31), sg = t >> 5;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int g = sg * 4 + s, b = s_list[g];
+        const float v = (b >= 0 && p.sv.p1[(size_t)b * 256 + col] > 0.f) ? acc[s] * ks : 0.f;
+        bcast_f32(dB, 256, g, col, v);
+        if (b >= 0) p.sv.d_sp0[(size_t)b * 256 + col] = v;
+      }
     }
-    __syncthreads();
-    gemv_cols(p.w.sp0_w, 512, d_b, 512, 256, dx2, scratch);
-    __syncthreads();
-    for (int i = t; i < 512; i += HD_THREADS) p.dfeat2[(size_t)b * 512 + i] = dx2[i];
-    return;
+    cluster_sync_all();
+    {
+      float acc[8];
+      cols_dot<64>(p.w.sp0_w, 512, 64 * (int)rank, 256, dB, 256, acc);
+      const int col = 64 * (int)rank + (t & 63), sg = t >> 6;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const int b = s_list[sg * 8 + s];
+        if (b >= 0) p.dfeat2[(size_t)b * 512 + col] = acc[s];
+      }
+    }
   }
-  // ---- control branch ----
-  if (t < 4) {
-    const float v = t < 3 ? p.dcontrols[(size_t)b * 3 + t] : 0.f;
-    d3[t] = v;
-    p.sv.d_br6[(size_t)b * 4 + t] = v;
-  }
-  __syncthreads();
-  gemv_cols(p.w.br6_w[k], 256, d3, 256, 3, d_a, scratch);
-  __syncthreads();
-  {
-    const float v = p.sv.b2[(size_t)b * 256 + t] > 0.f ? d_a[t] * ks : 0.f;
-    d_a[t] = v;
-    p.sv.d_br3[(size_t)b * 256 + t] = v;
-  }
-  __syncthreads();
-  gemv_cols(p.w.br3_w[k], 256, d_a, 256, 256, d_b, scratch);
-  __syncthreads();
-  {
-    const float v = p.sv.b1[(size_t)b * 256 + t] > 0.f ? d_b[t] * ks : 0.f;
-    d_b[t] = v;
-    p.sv.d_br0[(size_t)b * 256 + t] = v;
-  }
-  __syncthreads();
-  gemv_cols(p.w.br0_w[k], 640, d_b, 512, 256, dx, scratch);
-  gemv_cols(p.w.br0_w[k] + 512, 640, d_b, 128, 256, dx + 512, scratch);
-  __syncthreads();
-  for (int i = t; i < 512; i += HD_THREADS) p.dfeat[(size_t)b * 512 + i] = dx[i];
-  // ---- speed encoder ----
-  if (t < 128) {
-    const float v = p.sv.sfeat[(size_t)b * 128 + t] > 0.f ? dx[512 + t] : 0.f;
-    d_a[t] = v;
-    p.sv.d_se3[(size_t)b * 128 + t] = v;
-  }
-  __syncthreads();
-  gemv_cols(p.w.se3_w, 128, d_a, 128, 128, d_b, scratch);
-  __syncthreads();
-  if (t < 128) {
-    const float v = p.sv.s1[(size_t)b * 128 + t] > 0.f ? d_b[t] * ks : 0.f;
-    p.sv.d_se0[(size_t)b * 128 + t] = v;
-  }
+  cluster_sync_all();   // nobody leaves while a peer may still write into its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -424,7 +630,7 @@ struct HeadsWgradParams {
   const float* speed;  // x of the first speed-encoder layer (ld 1)
 };
 
-__global__ void __launch_bounds__(256) heads_wgrad_kernel(const HeadsWgradParams p) {
+static __global__ void __launch_bounds__(256) heads_wgrad_kernel(const HeadsWgradParams p) {
   __shared__ float ds[32][17];
   __shared__ float xs[32][65];
   int j = 0;
@@ -442,7 +648,11 @@ __global__ void __launch_bounds__(256) heads_wgrad_kernel(const HeadsWgradParams
       const int bb = e >> 4, oo = e & 15;
       const int b = b0 + bb, o = o0 + oo;
       float v = 0.f;
-      if (b < p.batch && o < jb.out && (jb.branch < 0 || p.command[b] == jb.branch)) v = jb.delta[(size_t)b * jb.ld_delta + o];
+      if (b < p.batch && o < jb.out) {
+        long long c = p.command[b];
+        c = c < 0 ? 0 : (c > 3 ? 3 : c);   // same clamp as the forward (which also raised the error flag)
+        if (jb.branch < 0 || c == jb.branch) v = jb.delta[(size_t)b * jb.ld_delta + o];
+      }
       ds[bb][oo] = v;
     }
     for (int e = threadIdx.x; e < 32 * 64; e += 256) {
@@ -471,6 +681,25 @@ __global__ void __launch_bounds__(256) heads_wgrad_kernel(const HeadsWgradParams
     }
   }
   if (ti == 0 && threadIdx.x < 16 && o0 + (int)threadIdx.x < jb.out) jb.db[o0 + threadIdx.x] += bacc;
+}
+
+// launch with a cluster of HD_CL CTAs and the dynamic shared memory both kernels need
+template <typename P>
+inline cudaError_t heads_launch_cluster(void (*kernel)(P), int batch, cudaStream_t s, const P& prm) {
+  static bool attr_set = false;   // (one instance per kernel parameter type = per kernel)
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)heads_grid(batch)); cfg.blockDim = dim3(HD_THREADS); cfg.dynamicSmemBytes = HD_SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = HD_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, prm);
 }
 
 }  // namespace cilrs

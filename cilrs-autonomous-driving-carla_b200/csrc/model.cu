@@ -7,7 +7,7 @@
 #include "conv_params.h"
 #include "conv_host.h"
 #include "elementwise.cuh"
-#include "heads.cuh"
+#include "heads_run.cuh"
 #include "adam.cuh"
 #include <new>
 #include <string.h>
@@ -524,18 +524,13 @@ static int launch_flat_fwd(Model& m, int idx, const BnRef& bn, double count, int
   return launch_flat_conv(&f, s);
 }
 
-static HeadsWeights head_weights(const Model& m, const float* base) {
-  HeadsWeights w;
-  int s = m.head_slot0;
-  auto P = [&](int i) { return base + m.slots[i].off; };
-  w.se0_w = P(s); w.se0_b = P(s + 1); w.se3_w = P(s + 2); w.se3_b = P(s + 3);
-  s += 4;
-  for (int k = 0; k < 4; ++k) {
-    w.br0_w[k] = P(s); w.br0_b[k] = P(s + 1); w.br3_w[k] = P(s + 2); w.br3_b[k] = P(s + 3); w.br6_w[k] = P(s + 4); w.br6_b[k] = P(s + 5);
-    s += 6;
-  }
-  w.sp0_w = P(s); w.sp0_b = P(s + 1); w.sp3_w = P(s + 2); w.sp3_b = P(s + 3); w.sp5_w = P(s + 4); w.sp5_b = P(s + 5);
-  return w;
+static HeadsCtx heads_ctx(const Model& m) {
+  HeadsCtx c;
+  c.params = m.params; c.grads = m.grads;
+  for (int i = 0; i < HD_NUM_SLOTS; ++i) c.off[i] = m.slots[m.head_slot0 + i].off;
+  c.feat = m.feat; c.dfeat = m.dfeat; c.dfeat2 = m.dfeat2; c.head_comb = m.head_comb; c.hs = m.hs; c.err_flag = m.err_flag;
+  c.drop_counter = m.drop_counter; c.loss_counter = m.counters + 8;
+  return c;
 }
 
 // re-derive everything that depends on parameter values: packed bf16 conv weights (+ eval-mode BN folding)
@@ -557,11 +552,11 @@ static int refresh(Model& m, int what, cudaStream_t s) {
 }
 
 static int heads_forward(Model& m, int B, const float* speed, const long long* command, float* controls, float* pred_speed,
-                         int keep_for_backward, float dropout_p, unsigned long long seed, cudaStream_t s);
+                         int keep_for_backward, float dropout_p, unsigned long long seed, cudaStream_t s, const HeadsLossArgs* loss = nullptr);
 
 static int forward(Model& m, int B, int mode, const float* image, const void* x_s2d_in, const float* speed, const long long* command,
                    float* controls, float* pred_speed, int update_running, int keep_for_backward, float dropout_p,
-                   unsigned long long seed, cudaStream_t s) {
+                   unsigned long long seed, cudaStream_t s, const HeadsLossArgs* loss = nullptr) {
   if (B < 1 || B > m.maxB) return ERR_INVALID;
   if (!m.params || !m.buffers) return ERR_INVALID;
   CK(build_plans(m, B, mode));
@@ -620,20 +615,13 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
   }
   avgpool_kernel<<<(B * 512 + 255) / 256, 256, 0, s>>>(m.blocks.back().out, m.feat, B, 512, m.blocks.back().b.gout); ++g_cilrs_launches;
   CKL();
-  PROF(m, PC_HEADS, s, CK(heads_forward(m, B, speed, command, controls, pred_speed, keep_for_backward, dropout_p, seed, s)));
+  PROF(m, PC_HEADS, s, CK(heads_forward(m, B, speed, command, controls, pred_speed, keep_for_backward, dropout_p, seed, s, loss)));
   return OK;
 }
 
 static int heads_forward(Model& m, int B, const float* speed, const long long* command, float* controls, float* pred_speed,
-                         int keep_for_backward, float dropout_p, unsigned long long seed, cudaStream_t s) {
-  HeadsFwdParams hp;
-  hp.w = head_weights(m, m.params);
-  if (keep_for_backward) hp.sv = m.hs; else memset(&hp.sv, 0, sizeof(hp.sv));
-  hp.feat = m.feat; hp.speed = speed; hp.command = command; hp.controls = controls; hp.pred_speed = pred_speed;
-  hp.batch = B; hp.dropout_p = dropout_p; hp.seed = seed; hp.seed_counter = m.drop_counter; hp.error_flag = m.err_flag;
-  heads_fwd_kernel<<<2 * B, HD_THREADS, 0, s>>>(hp); ++g_cilrs_launches;  // two CTAs per sample
-  CKL();
-  return OK;
+                         int keep_for_backward, float dropout_p, unsigned long long seed, cudaStream_t s, const HeadsLossArgs* loss) {
+  return heads_forward_run(heads_ctx(m), B, speed, command, controls, pred_speed, keep_for_backward, dropout_p, seed, loss, s);
 }
 
 // ---- backward building blocks ----
@@ -686,62 +674,11 @@ static int run_bn_bwd_apply(Model& m, int B, const PadGeom& g, const BnRef& bn, 
   return cuda_status(launch_pdl(bn_bwd_apply_kernel<false>, dim3(ew_grid(nvec, bn.C, 4, 2)), dim3(EW_THREADS), 0, s, ap));
 }
 
-// deltas + d(features) on stream s; the weight / bias gradients on stream ws (the side stream of the backward when it is in
-// use: nothing on the trunk's chain depends on them)
 static int heads_backward(Model& m, int B, const float* dcontrols, const float* dspeed, const float* speed,
                           const long long* command, float dropout_p, cudaStream_t s, cudaStream_t ws) {
-  // ---- heads ----
-  HeadsBwdParams bp;
-  bp.w = head_weights(m, m.params); bp.sv = m.hs; bp.dcontrols = dcontrols; bp.dspeed = dspeed; bp.command = command;
-  bp.dfeat = m.dfeat; bp.dfeat2 = m.dfeat2; bp.batch = B; bp.dropout_p = dropout_p;
-  heads_bwd_kernel<<<2 * B, HD_THREADS, 0, s>>>(bp); ++g_cilrs_launches;  // two CTAs per sample
-  CKL();
-  if (ws != s) {
-    CK(cuda_status(cudaEventRecord(m.ev_heads, s)));
-    CK(cuda_status(cudaStreamWaitEvent(ws, m.ev_heads, 0)));
-  }
-  {
-    HeadsWgradParams wp;
-    memset(&wp, 0, sizeof(wp));
-    wp.batch = B; wp.command = command; wp.speed = speed;
-    int sidx = m.head_slot0, tiles = 0, nj = 0;
-    auto G = [&](int i) { return m.grads + m.slots[i].off; };
-    auto add = [&](const float* delta, int ldd, const float* x, int ldx, int out, int in, int slot_w, int branch) {
-      HeadsWgradJob& j = wp.job[nj++];
-      j.delta = delta; j.x = x; j.dw = G(slot_w); j.db = G(slot_w + 1); j.out = out; j.in = in; j.ld_delta = ldd; j.ld_x = ldx;
-      j.branch = branch; j.tile_begin = tiles; j.tiles_i = (in + 63) / 64;
-      tiles += j.tiles_i * ((out + 15) / 16);
-    };
-    add(m.hs.d_se0, 128, speed, 1, 128, 1, sidx, -1);
-    add(m.hs.d_se3, 128, m.hs.s1, 128, 128, 128, sidx + 2, -1);
-    sidx += 4;
-    for (int k = 0; k < 4; ++k) {
-      // x of the first branch layer is [feat | sfeat]: two jobs would need two sources; stage it as two column ranges
-      add(m.hs.d_br0, 256, nullptr, 0, 256, 640, sidx, k);      // patched below (combined input)
-      add(m.hs.d_br3, 256, m.hs.b1, 256, 256, 256, sidx + 2, k);
-      add(m.hs.d_br6, 4, m.hs.b2, 256, 3, 256, sidx + 4, k);
-      sidx += 6;
-    }
-    add(m.hs.d_sp0, 256, m.feat, 512, 256, 512, sidx, -1);
-    add(m.hs.d_sp3, 256, m.hs.p1, 256, 256, 256, sidx + 2, -1);
-    add(m.hs.d_sp5, 1, m.hs.p2, 256, 1, 256, sidx + 4, -1);
-    wp.num_jobs = nj;
-    // combined input [B,640] = [feat(512) | sfeat(128)] lives in dfeat-sized scratch: build it once
-    float* comb = m.head_comb;
-    CK(cuda_status(cudaMemcpy2DAsync(comb, 640 * 4, m.feat, 512 * 4, 512 * 4, B, cudaMemcpyDeviceToDevice, ws)));
-    CK(cuda_status(cudaMemcpy2DAsync(comb + 512, 640 * 4, m.hs.sfeat, 128 * 4, 128 * 4, B, cudaMemcpyDeviceToDevice, ws)));
-    for (int j = 0; j < nj; ++j)
-      if (!wp.job[j].x) { wp.job[j].x = comb; wp.job[j].ld_x = 640; }
-    heads_wgrad_kernel<<<tiles, 256, 0, ws>>>(wp); ++g_cilrs_launches;
-    CKL();
-  }
-  return OK;
+  return heads_backward_run(heads_ctx(m), B, dcontrols, dspeed, speed, command, dropout_p, s, ws, m.ev_heads);
 }
 
-// part: -1 = whole backward; 0 = heads + layer4, 1 = layer3, 2 = layer2, 3 = layer1, 4 = stem (must be called in order)
-// async_part: do not make the caller's stream wait for the weight-gradient stream at the end of the part; instead the
-// weight-gradient stream waits for the caller's stream, so that "everything this part wrote" is complete in THAT stream's order
-// (the host enqueues the part's allreduce there and joins once, after the last part: cilrs_model_backward_join)
 static __nv_bfloat16* debug_gradient_buffer(Model& m, int hi) { return (hi >= 0 && ((15 - hi) & 1)) ? m.g1 : m.g0; }
 
 // dbg_hi / dbg_lo (test hook, cilrs_model_debug_backward): run only blocks dbg_hi..max(dbg_lo,0) (none if dbg_hi < 0) from the
@@ -1041,6 +978,23 @@ int cilrs_model_forward(cilrs_model* h, int batch, int mode, const float* image_
   if (mode == MODE_INFER && keep_for_backward) return ERR_INVALID;
   return forward(h->m, batch, mode, image_nchw, image_s2d, speed, command, controls, pred_speed, update_running_stats,
                  keep_for_backward, dropout_p, seed, (cudaStream_t)stream);
+}
+
+// forward + the training loss fused into the heads kernel (the last cluster to finish reduces over the batch): one launch
+// less on the step's critical path. The speed head's target is the speed INPUT (notebook/notebook.ipynb:550).
+int cilrs_model_forward_loss(cilrs_model* h, int batch, int mode, const float* image_nchw, const void* image_s2d, const float* speed,
+                             const long long* command, float* controls, float* pred_speed, int update_running_stats,
+                             float dropout_p, unsigned long long seed, const float* targets, int loss_mode, float w_steer,
+                             float w_throttle, float w_brake, float w_speed, float grad_scale, float* out6, float* dcontrols,
+                             float* dspeed, void* stream) {
+  if (!h || !speed || !command || !controls || !pred_speed || !targets || !out6) return ERR_INVALID;
+  if (mode != MODE_TRAIN && mode != MODE_FROZEN) return ERR_INVALID;
+  if (loss_mode != 0 && loss_mode != 1) return ERR_INVALID;
+  HeadsLossArgs la;
+  la.targets = targets; la.speed_target = speed; la.mode = loss_mode; la.w_steer = w_steer; la.w_throttle = w_throttle;
+  la.w_brake = w_brake; la.w_speed = w_speed; la.grad_scale = grad_scale; la.out6 = out6; la.dcontrols = dcontrols; la.dspeed = dspeed;
+  return forward(h->m, batch, mode, image_nchw, image_s2d, speed, command, controls, pred_speed, update_running_stats, 1, dropout_p,
+                 seed, (cudaStream_t)stream, &la);
 }
 
 int cilrs_model_backward(cilrs_model* h, int batch, int mode, int part, const float* dcontrols, const float* dspeed,

@@ -122,9 +122,9 @@ class FusedTrainer:
         else:
             img, s2d = self.d_image, None
         m._seed = (m._seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
-        _lib.call("cilrs_model_forward", m._handle, b, MODE_TRAIN, img, s2d, self.d_speed, self.d_command, self.controls,
-                  self.pred_speed, 1, 1, ctypes.c_float(m.dropout), ctypes.c_ulonglong(m._seed), sp)
-        _lib.call("cilrs_loss", self.controls, self.pred_speed, self.d_targets, self.d_speed, b, self.loss_mode,
+        # forward with the loss (and its gradients w.r.t. controls / pred_speed) fused into the heads kernel
+        _lib.call("cilrs_model_forward_loss", m._handle, b, MODE_TRAIN, img, s2d, self.d_speed, self.d_command, self.controls,
+                  self.pred_speed, 1, ctypes.c_float(m.dropout), ctypes.c_ulonglong(m._seed), self.d_targets, self.loss_mode,
                   ctypes.c_float(self.ws[0]), ctypes.c_float(self.ws[1]), ctypes.c_float(self.ws[2]), ctypes.c_float(self.ws[3]),
                   ctypes.c_float(1.0), self.loss6, self.dcontrols, self.dspeed, sp)
         g = m.flat_gradients()   # zero on entry: the previous step's Adam / bf16 conversion cleared it (optimizer.zero_grad())

@@ -189,6 +189,14 @@ int cilrs_model_forward(cilrs_model* m, int batch, int mode, const float* image_
                         const float* speed, const long long* command, float* controls, float* pred_speed,
                         int update_running_stats, int keep_for_backward, float dropout_p, unsigned long long seed,
                         void* stream);
+/* The same forward (keep_for_backward = 1, mode TRAIN or FROZEN) with the training loss of cilrs_loss fused into the heads kernel:
+ * out6, dcontrols [batch,3], dspeed [batch] as cilrs_loss writes them; the speed head's target is the speed input
+ * (criterion(pred_ctrl, tgts, pred_spd, speeds), notebook/notebook.ipynb:550). */
+int cilrs_model_forward_loss(cilrs_model* m, int batch, int mode, const float* image_nchw, const void* image_s2d,
+                             const float* speed, const long long* command, float* controls, float* pred_speed,
+                             int update_running_stats, float dropout_p, unsigned long long seed, const float* targets,
+                             int loss_mode, float w_steer, float w_throttle, float w_brake, float w_speed, float grad_scale,
+                             float* out6, float* dcontrols, float* dspeed, void* stream);
 /* gradients of a scalar w.r.t. controls / pred_speed in, parameter gradients accumulated into `grads`.
  * part = -1 runs the whole backward; parts 0..4 (heads+layer4, layer3, layer2, layer1, stem; in that order) let the
  * host start the allreduce of the gradient range a part completed while the next part runs (data parallelism). */
