@@ -4,12 +4,13 @@
 // Reference: CILRS.forward model/autonomous_drive.py:389-399 (all 4 branches evaluated then gather(0, command));
 // only the selected branch is computed here - the others receive exactly zero gradient.
 //
-// Batched form (round 2): a thread-block CLUSTER of 8 CTAs owns a group of up to 32 samples that share their weights (the
-// samples of one command for the branch role, 32 consecutive samples for the speed-predictor role). Every CTA computes a
-// 1/8 column slice of each layer for all 32 samples, so each weight byte is read ONCE per sample group (round 1: once per
+// Batched form (round 2): a thread-block CLUSTER of 8 CTAs owns a group of up to 16 samples that share their weights (the
+// samples of one command for the branch role, 16 consecutive samples for the speed-predictor role). Every CTA computes a
+// 1/8 column slice of each layer for all 16 samples, so each weight byte is read ONCE per sample group (round 1: once per
 // sample - 228 MB of L2->SM traffic per forward at B = 128), and hands its slice of the activations to the other seven CTAs
 // through distributed shared memory (st.shared::cluster) before a cluster barrier starts the next layer. One launch per
-// direction, no global-memory round trips between layers.
+// direction, no global-memory round trips between layers. The layers are latency-bound (few CTAs, dependent chain), so every
+// layer issues ALL its weight loads before the first FMA (one L2 round trip per layer).
 #pragma once
 #include "common.cuh"
 #include "pair.cuh"
@@ -17,10 +18,12 @@
 namespace cilrs {
 
 constexpr int HD_THREADS = 256;
-constexpr int HD_G = 32;    // samples per cluster
+constexpr int HD_G = 16;    // samples per cluster
 constexpr int HD_CL = 8;    // CTAs per cluster
-constexpr int HD_SMEM_FLOATS = HD_G * 640 + 2 * HD_G * 256;   // X | H1 | H2  (forward)  /  dA | dB | dC (backward)
+// X | H1 | H2 (forward)  /  dA | dB | dC | cross-warp partials [8][HD_G][64] (backward)
+constexpr int HD_SMEM_FLOATS = HD_G * 640 + 2 * HD_G * 256;
 constexpr int HD_SMEM_BYTES = HD_SMEM_FLOATS * 4;
+static_assert(HD_G * 640 + 2 * HD_G * 256 >= 2 * HD_G * 256 + HD_G * 128 + 8 * HD_G * 64, "backward layout fits the forward's allocation");
 
 struct HeadsWeights {
   const float *se0_w, *se0_b, *se3_w, *se3_b;
@@ -189,8 +192,8 @@ CILRS_DEVINL void st_cluster_v4(uint32_t addr, float4 v) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// The sample list of a cluster. Branch role (k in 0..3): the samples whose (clamped) command is k, ranks [j*32, j*32+32) in
-// batch order; speed-predictor role (k < 0): samples [j*32, j*32+32). Every CTA of the cluster computes the same list.
+// The sample list of a cluster. Branch role (k in 0..3): the samples whose (clamped) command is k, ranks [j*G, j*G+G) in
+// batch order; speed-predictor role (k < 0): samples [j*G, j*G+G). Every CTA of the cluster computes the same list.
 // Returns the number of samples (0 = nothing to do; uniform over the cluster). Contains __syncthreads().
 CILRS_DEVINL int heads_sample_list(const long long* __restrict__ command, int batch, int k, int j, int* s_list, int* s_wcnt,
                                    int* error_flag) {
@@ -234,10 +237,13 @@ CILRS_DEVINL int heads_sample_list(const long long* __restrict__ command, int ba
   return max(0, min(HD_G, base - lo));
 }
 
-// v[32] per lane -> v[0] = sum over the 32 lanes of their v[lane] (recursive halving: 31 shuffles instead of 160)
-CILRS_DEVINL void reduce_transpose32(float (&v)[HD_G], int lane) {
+// v[16] per lane -> v[0] = sum over the 32 lanes of their v[lane & 15]: one full-width add across the two half-warps, then
+// recursive halving (31 shuffles instead of 80 for sixteen butterflies)
+CILRS_DEVINL void reduce_transpose16(float (&v)[HD_G], int lane) {
 #pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
+  for (int i = 0; i < HD_G; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
     const bool up = (lane & s) != 0;
 #pragma unroll
     for (int i = 0; i < s; ++i) {
@@ -248,42 +254,47 @@ CILRS_DEVINL void reduce_transpose32(float (&v)[HD_G], int lane) {
   }
 }
 
-// One layer slice, forward: this warp computes output rows o0..o0+3 of W [out, in] (row-major, in % 128 == 0) for the 32
-// samples x[32][ldx] (shared memory). Lanes split K (float4 per lane and step); afterwards lane l holds the four sums of
-// sample l in r[0..3].
-CILRS_DEVINL void rows_dot4(const float* __restrict__ W, int in, int o0, int out, const float* x, int ldx, int lane, float (&r)[4]) {
+// One layer slice, forward: this warp computes output rows o0..o0+3 of W [out, in] (row-major, in = NIT * 128) for the 16
+// samples x[16][ldx] (shared memory). Lanes split K (float4 per lane and step); ALL weight loads are issued before the first
+// FMA. Afterwards lane l holds the four sums of sample (l & 15) in r[0..3].
+template <int NIT>
+CILRS_DEVINL void rows_dot4(const float* __restrict__ W, int o0, int out, const float* x, int ldx, int lane, float (&r)[4]) {
+  constexpr int in = NIT * 128;
+  float4 w4[NIT][4];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      w4[it][q] = (o0 + q < out) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(o0 + q) * in) + lane + 32 * it)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
   float acc[4][HD_G];
 #pragma unroll
   for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int t = 0; t < HD_G; ++t) acc[q][t] = 0.f;
-  const int n4 = in >> 2;
-  for (int i = lane; i < n4; i += 32) {
-    float4 w4[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      w4[q] = (o0 + q < out) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(o0 + q) * in) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int it = 0; it < NIT; ++it) {
 #pragma unroll
     for (int t = 0; t < HD_G; ++t) {
-      const float4 x4 = *reinterpret_cast<const float4*>(x + t * ldx + 4 * i);
+      const float4 x4 = *reinterpret_cast<const float4*>(x + t * ldx + 4 * (lane + 32 * it));
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        acc[q][t] = fmaf(w4[q].x, x4.x, acc[q][t]); acc[q][t] = fmaf(w4[q].y, x4.y, acc[q][t]);
-        acc[q][t] = fmaf(w4[q].z, x4.z, acc[q][t]); acc[q][t] = fmaf(w4[q].w, x4.w, acc[q][t]);
+        acc[q][t] = fmaf(w4[it][q].x, x4.x, acc[q][t]); acc[q][t] = fmaf(w4[it][q].y, x4.y, acc[q][t]);
+        acc[q][t] = fmaf(w4[it][q].z, x4.z, acc[q][t]); acc[q][t] = fmaf(w4[it][q].w, x4.w, acc[q][t]);
       }
     }
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    reduce_transpose32(acc[q], lane);
+    reduce_transpose16(acc[q], lane);
     r[q] = acc[q][0];
   }
 }
 
 // write this lane's (sample = lane) four consecutive outputs [col, col+4) into row `lane` of the buffer `dst` (row length ld)
 // of EVERY CTA of the cluster
-CILRS_DEVINL void bcast_row4(float* dst, int ld, int lane, int col, float4 v) {
-  float* p = dst + lane * ld + col;
+CILRS_DEVINL void bcast_row4(float* dst, int ld, int row, int col, float4 v) {
+  float* p = dst + row * ld + col;
 #pragma unroll
   for (int rk = 0; rk < HD_CL; ++rk) st_cluster_v4(mapa_u32(p, (uint32_t)rk), v);
 }
@@ -314,8 +325,9 @@ __host__ __device__ inline int heads_groups(int batch) { return (batch + HD_G - 
 inline int heads_grid(int batch) { return 5 * heads_groups(batch) * HD_CL; }   // 4 branch roles + the speed predictor
 
 // generic hidden layer of a role: out columns [32*rank + 4*warp, +4) (or 16 per CTA when out == 128), ReLU, optional dropout,
-// broadcast into `dst` of every CTA, optional global save
-CILRS_DEVINL void heads_layer(const float* __restrict__ W, const float* __restrict__ bias, int in, int out, const float* x, int ldx,
+// broadcast into `dst` of every CTA, optional global save. in = NIT * 128.
+template <int NIT>
+CILRS_DEVINL void heads_layer(const float* __restrict__ W, const float* __restrict__ bias, int out, const float* x, int ldx,
                               float* dst, int ldd, int dst_col0, float* save, int save_ld, const int* s_list, int cnt, uint32_t rank,
                               float dropout_p, float keep_scale, unsigned long long seed, int site) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -323,7 +335,8 @@ CILRS_DEVINL void heads_layer(const float* __restrict__ W, const float* __restri
   if (warp * 4 >= per_cta) return;
   const int o0 = (int)rank * per_cta + warp * 4;
   float r[4];
-  rows_dot4(W, in, o0, out, x, ldx, lane, r);
+  rows_dot4<NIT>(W, o0, out, x, ldx, lane, r);
+  if (lane >= HD_G) return;                  // lanes 16..31 hold duplicates
   const int b = s_list[lane];
   float v[4];
 #pragma unroll
@@ -343,9 +356,9 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_fwd_kernel(const H
   __shared__ int s_wcnt[HD_THREADS / 32];
   __shared__ float s_red[4][256];
   __shared__ int s_last;
-  float* X = hd_smem;                    // [32][640]  features | speed features
-  float* H1 = X + HD_G * 640;            // [32][256]
-  float* H2 = H1 + HD_G * 256;           // [32][256]  (its first half doubles as the speed encoder's hidden layer [32][128])
+  float* X = hd_smem;                    // [G][640]  features | speed features
+  float* H1 = X + HD_G * 640;            // [G][256]
+  float* H2 = H1 + HD_G * 256;           // [G][256]  (its first half doubles as the speed encoder's hidden layer [G][128])
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const uint32_t rank = cluster_ctarank();
   const int cluster = blockIdx.x / HD_CL;
@@ -380,16 +393,16 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_fwd_kernel(const H
       __syncthreads();
       cluster_sync_all();   // every CTA's X / H2 are written before peers start to store speed features into them
       // speed encoder layer 3: Linear(128,128) + ReLU -> X[:, 512:640] of every CTA
-      heads_layer(p.w.se3_w, p.w.se3_b, 128, 128, H2, 128, X, 640, 512, p.sv.sfeat, 128, s_list, cnt, rank, 0.f, 1.f, seed, 0);
+      heads_layer<1>(p.w.se3_w, p.w.se3_b, 128, H2, 128, X, 640, 512, p.sv.sfeat, 128, s_list, cnt, rank, 0.f, 1.f, seed, 0);
       cluster_sync_all();
       // branch k: Linear(640,256)+ReLU+Drop, Linear(256,256)+ReLU+Drop, Linear(256,3)
-      heads_layer(p.w.br0_w[k], p.w.br0_b[k], 640, 256, X, 640, H1, 256, 0, p.sv.b1, 256, s_list, cnt, rank, p.dropout_p, keep_scale, seed, 1);
+      heads_layer<5>(p.w.br0_w[k], p.w.br0_b[k], 256, X, 640, H1, 256, 0, p.sv.b1, 256, s_list, cnt, rank, p.dropout_p, keep_scale, seed, 1);
       cluster_sync_all();
-      heads_layer(p.w.br3_w[k], p.w.br3_b[k], 256, 256, H1, 256, H2, 256, 0, p.sv.b2, 256, s_list, cnt, rank, p.dropout_p, keep_scale, seed, 2);
+      heads_layer<2>(p.w.br3_w[k], p.w.br3_b[k], 256, H1, 256, H2, 256, 0, p.sv.b2, 256, s_list, cnt, rank, p.dropout_p, keep_scale, seed, 2);
       cluster_sync_all();
       if (rank == 0 && warp == 0) {
         float r[4];
-        rows_dot4(p.w.br6_w[k], 256, 0, 3, H2, 256, lane, r);
+        rows_dot4<2>(p.w.br6_w[k], 0, 3, H2, 256, lane, r);
         if (lane < cnt) {
           const int b = s_list[lane];
 #pragma unroll
@@ -400,13 +413,13 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_fwd_kernel(const H
       __syncthreads();
       cluster_sync_all();
       // speed predictor on the visual features only: Linear(512,256)+ReLU+Drop, Linear(256,256)+ReLU, Linear(256,1)
-      heads_layer(p.w.sp0_w, p.w.sp0_b, 512, 256, X, 640, H1, 256, 0, p.sv.p1, 256, s_list, cnt, rank, p.dropout_p, keep_scale, seed, 3);
+      heads_layer<4>(p.w.sp0_w, p.w.sp0_b, 256, X, 640, H1, 256, 0, p.sv.p1, 256, s_list, cnt, rank, p.dropout_p, keep_scale, seed, 3);
       cluster_sync_all();
-      heads_layer(p.w.sp3_w, p.w.sp3_b, 256, 256, H1, 256, H2, 256, 0, p.sv.p2, 256, s_list, cnt, rank, 0.f, 1.f, seed, 0);
+      heads_layer<2>(p.w.sp3_w, p.w.sp3_b, 256, H1, 256, H2, 256, 0, p.sv.p2, 256, s_list, cnt, rank, 0.f, 1.f, seed, 0);
       cluster_sync_all();
       if (rank == 0 && warp == 0) {
         float r[4];
-        rows_dot4(p.w.sp5_w, 256, 0, 1, H2, 256, lane, r);
+        rows_dot4<2>(p.w.sp5_w, 0, 1, H2, 256, lane, r);
         if (lane < cnt) p.pred_speed[s_list[lane]] = r[0] + __ldg(p.w.sp5_b);
       }
     }
@@ -449,28 +462,70 @@ struct HeadsBwdParams {
   float dropout_p;
 };
 
-// acc[s] = sum_{o < K} W[o*ld + col] * d[(sg*SPT + s)*ldd + o]   with col = c0 + (t % WD), sg = t / WD, SPT = 32 / (256 / WD)
-template <int WD>
-CILRS_DEVINL void cols_dot(const float* __restrict__ W, int ld, int c0, int K, const float* d, int ldd, float (&acc)[HD_G * WD / HD_THREADS]) {
-  constexpr int SPT = HD_G * WD / HD_THREADS;
-  const int c = threadIdx.x % WD, sg = threadIdx.x / WD;
-  const float* wp = W + c0 + c;
-  const float* dp = d + (sg * SPT) * ldd;
+// Transposed layer slice: y[g][c] = sum_{o < K} W[o*ld + c0 + c] * d[g*ldd + o] for c < WD, g < HD_G.
+// The K rows are split over the 8 warps and, inside a warp, over RPW = 128 / WD lane groups (a warp reads RPW whole row slices
+// per step: contiguous float4 loads); every thread's loads are independent and issued up front (one L2 round trip). The partial
+// sums are combined by shuffles inside the warp and across warps through `part` ([8][HD_G][WD] floats) in a FIXED order
+// (deterministic). On return thread t < HD_G * WD / 4 holds y[g][c..c+3] with g = t / (WD/4), c = 4 * (t % (WD/4)) in `res`.
+// Contains __syncthreads(): the whole CTA calls it.
+template <int WD, int K>
+CILRS_DEVINL bool cols_dot(const float* __restrict__ W, int ld, int c0, const float* d, int ldd, float* part, float4& res, int& g_out, int& c_out) {
+  constexpr int QW = WD / 4, RPW = 32 / QW, NSTEP = K / (8 * RPW);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int q = lane % QW, rg = lane / QW;
+  float4 w4[NSTEP];
 #pragma unroll
-  for (int s = 0; s < SPT; ++s) acc[s] = 0.f;
-#pragma unroll 8
-  for (int o = 0; o < K; ++o) {
-    const float w = __ldg(wp + (size_t)o * ld);
-#pragma unroll
-    for (int s = 0; s < SPT; ++s) acc[s] = fmaf(w, dp[s * ldd + o], acc[s]);
+  for (int i = 0; i < NSTEP; ++i) {
+    const int o = (i * 8 + warp) * RPW + rg;
+    w4[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * ld + c0) + q);
   }
+  float4 acc[HD_G];
+#pragma unroll
+  for (int g = 0; g < HD_G; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NSTEP; ++i) {
+    const int o = (i * 8 + warp) * RPW + rg;
+#pragma unroll
+    for (int g = 0; g < HD_G; ++g) {
+      const float dv = d[g * ldd + o];
+      acc[g].x = fmaf(w4[i].x, dv, acc[g].x); acc[g].y = fmaf(w4[i].y, dv, acc[g].y);
+      acc[g].z = fmaf(w4[i].z, dv, acc[g].z); acc[g].w = fmaf(w4[i].w, dv, acc[g].w);
+    }
+  }
+  // lanes with the same column quad (different row group) -> lane group 0
+#pragma unroll
+  for (int sft = QW; sft < 32; sft <<= 1) {
+#pragma unroll
+    for (int g = 0; g < HD_G; ++g) {
+      acc[g].x += __shfl_xor_sync(0xffffffffu, acc[g].x, sft); acc[g].y += __shfl_xor_sync(0xffffffffu, acc[g].y, sft);
+      acc[g].z += __shfl_xor_sync(0xffffffffu, acc[g].z, sft); acc[g].w += __shfl_xor_sync(0xffffffffu, acc[g].w, sft);
+    }
+  }
+  __syncthreads();   // `part` is free (previous call's readers are done)
+  if (rg == 0) {
+#pragma unroll
+    for (int g = 0; g < HD_G; ++g) *reinterpret_cast<float4*>(part + (warp * HD_G + g) * WD + 4 * q) = acc[g];
+  }
+  __syncthreads();
+  const bool active = t < HD_G * QW;
+  g_out = t / QW; c_out = 4 * (t % QW);
+  res = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(part + (w * HD_G + g_out) * WD + c_out);
+      res.x += v.x; res.y += v.y; res.z += v.z; res.w += v.w;
+    }
+  }
+  return active;
 }
 
-// store value v of (sample g, column col) into `dst[g*ld + col]` of every CTA of the cluster
-CILRS_DEVINL void bcast_f32(float* dst, int ld, int g, int col, float v) {
-  float* p = dst + g * ld + col;
-#pragma unroll
-  for (int rk = 0; rk < HD_CL; ++rk) st_cluster_f32(mapa_u32(p, (uint32_t)rk), v);
+// store four consecutive values of (sample g, columns col..col+3) into `dst[g*ld + col]` of every CTA of the cluster
+CILRS_DEVINL void bcast4(float* dst, int ld, int g, int col, float4 v) { bcast_row4(dst, ld, g, col, v); }
+
+CILRS_DEVINL float4 mask4(const float* act, float4 v, float scale) {
+  const float4 a = *reinterpret_cast<const float4*>(act);
+  return make_float4(a.x > 0.f ? v.x * scale : 0.f, a.y > 0.f ? v.y * scale : 0.f, a.z > 0.f ? v.z * scale : 0.f, a.w > 0.f ? v.w * scale : 0.f);
 }
 
 static __global__ void __launch_bounds__(HD_THREADS, 1) heads_bwd_kernel(const HeadsBwdParams p) {
@@ -478,9 +533,10 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_bwd_kernel(const H
   __shared__ int s_list[HD_G];
   __shared__ int s_wcnt[HD_THREADS / 32];
   __shared__ float s_d3[HD_G][4];
-  float* dA = hd_smem;                 // [32][256]
-  float* dB = dA + HD_G * 256;         // [32][256]
-  float* dC = dB + HD_G * 256;         // [32][128]
+  float* dA = hd_smem;                 // [G][256]
+  float* dB = dA + HD_G * 256;         // [G][256]
+  float* dC = dB + HD_G * 256;         // [G][128]
+  float* part = dC + HD_G * 128;       // [8][G][64]
   const int t = threadIdx.x;
   const uint32_t rank = cluster_ctarank();
   const int cluster = blockIdx.x / HD_CL;
@@ -491,73 +547,56 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_bwd_kernel(const H
   const int cnt = heads_sample_list(p.command, p.batch, k, j, s_list, s_wcnt, nullptr);
   if (cnt == 0) return;   // uniform over the cluster
   const float ks = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 res;
+  int g, c;
   if (branch_role) {
     // ---- control branch ----
     if (t < HD_G * 4) {
-      const int g = t >> 2, q = t & 3;
-      const int b = s_list[g];
+      const int gg = t >> 2, q = t & 3;
+      const int b = s_list[gg];
       const float v = (b >= 0 && q < 3) ? p.dcontrols[(size_t)b * 3 + q] : 0.f;
-      s_d3[g][q] = v;
+      s_d3[gg][q] = v;
       if (b >= 0 && rank == 0) p.sv.d_br6[(size_t)b * 4 + q] = v;
     }
     __syncthreads();
     {  // delta of layer .3's output: every CTA needs all 256 columns, three terms each - computed redundantly
       const float w0 = __ldg(p.w.br6_w[k] + t), w1 = __ldg(p.w.br6_w[k] + 256 + t), w2 = __ldg(p.w.br6_w[k] + 512 + t);
-      for (int g = 0; g < HD_G; ++g) {
-        const int b = s_list[g];
+      for (int gg = 0; gg < HD_G; ++gg) {
+        const int b = s_list[gg];
         float v = 0.f;
-        if (b >= 0 && p.sv.b2[(size_t)b * 256 + t] > 0.f) v = (w0 * s_d3[g][0] + w1 * s_d3[g][1] + w2 * s_d3[g][2]) * ks;
-        dA[g * 256 + t] = v;
+        if (b >= 0 && p.sv.b2[(size_t)b * 256 + t] > 0.f) v = (w0 * s_d3[gg][0] + w1 * s_d3[gg][1] + w2 * s_d3[gg][2]) * ks;
+        dA[gg * 256 + t] = v;
         if (b >= 0 && (t >> 5) == (int)rank) p.sv.d_br3[(size_t)b * 256 + t] = v;
       }
     }
     __syncthreads();
     cluster_sync_all();   // peers' dB / dC are free to be written
-    {  // delta of layer .0's output, this CTA's 32 columns
-      float acc[4];
-      cols_dot<32>(p.w.br3_w[k], 256, 32 * (int)rank, 256, dA, 256, acc);
-      const int col = 32 * (int)rank + (t & 31), sg = t >> 5;
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int g = sg * 4 + s, b = s_list[g];
-        const float v = (b >= 0 && p.sv.b1[(size_t)b * 256 + col] > 0.f) ? acc[s] * ks : 0.f;
-        bcast_f32(dB, 256, g, col, v);
-        if (b >= 0) p.sv.d_br0[(size_t)b * 256 + col] = v;
-      }
+    // delta of layer .0's output, this CTA's 32 columns
+    if (cols_dot<32, 256>(p.w.br3_w[k], 256, 32 * (int)rank, dA, 256, part, res, g, c)) {
+      const int b = s_list[g], col = 32 * (int)rank + c;
+      const float4 v = b >= 0 ? mask4(p.sv.b1 + (size_t)b * 256 + col, res, ks) : zero4;
+      bcast4(dB, 256, g, col, v);
+      if (b >= 0) *reinterpret_cast<float4*>(p.sv.d_br0 + (size_t)b * 256 + col) = v;
     }
     cluster_sync_all();
-    {  // d(features): 64 of the 512 feature columns of W0
-      float acc[8];
-      cols_dot<64>(p.w.br0_w[k], 640, 64 * (int)rank, 256, dB, 256, acc);
-      const int col = 64 * (int)rank + (t & 63), sg = t >> 6;
-#pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const int b = s_list[sg * 8 + s];
-        if (b >= 0) p.dfeat[(size_t)b * 512 + col] = acc[s];
-      }
+    // d(features): 64 of the 512 feature columns of W0
+    if (cols_dot<64, 256>(p.w.br0_w[k], 640, 64 * (int)rank, dB, 256, part, res, g, c)) {
+      const int b = s_list[g];
+      if (b >= 0) *reinterpret_cast<float4*>(p.dfeat + (size_t)b * 512 + 64 * (int)rank + c) = res;
     }
-    {  // d(speed features): 16 of the 128 columns 512..639 of W0, through the speed encoder's last ReLU
-      float acc[2];
-      cols_dot<16>(p.w.br0_w[k], 640, 512 + 16 * (int)rank, 256, dB, 256, acc);
-      const int col = 16 * (int)rank + (t & 15), sg = t >> 4;
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int g = sg * 2 + s, b = s_list[g];
-        const float v = (b >= 0 && p.sv.sfeat[(size_t)b * 128 + col] > 0.f) ? acc[s] : 0.f;
-        bcast_f32(dC, 128, g, col, v);
-        if (b >= 0) p.sv.d_se3[(size_t)b * 128 + col] = v;
-      }
+    // d(speed features): 16 of the 128 columns 512..639 of W0, through the speed encoder's last ReLU
+    if (cols_dot<16, 256>(p.w.br0_w[k], 640, 512 + 16 * (int)rank, dB, 256, part, res, g, c)) {
+      const int b = s_list[g], col = 16 * (int)rank + c;
+      const float4 v = b >= 0 ? mask4(p.sv.sfeat + (size_t)b * 128 + col, res, 1.f) : zero4;
+      bcast4(dC, 128, g, col, v);
+      if (b >= 0) *reinterpret_cast<float4*>(p.sv.d_se3 + (size_t)b * 128 + col) = v;
     }
     cluster_sync_all();
-    {  // speed encoder layer 0 delta
-      float acc[2];
-      cols_dot<16>(p.w.se3_w, 128, 16 * (int)rank, 128, dC, 128, acc);
-      const int col = 16 * (int)rank + (t & 15), sg = t >> 4;
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int b = s_list[sg * 2 + s];
-        if (b >= 0) p.sv.d_se0[(size_t)b * 128 + col] = p.sv.s1[(size_t)b * 128 + col] > 0.f ? acc[s] * ks : 0.f;
-      }
+    // speed encoder layer 0 delta
+    if (cols_dot<16, 128>(p.w.se3_w, 128, 16 * (int)rank, dC, 128, part, res, g, c)) {
+      const int b = s_list[g], col = 16 * (int)rank + c;
+      if (b >= 0) *reinterpret_cast<float4*>(p.sv.d_se0 + (size_t)b * 128 + col) = mask4(p.sv.s1 + (size_t)b * 128 + col, res, ks);
     }
   } else {
     // ---- speed predictor ----
@@ -570,38 +609,26 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_bwd_kernel(const H
     __syncthreads();
     {
       const float w = __ldg(p.w.sp5_w + t);
-      for (int g = 0; g < HD_G; ++g) {
-        const int b = s_list[g];
+      for (int gg = 0; gg < HD_G; ++gg) {
+        const int b = s_list[gg];
         float v = 0.f;
-        if (b >= 0 && p.sv.p2[(size_t)b * 256 + t] > 0.f) v = w * s_d3[g][0];
-        dA[g * 256 + t] = v;
+        if (b >= 0 && p.sv.p2[(size_t)b * 256 + t] > 0.f) v = w * s_d3[gg][0];
+        dA[gg * 256 + t] = v;
         if (b >= 0 && (t >> 5) == (int)rank) p.sv.d_sp3[(size_t)b * 256 + t] = v;
       }
     }
     __syncthreads();
     cluster_sync_all();
-    {
-      float acc[4];
-      cols_dot<32>(p.w.sp3_w, 256, 32 * (int)rank, 256, dA, 256, acc);
-      const int col = 32 * (int)rank + (t & 31), sg = t >> 5;
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int g = sg * 4 + s, b = s_list[g];
-        const float v = (b >= 0 && p.sv.p1[(size_t)b * 256 + col] > 0.f) ? acc[s] * ks : 0.f;
-        bcast_f32(dB, 256, g, col, v);
-        if (b >= 0) p.sv.d_sp0[(size_t)b * 256 + col] = v;
-      }
+    if (cols_dot<32, 256>(p.w.sp3_w, 256, 32 * (int)rank, dA, 256, part, res, g, c)) {
+      const int b = s_list[g], col = 32 * (int)rank + c;
+      const float4 v = b >= 0 ? mask4(p.sv.p1 + (size_t)b * 256 + col, res, ks) : zero4;
+      bcast4(dB, 256, g, col, v);
+      if (b >= 0) *reinterpret_cast<float4*>(p.sv.d_sp0 + (size_t)b * 256 + col) = v;
     }
     cluster_sync_all();
-    {
-      float acc[8];
-      cols_dot<64>(p.w.sp0_w, 512, 64 * (int)rank, 256, dB, 256, acc);
-      const int col = 64 * (int)rank + (t & 63), sg = t >> 6;
-#pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const int b = s_list[sg * 8 + s];
-        if (b >= 0) p.dfeat2[(size_t)b * 512 + col] = acc[s];
-      }
+    if (cols_dot<64, 256>(p.w.sp0_w, 512, 64 * (int)rank, dB, 256, part, res, g, c)) {
+      const int b = s_list[g];
+      if (b >= 0) *reinterpret_cast<float4*>(p.dfeat2 + (size_t)b * 512 + 64 * (int)rank + c) = res;
     }
   }
   cluster_sync_all();   // nobody leaves while a peer may still write into its shared memory

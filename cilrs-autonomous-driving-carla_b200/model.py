@@ -92,6 +92,7 @@ def _mlp(spec):
 class _Function(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, image, speed, command, *params):
+        ctx.image = image if model.compute_dtype == "fp32" else None
         controls, pred_speed = model._launch_forward(image, speed, command, keep=True)
         ctx.model = model
         ctx.gen = model._fwd_gen
@@ -113,16 +114,28 @@ class _Function(torch.autograd.Function):
         dcontrols = torch.zeros(b, 3, device=dev) if dcontrols is None else dcontrols.contiguous().float()
         dspeed = torch.zeros(b, device=dev) if dspeed is None else dspeed.contiguous().float()
         grads = model._fresh_grad_arena()
-        _lib.call("cilrs_model_backward", model._handle, b, ctx.mode, -1, dcontrols, dspeed, ctx.speed, ctx.command,
-                  float(ctx.dropout), _lib.stream_ptr())
+        if model.compute_dtype == "fp32":
+            _lib.call("cilrs_model32_backward", model._handle, b, ctx.mode, dcontrols, dspeed, ctx.speed, ctx.command,
+                      float(ctx.dropout), _lib.stream_ptr())
+        else:
+            _lib.call("cilrs_model_backward", model._handle, b, ctx.mode, -1, dcontrols, dspeed, ctx.speed, ctx.command,
+                      float(ctx.dropout), _lib.stream_ptr())
         return (None, None, None, None) + tuple(model._views(grads))
 
 
 class CILRS(nn.Module):
-    def __init__(self, num_commands=4, dropout=0.0):
+    """compute_dtype (opt-in keyword, the reference's two ctor arguments keep their meaning and defaults):
+      "bf16" (default) - bf16 operands / fp32 accumulate on the tcgen05 tensor cores: the throughput mode (2e-2 parity)
+      "fp32"           - fp32 storage and arithmetic end to end (csrc/fp32_path.cu): reproduces the reference's fp32 numbers to
+                         1e-4 (configs/train_config.json:54 "mixed_precision": false); slower, same interface, same state_dict."""
+
+    def __init__(self, num_commands=4, dropout=0.0, compute_dtype="bf16"):
         super().__init__()
         if num_commands != 4:
             raise ValueError("cilrs_b200 supports the reference's num_commands=4 only")
+        if compute_dtype not in ("bf16", "fp32"):
+            raise ValueError("compute_dtype must be 'bf16' or 'fp32'")
+        self.compute_dtype = compute_dtype
         self.num_commands = num_commands
         self.dropout = float(dropout)
         ve = _Holder()
@@ -217,7 +230,10 @@ class CILRS(nn.Module):
 
     def _destroy_handle(self):
         if getattr(self, "_handle", None) is not None:
-            _lib.lib().cilrs_model_destroy(self._handle)
+            if self.compute_dtype == "fp32":
+                _lib.lib().cilrs_model32_destroy(self._handle)
+            else:
+                _lib.lib().cilrs_model_destroy(self._handle)
         self._handle = None
         self._workspace = None
         self._max_batch = 0
@@ -266,13 +282,16 @@ class CILRS(nn.Module):
         if self._handle is None or batch > self._max_batch:
             self._destroy_handle()
             lib = _lib.lib()
-            nbytes = lib.cilrs_model_workspace_bytes(int(batch))
+            fp32 = self.compute_dtype == "fp32"
+            ws_bytes = lib.cilrs_model32_workspace_bytes if fp32 else lib.cilrs_model_workspace_bytes
+            ws_bytes.restype = ctypes.c_size_t
+            create = lib.cilrs_model32_create if fp32 else lib.cilrs_model_create
+            nbytes = ws_bytes(int(batch))
             with torch.cuda.device(self._flat.device):
                 self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self._flat.device)
                 base = (self._workspace.data_ptr() + 1023) // 1024 * 1024
                 h = ctypes.c_void_p()
-                st = lib.cilrs_model_create(ctypes.byref(h), int(batch), ctypes.c_void_p(base), ctypes.c_size_t(nbytes),
-                                            _lib.stream_ptr())
+                st = create(ctypes.byref(h), int(batch), ctypes.c_void_p(base), ctypes.c_size_t(nbytes), _lib.stream_ptr())
             if st != 0:
                 raise RuntimeError("cilrs_model_create failed: %s" % lib.cilrs_status_string(st).decode())
             self._handle = h
@@ -281,7 +300,8 @@ class CILRS(nn.Module):
 
     def _bind(self):
         if self._handle is not None:
-            _lib.call("cilrs_model_bind", self._handle, self._flat, self._flat_grad, self._flat_buf, self._flat_nbt)
+            _lib.call("cilrs_model32_bind" if self.compute_dtype == "fp32" else "cilrs_model_bind", self._handle, self._flat,
+                      self._flat_grad, self._flat_buf, self._flat_nbt)
 
     def _param_version(self):
         # `p.data = flat[...]` (see _flatten) leaves every parameter with its OWN version counter: in-place updates made through
@@ -289,6 +309,8 @@ class CILRS(nn.Module):
         return sum(p._version for p in self._plist) + self._flat._version
 
     def _refresh_if_needed(self, infer):
+        if self.compute_dtype == "fp32":
+            return  # the fp32 plan re-derives its operands from the masters in every forward
         wkey = (self._param_version(), self._extra_w)
         what = 0
         if wkey != self._wkey:
@@ -333,9 +355,16 @@ class CILRS(nn.Module):
         controls = torch.empty(b, 3, dtype=torch.float32, device=speed.device)
         pred_speed = torch.empty(b, dtype=torch.float32, device=speed.device)
         img = None if s2d is not None else image.contiguous().float()
-        _lib.call("cilrs_model_forward", self._handle, b, mode, img, s2d, speed.contiguous().float(), command.contiguous(),
-                  controls, pred_speed, int(self.training), int(need_keep), ctypes.c_float(dropout),
-                  ctypes.c_ulonglong(self._seed), _lib.stream_ptr())
+        if self.compute_dtype == "fp32":
+            if img is None:
+                raise RuntimeError("cilrs_b200: the fp32 mode takes the normalised image tensor, not the bf16 space-to-depth buffer")
+            _lib.call("cilrs_model32_forward", self._handle, b, mode, img, speed.contiguous().float(), command.contiguous(),
+                      controls, pred_speed, int(self.training), int(need_keep), ctypes.c_float(dropout),
+                      ctypes.c_ulonglong(self._seed), _lib.stream_ptr())
+        else:
+            _lib.call("cilrs_model_forward", self._handle, b, mode, img, s2d, speed.contiguous().float(), command.contiguous(),
+                      controls, pred_speed, int(self.training), int(need_keep), ctypes.c_float(dropout),
+                      ctypes.c_ulonglong(self._seed), _lib.stream_ptr())
         if self.training:
             self._extra_b += 1  # running statistics were updated through raw pointers
         self._fwd_gen += 1
@@ -360,8 +389,9 @@ class CILRS(nn.Module):
         would raise, model/autonomous_drive.py:395-398; here the command is clamped and the flag raised)."""
         self._ensure(max(1, self._max_batch))
         lib = _lib.lib()
-        lib.cilrs_model_error_flag.restype = ctypes.c_void_p
-        return self._workspace_view(lib.cilrs_model_error_flag(self._handle), 4).view(torch.int32)
+        fn = lib.cilrs_model32_error_flag if self.compute_dtype == "fp32" else lib.cilrs_model_error_flag
+        fn.restype = ctypes.c_void_p
+        return self._workspace_view(fn(self._handle), 4).view(torch.int32)
 
     def check_errors(self):
         """Synchronising check of the device error flag; raises like the reference's out-of-range gather would."""
@@ -372,9 +402,14 @@ class CILRS(nn.Module):
             flag.zero_()
             raise IndexError("cilrs_b200: a command index outside [0, %d) reached the model" % self.num_commands)
 
+    def _bf16_plan_only(self, what):
+        if self.compute_dtype != "bf16":
+            raise RuntimeError("cilrs_b200: %s is a hook of the bf16 plan" % what)
+
     def debug_backward(self, batch, hi, lo, g_out):
         """Test hook (cilrs_model_debug_backward): backward of blocks hi..max(lo,0) (+ the stem when lo < 0) from `g_out`, a bf16
         padded-flat gradient w.r.t. block hi's output; returns the bf16 padded-flat gradient w.r.t. the input of block max(lo,0)."""
+        self._bf16_plan_only("debug_backward")
         lib = _lib.lib()
         _lib.call("cilrs_model_debug_backward", self._handle, int(batch), self._last_mode, int(hi), int(lo), g_out.contiguous(),
                   _lib.stream_ptr())
@@ -392,6 +427,7 @@ class CILRS(nn.Module):
 
     def debug_heads_saved(self, which, batch):
         """Test hook: fp32 [batch, width] head activation kept by the last forward (post-ReLU, post-Dropout); see the header."""
+        self._bf16_plan_only("debug_heads_saved")
         lib = _lib.lib()
         lib.cilrs_model_debug_heads_saved.restype = ctypes.c_void_p
         width = ctypes.c_int()
@@ -402,6 +438,8 @@ class CILRS(nn.Module):
 
     def input_s2d_buffer(self, batch):
         """bf16 [batch,47,103,16] view of the plan's conv1 input: the preprocessing kernel can write frames there directly."""
+        if self.compute_dtype == "fp32":
+            raise RuntimeError("cilrs_b200: FusedTrainer / InferenceSession drive the bf16 plan; use the module interface in fp32 mode")
         self._ensure(batch)
         lib = _lib.lib()
         lib.cilrs_model_input_s2d.restype = ctypes.c_void_p
@@ -413,6 +451,7 @@ class CILRS(nn.Module):
     def debug_activation(self, which, batch):
         """Test hook: bf16 [batch,H,W,C] activation of the last forward (0 = max-pool out, 1..16 = block outputs).
         Inside the plan the tensors are in the padded-flat layout [batch,H+1,W+1,C]; the real pixels are returned."""
+        self._bf16_plan_only("debug_activation")
         lib = _lib.lib()
         lib.cilrs_model_debug_activation.restype = ctypes.c_void_p
         dims = (ctypes.c_int * 5)()

@@ -240,6 +240,23 @@ float* cilrs_model_debug_heads_saved(cilrs_model* m, int which, int* width);
  * forward becomes seed + c * (*counter_dev + 1); counter_dev is a device int64 that changes between replays. NULL = off. */
 int cilrs_model_set_dropout_counter(cilrs_model* m, const long long* counter_dev);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * fp32 compute mode of the same network (csrc/fp32_path.cu): fp32 storage and fp32 FMA end to end, the precision the
+ * reference runs in (configs/train_config.json:54 "mixed_precision": false; model/autonomous_drive.py:495). Same arenas
+ * (cilrs_model_param_layout), same modes, same call pattern; image_nchw only (no bf16 input). Parity 1e-4 vs the fp64 oracle.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct cilrs_model32 cilrs_model32;
+size_t cilrs_model32_workspace_bytes(int max_batch);
+int cilrs_model32_create(cilrs_model32** out, int max_batch, void* workspace, size_t workspace_bytes, void* stream);
+void cilrs_model32_destroy(cilrs_model32* m);
+int cilrs_model32_bind(cilrs_model32* m, float* params, float* grads, float* buffers, long long* num_batches_tracked);
+int cilrs_model32_forward(cilrs_model32* m, int batch, int mode, const float* image_nchw, const float* speed,
+                          const long long* command, float* controls, float* pred_speed, int update_running_stats,
+                          int keep_for_backward, float dropout_p, unsigned long long seed, void* stream);
+int cilrs_model32_backward(cilrs_model32* m, int batch, int mode, const float* dcontrols, const float* dspeed,
+                           const float* speed, const long long* command, float dropout_p, void* stream);
+int* cilrs_model32_error_flag(cilrs_model32* m);
+
 /* heads only (speed encoder + selected branch + speed predictor; model/autonomous_drive.py:371-398) on given
  * features f32 [batch,512]; the backward also accumulates the head parameter gradients and returns d(features) */
 int cilrs_model_heads_forward(cilrs_model* m, int batch, const float* feat, const float* speed, const long long* command,
