@@ -442,7 +442,6 @@ static __global__ void maxpool32_bwd_kernel(const float* __restrict__ g, const u
     const long long p = i / C;
     const int w = (int)(p % W), h = (int)((p / W) % H), b = (int)(p / ((long long)W * H));
     float s = 0.f;
-    for (int oh = (h + 1) / 2 - ((h & 1) ? 0 : 0); oh <= (h + 1) / 2; ++oh) { (void)oh; break; }
     // windows (oh, ow) with oh*2-1 <= h <= oh*2+1  <=>  oh in [ceil((h-1)/2), floor((h+1)/2)]
     const int oh_lo = h >= 1 ? (h - 1 + 1) / 2 : 0, oh_hi = min(OH - 1, (h + 1) / 2);
     const int ow_lo = w >= 1 ? (w - 1 + 1) / 2 : 0, ow_hi = min(OW - 1, (w + 1) / 2);

@@ -192,34 +192,67 @@ CILRS_DEVINL void st_cluster_v4(uint32_t addr, float4 v) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// The sample list of a cluster. Branch role (k in 0..3): the samples whose (clamped) command is k, ranks [j*G, j*G+G) in
-// batch order; speed-predictor role (k < 0): samples [j*G, j*G+G). Every CTA of the cluster computes the same list.
-// Returns the number of samples (0 = nothing to do; uniform over the cluster). Contains __syncthreads().
-CILRS_DEVINL int heads_sample_list(const long long* __restrict__ command, int batch, int k, int j, int* s_list, int* s_wcnt,
-                                   int* error_flag) {
+// The sample list of a cluster. Branch role: branch cluster c (0 .. groups(batch) + 2) owns the c-th non-empty group when the
+// groups of 16 samples with equal (clamped) command are numbered command-major - at most groups(batch) + 3 such groups exist,
+// so the grid does not need 4 x groups(batch) clusters; k_out receives the command. Speed-predictor role (branch = false):
+// samples [c*16, c*16+16). Every CTA of the cluster computes the same list. Returns the number of samples (0 = nothing to do;
+// uniform over the cluster). s_tmp: 12 ints of shared memory. Contains __syncthreads().
+CILRS_DEVINL int heads_sample_list(const long long* __restrict__ command, int batch, bool branch, int c, int* s_list, int* s_tmp,
+                                   int* error_flag, int& k_out) {
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  int* s_wcnt = s_tmp;        // [8]
+  int* s_cnt4 = s_tmp + 8;    // [4]
   if (t < HD_G) s_list[t] = -1;
+  if (t < 4) s_cnt4[t] = 0;
   __syncthreads();
-  if (k < 0) {
-    const int b = j * HD_G + t;
+  k_out = -1;
+  if (!branch) {
+    const int b = c * HD_G + t;
     if (t < HD_G && b < batch) s_list[t] = b;
     __syncthreads();
-    return min(HD_G, batch - j * HD_G);
+    return max(0, min(HD_G, batch - c * HD_G));
   }
+  // pass 1: samples per command
+  for (int b0 = 0; b0 < batch; b0 += HD_THREADS) {
+    const int b = b0 + t;
+    int cm = -1;
+    if (b < batch) {
+      long long cc = command[b];
+      if (cc < 0 || cc > 3) {
+        if (error_flag) *error_flag = 1;   // the reference's gather(0, command) would raise; clamp and flag
+        cc = cc < 0 ? 0 : 3;
+      }
+      cm = (int)cc;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const unsigned bal = __ballot_sync(0xffffffffu, cm == kk);
+      if (lane == 0 && bal) atomicAdd(&s_cnt4[kk], __popc(bal));
+    }
+  }
+  __syncthreads();
+  int k = -1, j = 0, pref = 0;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const int gk = (s_cnt4[kk] + HD_G - 1) / HD_G;
+    if (k < 0 && c < pref + gk) { k = kk; j = c - pref; }
+    pref += gk;
+  }
+  if (k < 0) return 0;
+  k_out = k;
+  // pass 2: the samples of command k with rank [j*16, j*16+16) in batch order
   int base = 0;
   const int lo = j * HD_G, hi = lo + HD_G;
   for (int b0 = 0; b0 < batch; b0 += HD_THREADS) {
     const int b = b0 + t;
     bool match = false;
     if (b < batch) {
-      long long c = command[b];
-      if (c < 0 || c > 3) {
-        if (error_flag) *error_flag = 1;   // the reference's gather(0, command) would raise; clamp and flag
-        c = c < 0 ? 0 : 3;
-      }
-      match = (int)c == k;
+      long long cc = command[b];
+      cc = cc < 0 ? 0 : (cc > 3 ? 3 : cc);
+      match = (int)cc == k;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, match);
+    __syncthreads();   // s_wcnt of the previous iteration has been read
     if (lane == 0) s_wcnt[warp] = __popc(bal);
     __syncthreads();
     int off = base, tot = 0;
@@ -231,9 +264,9 @@ CILRS_DEVINL int heads_sample_list(const long long* __restrict__ command, int ba
     const int r = off + __popc(bal & ((1u << lane) - 1u));
     if (match && r >= lo && r < hi) s_list[r - lo] = b;
     base += tot;
-    __syncthreads();
     if (base >= hi) break;
   }
+  __syncthreads();
   return max(0, min(HD_G, base - lo));
 }
 
@@ -254,41 +287,52 @@ CILRS_DEVINL void reduce_transpose16(float (&v)[HD_G], int lane) {
   }
 }
 
-// One layer slice, forward: this warp computes output rows o0..o0+3 of W [out, in] (row-major, in = NIT * 128) for the 16
-// samples x[16][ldx] (shared memory). Lanes split K (float4 per lane and step); ALL weight loads are issued before the first
-// FMA. Afterwards lane l holds the four sums of sample (l & 15) in r[0..3].
-template <int NIT>
-CILRS_DEVINL void rows_dot4(const float* __restrict__ W, int o0, int out, const float* x, int ldx, int lane, float (&r)[4]) {
-  constexpr int in = NIT * 128;
-  float4 w4[NIT][4];
+// One layer slice, forward: this warp computes output rows o0..o0+3 of W [out, in] (row-major, in = nit * 128) for the 16
+// samples x[16][ldx] (shared memory). Lanes split K (float4 per lane and step); the weights of step it+1 are in flight while
+// step it is multiplied. Afterwards lane l holds the four sums of sample (l & 15).
+// ONE copy of this code serves every layer (__noinline__, the K loop is not unrolled): the first version inlined and fully
+// unrolled it per call site - 124 KB of straight-line SASS executed once per launch, i.e. an instruction-fetch-bound kernel.
+static __device__ __noinline__ float4 rows_dot4(const float* __restrict__ W, int nit, int o0, int out, const float* x, int ldx, int lane) {
+  const int in = nit * 128;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* wrow[4];
 #pragma unroll
-  for (int it = 0; it < NIT; ++it)
+  for (int q = 0; q < 4; ++q) wrow[q] = reinterpret_cast<const float4*>(W + (size_t)(o0 + q < out ? o0 + q : 0) * in) + lane;
+  float4 wn[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      w4[it][q] = (o0 + q < out) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(o0 + q) * in) + lane + 32 * it)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = 0; q < 4; ++q) wn[q] = (o0 + q < out) ? __ldg(wrow[q]) : zero;
   float acc[4][HD_G];
 #pragma unroll
   for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int t = 0; t < HD_G; ++t) acc[q][t] = 0.f;
+#pragma unroll 1
+  for (int it = 0; it < nit; ++it) {
+    float4 wc[4];
 #pragma unroll
-  for (int it = 0; it < NIT; ++it) {
+    for (int q = 0; q < 4; ++q) wc[q] = wn[q];
+    if (it + 1 < nit) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wn[q] = (o0 + q < out) ? __ldg(wrow[q] + 32 * (it + 1)) : zero;
+    }
+    const float* xp = x + 4 * (lane + 32 * it);
 #pragma unroll
     for (int t = 0; t < HD_G; ++t) {
-      const float4 x4 = *reinterpret_cast<const float4*>(x + t * ldx + 4 * (lane + 32 * it));
+      const float4 x4 = *reinterpret_cast<const float4*>(xp + t * ldx);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        acc[q][t] = fmaf(w4[it][q].x, x4.x, acc[q][t]); acc[q][t] = fmaf(w4[it][q].y, x4.y, acc[q][t]);
-        acc[q][t] = fmaf(w4[it][q].z, x4.z, acc[q][t]); acc[q][t] = fmaf(w4[it][q].w, x4.w, acc[q][t]);
+        acc[q][t] = fmaf(wc[q].x, x4.x, acc[q][t]); acc[q][t] = fmaf(wc[q].y, x4.y, acc[q][t]);
+        acc[q][t] = fmaf(wc[q].z, x4.z, acc[q][t]); acc[q][t] = fmaf(wc[q].w, x4.w, acc[q][t]);
       }
     }
   }
+  float r[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     reduce_transpose16(acc[q], lane);
     r[q] = acc[q][0];
   }
+  return make_float4(r[0], r[1], r[2], r[3]);
 }
 
 // write this lane's (sample = lane) four consecutive outputs [col, col+4) into row `lane` of the buffer `dst` (row length ld)
@@ -322,38 +366,52 @@ struct HeadsFwdParams {
 };
 
 __host__ __device__ inline int heads_groups(int batch) { return (batch + HD_G - 1) / HD_G; }
-inline int heads_grid(int batch) { return 5 * heads_groups(batch) * HD_CL; }   // 4 branch roles + the speed predictor
+__host__ __device__ inline int heads_branch_clusters(int batch) { return heads_groups(batch) + 3; }   // >= non-empty (command, group) pairs
+inline int heads_grid(int batch) { return (heads_branch_clusters(batch) + heads_groups(batch)) * HD_CL; }   // + the speed-predictor groups
 
 // generic hidden layer of a role: out columns [32*rank + 4*warp, +4) (or 16 per CTA when out == 128), ReLU, optional dropout,
-// broadcast into `dst` of every CTA, optional global save. in = NIT * 128.
-template <int NIT>
-CILRS_DEVINL void heads_layer(const float* __restrict__ W, const float* __restrict__ bias, int out, const float* x, int ldx,
-                              float* dst, int ldd, int dst_col0, float* save, int save_ld, const int* s_list, int cnt, uint32_t rank,
-                              float dropout_p, float keep_scale, unsigned long long seed, int site) {
+// broadcast into `dst` of every CTA, optional global save. in = nit * 128.
+struct HeadsLayerArgs {
+  const float* W; const float* bias; int nit, out;
+  const float* x; int ldx;
+  float* dst; int ldd, dst_col0;
+  float* save; int save_ld;
+  float dropout_p; int site;
+};
+static __device__ __noinline__ void heads_layer(const HeadsLayerArgs a, const int* s_list, int cnt, uint32_t rank, float keep_scale,
+                                         unsigned long long seed) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_cta = out / HD_CL;           // 32 or 16
+  const int per_cta = a.out / HD_CL;           // 32 or 16
   if (warp * 4 >= per_cta) return;
   const int o0 = (int)rank * per_cta + warp * 4;
-  float r[4];
-  rows_dot4<NIT>(W, o0, out, x, ldx, lane, r);
+  const float4 r4 = rows_dot4(a.W, a.nit, o0, a.out, a.x, a.ldx, lane);
   if (lane >= HD_G) return;                  // lanes 16..31 hold duplicates
+  const float r[4] = {r4.x, r4.y, r4.z, r4.w};
   const int b = s_list[lane];
   float v[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    float u = fmaxf(r[q] + __ldg(bias + o0 + q), 0.f);
-    if (dropout_p > 0.f && b >= 0) u = drop_keep(seed, b, site, o0 + q, dropout_p) ? u * keep_scale : 0.f;
+    float u = fmaxf(r[q] + __ldg(a.bias + o0 + q), 0.f);
+    if (a.dropout_p > 0.f && b >= 0) u = drop_keep(seed, b, a.site, o0 + q, a.dropout_p) ? u * keep_scale : 0.f;
     v[q] = (lane < cnt) ? u : 0.f;
   }
   const float4 v4 = make_float4(v[0], v[1], v[2], v[3]);
-  bcast_row4(dst, ldd, lane, dst_col0 + o0, v4);
-  if (save && lane < cnt) *reinterpret_cast<float4*>(save + (size_t)b * save_ld + o0) = v4;
+  bcast_row4(a.dst, a.ldd, lane, a.dst_col0 + o0, v4);
+  if (a.save && lane < cnt) *reinterpret_cast<float4*>(a.save + (size_t)b * a.save_ld + o0) = v4;
 }
+
+// optional phase trace of one CTA (tools/heads_trace.cu; compiled in only with -DHD_TRACE=<blockIdx>)
+#ifdef HD_TRACE
+__device__ unsigned long long g_hd_trace[32];
+#define HD_STAMP(i) do { if (blockIdx.x == (HD_TRACE) && threadIdx.x == 0) g_hd_trace[i] = globaltimer_ns(); } while (0)
+#else
+#define HD_STAMP(i) do { } while (0)
+#endif
 
 static __global__ void __launch_bounds__(HD_THREADS, 1) heads_fwd_kernel(const HeadsFwdParams p) {
   extern __shared__ __align__(16) float hd_smem[];
   __shared__ int s_list[HD_G];
-  __shared__ int s_wcnt[HD_THREADS / 32];
+  __shared__ int s_tmp[12];
   __shared__ float s_red[4][256];
   __shared__ int s_last;
   float* X = hd_smem;                    // [G][640]  features | speed features
@@ -362,15 +420,17 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_fwd_kernel(const H
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const uint32_t rank = cluster_ctarank();
   const int cluster = blockIdx.x / HD_CL;
-  const int ngrp = heads_groups(p.batch);
-  const bool branch_role = cluster < 4 * ngrp;
-  const int k = branch_role ? cluster / ngrp : -1;
-  const int j = branch_role ? cluster % ngrp : cluster - 4 * ngrp;
-  const int cnt = heads_sample_list(p.command, p.batch, k, j, s_list, s_wcnt, p.error_flag);
+  const int nbr = heads_branch_clusters(p.batch);
+  const bool branch_role = cluster < nbr;
+  int k;
+  HD_STAMP(0);
+  const int cnt = heads_sample_list(p.command, p.batch, branch_role, branch_role ? cluster : cluster - nbr, s_list, s_tmp, p.error_flag, k);
+  HD_STAMP(1);
   const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
   const unsigned long long seed = p.seed + (p.seed_counter ? 0x9E3779B97F4A7C15ull * (unsigned long long)(*p.seed_counter + 1) : 0ull);
   if (cnt > 0) {   // (uniform over the cluster: empty clusters skip every cluster barrier together)
     // features of the group's samples (rows of absent samples are zero)
+#pragma unroll
     for (int e = t; e < HD_G * 128; e += HD_THREADS) {
       const int g = e >> 7, c4 = e & 127;
       const int b = s_list[g];
@@ -391,39 +451,48 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_fwd_kernel(const H
         H2[g * 128 + c] = v;
       }
       __syncthreads();
+      HD_STAMP(2);
       cluster_sync_all();   // every CTA's X / H2 are written before peers start to store speed features into them
+      HD_STAMP(3);
       // speed encoder layer 3: Linear(128,128) + ReLU -> X[:, 512:640] of every CTA
-      heads_layer<1>(p.w.se3_w, p.w.se3_b, 128, H2, 128, X, 640, 512, p.sv.sfeat, 128, s_list, cnt, rank, 0.f, 1.f, seed, 0);
+      heads_layer(HeadsLayerArgs{p.w.se3_w, p.w.se3_b, 1, 128, H2, 128, X, 640, 512, p.sv.sfeat, 128, 0.f, 0}, s_list, cnt, rank, 1.f, seed);
+      HD_STAMP(4);
       cluster_sync_all();
+      HD_STAMP(5);
       // branch k: Linear(640,256)+ReLU+Drop, Linear(256,256)+ReLU+Drop, Linear(256,3)
-      heads_layer<5>(p.w.br0_w[k], p.w.br0_b[k], 256, X, 640, H1, 256, 0, p.sv.b1, 256, s_list, cnt, rank, p.dropout_p, keep_scale, seed, 1);
+      heads_layer(HeadsLayerArgs{p.w.br0_w[k], p.w.br0_b[k], 5, 256, X, 640, H1, 256, 0, p.sv.b1, 256, p.dropout_p, 1}, s_list, cnt, rank, keep_scale, seed);
+      HD_STAMP(6);
       cluster_sync_all();
-      heads_layer<2>(p.w.br3_w[k], p.w.br3_b[k], 256, H1, 256, H2, 256, 0, p.sv.b2, 256, s_list, cnt, rank, p.dropout_p, keep_scale, seed, 2);
+      HD_STAMP(7);
+      heads_layer(HeadsLayerArgs{p.w.br3_w[k], p.w.br3_b[k], 2, 256, H1, 256, H2, 256, 0, p.sv.b2, 256, p.dropout_p, 2}, s_list, cnt, rank, keep_scale, seed);
+      HD_STAMP(8);
       cluster_sync_all();
+      HD_STAMP(9);
       if (rank == 0 && warp == 0) {
-        float r[4];
-        rows_dot4<2>(p.w.br6_w[k], 0, 3, H2, 256, lane, r);
+        const float4 r4 = rows_dot4(p.w.br6_w[k], 2, 0, 3, H2, 256, lane);
         if (lane < cnt) {
           const int b = s_list[lane];
-#pragma unroll
-          for (int q = 0; q < 3; ++q) p.controls[(size_t)b * 3 + q] = r[q] + __ldg(p.w.br6_b[k] + q);
+          p.controls[(size_t)b * 3 + 0] = r4.x + __ldg(p.w.br6_b[k] + 0);
+          p.controls[(size_t)b * 3 + 1] = r4.y + __ldg(p.w.br6_b[k] + 1);
+          p.controls[(size_t)b * 3 + 2] = r4.z + __ldg(p.w.br6_b[k] + 2);
         }
       }
     } else {
       __syncthreads();
       cluster_sync_all();
       // speed predictor on the visual features only: Linear(512,256)+ReLU+Drop, Linear(256,256)+ReLU, Linear(256,1)
-      heads_layer<4>(p.w.sp0_w, p.w.sp0_b, 256, X, 640, H1, 256, 0, p.sv.p1, 256, s_list, cnt, rank, p.dropout_p, keep_scale, seed, 3);
+      heads_layer(HeadsLayerArgs{p.w.sp0_w, p.w.sp0_b, 4, 256, X, 640, H1, 256, 0, p.sv.p1, 256, p.dropout_p, 3}, s_list, cnt, rank, keep_scale, seed);
       cluster_sync_all();
-      heads_layer<2>(p.w.sp3_w, p.w.sp3_b, 256, H1, 256, H2, 256, 0, p.sv.p2, 256, s_list, cnt, rank, 0.f, 1.f, seed, 0);
+      heads_layer(HeadsLayerArgs{p.w.sp3_w, p.w.sp3_b, 2, 256, H1, 256, H2, 256, 0, p.sv.p2, 256, 0.f, 0}, s_list, cnt, rank, 1.f, seed);
       cluster_sync_all();
       if (rank == 0 && warp == 0) {
-        float r[4];
-        rows_dot4<2>(p.w.sp5_w, 0, 1, H2, 256, lane, r);
-        if (lane < cnt) p.pred_speed[s_list[lane]] = r[0] + __ldg(p.w.sp5_b);
+        const float4 r4 = rows_dot4(p.w.sp5_w, 2, 0, 1, H2, 256, lane);
+        if (lane < cnt) p.pred_speed[s_list[lane]] = r4.x + __ldg(p.w.sp5_b);
       }
     }
+    HD_STAMP(10);
     cluster_sync_all();   // nobody leaves while a peer may still write into its shared memory
+    HD_STAMP(11);
   }
   // ---- fused loss: the last cluster to finish (rank 0 CTAs count) reduces over the whole batch ----
   if (p.loss.enabled && rank == 0) {
@@ -464,35 +533,36 @@ struct HeadsBwdParams {
 
 // Transposed layer slice: y[g][c] = sum_{o < K} W[o*ld + c0 + c] * d[g*ldd + o] for c < WD, g < HD_G.
 // The K rows are split over the 8 warps and, inside a warp, over RPW = 128 / WD lane groups (a warp reads RPW whole row slices
-// per step: contiguous float4 loads); every thread's loads are independent and issued up front (one L2 round trip). The partial
+// per step: contiguous float4 loads), the next step's weights in flight while the current ones are multiplied. The partial
 // sums are combined by shuffles inside the warp and across warps through `part` ([8][HD_G][WD] floats) in a FIXED order
 // (deterministic). On return thread t < HD_G * WD / 4 holds y[g][c..c+3] with g = t / (WD/4), c = 4 * (t % (WD/4)) in `res`.
-// Contains __syncthreads(): the whole CTA calls it.
-template <int WD, int K>
-CILRS_DEVINL bool cols_dot(const float* __restrict__ W, int ld, int c0, const float* d, int ldd, float* part, float4& res, int& g_out, int& c_out) {
-  constexpr int QW = WD / 4, RPW = 32 / QW, NSTEP = K / (8 * RPW);
+// Contains __syncthreads(): the whole CTA calls it. Not inlined, K loop not unrolled (code size, see rows_dot4).
+template <int WD>
+__device__ __noinline__ bool cols_dot(const float* __restrict__ W, int ld, int c0, int K, const float* d, int ldd, float* part, float4& res,
+                                      int& g_out, int& c_out) {
+  constexpr int QW = WD / 4, RPW = 32 / QW;
+  const int nstep = K / (8 * RPW);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int q = lane % QW, rg = lane / QW;
-  float4 w4[NSTEP];
-#pragma unroll
-  for (int i = 0; i < NSTEP; ++i) {
-    const int o = (i * 8 + warp) * RPW + rg;
-    w4[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * ld + c0) + q);
-  }
+  const float4* wp = reinterpret_cast<const float4*>(W + (size_t)(warp * RPW + rg) * ld + c0) + q;
+  const size_t wstep = (size_t)8 * RPW * ld / 4;   // float4 elements between this thread's consecutive rows
   float4 acc[HD_G];
 #pragma unroll
   for (int g = 0; g < HD_G; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int i = 0; i < NSTEP; ++i) {
+  float4 wn = __ldg(wp);
+#pragma unroll 1
+  for (int i = 0; i < nstep; ++i) {
+    const float4 wc = wn;
+    if (i + 1 < nstep) wn = __ldg(wp + (size_t)(i + 1) * wstep);
     const int o = (i * 8 + warp) * RPW + rg;
 #pragma unroll
     for (int g = 0; g < HD_G; ++g) {
       const float dv = d[g * ldd + o];
-      acc[g].x = fmaf(w4[i].x, dv, acc[g].x); acc[g].y = fmaf(w4[i].y, dv, acc[g].y);
-      acc[g].z = fmaf(w4[i].z, dv, acc[g].z); acc[g].w = fmaf(w4[i].w, dv, acc[g].w);
+      acc[g].x = fmaf(wc.x, dv, acc[g].x); acc[g].y = fmaf(wc.y, dv, acc[g].y);
+      acc[g].z = fmaf(wc.z, dv, acc[g].z); acc[g].w = fmaf(wc.w, dv, acc[g].w);
     }
   }
-  // lanes with the same column quad (different row group) -> lane group 0
+  // lanes with the same column quad (different row group) -> every lane
 #pragma unroll
   for (int sft = QW; sft < 32; sft <<= 1) {
 #pragma unroll
@@ -531,7 +601,7 @@ CILRS_DEVINL float4 mask4(const float* act, float4 v, float scale) {
 static __global__ void __launch_bounds__(HD_THREADS, 1) heads_bwd_kernel(const HeadsBwdParams p) {
   extern __shared__ __align__(16) float hd_smem[];
   __shared__ int s_list[HD_G];
-  __shared__ int s_wcnt[HD_THREADS / 32];
+  __shared__ int s_tmp[12];
   __shared__ float s_d3[HD_G][4];
   float* dA = hd_smem;                 // [G][256]
   float* dB = dA + HD_G * 256;         // [G][256]
@@ -540,11 +610,10 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_bwd_kernel(const H
   const int t = threadIdx.x;
   const uint32_t rank = cluster_ctarank();
   const int cluster = blockIdx.x / HD_CL;
-  const int ngrp = heads_groups(p.batch);
-  const bool branch_role = cluster < 4 * ngrp;
-  const int k = branch_role ? cluster / ngrp : -1;
-  const int j = branch_role ? cluster % ngrp : cluster - 4 * ngrp;
-  const int cnt = heads_sample_list(p.command, p.batch, k, j, s_list, s_wcnt, nullptr);
+  const int nbr = heads_branch_clusters(p.batch);
+  const bool branch_role = cluster < nbr;
+  int k;
+  const int cnt = heads_sample_list(p.command, p.batch, branch_role, branch_role ? cluster : cluster - nbr, s_list, s_tmp, nullptr, k);
   if (cnt == 0) return;   // uniform over the cluster
   const float ks = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -573,7 +642,7 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_bwd_kernel(const H
     __syncthreads();
     cluster_sync_all();   // peers' dB / dC are free to be written
     // delta of layer .0's output, this CTA's 32 columns
-    if (cols_dot<32, 256>(p.w.br3_w[k], 256, 32 * (int)rank, dA, 256, part, res, g, c)) {
+    if (cols_dot<32>(p.w.br3_w[k], 256, 32 * (int)rank, 256, dA, 256, part, res, g, c)) {
       const int b = s_list[g], col = 32 * (int)rank + c;
       const float4 v = b >= 0 ? mask4(p.sv.b1 + (size_t)b * 256 + col, res, ks) : zero4;
       bcast4(dB, 256, g, col, v);
@@ -581,12 +650,12 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_bwd_kernel(const H
     }
     cluster_sync_all();
     // d(features): 64 of the 512 feature columns of W0
-    if (cols_dot<64, 256>(p.w.br0_w[k], 640, 64 * (int)rank, dB, 256, part, res, g, c)) {
+    if (cols_dot<64>(p.w.br0_w[k], 640, 64 * (int)rank, 256, dB, 256, part, res, g, c)) {
       const int b = s_list[g];
       if (b >= 0) *reinterpret_cast<float4*>(p.dfeat + (size_t)b * 512 + 64 * (int)rank + c) = res;
     }
     // d(speed features): 16 of the 128 columns 512..639 of W0, through the speed encoder's last ReLU
-    if (cols_dot<16, 256>(p.w.br0_w[k], 640, 512 + 16 * (int)rank, dB, 256, part, res, g, c)) {
+    if (cols_dot<16>(p.w.br0_w[k], 640, 512 + 16 * (int)rank, 256, dB, 256, part, res, g, c)) {
       const int b = s_list[g], col = 16 * (int)rank + c;
       const float4 v = b >= 0 ? mask4(p.sv.sfeat + (size_t)b * 128 + col, res, 1.f) : zero4;
       bcast4(dC, 128, g, col, v);
@@ -594,7 +663,7 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_bwd_kernel(const H
     }
     cluster_sync_all();
     // speed encoder layer 0 delta
-    if (cols_dot<16, 128>(p.w.se3_w, 128, 16 * (int)rank, dC, 128, part, res, g, c)) {
+    if (cols_dot<16>(p.w.se3_w, 128, 16 * (int)rank, 128, dC, 128, part, res, g, c)) {
       const int b = s_list[g], col = 16 * (int)rank + c;
       if (b >= 0) *reinterpret_cast<float4*>(p.sv.d_se0 + (size_t)b * 128 + col) = mask4(p.sv.s1 + (size_t)b * 128 + col, res, ks);
     }
@@ -619,14 +688,14 @@ static __global__ void __launch_bounds__(HD_THREADS, 1) heads_bwd_kernel(const H
     }
     __syncthreads();
     cluster_sync_all();
-    if (cols_dot<32, 256>(p.w.sp3_w, 256, 32 * (int)rank, dA, 256, part, res, g, c)) {
+    if (cols_dot<32>(p.w.sp3_w, 256, 32 * (int)rank, 256, dA, 256, part, res, g, c)) {
       const int b = s_list[g], col = 32 * (int)rank + c;
       const float4 v = b >= 0 ? mask4(p.sv.p1 + (size_t)b * 256 + col, res, ks) : zero4;
       bcast4(dB, 256, g, col, v);
       if (b >= 0) *reinterpret_cast<float4*>(p.sv.d_sp0 + (size_t)b * 256 + col) = v;
     }
     cluster_sync_all();
-    if (cols_dot<64, 256>(p.w.sp0_w, 512, 64 * (int)rank, dB, 256, part, res, g, c)) {
+    if (cols_dot<64>(p.w.sp0_w, 512, 64 * (int)rank, 256, dB, 256, part, res, g, c)) {
       const int b = s_list[g];
       if (b >= 0) *reinterpret_cast<float4*>(p.dfeat2 + (size_t)b * 512 + 64 * (int)rank + c) = res;
     }

@@ -88,6 +88,7 @@ class FusedTrainer:
         model.flat_gradients().zero_()   # from here on Adam / the bf16 conversion leave the arena zeroed for the next step
         self.graph = None
         self.graph_error = None
+        self.skip_optimizer = False   # test hook: leave the exchanged gradient in place (no clip / Adam / repack / zeroing)
         if use_graph:
             if self.world > 1:
                 # the NCCL allreduces are captured into the graph with the kernels (PyTorch records them on the process
@@ -154,6 +155,8 @@ class FusedTrainer:
                 w.wait()
         else:
             _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, -1, *self._backward_args())
+        if self.skip_optimizer:
+            return
         scale_dev = None
         if self.grad_clip > 0:
             # clip_grad_norm_ on the AVERAGED gradient: norm(avg) = norm(sum) / world, so the bound is scaled instead
