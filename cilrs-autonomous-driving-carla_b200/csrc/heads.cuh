@@ -782,11 +782,16 @@ static __global__ void __launch_bounds__(256) heads_wgrad_kernel(const HeadsWgra
 // launch with a cluster of HD_CL CTAs and the dynamic shared memory both kernels need
 template <typename P>
 inline cudaError_t heads_launch_cluster(void (*kernel)(P), int batch, cudaStream_t s, const P& prm) {
-  static bool attr_set = false;   // (one instance per kernel parameter type = per kernel)
-  if (!attr_set) {
+  // The kernels are `static` (one copy per translation unit that includes this header: the bf16 plan and the fp32 plan) while
+  // this template has ONE instance per parameter type across the library, so the attribute is tracked per kernel pointer.
+  static const void* attr_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool done = false;
+  for (int i = 0; i < 4; ++i) done = done || attr_done[i] == (const void*)kernel;
+  if (!done) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    for (int i = 0; i < 4; ++i)
+      if (!attr_done[i]) { attr_done[i] = (const void*)kernel; break; }
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)heads_grid(batch)); cfg.blockDim = dim3(HD_THREADS); cfg.dynamicSmemBytes = HD_SMEM_BYTES; cfg.stream = s;
