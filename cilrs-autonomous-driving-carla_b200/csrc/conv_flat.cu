@@ -253,7 +253,7 @@ int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channe
 // tensor maps of the epilogue's operand tiles (residual, y1, y2): call after the pointers are set, before the launch
 int flat_conv_bind_operands(FlatConvParams* p) {
   p->operand_maps = 0;
-  if ((p->flags & CF_RESIDUAL) && p->residual) {
+  if ((p->flags & (CF_RESIDUAL | CF_FUSE_RES)) && p->residual) {
     int st = encode_2d_map(&p->tmRes, p->residual, p->n_total, p->total_rows, 64, 32);
     if (st) return st;
   }
@@ -267,6 +267,27 @@ int flat_conv_bind_operands(FlatConvParams* p) {
   }
   p->operand_maps = 1;
   return OK;
+}
+
+// CF_FUSE (grid-synchronous BatchNorm): possible when every tile's accumulator can stay in TMEM until the grid barrier, i.e. no
+// CTA gets more tiles than it has accumulator sets. CILRS_NO_FUSE=1 switches it off (A/B measurements, equivalence tests).
+static int g_fuse_enabled = -1;   // -1: not decided yet (CILRS_NO_FUSE=1 switches it off), see cilrs_set_bn_fusion
+int flat_conv_fuse_ok(const FlatConvParams* p) {
+  if (g_fuse_enabled < 0) g_fuse_enabled = getenv("CILRS_NO_FUSE") ? 0 : 1;
+  if (!g_fuse_enabled) return 0;
+  const long long total = (long long)p->m_tiles * p->n_blocks;
+  const int grid = flat_conv_grid(p);
+  const int n = p->pair ? grid / 2 : grid;
+  if (n < 1) return 0;
+  return (total + n - 1) / n <= p->acc_sets ? 1 : 0;
+}
+// tensor maps of the second-pass outputs (same [rows][n_total] geometry as `out`)
+int flat_conv_bind_fuse(FlatConvParams* p, void* out2, void* out3) {
+  if (!out2) return ERR_INVALID;
+  int st = encode_2d_map(&p->tmOut2, out2, p->n_total, p->total_rows, 64, 32);
+  if (st) return st;
+  if (out3) st = encode_2d_map(&p->tmOut3, out3, p->n_total, p->total_rows, 64, 32);
+  return st;
 }
 
 // CTAs of the launch: one per tile up to the SM count (pairs: two per tile up to the resident pair count), a multiple of
@@ -284,6 +305,13 @@ int launch_flat_conv(const FlatConvParams* p, cudaStream_t s) {
   if (st) return st;
   if ((p->flags & CF_BNBWD) && (!p->operand_maps || !p->y1 || ((p->flags & CF_BNBWD2) && !p->y2))) return ERR_INVALID;
   if ((p->flags & (CF_STATS | CF_BNBWD)) && (!p->partials || (!(p->flags & CF_DEFER) && !p->counter))) return ERR_INVALID;
+  if (p->flags & CF_FUSE) {
+    if (!(p->flags & CF_DEFER) || !(p->flags & (CF_STATS | CF_BNBWD)) || !p->grid_bar || !flat_conv_fuse_ok(p)) return ERR_INVALID;
+    if ((p->flags & CF_STATS) && (!p->gamma || !p->beta || !p->vec)) return ERR_INVALID;
+    if ((p->flags & CF_BNBWD) && (!p->stat1 || !p->gamma1 || !p->bred1 || ((p->flags & CF_BNBWD2) && (!p->stat2 || !p->gamma2 || !p->bred2)))) return ERR_INVALID;
+    if ((p->flags & CF_NO_STORE) && ((p->flags & CF_RESIDUAL) || !(p->flags & CF_BNBWD) || ((p->flags & CF_MASK) && !p->mask_bits))) return ERR_INVALID;
+    if ((p->flags & CF_FUSE_RES) && (!p->operand_maps || !p->residual)) return ERR_INVALID;
+  }
   const int grid = flat_conv_grid(p);
   void (*kernel)(FlatConvParams) = flat_kernel(p->mt, p->pair);
   if (!kernel || grid < 1) return ERR_INVALID;
@@ -366,6 +394,15 @@ using namespace cilrs;
 extern "C" {
 
 long long cilrs_flat_rows(int batch, int H, int W) { return (long long)batch * (H + 1) * (W + 1); }
+
+// Grid-synchronous BatchNorm inside the flat convolutions (conv_params.h: CF_FUSE) on / off for plans built AFTER the call
+// (a cilrs_model rebuilds its plans when the batch size or mode changes, or via cilrs_model_invalidate_plans). Returns the
+// previous setting. Measurement / test aid: both settings compute the same network.
+int cilrs_set_bn_fusion(int enable) {
+  const int prev = g_fuse_enabled < 0 ? (getenv("CILRS_NO_FUSE") ? 0 : 1) : g_fuse_enabled;
+  g_fuse_enabled = enable ? 1 : 0;
+  return prev;
+}
 
 int cilrs_conv_flat(const cilrs_flat_conv_args* a, void* stream) {
   if (!a || !a->x || !a->w || !a->y) return ERR_INVALID;

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "pair.cuh"
 #include "conv_params.h"
+#include "bn_math.cuh"
 
 namespace cilrs {
 
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmOut);
     if (p.operand_maps) { tma_prefetch_desc(&p.tmRes); tma_prefetch_desc(&p.tmY1); }
+    if (p.flags & CF_FUSE) tma_prefetch_desc(&p.tmOut2);
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < p.acc_sets; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 16 : 8); }  // 8 epilogue warps (per CTA)
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
             *(uint4*)(w_out + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(p.flags & CF_NO_STORE)) {   // (CF_NO_STORE: only the sums of this tile are needed; pass 2 recomputes it)
             tma_store_2d(&p.tmOut, w_out, n_base, row_first);
             tma_store_commit();
           }
@@ -433,6 +435,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
 
     tma_store_wait_all();  // this warp's output stores have been written
 
+    const bool fuse = (p.flags & CF_FUSE) != 0;
     if (do_stats) {
       // ---- per-CTA partial (the eight warps' sums in a fixed order), then the last CTA to finish folds all partials ----
       const int tid = ew * 32 + lane;  // 0..255
@@ -533,6 +536,226 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
           if (!bwd && p.update_running && p.nbt) *p.nbt += 1;
         }
       }
+    }
+
+    if (fuse) {
+      // ================= grid-synchronous BatchNorm (CF_FUSE) =================
+      // Every accumulator of this CTA is still in TMEM (the host guarantees tiles per CTA <= acc_sets) and every CTA's
+      // per-channel sums are on their way to `partials`: meet all CTAs of the launch, derive this CTA's channel constants
+      // exactly as bn_apply / bn_bwd_apply do in their deferred prologue, then run the epilogue a second time.
+      const int tid = ew * 32 + lane;
+      bar_sync_named(3, 256);   // every epilogue thread of this CTA has issued its atomics / finished its stores
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(p.grid_bar, 1u);
+        const uint64_t t0 = globaltimer_ns();
+        unsigned int seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.grid_bar) : "memory");
+          if (seen < gridDim.x && globaltimer_ns() - t0 > 2000000000ull) __trap();   // a CTA of the launch never arrived
+        } while (seen < gridDim.x);
+        __threadfence();
+      }
+      bar_sync_named(3, 256);
+      const int bn_ = p.block_n;
+      float* s_par = s_wacc;    // [10][block_n] per-channel constants (the running sums are not needed any more)
+      const int nb = pair_id % p.n_blocks;
+      const bool writer = pair_id < p.n_blocks && rank == 0;   // the CTA that owns m_tile 0 of this channel block publishes
+      for (int c = tid; c < bn_; c += 256) {
+        const int cg = nb * bn_ + c;
+        if (!bwd) {
+          const BnStat st = bn_stat_from_sums(__ldcg(p.partials + cg), __ldcg(p.partials + p.n_total + cg), p.inv_count, p.unbias, p.eps,
+                                              __ldg(p.gamma + cg), __ldg(p.beta + cg));
+          s_par[c] = st.scale; s_par[bn_ + c] = st.shift;
+          if (p.fuse_rvec) { s_par[2 * bn_ + c] = __ldg(p.fuse_rvec + cg); s_par[3 * bn_ + c] = __ldg(p.fuse_rvec + p.n_total + cg); }
+          if (writer) {
+            p.vec[cg] = st.scale; p.vec[p.n_total + cg] = st.shift; p.vec[2 * p.n_total + cg] = st.mean; p.vec[3 * p.n_total + cg] = st.rstd;
+            if (p.update_running) {
+              p.running_mean[cg] = (1.f - p.momentum) * p.running_mean[cg] + p.momentum * st.mean;
+              p.running_var[cg] = (1.f - p.momentum) * p.running_var[cg] + p.momentum * st.unbiased_var;
+            }
+          }
+        } else {
+          const float invc = (float)p.inv_count;
+          const double S0 = __ldcg(p.partials + cg);
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2) {
+            if (k2 == 1 && !bwd2) break;
+            const float* stat = k2 ? p.stat2 : p.stat1;
+            const float mean = __ldg(stat + 2 * p.n_total + cg), rstd = __ldg(stat + 3 * p.n_total + cg);
+            const double S1 = __ldcg(p.partials + (1 + k2) * p.n_total + cg);
+            const float bs = (float)S0, bd = bn_bdot_from_sums(S0, S1, mean, rstd);
+            float* sp = s_par + 5 * k2 * bn_;
+            sp[c] = mean; sp[bn_ + c] = rstd; sp[2 * bn_ + c] = __ldg((k2 ? p.gamma2 : p.gamma1) + cg);
+            sp[3 * bn_ + c] = bs * invc; sp[4 * bn_ + c] = bd * invc;
+            if (writer) {
+              float* bred = k2 ? p.bred2 : p.bred1;
+              float* dg = k2 ? p.dgamma2 : p.dgamma1;
+              float* db = k2 ? p.dbeta2 : p.dbeta1;
+              bred[cg] = bs; bred[p.n_total + cg] = bd;
+              if (dg) dg[cg] += bd;
+              if (db) db[cg] += bs;
+            }
+          }
+        }
+      }
+      if (writer && nb == 0 && tid == 0 && !bwd && p.update_running && p.nbt) *p.nbt += 1;
+      bar_sync_named(3, 256);
+      tc_fence_after();
+      const bool no_store = (p.flags & CF_NO_STORE) != 0;
+      const bool fres = (p.flags & CF_FUSE_RES) != 0;
+      int acc2 = 0;
+      uint32_t uc2 = 0;
+      for (int tile = pair_id; tile < total_tiles; tile += n_pairs, ++acc2) {
+        const int m_tile = tile / p.n_blocks;
+        const int n_blk = tile - m_tile * p.n_blocks;
+        const int row0 = (m_tile * (PAIR ? 2 : 1) + (int)rank) * MT * 128;
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
+          const int f = row0 + m * 128 + row;
+          const bool in_range = f < p.total_rows;
+          bool valid = in_range;
+          if (valid) {
+            const unsigned int uf = (unsigned int)f;
+            const unsigned int wq = uf / (unsigned int)p.g.Wp;
+            const unsigned int w = uf - wq * (unsigned int)p.g.Wp;
+            const unsigned int h = wq % (unsigned int)p.g.Hp;
+            valid = (w < (unsigned int)p.g.W) && (h < (unsigned int)p.g.H);
+          }
+#pragma unroll 1
+          for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            if (((uc2++) & 1u) != (uint32_t)grp) continue;
+            const int n_base = n_blk * p.block_n + chunk * 64;
+            const int cl = chunk * 64;   // channel offset inside this CTA's block
+            const long long goff = (long long)f * p.n_total + n_base;
+            const int row_first = row0 + m * 128 + q * 32;
+            tma_store_wait_read();
+            __syncwarp();
+            if (lane == 0) {
+              if (!bwd && fres) {
+                mbar_arrive_expect_tx(bar_res, 32 * 128);
+                tma_load_2d(&p.tmRes, bar_res, w_out, n_base, row_first);
+              }
+              if (bwd) {
+                mbar_arrive_expect_tx(bar_y, 32 * 128);
+                tma_load_2d(&p.tmY1, bar_y, w_y, n_base, row_first);
+                if (!no_store) {   // the dz tile this warp stored in pass 1 (complete: tma_store_wait_all above)
+                  mbar_arrive_expect_tx(bar_res, 32 * 128);
+                  tma_load_2d(&p.tmOut, bar_res, w_out, n_base, row_first);
+                }
+              }
+            }
+            float x[64];   // forward: bf16-rounded conv output; backward: dz
+            if (!bwd || no_store) {
+              uint32_t v[64];
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc2 * acc_stride + m * p.block_n + chunk * 64);
+              tmem_ld_32x32(taddr, v);
+              tmem_ld_32x32(taddr + 32, v + 32);
+              tmem_ld_wait();
+              if (bwd) {
+                uint2 mbits = make_uint2(0xffffffffu, 0xffffffffu);
+                if ((p.flags & CF_MASK) && p.mask_bits != nullptr && valid) mbits = __ldg(reinterpret_cast<const uint2*>(p.mask_bits + (goff >> 3)));
+#pragma unroll
+                for (int j = 0; j < 64; ++j)
+                  if (!(((j < 32 ? mbits.x : mbits.y) >> (j & 31)) & 1u)) v[j] = 0u;
+              }
+#pragma unroll
+              for (int j = 0; j < 64; ++j) x[j] = valid ? __bfloat162float(__float2bfloat16(__uint_as_float(v[j]))) : 0.f;
+            } else {
+              mbar_wait(bar_res, ph_res);
+              ph_res ^= 1;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 t4 = *(const uint4*)(w_out + lane * 128 + ((j ^ (lane & 7)) << 4));
+                x[8 * j] = bf16lo(t4.x); x[8 * j + 1] = bf16hi(t4.x); x[8 * j + 2] = bf16lo(t4.y); x[8 * j + 3] = bf16hi(t4.y);
+                x[8 * j + 4] = bf16lo(t4.z); x[8 * j + 5] = bf16hi(t4.z); x[8 * j + 6] = bf16lo(t4.w); x[8 * j + 7] = bf16hi(t4.w);
+              }
+            }
+            uint32_t u[32];
+            if (!bwd) {
+              // out2 = relu( x * scale + shift [+ res | + res * rscale + rshift] ), and its ReLU bits
+#pragma unroll
+              for (int j = 0; j < 64; ++j) x[j] = fmaf(x[j], s_par[cl + j], s_par[bn_ + cl + j]);
+              if (fres) {
+                mbar_wait(bar_res, ph_res);
+                ph_res ^= 1;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const uint4 t4 = *(const uint4*)(w_out + lane * 128 + ((j ^ (lane & 7)) << 4));
+                  float r[8] = {bf16lo(t4.x), bf16hi(t4.x), bf16lo(t4.y), bf16hi(t4.y), bf16lo(t4.z), bf16hi(t4.z), bf16lo(t4.w), bf16hi(t4.w)};
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    if (p.fuse_rvec) r[e] = fmaf(r[e], s_par[2 * bn_ + cl + 8 * j + e], s_par[3 * bn_ + cl + 8 * j + e]);
+                    x[8 * j + e] += r[e];
+                  }
+                }
+              }
+              uint2 ob = make_uint2(0u, 0u);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float a = fmaxf(x[2 * j], 0.f), b = fmaxf(x[2 * j + 1], 0.f);
+                u[j] = valid ? pack_bf16x2(a, b) : 0u;
+                const uint32_t bits2 = ((u[j] & 0xFFFFu) != 0u && !(u[j] & 0x8000u) ? 1u : 0u) | ((u[j] >> 16) != 0u && !(u[j] & 0x80000000u) ? 2u : 0u);
+                if (j < 16) ob.x |= bits2 << (2 * j); else ob.y |= bits2 << (2 * (j - 16));
+              }
+              if (in_range && p.bits_out) *reinterpret_cast<uint2*>(p.bits_out + (goff >> 3)) = ob;
+              __syncwarp();  // every lane has read its residual row out of the staging tile
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *(uint4*)(w_out + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&p.tmOut2, w_out, n_base, row_first);
+                tma_store_commit();
+              }
+            } else {
+              // dy = gamma * rstd * (dz - k0 - xhat * k1), xhat = (y - mean) * rstd, for BN 1 (and BN 2 on the same dz)
+#pragma unroll 1
+              for (int k2 = 0; k2 < 2; ++k2) {
+                if (k2 == 1 && !bwd2) break;
+                if (k2 == 1) {
+                  __syncwarp();   // every lane has read its y1 row
+                  if (lane == 0) {
+                    mbar_arrive_expect_tx(bar_y, 32 * 128);
+                    tma_load_2d(&p.tmY2, bar_y, w_y, n_base, row_first);
+                  }
+                }
+                mbar_wait(bar_y, ph_y);
+                ph_y ^= 1;
+                const float* sp = s_par + 5 * k2 * bn_ + cl;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const uint4 t4 = *(const uint4*)(w_y + lane * 128 + ((j ^ (lane & 7)) << 4));
+                  const float yv[8] = {bf16lo(t4.x), bf16hi(t4.x), bf16lo(t4.y), bf16hi(t4.y), bf16lo(t4.z), bf16hi(t4.z), bf16lo(t4.w), bf16hi(t4.w)};
+                  float o[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const int cc = 8 * j + e;
+                    const float mean = sp[cc], rstd = sp[bn_ + cc], gam = sp[2 * bn_ + cc], k0 = sp[3 * bn_ + cc], k1 = sp[4 * bn_ + cc];
+                    const float xhat = (yv[e] - mean) * rstd;
+                    o[e] = gam * rstd * (x[cc] - k0 - xhat * k1);
+                  }
+                  u[4 * j] = valid ? pack_bf16x2(o[0], o[1]) : 0u; u[4 * j + 1] = valid ? pack_bf16x2(o[2], o[3]) : 0u;
+                  u[4 * j + 2] = valid ? pack_bf16x2(o[4], o[5]) : 0u; u[4 * j + 3] = valid ? pack_bf16x2(o[6], o[7]) : 0u;
+                }
+                if (k2 == 1) tma_store_wait_read();   // the dy1 store has read the staging tile
+                __syncwarp();  // every lane has read its dz row out of the staging tile
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  *(uint4*)(w_out + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(k2 ? &p.tmOut3 : &p.tmOut2, w_out, n_base, row_first);
+                  tma_store_commit();
+                }
+              }
+            }
+          }
+        }
+      }
+      tma_store_wait_all();
     }
   }
 

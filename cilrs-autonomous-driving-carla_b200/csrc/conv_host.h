@@ -57,6 +57,8 @@ int build_flat_conv(FlatConvParams* p, int batch, const PadGeom& g, int k_channe
                     const void* w, void* out, int flags);
 int flat_conv_bind_operands(FlatConvParams* p);  // after residual / y1 / y2 are set
 int flat_conv_grid(const FlatConvParams* p);
+int flat_conv_fuse_ok(const FlatConvParams* p);                          // CF_FUSE possible for this plan (tiles per CTA <= accumulator sets)
+int flat_conv_bind_fuse(FlatConvParams* p, void* out2, void* out3);      // tensor maps of the second-pass outputs
 int launch_flat_conv(const FlatConvParams* p, cudaStream_t s);
 struct WgradReduceJobs;
 // scratch: WF_SCRATCH_BYTES of split-K partial tiles, folded into the OIHW gradient by the reduce launch

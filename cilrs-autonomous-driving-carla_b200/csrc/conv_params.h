@@ -105,6 +105,15 @@ enum FlatConvFlags : int {
   CF_DEFER = 128,     // CF_STATS / CF_BNBWD: only add the per-channel sums to `partials` (a per-BatchNorm accumulator that the
                       // caller zeroed); the elementwise kernel that consumes them finalizes (elementwise.cuh: BnDefer / BnBwdDefer).
                       // Saves the counter round trip and the last-CTA tail (~6 k clocks per launch).
+  CF_FUSE = 256,      // (with CF_DEFER) grid-synchronous BatchNorm: every tile's accumulator STAYS in TMEM (the launch has at most
+                      // acc_sets tiles per CTA - 148 SMs x 512 columns hold a whole layer's output at batch 128), the CTAs meet at
+                      // a grid barrier once the per-channel sums are complete, and a second epilogue pass applies the
+                      // BatchNorm the sums belong to:
+                      //   CF_STATS: out2 = relu(bn(y) [+ residual | + bn2(residual)]) + its ReLU bit mask (what bn_apply did)
+                      //   CF_BNBWD: dy1 = BatchNorm-backward(dz, y1) -> out2 [, dy2 -> out3 with CF_BNBWD2] (what bn_bwd_apply did)
+                      // One launch instead of two, and the elementwise pass's re-read of the conv output disappears.
+  CF_FUSE_RES = 512,  // CF_STATS | CF_FUSE: the second pass adds `fuse_res` (through tmRes), scaled by fuse_rvec if given
+  CF_NO_STORE = 1024, // CF_BNBWD | CF_FUSE: pass 1 does not store dz (nobody else reads it); pass 2 recomputes it from TMEM
 };
 
 struct FlatConvParams {
@@ -158,6 +167,16 @@ struct FlatConvParams {
   float* bred2;
   float* dgamma2;
   float* dbeta2;
+  // CF_FUSE
+  unsigned int* grid_bar;      // zeroed device word: the launch's grid barrier
+  CUtensorMap tmOut2;          // second-pass output (activation / dy1), box (64, 32)
+  CUtensorMap tmOut3;          // dy2 (CF_BNBWD2)
+  uint8_t* bits_out;           // CF_STATS: ReLU bit mask of out2 ([rows][n_total / 8] bytes)
+  const float* fuse_rvec;      // CF_FUSE_RES: [4][n_total] vectors of the BatchNorm applied to the residual (downsample branch) or null
+  const float* gamma1;         // CF_BNBWD: BatchNorm weights of BN 1 / BN 2
+  const float* gamma2;
+  double inv_count;            // 1 / (batch * H * W)
+  double unbias;               // count / (count - 1)
 };
 
 constexpr int WF_THREADS = 192;

@@ -5,6 +5,7 @@
 #pragma once
 #include "common.cuh"
 #include "conv_params.h"
+#include "bn_math.cuh"
 
 namespace cilrs {
 
@@ -87,21 +88,6 @@ struct BnDefer {
   float momentum, eps;
   int update_running;
 };
-struct BnStat {
-  float scale, shift, mean, rstd, unbiased_var;
-};
-CILRS_DEVINL BnStat bn_stat_from_sums(double S0, double S1, double inv_count, double unbias, float eps, float gamma, float beta) {
-  const double mean_d = S0 * inv_count;
-  double var_d = S1 * inv_count - mean_d * mean_d;
-  if (var_d < 0.0) var_d = 0.0;
-  BnStat r;
-  r.mean = (float)mean_d;
-  r.unbiased_var = (float)(var_d * unbias);
-  r.rstd = 1.0f / sqrtf((float)var_d + eps);
-  r.scale = gamma * r.rstd;
-  r.shift = beta - r.mean * r.scale;
-  return r;
-}
 struct BnBwdDefer {
   const double* acc_sum;  // [C] sum dz
   const double* acc_dot;  // [C] sum dz * y (raw conv output); bdot = rstd * (acc_dot - mean * acc_sum)
@@ -109,10 +95,6 @@ struct BnBwdDefer {
   float* dgamma;          // += bdot (may be null)
   float* dbeta;           // += bsum
 };
-CILRS_DEVINL float bn_bdot_from_sums(double S0, double S1, float mean, float rstd) {
-  return (float)((double)rstd * (S1 - (double)mean * S0));
-}
-
 // ---------------------------------------------------------------------------------------------
 // bn_finalize: per-tile (sum, sumsq) partials -> batch statistics -> scale/shift (+ running stats update)
 //   training: mean = S/n, var_b = Q/n - mean^2 (biased, used to normalise), running_var gets the unbiased one,

@@ -132,6 +132,9 @@ struct Model {
   double* acc_fwd;       // per-BatchNorm accumulators of the deferred finalize (conv_params.h: CF_DEFER): forward, backward
   double* acc_bwd;
   long long acc_fwd_bytes, acc_bwd_bytes;
+  unsigned int *bar_fwd = nullptr, *bar_bwd = nullptr;  // grid-barrier words of the fused launches (CF_FUSE), zeroed with the accumulators
+  int bar_fwd_next = 0, bar_bwd_next = 0;
+  bool bw_fused_prev = false;  // dy of the current block's conv_b (and downsample) BatchNorms was already written by the fused dgrad of the block above
   bool bw_deferred = false;  // the reductions of the current block-output gradient sit in bn_b.bacc (fused dgrad) rather than in bred
   unsigned int* counters;
   float* unit_vec;       // [2][64]: ones, zeros (max-pool on already-activated stem output)
@@ -288,9 +291,11 @@ static long long carve(Model& m, char* base) {
   {
     long long ch = m.stem.bn.C;
     for (auto& blk : m.blocks) ch += blk.a.bn.C + blk.b.bn.C + (blk.has_ds ? blk.ds.bn.C : 0);
-    m.acc_fwd_bytes = ch * 2 * 8; m.acc_bwd_bytes = ch * 3 * 8;
+    m.acc_fwd_bytes = ch * 2 * 8 + 64 * 4; m.acc_bwd_bytes = ch * 3 * 8 + 64 * 4;   // + 64 grid-barrier words each
     m.acc_fwd = (double*)bp.take(m.acc_fwd_bytes);
     m.acc_bwd = (double*)bp.take(m.acc_bwd_bytes);
+    m.bar_fwd = m.acc_fwd ? (unsigned int*)(m.acc_fwd + ch * 2) : nullptr;
+    m.bar_bwd = m.acc_bwd ? (unsigned int*)(m.acc_bwd + ch * 3) : nullptr;
     long long off = 0;
     auto give = [&](BnRef& bn) {
       bn.acc = m.acc_fwd ? m.acc_fwd + 2 * off : nullptr;
@@ -383,6 +388,11 @@ static int build_plans(Model& m, int B, int mode) {
       const int fl = infer ? (CF_SCALE_BIAS | CF_RELU) : (training ? CF_STATS : 0);
       CK(build_flat_conv(&f, B, blk.a.gin, blk.a.d.in_c, blk.a.d.out_c, 0, blk.in, blk.a.wf, infer ? blk.act_a : blk.a.y, fl));
       if (infer) { f.scale = blk.a.bn.vec; f.bias = blk.a.bn.vec + blk.a.bn.C; }
+      if (training && flat_conv_fuse_ok(&f)) {   // BatchNorm + ReLU applied by the conv's own second pass (CF_FUSE)
+        f.flags |= CF_FUSE;
+        f.bits_out = blk.bits_a;
+        CK(flat_conv_bind_fuse(&f, blk.act_a, nullptr));
+      }
       blk.pl.f_a_flat = add_flat(m, f);
     } else {
       if (infer) CK(build_fprop(&p, &blk.a.d, blk.in, blk.a.wf, blk.act_a, blk.a.bn.vec, blk.a.bn.vec + blk.a.bn.C, nullptr, nullptr,
@@ -403,6 +413,14 @@ static int build_plans(Model& m, int B, int mode) {
         f.scale = blk.b.bn.vec; f.bias = blk.b.bn.vec + blk.b.bn.C;
         f.residual = blk.has_ds ? blk.ds.y : blk.in;
         CK(flat_conv_bind_operands(&f));
+      }
+      if (training && flat_conv_fuse_ok(&f)) {   // out = relu(bn_b(y_b) + identity | bn_ds(y_ds)) by the conv's second pass
+        f.flags |= CF_FUSE | CF_FUSE_RES;
+        f.residual = blk.has_ds ? blk.ds.y : blk.in;
+        f.fuse_rvec = blk.has_ds ? blk.ds.bn.vec : nullptr;
+        f.bits_out = blk.bits_out;
+        CK(flat_conv_bind_operands(&f));
+        CK(flat_conv_bind_fuse(&f, blk.out, nullptr));
       }
       blk.pl.f_b_flat = add_flat(m, f);
     }
@@ -433,6 +451,10 @@ static int build_plans(Model& m, int B, int mode) {
       CK(build_flat_conv(&f, B, blk.b.gin, blk.b.d.out_c, blk.b.d.in_c, 1, dyb, blk.b.wd, m.ga, CF_MASK | CF_BNBWD));
       f.mask = blk.act_a; f.mask_bits = blk.bits_a; f.y1 = blk.a.y; f.stat1 = blk.a.bn.vec; f.bred1 = blk.a.bn.bred;
       CK(flat_conv_bind_operands(&f));
+      if (training && flat_conv_fuse_ok(&f)) {   // dy_a straight from the dgrad's accumulators: dz_a is never stored
+        f.flags |= CF_FUSE | CF_NO_STORE;
+        CK(flat_conv_bind_fuse(&f, dya, nullptr));
+      }
       blk.pl.d_b = add_flat(m, f);
       // conv_a: dW_a = wgrad(dy_a = d1, in); downsample: dW_ds = wgrad(dy_ds = d2, in)
       if (blk.a.flat) {
@@ -459,6 +481,12 @@ static int build_plans(Model& m, int B, int mode) {
           if (pb.has_ds) { f.y2 = pb.ds.y; f.stat2 = pb.ds.bn.vec; f.bred2 = pb.ds.bn.bred; }
         }
         CK(flat_conv_bind_operands(&f));
+        if (training && bi > 0 && flat_conv_fuse_ok(&f)) {   // dy of the block below's conv_b (and downsample) BatchNorms by the second pass
+          Block& pb = m.blocks[bi - 1];
+          const int pb_part = (bi - 1) >= 13 ? 0 : ((bi - 1) >= 7 ? 1 : ((bi - 1) >= 3 ? 2 : 3));
+          f.flags |= CF_FUSE;
+          CK(flat_conv_bind_fuse(&f, m.dyb[(bi - 1) & 1], pb.has_ds ? m.dyd[pb_part & 1] : nullptr));
+        }
         blk.pl.d_a_flat = add_flat(m, f);
       } else {
         for (int ph = 0; ph < 2; ++ph)
@@ -520,6 +548,11 @@ static int launch_flat_fwd(Model& m, int idx, const BnRef& bn, double count, int
     f.running_mean = m.buffers + bn.rm_off; f.running_var = m.buffers + bn.rv_off;
     f.nbt = m.nbt ? m.nbt + bn.nbt_idx : nullptr;
     f.vec = bn.vec; f.count = count; f.momentum = 0.1f; f.eps = 1e-5f; f.update_running = update_running;
+    if (f.flags & CF_FUSE) {
+      if (m.bar_fwd_next >= 64) return ERR_INVALID;
+      f.grid_bar = m.bar_fwd + m.bar_fwd_next++;
+      f.inv_count = 1.0 / count; f.unbias = count > 1.0 ? count / (count - 1.0) : 1.0;
+    }
   }
   return launch_flat_conv(&f, s);
 }
@@ -569,7 +602,8 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
     return ERR_INVALID;
   }
   const int training = mode == MODE_TRAIN;
-  if (training) CK(cuda_status(cudaMemsetAsync(m.acc_fwd, 0, (size_t)m.acc_fwd_bytes, s)));  // accumulators of the deferred BN finalize
+  if (training) CK(cuda_status(cudaMemsetAsync(m.acc_fwd, 0, (size_t)m.acc_fwd_bytes, s)));  // accumulators of the deferred BN finalize (+ grid-barrier words)
+  m.bar_fwd_next = 0;
   const long long pool_vec = act_elems(B, 22, 50, 64) / 8;
   PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.old_plans[m.stem_fwd], s)));
   if (mode == MODE_INFER) {
@@ -603,10 +637,14 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
       };
       CK(conv_bn(blk.a, blk.pl.f_a_flat, blk.pl.f_a_old));
       const int def_a = training && blk.pl.f_a_flat >= 0, def_b = training;
-      PROF(m, PC_BN_FWD, s, CK(run_bn_apply(m, B, blk.a.gout, blk.a.y, blk.a.bn, nullptr, nullptr, nullptr, blk.act_a, 1, blk.bits_a, def_a,
-                                            update_running, s)));
+      const bool fused_a = blk.pl.f_a_flat >= 0 && (m.flat_plans[blk.pl.f_a_flat].flags & CF_FUSE);
+      const bool fused_b = (m.flat_plans[blk.pl.f_b_flat].flags & CF_FUSE) != 0;
+      if (!fused_a)
+        PROF(m, PC_BN_FWD, s, CK(run_bn_apply(m, B, blk.a.gout, blk.a.y, blk.a.bn, nullptr, nullptr, nullptr, blk.act_a, 1, blk.bits_a, def_a,
+                                              update_running, s)));
       if (blk.has_ds) CK(conv_bn(blk.ds, -1, blk.pl.f_ds_old));
       CK(conv_bn(blk.b, blk.pl.f_b_flat, -1));
+      if (fused_b) continue;   // the conv's second pass wrote blk.out and its ReLU bits
       if (blk.has_ds) PROF(m, PC_BN_FWD, s, CK(run_bn_apply(m, B, blk.b.gout, blk.b.y, blk.b.bn, nullptr, blk.ds.y, &blk.ds.bn, blk.out, 1,
                                                             blk.bits_out, def_b, update_running, s)));
       else PROF(m, PC_BN_FWD, s, CK(run_bn_apply(m, B, blk.b.gout, blk.b.y, blk.b.bn, blk.in, nullptr, nullptr, blk.out, 1, blk.bits_out,
@@ -632,13 +670,20 @@ static int run_wgrad_old(Model& m, int idx, int slot, cudaStream_t s) {
 }
 static int run_wgrad_flat(Model& m, int idx, cudaStream_t s) { return launch_wgrad_flat(&m.wflat_plans[idx], s); }
 // flat dgrad with the fused ReLU mask + BatchNorm-backward reductions: bind workspace and dgamma / dbeta at launch time
-static int launch_flat_bwd(Model& m, int idx, const BnRef* bn1, const BnRef* bn2, cudaStream_t s) {
+static int launch_flat_bwd(Model& m, int idx, const BnRef* bn1, const BnRef* bn2, double count, cudaStream_t s) {
   FlatConvParams f = m.flat_plans[idx];
   if (f.flags & CF_BNBWD) {
     f.flags |= CF_DEFER;  // the bn_bwd_apply kernels that follow finalize (run_bn_bwd_apply, deferred)
     f.partials = bn1->bacc; f.counter = nullptr;
     f.dgamma1 = m.grads + m.slots[bn1->gamma].off; f.dbeta1 = m.grads + m.slots[bn1->beta].off;
     if (f.flags & CF_BNBWD2) { f.dgamma2 = m.grads + m.slots[bn2->gamma].off; f.dbeta2 = m.grads + m.slots[bn2->beta].off; }
+    if (f.flags & CF_FUSE) {
+      if (m.bar_bwd_next >= 64) return ERR_INVALID;
+      f.grid_bar = m.bar_bwd + m.bar_bwd_next++;
+      f.inv_count = 1.0 / count;
+      f.gamma1 = m.params + m.slots[bn1->gamma].off;
+      if (f.flags & CF_BNBWD2) f.gamma2 = m.params + m.slots[bn2->gamma].off;
+    }
   }
   return launch_flat_conv(&f, s);
 }
@@ -714,6 +759,8 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     }
     m.bw_gcur = gin; m.bw_gnext = gin == m.g0 ? m.g1 : m.g0;
     m.bw_deferred = false;
+    m.bw_fused_prev = false;
+    m.bar_bwd_next = 0;
   } else if (part <= 0) {
     CK(cuda_status(cudaMemsetAsync(m.acc_bwd, 0, (size_t)m.acc_bwd_bytes, s)));  // accumulators of the deferred BN-backward finalize
     {
@@ -727,6 +774,8 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_reduce(m, B, last.b.gout, last.b.bn, m.g0, last.out, last.b.y, s)));
     m.bw_gcur = m.g0; m.bw_gnext = m.g1;
     m.bw_deferred = false;
+    m.bw_fused_prev = false;
+    m.bar_bwd_next = 0;
   }
   __nv_bfloat16*& gcur = m.bw_gcur;
   __nv_bfloat16*& gnext = m.bw_gnext;
@@ -770,21 +819,27 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     __nv_bfloat16* dya = m.dya[bi & 1];
     __nv_bfloat16* dyd = m.dyd[blk_part & 1];
     // gcur = dz of this block's output (ReLU-masked), with the reductions of bn_b (and bn_ds) already in their bred
-    CK(slot_write(sb));
     const int Cb = blk.b.bn.C;
-    const double* bsum_acc = m.bw_deferred ? blk.b.bn.bacc : nullptr;  // sum dz | sum dz*y_b | sum dz*y_ds
-    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.b.bn, gcur, blk.b.y, cnt, frozen, dyb, bsum_acc, bsum_acc ? bsum_acc + Cb : nullptr, s)));
-    CK(slot_ready(sb));
-    if (blk.has_ds) {
-      CK(slot_write(sd));
-      PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.ds.bn, gcur, blk.ds.y, cnt, frozen, dyd, bsum_acc, bsum_acc ? bsum_acc + 2 * Cb : nullptr, s)));
-      CK(slot_ready(sd));
-    }
+    if (!m.bw_fused_prev) {
+      CK(slot_write(sb));
+      const double* bsum_acc = m.bw_deferred ? blk.b.bn.bacc : nullptr;  // sum dz | sum dz*y_b | sum dz*y_ds
+      PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.b.bn, gcur, blk.b.y, cnt, frozen, dyb, bsum_acc, bsum_acc ? bsum_acc + Cb : nullptr, s)));
+      CK(slot_ready(sb));
+      if (blk.has_ds) {
+        CK(slot_write(sd));
+        PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.ds.bn, gcur, blk.ds.y, cnt, frozen, dyd, bsum_acc, bsum_acc ? bsum_acc + 2 * Cb : nullptr, s)));
+        CK(slot_ready(sd));
+      }
+    }  // else: the fused dgrad of the block above (CF_FUSE) already wrote dyb (and dyd) and signalled the slots
     PROF(m, PC_WGRAD, ws, CK(run_wgrad_flat(m, blk.pl.w_b, ws)));                     // dW_b
     CK(slot_read_done(sb));
-    PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_b, &blk.a.bn, nullptr, s)));  // ga = dz_a (+ BN_a reductions)
-    CK(slot_write(sa));
-    PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.a.bn, m.ga, blk.a.y, cnt, frozen, dya, blk.a.bn.bacc, blk.a.bn.bacc + blk.a.bn.C, s)));
+    const bool fused_b = (m.flat_plans[blk.pl.d_b].flags & CF_FUSE) != 0;             // dgrad_b's second pass writes dy_a itself
+    if (fused_b) CK(slot_write(sa));
+    PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_b, &blk.a.bn, nullptr, cnt, s)));  // ga = dz_a (+ BN_a reductions)
+    if (!fused_b) {
+      CK(slot_write(sa));
+      PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_apply(m, B, go, blk.a.bn, m.ga, blk.a.y, cnt, frozen, dya, blk.a.bn.bacc, blk.a.bn.bacc + blk.a.bn.C, s)));
+    }
     CK(slot_ready(sa));
     if (blk.pl.w_a_flat >= 0) PROF(m, PC_WGRAD, ws, CK(run_wgrad_flat(m, blk.pl.w_a_flat, ws)));
     else PROF(m, PC_WGRAD, ws, CK(run_wgrad_old(m, blk.pl.w_a_old, blk.a.w, ws)));
@@ -795,14 +850,27 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     }
     if (blk.pl.d_a_flat >= 0) {
       Block* pb = bi > 0 ? &m.blocks[bi - 1] : nullptr;
-      PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_a_flat, pb ? &pb->b.bn : nullptr, (pb && pb->has_ds) ? &pb->ds.bn : nullptr, s)));
+      const bool fused_a = (m.flat_plans[blk.pl.d_a_flat].flags & CF_FUSE) != 0;      // ... and dy of the block below's conv_b / downsample BatchNorms
+      const int pb_part = (bi - 1) >= 13 ? 0 : ((bi - 1) >= 7 ? 1 : ((bi - 1) >= 3 ? 2 : 3));
+      const int sbp = (bi - 1) & 1, sdp = 4 + (pb_part & 1);
+      if (fused_a) {
+        CK(slot_write(sbp));
+        if (pb->has_ds) CK(slot_write(sdp));
+      }
+      PROF(m, PC_DGRAD, s, CK(launch_flat_bwd(m, blk.pl.d_a_flat, pb ? &pb->b.bn : nullptr, (pb && pb->has_ds) ? &pb->ds.bn : nullptr, cnt, s)));
+      if (fused_a) {
+        CK(slot_ready(sbp));
+        if (pb->has_ds) CK(slot_ready(sdp));
+      }
       m.bw_deferred = true;
+      m.bw_fused_prev = fused_a;
     } else {
       PROF(m, PC_DGRAD, s, CK(launch_conv_gemm_multi(&m.old_plans[blk.pl.d_a_old], 4, s)));  // the four output parities
       // the parity launches write the raw gradient of the previous block's output: mask + reduce it here
       Block& pb = m.blocks[bi - 1];
       PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_reduce(m, B, pb.b.gout, pb.b.bn, gnext, pb.out, pb.b.y, s)));
       m.bw_deferred = false;
+      m.bw_fused_prev = false;
     }
     __nv_bfloat16* t = gcur; gcur = gnext; gnext = t;
   }
@@ -1130,6 +1198,13 @@ float* cilrs_model_debug_heads_saved(cilrs_model* h, int which, int* width) {
 int cilrs_model_set_dropout_counter(cilrs_model* h, const long long* counter_dev) {
   if (!h) return ERR_INVALID;
   h->m.drop_counter = counter_dev;
+  return OK;
+}
+
+// forget the cached plans (tensor maps, tile shapes, fusion decisions): the next forward rebuilds them
+int cilrs_model_invalidate_plans(cilrs_model* h) {
+  if (!h) return ERR_INVALID;
+  h->m.planB = 0; h->m.planMode = -1;
   return OK;
 }
 

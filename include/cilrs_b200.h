@@ -137,6 +137,11 @@ typedef struct cilrs_flat_conv_args {
   unsigned int* counter_ws; /* one zeroed uint32, left zero by the kernel */
 } cilrs_flat_conv_args;
 long long cilrs_flat_rows(int batch, int H, int W);
+/* Train-mode BatchNorm fused into the flat convolutions ("grid-synchronous BatchNorm": the accumulators of a whole layer stay in
+ * tensor memory across a grid barrier and a second epilogue pass applies the BatchNorm + ReLU / the BatchNorm backward) on or
+ * off for plans built after the call; returns the previous setting. Test / measurement aid - both settings compute the same
+ * network (replaces the ATen BatchNorm launches under torchvision/models/resnet.py:89-105 either way). */
+int cilrs_set_bn_fusion(int enable);
 size_t cilrs_conv_flat_workspace_floats(int out_c);
 int cilrs_conv_flat(const cilrs_flat_conv_args* a, void* stream);
 /* dw_oihw (fp32 [out_c,in_c,3,3]) += dy^T * shifted(x), both padded-flat (two launches: split-K partial tiles into
@@ -220,6 +225,7 @@ int cilrs_model_backward_join(cilrs_model* m, void* stream);
 int cilrs_model_profile(cilrs_model* m, int enable);
 int cilrs_model_profile_collect(cilrs_model* m, float* out_ms7, int* out_launches7);
 void* cilrs_model_input_s2d(cilrs_model* m); /* where K0 may write the conv1-ready frames directly */
+int cilrs_model_invalidate_plans(cilrs_model* m); /* rebuild tensor maps / tile shapes / fusion decisions at the next forward */
 /* test hook: bf16 activation of the last forward. which: 0 = max-pool output, 1..16 = BasicBlock outputs,
  * 17 = raw stem conv output; dims receives {H, W, C, Hp, Wp}: the tensor is [batch, Hp, Wp, C] with the real pixels in
  * [:, :H, :W] (padded-flat layout; the stem output is dense, Hp = H, Wp = W) */

@@ -194,3 +194,47 @@ def test_layer_group_backward_b128(net, hi, lo, bar):
     e_fwd, e_glob, e_dx, worst = _chain(net, hi, lo)
     print("blocks %d..%d: forward %.2e, global param-grad %.2e, dx %.2e, worst tensors %s" % (lo, hi, e_fwd, e_glob, e_dx, worst))
     assert e_fwd <= (BAR if hi - lo < 8 else 1e-1) and e_glob <= bar and e_dx <= bar, (e_fwd, e_glob, e_dx)
+
+
+@pytest.mark.parametrize("B2", [16, 128, 160])
+def test_fused_batchnorm_equals_the_unfused_kernels(B2):
+    """The grid-synchronous BatchNorm inside the flat convolutions (CF_FUSE) against the separate bn_apply / bn_bwd_apply
+    launches it replaces: same model, same batch, train-mode forward + backward with the fusion on and off. Both derive the
+    per-channel constants with the same code and apply them to the same bf16-rounded tensors, so activations, running
+    statistics and gradients agree to the last bit or two of bf16 (a different FMA contraction is the only freedom). B = 160:
+    layer1 does not fit tensor memory (10 tiles per CTA pair > 8 accumulator sets) and stays unfused while layers 2-4 fuse."""
+    from cilrs_b200 import _lib
+    from cilrs_b200.model import CILRS
+    O = _O()
+    sd = O.synthetic_state_dict(0)
+    g = torch.Generator().manual_seed(5)
+    coarse = torch.randn(B2, 3, 11, 25, generator=g)
+    image = torch.nn.functional.interpolate(coarse, size=(88, 200), mode="bicubic", align_corners=False).contiguous().cuda()
+    speed = torch.rand(B2, generator=g).cuda()
+    command = torch.randint(0, 4, (B2,), generator=g).cuda()
+    targets = torch.rand(B2, 3, generator=g).cuda()
+    lib = _lib.lib()
+    results = []
+    prev = lib.cilrs_set_bn_fusion(1)
+    try:
+        for fuse in (1, 0):
+            lib.cilrs_set_bn_fusion(fuse)
+            m = CILRS(num_commands=4, dropout=0.0)
+            m.load_state_dict(sd, strict=True)
+            m = m.to("cuda").train()
+            c, p = m(image, speed, command)
+            loss, _ = O.loss_mse(c, targets, p, speed)
+            loss.backward()
+            torch.cuda.synchronize()
+            acts = [m.debug_activation(i, B2).float().clone() for i in (1, 4, 8, 16)]
+            results.append((c.detach().clone(), m.flat_gradients().clone(), m._flat_buf.clone(), acts))
+    finally:
+        lib.cilrs_set_bn_fusion(prev)
+    (c1, g1, b1, a1), (c0, g0, b0, a0) = results
+    for x, y in zip(a1, a0):
+        assert _rel_max(x, y) <= 1e-2      # (one bf16 ulp on isolated elements at most)
+    assert _rel_max(b1, b0) <= 1e-6        # running statistics: same sums, same finalize
+    assert _rel_max(c1, c0) <= 1e-2
+    e = _rel_l2(g1, g0)
+    print("B=%d fused vs unfused BatchNorm: controls %.2e, global gradient %.2e" % (B2, _rel_max(c1, c0), e))
+    assert e <= 2e-2
