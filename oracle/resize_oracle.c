@@ -12,7 +12,7 @@
  *     ialpha = { saturate_cast<short>((1-fx)*2048), saturate_cast<short>(fx*2048) }   (same per row with fy/ibeta)
  *     H[dx]  = S[sx]*ialpha0 + S[sx+1]*ialpha1                                        (int32, scaled 2^11)
  *     dst    = (((ibeta0 * (H0 >> 4)) >> 16) + ((ibeta1 * (H1 >> 4)) >> 16) + 2) >> 2
- * Pinned against cv2.resize itself (tests/test_oracle_preprocess.py, bit-exact) and against committed golden frames
+ * Pinned against cv2.resize itself (tests/test_oracle_cpu.py, bit-exact) and against committed golden frames
  * produced by the reference call (tests/golden/make_golden.py).
  */
 #include <math.h>
