@@ -43,10 +43,15 @@ def _rel_max(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-300))
 
 
-@pytest.fixture(scope="module")
-def net():
-    """One train-mode forward at B=128 (activations, ReLU bits and BatchNorm vectors of every layer are then in the plan)."""
+@pytest.fixture(scope="module", params=["separate-bn", "fused-bn"])
+def net(request):
+    """One train-mode forward at B=128 (activations, ReLU bits and BatchNorm vectors of every layer are then in the plan).
+    Every test below runs twice: with the separate bn_apply / bn_bwd_apply launches (the default) and with the grid-synchronous
+    BatchNorm fused into the flat convolutions (conv_params.h: CF_FUSE)."""
+    from cilrs_b200 import _lib
     from cilrs_b200.model import CILRS
+    prev = _lib.lib().cilrs_set_bn_fusion(1 if request.param == "fused-bn" else 0)
+    request.addfinalizer(lambda: _lib.lib().cilrs_set_bn_fusion(prev))
     O = _O()
     sd = O.synthetic_state_dict(0)
     m = CILRS(num_commands=4, dropout=0.0)
