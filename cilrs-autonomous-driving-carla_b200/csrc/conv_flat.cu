@@ -376,8 +376,9 @@ int add_wgrad_reduce_job(WgradReduceJobs* jobs, const WgradFlatParams* p, long l
   if (jobs->n >= 16) return ERR_INVALID;
   WgradReduceJob& j = jobs->job[jobs->n++];
   j.scratch = p->scratch; j.grad_off = grad_off; j.cout = p->cout; j.cin = p->cin; j.ci_chunks = p->ci_chunks; j.split_z = p->split_z;
+  j.rows = p->split_z == 1 ? 8 : (p->split_z <= 8 ? 4 : 1);
   j.first_block = jobs->total_blocks;
-  jobs->total_blocks += p->cout * p->ci_chunks;
+  jobs->total_blocks += p->cout / j.rows * p->ci_chunks;
   return OK;
 }
 

@@ -200,7 +200,8 @@ struct WgradReduceJob {
   const float* scratch;
   long long grad_off;   // float offset of the OIHW gradient inside the gradient arena
   int cout, cin, ci_chunks, split_z;
-  int first_block;      // CTAs [first_block, first_block + cout * ci_chunks) belong to this job
+  int rows;             // output channels served by one CTA (1 for deep splits; 4 / 8 for the shallow ones of layers 3-4)
+  int first_block;      // CTAs [first_block, first_block + cout / rows * ci_chunks) belong to this job
 };
 struct WgradReduceJobs {  // passed by value as the kernel parameter: no device-side table
   int n, total_blocks;

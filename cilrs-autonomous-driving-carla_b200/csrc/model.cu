@@ -1325,8 +1325,8 @@ int cilrs_validate_accumulate(const float* controls, const float* pred_speed, co
   return cuda_status(cudaGetLastError());
 }
 
-static int adam_launch(AdamParams& a, long long* step_dev, cudaStream_t s) {
-  if (step_dev) {
+static int adam_launch(AdamParams& a, long long* step_dev, cudaStream_t s, bool advance = true) {
+  if (step_dev && advance) {
     step_increment_kernel<<<1, 1, 0, s>>>(step_dev); ++g_cilrs_launches;
     int st = cuda_status(cudaGetLastError());
     if (st) return st;
@@ -1365,8 +1365,8 @@ int cilrs_adam_step_ex(float* p, float* g, const void* g_bf16, float* m, float* 
   AdamParams a{};
   a.p = p; a.g = g; a.g16 = (const __nv_bfloat16*)g_bf16; a.m = m; a.v = v; a.n = n;
   a.bias_correction1 = 1.f; a.bias_correction2_sqrt = 1.f; a.grad_scale = 1.f;
-  a.grad_scale_dev = grad_scale_dev; a.step_dev = step_dev; a.hyper_dev = hyper_dev; a.zero_grad = zero_grad;
-  return adam_launch(a, step_dev, (cudaStream_t)stream);
+  a.grad_scale_dev = grad_scale_dev; a.step_dev = step_dev; a.hyper_dev = hyper_dev; a.zero_grad = zero_grad & 1;
+  return adam_launch(a, step_dev, (cudaStream_t)stream, !(zero_grad & 2));
 }
 
 static int sumsq_launch(const float* g, const void* g16, long long n, double* partial_ws, unsigned int* counter_ws, float max_norm,

@@ -159,17 +159,53 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
 // 576 contiguous floats to the gradient. All flat convolutions of a backward part are served by one launch (job table).
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(768) wgrad_reduce_kernel(const __grid_constant__ WgradReduceJobs jobs, float* __restrict__ grads) {
-  __shared__ float s_part[4][576];
+  __shared__ float s_part[8][576];   // [K-slice chain][576] when a CTA serves one output channel, [output channel][576] when it serves several
   pdl_entry();
   int j = 0;
   while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.job[j + 1].first_block) ++j;
   const WgradReduceJob& jb = jobs.job[j];
   const int u = blockIdx.x - jb.first_block;
-  const int co = u / jb.ci_chunks, cic = u - co * jb.ci_chunks;
-  const int cob = co >> 7, row = co & 127;
+  const int cgrp = u / jb.ci_chunks, cic = u - cgrp * jb.ci_chunks;
   const int t = threadIdx.x % 192;   // column of the 192-wide tile: tap-in-row (t >> 6), input channel (t & 63)
   const int zs = threadIdx.x / 192;  // this thread sums the K slices z = zs, zs + nz, ... (nz = blockDim.x / 192 chains per column)
   const int nz = blockDim.x / 192;
+  if (jb.rows > 1) {
+    // Shallow splits (layers 3-4: 6 / 1 K slices): one CTA per output channel was ~20 000 CTAs of three 768-byte reads each -
+    // pure CTA-launch overhead (61-90 us per launch measured). A CTA now serves `rows` (4 / 8) output channels: every load is
+    // issued before the first use, one barrier, `rows` x 2304 contiguous bytes out.
+    const int co0 = cgrp * jb.rows;
+    if (zs == 0) {
+      float acc[8][3];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r < jb.rows) {
+          const int co = co0 + r, cob = co >> 7, row = co & 127;
+#pragma unroll
+          for (int tg = 0; tg < 3; ++tg) {
+            const int tile = (cob * jb.ci_chunks + cic) * 3 + tg;
+            const float* src = jb.scratch + (((size_t)tile * jb.split_z) * 128 + row) * 192 + t;
+            float a = 0.f;
+            for (int z = 0; z < jb.split_z; ++z) a += __ldcg(src + (size_t)z * 128 * 192);
+            acc[r][tg] = a;
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < jb.rows) {
+#pragma unroll
+          for (int tg = 0; tg < 3; ++tg) s_part[r][(t & 63) * 9 + tg * 3 + (t >> 6)] = acc[r][tg];
+        }
+    }
+    __syncthreads();
+    for (int r = 0; r < jb.rows; ++r) {
+      float* g = grads + jb.grad_off + ((size_t)(co0 + r) * jb.cin + cic * 64) * 9;
+      for (int o = threadIdx.x; o < 576; o += blockDim.x) g[o] += s_part[r][o];
+    }
+    return;
+  }
+  const int co = cgrp;
+  const int cob = co >> 7, row = co & 127;
 #pragma unroll
   for (int tg = 0; tg < 3; ++tg) {
     const int tile = (cob * jb.ci_chunks + cic) * 3 + tg;

@@ -70,10 +70,12 @@ class FusedAdam(torch.optim.Optimizer):
         return g
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale=1.0, grad_scale_dev=None, grads_in_arena=False, grads_bf16=None, zero_grad=False):
+    def step(self, closure=None, grad_scale=1.0, grad_scale_dev=None, grads_in_arena=False, grads_bf16=None, zero_grad=False,
+             arena_range=None, advance=True):
         """grad_scale / grad_scale_dev: host / device factors applied to the gradient first (1/world, clip coefficient).
         grads_bf16: bf16 gradient buffer (arena layout) used instead of the fp32 arena. zero_grad: also clear the fp32 arena
-        (the next step's optimizer.zero_grad())."""
+        (the next step's optimizer.zero_grad()). arena_range=(lo, hi): update only that element range of the arena (multiples of
+        16); advance=False: a further range of the SAME optimizer step (the step counter is not advanced again)."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -84,9 +86,14 @@ class FusedAdam(torch.optim.Optimizer):
             raise RuntimeError("FusedAdam: the model moved to another device after the optimizer was created")
         g = model.flat_gradients() if (grads_in_arena or grads_bf16 is not None) else self._gather_grads()
         self._sync_hyper(grad_scale)
-        self._step += 1
-        _lib.call("cilrs_adam_step_ex", flat, g, grads_bf16, self._m, self._v, ctypes.c_longlong(flat.numel()), self._hyper,
-                  self._step_dev, grad_scale_dev, int(bool(zero_grad)), _lib.stream_ptr())
+        if advance:
+            self._step += 1
+        lo, hi = arena_range if arena_range is not None else (0, flat.numel())
+        if lo % 16 or hi % 16 or not (0 <= lo <= hi <= flat.numel()):
+            raise ValueError("arena_range must be 16-element aligned and inside the arena")
+        _lib.call("cilrs_adam_step_ex", flat[lo:hi], g[lo:hi], None if grads_bf16 is None else grads_bf16[lo:hi], self._m[lo:hi],
+                  self._v[lo:hi], ctypes.c_longlong(hi - lo), self._hyper, self._step_dev, grad_scale_dev,
+                  int(bool(zero_grad)) | (0 if advance else 2), _lib.stream_ptr())
         model.mark_parameters_changed()
         return loss
 

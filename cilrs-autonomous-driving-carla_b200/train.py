@@ -151,8 +151,23 @@ class FusedTrainer:
                     works.extend(self._exchange(g, lo, hi))
             if gstream is not None:
                 _lib.call("cilrs_model_backward_join", m._handle, sp)
-            for w in works:
-                w.wait()
+            if self.skip_optimizer or self.grad_clip > 0 or len(works) < 2:
+                for w in works:
+                    w.wait()
+            else:
+                # The last group's allreduce (layer2 + layer1 + stem with the default schedule: 6 % of the gradients) is the
+                # only collective nothing hides. Adam already updates everything above it while that allreduce is in flight.
+                for w in works[:-1]:
+                    w.wait()
+                cut = self.part_ranges[self.schedule[-1][0]][1]
+                self.opt.step(grad_scale=1.0 / self.world, grads_in_arena=True, grads_bf16=self.g16, zero_grad=self.g16 is None,
+                              arena_range=(cut, g.numel()))
+                works[-1].wait()
+                self.opt.step(grad_scale=1.0 / self.world, grads_in_arena=True, grads_bf16=self.g16, zero_grad=self.g16 is None,
+                              arena_range=(0, cut), advance=False)
+                _lib.call("cilrs_model_refresh", m._handle, 1, sp)
+                self._after_step()
+                return
         else:
             _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, -1, *self._backward_args())
         if self.skip_optimizer:

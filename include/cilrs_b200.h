@@ -327,8 +327,10 @@ int cilrs_grad_sumsq(const float* g, long long n, double* partial_ws, unsigned i
 /* CUDA-graph form of the step: hyper_dev = device float[8] {lr, beta1, beta2, eps, weight_decay, grad_scale, -, -} read by the
  * kernel at run time (StepLR, notebook/notebook.ipynb:535-536,604, reaches a captured graph through a 32-byte copy);
  * step_dev (device int64, required) is incremented on the stream first. g_bf16 (optional): bf16 gradients used instead of g
- * (the all-reduced exchange buffer of data-parallel training); zero_grad != 0 also clears the fp32 arena g
- * (optimizer.zero_grad(), notebook/notebook.ipynb:551, of the next step). */
+ * (the all-reduced exchange buffer of data-parallel training). zero_grad is a bit mask: bit 0 also clears the fp32 arena g
+ * (optimizer.zero_grad(), notebook/notebook.ipynb:551, of the next step); bit 1 = do NOT advance step_dev (a further range of
+ * the arena within the same optimizer step: data-parallel training updates the already-exchanged ranges while the last
+ * allreduce is still in flight). */
 int cilrs_adam_step_ex(float* p, float* g, const void* g_bf16, float* m, float* v, long long n, const float* hyper_dev,
                        long long* step_dev, const float* grad_scale_dev, int zero_grad, void* stream);
 int cilrs_grad_sumsq_bf16(const void* g_bf16, long long n, double* partial_ws, unsigned int* counter_ws, float max_norm,
