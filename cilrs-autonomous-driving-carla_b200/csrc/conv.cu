@@ -422,12 +422,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
 
 // all layers in one launch: a CTA transposes a 32(co) x 32(ci) x kk block through shared memory, so the fp32 reads
 // (runs of 32*kk floats) and both bf16 writes (32 consecutive ci resp. co) are coalesced
-__global__ void __launch_bounds__(256) pack_all_kernel(const float* __restrict__ params, const PackJob* __restrict__ jobs, int njobs) {
+__global__ void __launch_bounds__(256) pack_all_kernel(const float* __restrict__ params, const PackJob* __restrict__ jobs, int njobs,
+                                                       int block_base) {
   __shared__ float tile[32][32 * 9 + 1];
+  const int bidx = (int)blockIdx.x + block_base;   // (a launch may cover a sub-range of the job table: one backward part)
   int j = 0;
-  while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].first_block) ++j;
+  while (j + 1 < njobs && bidx >= jobs[j + 1].first_block) ++j;
   const PackJob jb = jobs[j];
-  const int t_idx = blockIdx.x - jb.first_block;
+  const int t_idx = bidx - jb.first_block;
   const int ci_tiles = jb.cin >> 5;
   const int co0 = (t_idx / ci_tiles) * 32, ci0 = (t_idx % ci_tiles) * 32;
   const int kk = jb.kk, run = 32 * kk;
@@ -449,7 +451,13 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const float* __restrict__
 }
 
 int launch_pack_all(const float* params, const PackJob* jobs_dev, int njobs, int total_blocks, cudaStream_t s) {
-  pack_all_kernel<<<total_blocks, 256, 0, s>>>(params, jobs_dev, njobs); ++g_cilrs_launches;
+  pack_all_kernel<<<total_blocks, 256, 0, s>>>(params, jobs_dev, njobs, 0); ++g_cilrs_launches;
+  return cuda_status(cudaGetLastError());
+}
+// the blocks [block_lo, block_hi) of the job table only
+int launch_pack_range(const float* params, const PackJob* jobs_dev, int njobs, int block_lo, int block_hi, cudaStream_t s) {
+  if (block_hi <= block_lo) return OK;
+  pack_all_kernel<<<block_hi - block_lo, 256, 0, s>>>(params, jobs_dev, njobs, block_lo); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 

@@ -48,6 +48,7 @@ struct PackJob {
   int cout, cin, kk, first_block;
 };
 int launch_pack_all(const float* params, const PackJob* jobs_dev, int njobs, int total_blocks, cudaStream_t s);
+int launch_pack_range(const float* params, const PackJob* jobs_dev, int njobs, int block_lo, int block_hi, cudaStream_t s);
 
 // ---- padded-flat 3x3 stride-1 kernels (conv_flat.cu) ----
 int flat_total_rows(int batch, const PadGeom& g);

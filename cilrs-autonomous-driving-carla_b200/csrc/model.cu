@@ -161,6 +161,7 @@ struct Model {
   double* sumsq_partial;
   PackJob* pack_jobs;    // device table for the one-launch weight repack
   int pack_njobs = 0, pack_blocks = 0;
+  int pack_block_first[17] = {};  // first pack-kernel block of BasicBlock bi's jobs ([16] = total): repack of one backward part
   // plans (tensor maps) for the batch size they were built for
   int planB = 0;
   int planMode = -1;
@@ -971,11 +972,14 @@ int cilrs_model_create(cilrs_model** out, int max_batch, void* workspace, size_t
       blocks += (c.d.out_c / 32) * (c.d.in_c / 32);
       jobs.push_back(j);
     };
+    int bi = 0;
     for (auto& blk : h->m.blocks) {
+      h->m.pack_block_first[bi++] = blocks;
       add(blk.a);
       add(blk.b);
       if (blk.has_ds) add(blk.ds);
     }
+    h->m.pack_block_first[16] = blocks;
     h->m.pack_njobs = (int)jobs.size();
     h->m.pack_blocks = blocks;
   }
@@ -1036,6 +1040,17 @@ int cilrs_model_bind(cilrs_model* h, float* params, float* grads, float* buffers
 int cilrs_model_refresh(cilrs_model* h, int what, void* stream) {
   if (!h) return ERR_INVALID;
   return refresh(h->m, what, (cudaStream_t)stream);
+}
+
+// repack the bf16 operands of the convolutions whose gradients backward part `part` completes (0 = layer4, 1 = layer3,
+// 2 = layer2, 3 = layer1, 4 = stem): lets the optimizer + repack of a finished part run under the rest of the backward
+int cilrs_model_refresh_part(cilrs_model* h, int part, void* stream) {
+  if (!h || part < 0 || part > 4 || !h->m.params) return ERR_INVALID;
+  Model& m = h->m;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (part == 4) return cilrs_stem_pack_weight(m.params + m.slots[m.stem.w].off, m.stem.wf, s);
+  static const int lo[4] = {13, 7, 3, 0}, hi[4] = {16, 13, 7, 3};
+  return launch_pack_range(m.params, m.pack_jobs, m.pack_njobs, m.pack_block_first[lo[part]], m.pack_block_first[hi[part]], s);
 }
 
 int cilrs_model_forward(cilrs_model* h, int batch, int mode, const float* image_nchw, const void* image_s2d, const float* speed,

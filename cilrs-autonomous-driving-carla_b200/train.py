@@ -26,7 +26,7 @@ from .optim import FusedAdam
 class FusedTrainer:
     def __init__(self, model, batch, lr=2e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, loss="mse", steer_w=5.0,
                  throttle_w=1.0, brake_w=1.0, speed_w=0.05, grad_clip=0.0, process_group=None, use_graph=False, frames="f32",
-                 async_parts=False, overlap_allreduce="two", grad_comm="bf16"):
+                 async_parts=False, overlap_allreduce="two", grad_comm="bf16", optimizer_in_backward=True):
         # overlap_allreduce: a key of ddp.SCHEDULES (or True = "all", False = "tail"): which backward parts share an allreduce
         #   "all"   every part's range as soon as it is complete
         #   "two"   heads+layer4 | layer3 | layer2+layer1+stem  (the default: the exposed tail is 1.35 M of 22.4 M gradients)
@@ -89,6 +89,7 @@ class FusedTrainer:
         self.graph = None
         self.graph_error = None
         self.skip_optimizer = False   # test hook: leave the exchanged gradient in place (no clip / Adam / repack / zeroing)
+        self.optimizer_in_backward = optimizer_in_backward
         if use_graph:
             if self.world > 1:
                 # the NCCL allreduces are captured into the graph with the kernels (PyTorch records them on the process
@@ -169,6 +170,28 @@ class FusedTrainer:
                 self._after_step()
                 return
         else:
+            lib = _lib.lib()
+            lib.cilrs_model_gradient_stream.restype = ctypes.c_void_p
+            lib.cilrs_model_gradient_stream.argtypes = [ctypes.c_void_p]
+            gs_ptr = lib.cilrs_model_gradient_stream(m._handle) if self.optimizer_in_backward else None
+            if gs_ptr and self.grad_clip == 0 and not self.skip_optimizer:
+                # Optimizer in the backward: once a part's gradients are complete (in the order of the model's gradient
+                # stream) Adam and the bf16 repack of that part run THERE, under the dgrad chain of the lower layers. Layer4 +
+                # heads (64 % of the parameters) and layer3 (30 %) go this way; only the last 6 % wait for the end of the step.
+                gstream = torch.cuda.ExternalStream(gs_ptr, device=self.dev)
+                self.opt._sync_hyper(1.0)
+                for part in range(5):
+                    _lib.call("cilrs_model_backward_part_async", m._handle, b, MODE_TRAIN, part, *self._backward_args())
+                    if part < 2:
+                        with torch.cuda.stream(gstream):
+                            self.opt.step(grads_in_arena=True, zero_grad=True, arena_range=self.part_ranges[part], advance=(part == 0))
+                            _lib.call("cilrs_model_refresh_part", m._handle, part, _lib.stream_ptr())
+                _lib.call("cilrs_model_backward_join", m._handle, sp)
+                self.opt.step(grads_in_arena=True, zero_grad=True, arena_range=(0, self.part_ranges[1][0]), advance=False)
+                for part in (2, 3, 4):
+                    _lib.call("cilrs_model_refresh_part", m._handle, part, sp)
+                self._after_step()
+                return
             _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, -1, *self._backward_args())
         if self.skip_optimizer:
             return

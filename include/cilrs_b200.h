@@ -183,6 +183,9 @@ int cilrs_model_bind(cilrs_model* m, float* params, float* grads, float* buffers
 /* call after parameter values changed. what: bit 0 = repack the bf16 conv operands from the fp32 masters,
  * bit 1 = fold eval-mode BatchNorm (running statistics) into per-channel scale/shift for CILRS_MODE_INFER */
 int cilrs_model_refresh(cilrs_model* m, int what, void* stream);
+/* bit-0 refresh restricted to the convolutions whose gradients backward part `part` completes (0 = layer4 ... 3 = layer1,
+ * 4 = stem): the optimizer step + repack of a finished part can run under the rest of the backward */
+int cilrs_model_refresh_part(cilrs_model* m, int part, void* stream);
 
 enum { CILRS_MODE_TRAIN = 0,  /* BN uses batch statistics (module.train()) */
        CILRS_MODE_FROZEN = 1, /* BN uses running statistics, activations kept: eval() with autograd */
