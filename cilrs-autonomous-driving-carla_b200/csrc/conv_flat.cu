@@ -366,7 +366,8 @@ int launch_wgrad_flat(const WgradFlatParams* p, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = p->co_blocks * p->ci_chunks * p->tap_groups * p->split_z;
-  if ((long long)grid * 128 * 192 * 4 > WF_SCRATCH_BYTES || !p->scratch) return ERR_WORKSPACE;
+  if ((long long)p->co_blocks * p->ci_chunks * p->tap_groups * 128 * 192 * 4 > WF_SCRATCH_BYTES || !p->scratch) return ERR_WORKSPACE;
+  if ((long long)p->num_stages * (2LL * WG_SLAB + (long long)p->x_boxes * p->x_box_rows * 128) < 128LL * WF_STAGE_PITCH) return ERR_UNSUPPORTED;
   ++g_cilrs_launches;
   return cuda_status(launch_pdl(wgrad_flat_kernel, dim3(grid), dim3(WF_THREADS), CG_SMEM_TOTAL, s, *p));
 }
@@ -375,8 +376,9 @@ int launch_wgrad_flat(const WgradFlatParams* p, cudaStream_t s) {
 int add_wgrad_reduce_job(WgradReduceJobs* jobs, const WgradFlatParams* p, long long grad_off) {
   if (jobs->n >= 16) return ERR_INVALID;
   WgradReduceJob& j = jobs->job[jobs->n++];
-  j.scratch = p->scratch; j.grad_off = grad_off; j.cout = p->cout; j.cin = p->cin; j.ci_chunks = p->ci_chunks; j.split_z = p->split_z;
-  j.rows = p->split_z == 1 ? 8 : (p->split_z <= 8 ? 4 : 1);
+  // (the K slices of the wgrad kernel add into ONE accumulator tile: the reduce sees a single "slice" and clears it)
+  j.scratch = p->scratch; j.grad_off = grad_off; j.cout = p->cout; j.cin = p->cin; j.ci_chunks = p->ci_chunks; j.split_z = 1;
+  j.rows = 8; j.zero_src = 1;
   j.first_block = jobs->total_blocks;
   jobs->total_blocks += p->cout / j.rows * p->ci_chunks;
   return OK;

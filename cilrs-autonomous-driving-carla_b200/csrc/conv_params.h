@@ -200,7 +200,8 @@ struct WgradReduceJob {
   const float* scratch;
   long long grad_off;   // float offset of the OIHW gradient inside the gradient arena
   int cout, cin, ci_chunks, split_z;
-  int rows;             // output channels served by one CTA (1 for deep splits; 4 / 8 for the shallow ones of layers 3-4)
+  int rows;             // output channels served by one CTA
+  int zero_src;         // clear the accumulator tile after reading it (it is ADDED to by the next backward's K slices)
   int first_block;      // CTAs [first_block, first_block + cout / rows * ci_chunks) belong to this job
 };
 struct WgradReduceJobs {  // passed by value as the kernel parameter: no device-side table
@@ -208,6 +209,7 @@ struct WgradReduceJobs {  // passed by value as the kernel parameter: no device-
   WgradReduceJob job[16];
 };
 
-constexpr long long WF_SCRATCH_BYTES = 160LL * 128 * 192 * 4;  // >= (#CTAs <= SM count) tiles of 128 x 192 fp32 per convolution
+constexpr long long WF_SCRATCH_BYTES = 160LL * 128 * 192 * 4;  // >= the (co block, ci chunk, filter row) accumulator tiles of 128 x 192 fp32 of one convolution
+constexpr int WF_STAGE_PITCH = 784;                            // shared-memory pitch of a 768-byte accumulator row in the epilogue staging
 
 }  // namespace cilrs

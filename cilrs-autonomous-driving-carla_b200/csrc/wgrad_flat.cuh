@@ -7,9 +7,15 @@
 // 3 taps] and a slice of the 128-pixel K tiles. Per K tile ONE slab of 130 pixels of X is loaded; the three taps
 // (dw = -1, 0, +1) are ONE tcgen05.mma with N = 192 whose B descriptor walks its three 64-column slabs with a leading
 // byte offset of 128 = one pixel row, i.e. the slabs are the same shared-memory data shifted by one pixel each.
-// The accumulator stays in TMEM for the whole slice. Split-K partials are NOT combined with atomics (3.5 M scattered
-// red.global.add per conv cost 25 us, twice the MMA time): every CTA stores its 128 x 192 fp32 tile with coalesced 256-bit
-// stores to a scratch slot, and wgrad_reduce_kernel sums the slots in a fixed order into the OIHW gradient (deterministic).
+// The accumulator stays in TMEM for the whole slice. Split-K: every K slice ADDS its 128 x 192 fp32 tile into ONE accumulator
+// tile per (co block, ci chunk, filter row) with bulk asynchronous reductions (cp.reduce.async.bulk ... .add.f32: the tile is
+// staged row by row in the shared memory the finished main loop no longer needs, one 768-byte reduction per row, performed
+// by the L2). Round 1 stored every slice's tile to its own scratch slot and summed the slots in a separate launch: up to
+// 49 x the weight bytes per conv written and read again (420 MB per step, 0.22 ms of wgrad_reduce_kernel); now that launch
+// reads each accumulator once, clears it and permutes it into the OIHW gradient. (Scalar red.global.add straight into the OIHW
+// gradient - 3.5 M scattered atomics per conv - cost twice the MMA time; the OIHW strides (36 B) also rule out a TMA tensor
+// reduction.) The price: the order in which slices are added is not fixed, so weight gradients are reproducible to fp32
+// rounding (~1e-7), not bit for bit.
 //   warp 0 : TMA producer      warp 1 : MMA issuer (whole warp, one elected lane issues)      warps 2..5 : epilogue
 #pragma once
 #include "common.cuh"
@@ -121,28 +127,29 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    // scratch slot of this CTA: [tile = (cob, cic, tg)][z][128 rows][192 columns = 3 taps x 64 ci] fp32
+    // accumulator tile of this CTA's (cob, cic, tg): [128 rows][192 columns = 3 taps x 64 ci] fp32, shared by all K slices
     const int tile = (cob * p.ci_chunks + cic) * 3 + tg;
-    float* dst = p.scratch + (((size_t)tile * p.split_z + z) * 128 + row) * 192;
+    float* dst = p.scratch + ((size_t)tile * 128 + row) * 192;
     if (kt_end > kt_begin) {
-      mbar_wait(done_bar, 0);
+      mbar_wait(done_bar, 0);   // every MMA has completed: the stage buffers are free
       tc_fence_after();
+      // stage this thread's row (768 B) at a 784-byte pitch: 16-byte stores of a quarter warp then hit 8 different bank groups
+      uint8_t* srow = smem + (size_t)row * WF_STAGE_PITCH;
       for (int c0 = 0; c0 < 192; c0 += 32) {
         uint32_t v[32];
         __syncwarp();
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + c0 + j * 8), "r"(v[j * 8]), "r"(v[j * 8 + 1]),
-                       "r"(v[j * 8 + 2]), "r"(v[j * 8 + 3]), "r"(v[j * 8 + 4]), "r"(v[j * 8 + 5]), "r"(v[j * 8 + 6]), "r"(v[j * 8 + 7])
-                       : "memory");
+        for (int j = 0; j < 8; ++j) *(uint4*)(srow + (c0 + 4 * j) * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
-    } else {
-      // a K slice past the end (split_z does not divide the tile count): the reducer still reads this slot
-      const uint4 zz = make_uint4(0, 0, 0, 0);
-      for (int c0 = 0; c0 < 192; c0 += 4) *(uint4*)(dst + c0) = zz;
+      fence_proxy_async();   // the generic-proxy stores above are read by the async proxy
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                   ::"l"(dst), "r"(smem_u32(srow)), "r"(768) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+    // (a K slice past the end - split_z does not divide the tile count - has nothing to add)
   }
   tc_fence_before();
   __syncthreads();
@@ -186,6 +193,7 @@ __global__ void __launch_bounds__(768) wgrad_reduce_kernel(const __grid_constant
             const float* src = jb.scratch + (((size_t)tile * jb.split_z) * 128 + row) * 192 + t;
             float a = 0.f;
             for (int z = 0; z < jb.split_z; ++z) a += __ldcg(src + (size_t)z * 128 * 192);
+            if (jb.zero_src) *const_cast<float*>(src) = 0.f;   // the accumulator is ready for the next backward
             acc[r][tg] = a;
           }
         }

@@ -162,7 +162,7 @@ def wgrad_flat(dy_pad, x_pad):
     b, hp, wp, cout = dy_pad.shape
     cin = x_pad.shape[3]
     dw = torch.zeros(cout, cin, 3, 3, dtype=torch.float32, device=dy_pad.device)
-    ws = torch.empty(_lib.query("cilrs_wgrad_flat_workspace_bytes") // 4, dtype=torch.float32, device=dy_pad.device)
+    ws = torch.zeros(_lib.query("cilrs_wgrad_flat_workspace_bytes") // 4, dtype=torch.float32, device=dy_pad.device)
     _lib.call("cilrs_wgrad_flat", b, hp - 1, wp - 1, cin, cout, dy_pad, x_pad, dw, ws, _lib.stream_ptr())
     return dw
 

@@ -144,8 +144,9 @@ long long cilrs_flat_rows(int batch, int H, int W);
 int cilrs_set_bn_fusion(int enable);
 size_t cilrs_conv_flat_workspace_floats(int out_c);
 int cilrs_conv_flat(const cilrs_flat_conv_args* a, void* stream);
-/* dw_oihw (fp32 [out_c,in_c,3,3]) += dy^T * shifted(x), both padded-flat (two launches: split-K partial tiles into
- * scratch_ws, then a fixed-order reduction into dw: deterministic, no atomics). scratch_ws: cilrs_wgrad_flat_workspace_bytes(). */
+/* dw_oihw (fp32 [out_c,in_c,3,3]) += dy^T * shifted(x), both padded-flat. Two launches: the split-K slices add their tiles into
+ * accumulator tiles in scratch_ws with bulk asynchronous fp32 reductions, then one pass permutes the accumulators into dw and
+ * clears them. scratch_ws: cilrs_wgrad_flat_workspace_bytes() bytes, ZERO on entry, left zero. */
 size_t cilrs_wgrad_flat_workspace_bytes(void);
 int cilrs_wgrad_flat(int batch, int H, int W, int in_c, int out_c, const void* dy, const void* x, float* dw_oihw,
                      float* scratch_ws, void* stream);
