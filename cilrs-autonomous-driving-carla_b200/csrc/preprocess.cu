@@ -146,6 +146,124 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fast path for a horizontal scale of exactly 4 (the reference's 800 -> 200): every output column then reads source columns
+// 4 dx + 1 and 4 dx + 2 with weights 1024 / 1024 (f = 0.5 for every dx, no clamping), so
+//     H >> 4 = (S[4dx+1] + S[4dx+2]) * 64      and      (b * (H >> 4)) >> 16 = (b * (S[4dx+1] + S[4dx+2])) >> 10   (exactly),
+// the same integers as the general kernel (and OpenCV) produce. The general kernel was instruction-issue bound (ncu: 46 % issue
+// slots, 30 % DRAM; 734 instructions per warp: twelve byte loads from shared memory, per-element index arithmetic and three
+// table look-ups through L1 per output pixel). Here: the 2 x R source rows arrive by bulk asynchronous copies (no load / store
+// instructions), a pixel's six source bytes come out of three aligned 32-bit words per row, and the normalisation table lives
+// in shared memory.
+// ---------------------------------------------------------------------------------------------------------------------
+CILRS_DEVINL void bulk_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int PX4_ROWS = 4;      // output rows per CTA
+constexpr int PX4_THREADS = 224; // 7 warps: one thread per output column (dst_w <= 224)
+
+template <int SRC_C>
+__global__ void __launch_bounds__(PX4_THREADS) preprocess_x4_kernel(const PreParams p) {
+  extern __shared__ __align__(128) uint8_t rows[];   // [PX4_ROWS][2][row_bytes]
+  __shared__ float s_lut[3 * 256];
+  __shared__ AxisCoef s_cy[PX4_ROWS];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int row_blocks = (p.dst_h + PX4_ROWS - 1) / PX4_ROWS;
+  const int dy0 = (blockIdx.x % row_blocks) * PX4_ROWS;
+  const int n = blockIdx.x / row_blocks;
+  const int nr = min(PX4_ROWS, p.dst_h - dy0);
+  const int row_bytes = p.src_w * SRC_C;
+  const uint8_t* img = p.src + (size_t)n * p.src_h * row_bytes;
+  const int t = threadIdx.x;
+  if (t < nr) s_cy[t] = axis_coef(dy0 + t, p.src_h, p.scale_y);
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (t == 0) {
+    mbar_arrive_expect_tx(&s_bar, (uint32_t)(2 * nr * row_bytes));
+    for (int r = 0; r < nr; ++r) {
+      bulk_load_1d(rows + (size_t)(2 * r) * row_bytes, img + (size_t)s_cy[r].s0 * row_bytes, (uint32_t)row_bytes, &s_bar);
+      bulk_load_1d(rows + (size_t)(2 * r + 1) * row_bytes, img + (size_t)s_cy[r].s1 * row_bytes, (uint32_t)row_bytes, &s_bar);
+    }
+  }
+  for (int i = t; i < 768; i += PX4_THREADS) s_lut[i] = g_norm_lut[i];   // (overlaps the copies)
+  __syncthreads();
+  mbar_wait(&s_bar, 0);
+  const int dx = t;
+  if (dx >= p.dst_w) return;
+  const int c_first = p.reverse ? 2 : 0, c_step = p.reverse ? -1 : 1;   // output channel c reads source channel c_first + c * c_step
+#pragma unroll
+  for (int r = 0; r < PX4_ROWS; ++r) {
+    if (r >= nr) break;
+    const int dy = dy0 + r;
+    const int b0 = s_cy[r].a0, b1 = s_cy[r].a1;
+    const uint32_t* ra = reinterpret_cast<const uint32_t*>(rows + (size_t)(2 * r) * row_bytes);
+    const uint32_t* rb = reinterpret_cast<const uint32_t*>(rows + (size_t)(2 * r + 1) * row_bytes);
+    int sa[3], sb[3];   // per SOURCE channel: S[4dx+1] + S[4dx+2] of the two rows
+    if (SRC_C == 3) {
+      // bytes 12 dx + 3 .. 12 dx + 8 = byte 3 of word 3dx, all of word 3dx+1, byte 0 of word 3dx+2
+      const uint32_t a0 = ra[3 * dx], a1 = ra[3 * dx + 1], a2 = ra[3 * dx + 2];
+      const uint32_t q0 = rb[3 * dx], q1 = rb[3 * dx + 1], q2 = rb[3 * dx + 2];
+      sa[0] = (int)(a0 >> 24) + (int)((a1 >> 16) & 0xffu); sa[1] = (int)(a1 & 0xffu) + (int)(a1 >> 24); sa[2] = (int)((a1 >> 8) & 0xffu) + (int)(a2 & 0xffu);
+      sb[0] = (int)(q0 >> 24) + (int)((q1 >> 16) & 0xffu); sb[1] = (int)(q1 & 0xffu) + (int)(q1 >> 24); sb[2] = (int)((q1 >> 8) & 0xffu) + (int)(q2 & 0xffu);
+    } else {
+      // one word per pixel: words 4dx+1 and 4dx+2; channels 0 / 2 and 1 / alpha summed as packed 16-bit lanes
+      const uint32_t a1 = ra[4 * dx + 1], a2 = ra[4 * dx + 2], q1 = rb[4 * dx + 1], q2 = rb[4 * dx + 2];
+      const uint32_t ae = (a1 & 0x00ff00ffu) + (a2 & 0x00ff00ffu), ao = ((a1 >> 8) & 0x00ff00ffu) + ((a2 >> 8) & 0x00ff00ffu);
+      const uint32_t qe = (q1 & 0x00ff00ffu) + (q2 & 0x00ff00ffu), qo = ((q1 >> 8) & 0x00ff00ffu) + ((q2 >> 8) & 0x00ff00ffu);
+      sa[0] = (int)(ae & 0xffffu); sa[1] = (int)(ao & 0xffffu); sa[2] = (int)(ae >> 16);
+      sb[0] = (int)(qe & 0xffffu); sb[1] = (int)(qo & 0xffffu); sb[2] = (int)(qe >> 16);
+    }
+    int v[3];
+    float f[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int sc = c_first + c * c_step;
+      v[c] = (((b0 * sa[sc]) >> 10) + ((b1 * sb[sc]) >> 10) + 2) >> 2;
+      f[c] = s_lut[c * 256 + v[c]];
+    }
+    if (p.dst_u8) {
+      uint8_t* d = p.dst_u8 + (((size_t)n * p.dst_h + dy) * p.dst_w + dx) * 3;
+      d[0] = (uint8_t)v[0]; d[1] = (uint8_t)v[1]; d[2] = (uint8_t)v[2];
+    }
+    if (p.dst_f32) {
+      const size_t plane = (size_t)p.dst_h * p.dst_w;
+      float* d = p.dst_f32 + (size_t)n * 3 * plane + (size_t)dy * p.dst_w + dx;
+      d[0] = f[0]; d[plane] = f[1]; d[2 * plane] = f[2];
+    }
+    if (p.dst_s2d) {
+      const int y = dy + 3, x = dx + 3;
+      uint2 o;
+      o.x = pack_bf16x2(f[0], f[1]);
+      o.y = pack_bf16x2(f[2], 0.f);
+      *(uint2*)(p.dst_s2d + (((size_t)n * 47 + (y >> 1)) * 103 + (x >> 1)) * 16 + (y & 1) * 8 + (x & 1) * 4) = o;
+    }
+  }
+  if (p.dst_s2d) {
+    // zero padding of the 94 x 206 padded frame: 3 columns each side of every row, and whole rows 0-2 / 91-93
+    const uint2 z = make_uint2(0u, 0u);
+    for (int r = 0; r < nr; ++r) {
+      const int dy = dy0 + r;
+      const int y = dy + 3;
+      if (t < 6) {
+        const int x = t < 3 ? t : 200 + t;
+        *(uint2*)(p.dst_s2d + (((size_t)n * 47 + (y >> 1)) * 103 + (x >> 1)) * 16 + (y & 1) * 8 + (x & 1) * 4) = z;
+      }
+      if (dy == 0 || dy == p.dst_h - 1) {
+        const int ybase = dy == 0 ? 0 : 91;
+        for (int i = t; i < 3 * 206; i += PX4_THREADS) {
+          const int yy = ybase + i / 206, x = i % 206;
+          *(uint2*)(p.dst_s2d + (((size_t)n * 47 + (yy >> 1)) * 103 + (x >> 1)) * 16 + (yy & 1) * 8 + (x & 1) * 4) = z;
+        }
+      }
+    }
+  }
+}
+
 // image f32 NCHW [B,3,88,200] -> bf16 space-to-depth [B,47,103,16] (zero padded: 3 px each side, 4th channel 0)
 __global__ void __launch_bounds__(256) image_to_s2d_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ dst, int batch) {
   // one thread per padded pixel (y in [0,94), x in [0,206)) -> 8-byte store
@@ -234,6 +352,23 @@ int cilrs_preprocess_u8(const uint8_t* src, int batch, int src_h, int src_w, int
   p.dst_h = dst_h; p.dst_w = dst_w;
   p.scale_x = (double)src_w / dst_w; p.scale_y = (double)src_h / dst_h;
   p.dst_u8 = dst_u8; p.dst_f32 = dst_f32; p.dst_s2d = (__nv_bfloat16*)dst_s2d;
+  // fast path: horizontal scale exactly 4 (800 -> 200), rows 16-byte aligned for the bulk copies, one thread per output column
+  if (src_w == 4 * dst_w && dst_w <= PX4_THREADS && ((src_w * src_c) & 15) == 0 && (((uintptr_t)src) & 15) == 0 &&
+      2 * (size_t)PX4_ROWS * src_w * src_c <= 96 * 1024) {
+    const size_t smem4 = 2 * (size_t)PX4_ROWS * src_w * src_c;
+    static bool attr4 = false;
+    if (!attr4) {
+      cudaError_t e = cudaFuncSetAttribute(preprocess_x4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(preprocess_x4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e != cudaSuccess) return cuda_status(e);
+      attr4 = true;
+    }
+    const int rb4 = (dst_h + PX4_ROWS - 1) / PX4_ROWS;
+    if (src_c == 3) preprocess_x4_kernel<3><<<batch * rb4, PX4_THREADS, smem4, (cudaStream_t)stream>>>(p);
+    else preprocess_x4_kernel<4><<<batch * rb4, PX4_THREADS, smem4, (cudaStream_t)stream>>>(p);
+    ++g_cilrs_launches;
+    return cuda_status(cudaGetLastError());
+  }
   // four output rows per CTA when their eight source rows fit in 96 KB of shared memory (more bytes in flight per CTA, the
   // horizontal coefficients are computed once per thread)
   p.rows_per_cta = (8 * (size_t)row_pad <= 96 * 1024 && dst_h >= 4) ? 4 : 1;
