@@ -194,11 +194,10 @@ __global__ void __launch_bounds__(PX4_THREADS) preprocess_x4_kernel(const PrePar
   __syncthreads();
   mbar_wait(&s_bar, 0);
   const int dx = t;
-  if (dx >= p.dst_w) return;
   const int c_first = p.reverse ? 2 : 0, c_step = p.reverse ? -1 : 1;   // output channel c reads source channel c_first + c * c_step
 #pragma unroll
   for (int r = 0; r < PX4_ROWS; ++r) {
-    if (r >= nr) break;
+    if (r >= nr || dx >= p.dst_w) break;   // (threads past the last column still take part in the padding stores below)
     const int dy = dy0 + r;
     const int b0 = s_cy[r].a0, b1 = s_cy[r].a1;
     const uint32_t* ra = reinterpret_cast<const uint32_t*>(rows + (size_t)(2 * r) * row_bytes);

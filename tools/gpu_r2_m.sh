@@ -1,0 +1,11 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_preprocess_gpu.py -q -m gpu --tb=short 2>&1 | tail -2
+for mode in 0 2 1; do
+CILRS_BN_FUSION=$mode timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r2_bench_fuse$mode.json 2> gpurun_out/r2_bench_fuse$mode.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/r2_bench_fuse$mode.json').read().strip().splitlines()[-1])
+print('fusion mode $mode:', d['ms_per_step'], d['value'], d['e2e']['value'], d['gpu_launches'], json.dumps(d['roofline']['breakdown_ms']))
+PY
+done
