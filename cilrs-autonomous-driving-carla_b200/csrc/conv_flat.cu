@@ -276,13 +276,15 @@ int flat_conv_bind_operands(FlatConvParams* p) {
 // store, on 8 warps per SM), and the elementwise launches it removes were hiding the weight-gradient stream. Kept as an
 // option (CILRS_BN_FUSION=1 / cilrs_set_bn_fusion) and covered by the parity tests; see DESIGN.md.
 static int g_fuse_enabled = -1;   // -1: not decided yet
-// 0 = off, 1 = every flat convolution that fits tensor memory, 2 = only the 256- / 512-channel layers (layers 3-4: small tensors,
+// 0 = off, 3 / 4 = forward / data-gradient convolutions only, 1 = every flat convolution that fits tensor memory, 2 = only the 256- / 512-channel layers (layers 3-4: small tensors,
 // 98 / 128-CTA grids that leave SMs to the weight-gradient stream, one or two units per CTA in the second pass)
-static int fuse_default() { const char* e = getenv("CILRS_BN_FUSION"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }
+static int fuse_default() { const char* e = getenv("CILRS_BN_FUSION"); return (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 0; }
 int flat_conv_fuse_ok(const FlatConvParams* p) {
   if (g_fuse_enabled < 0) g_fuse_enabled = fuse_default();
   if (!g_fuse_enabled) return 0;
   if (g_fuse_enabled == 2 && p->n_total < 256) return 0;
+  if (g_fuse_enabled == 3 && !(p->flags & CF_STATS)) return 0;   // 3: forward convolutions only
+  if (g_fuse_enabled == 4 && !(p->flags & CF_BNBWD)) return 0;   // 4: data-gradient convolutions only
   const long long total = (long long)p->m_tiles * p->n_blocks;
   const int grid = flat_conv_grid(p);
   const int n = p->pair ? grid / 2 : grid;
@@ -394,6 +396,8 @@ int launch_wgrad_reduce(const WgradReduceJobs* jobs, float* grads, cudaStream_t 
   for (int i = 0; i < jobs->n; ++i) max_z = jobs->job[i].split_z > max_z ? jobs->job[i].split_z : max_z;
   int nz = (max_z + 11) / 12;
   nz = nz < 1 ? 1 : (nz > 4 ? 4 : nz);
+  for (int i = 0; i < jobs->n; ++i)   // the 8-channel path is written for one accumulator tile and 192 threads
+    if (jobs->job[i].rows > 1 && (jobs->job[i].rows != 8 || jobs->job[i].split_z != 1 || nz != 1 || jobs->job[i].cout % 8)) return ERR_INVALID;
   ++g_cilrs_launches;
   return cuda_status(launch_pdl(wgrad_reduce_kernel, dim3(jobs->total_blocks), dim3(192 * nz), 0, s, *jobs, grads));
 }
@@ -411,7 +415,7 @@ long long cilrs_flat_rows(int batch, int H, int W) { return (long long)batch * (
 // previous setting. Measurement / test aid: both settings compute the same network.
 int cilrs_set_bn_fusion(int enable) {
   const int prev = g_fuse_enabled < 0 ? fuse_default() : g_fuse_enabled;
-  g_fuse_enabled = enable < 0 ? 0 : (enable > 2 ? 1 : enable);
+  g_fuse_enabled = enable < 0 ? 0 : (enable > 4 ? 1 : enable);
   return prev;
 }
 

@@ -128,6 +128,7 @@ struct Model {
   __nv_bfloat16* pool_out;
   uint8_t* pool_arg;
   float* stats;          // shared stats-partials scratch
+  float* stats_ds;       // the same for the downsample convolutions (they run beside conv_a on the gradient stream)
   double* stat_acc;
   double* acc_fwd;       // per-BatchNorm accumulators of the deferred finalize (conv_params.h: CF_DEFER): forward, backward
   double* acc_bwd;
@@ -157,6 +158,8 @@ struct Model {
   cudaEvent_t ev_part = nullptr;   // end of an asynchronous backward part on the caller's stream
   cudaEvent_t ev_heads = nullptr;  // head deltas ready: the head weight gradients run on the side stream
   cudaEvent_t ev_ready[6] = {}, ev_done[6] = {}, ev_join = nullptr;  // slot order: dyb0, dyb1, dya0, dya1, dyd0, dyd1
+  cudaEvent_t ev_pack_fork = nullptr, ev_pack = nullptr;             // cilrs_model_refresh_async: repack beside the stem
+  bool pack_pending = false;
   bool pending[6] = {false, false, false, false, false, false};      // a side-stream wgrad still reads the slot
   double* sumsq_partial;
   PackJob* pack_jobs;    // device table for the one-launch weight repack
@@ -287,6 +290,7 @@ static long long carve(Model& m, char* base) {
   }
   // stats partial scratch: the stem has the most tiles (<= ceil(B*4400/100) ~ 44*B + slack), 2 x 64 floats each;
   // deeper layers have fewer tiles x more channels; bound by B*44*100/64 tiles * 2 * 64
+  m.stats_ds = (float*)bp.take(256LL * 2 * 512 * 4);
   m.stats = (float*)bp.take(256LL * 2 * 512 * 4);  // one (sum, sumsq)[C<=512] partial per persistent conv CTA (<= SM count)
   m.stat_acc = (double*)bp.take(3 * 512 * 8);  // per-channel fp64 statistics accumulators (kept zero between launches)
   {
@@ -404,7 +408,7 @@ static int build_plans(Model& m, int B, int mode) {
     if (blk.has_ds) {
       if (infer) CK(build_fprop(&p, &blk.ds.d, blk.in, blk.ds.wf, blk.ds.y, blk.ds.bn.vec, blk.ds.bn.vec + blk.ds.bn.C, nullptr, nullptr,
                                 CG_SCALE_BIAS, &blk.ds.gin, &blk.ds.gout));
-      else CK(build_fprop(&p, &blk.ds.d, blk.in, blk.ds.wf, blk.ds.y, nullptr, nullptr, nullptr, m.stats, CG_STATS, &blk.ds.gin, &blk.ds.gout));
+      else CK(build_fprop(&p, &blk.ds.d, blk.in, blk.ds.wf, blk.ds.y, nullptr, nullptr, nullptr, m.stats_ds, CG_STATS, &blk.ds.gin, &blk.ds.gout));
       blk.pl.f_ds_old = add_old(m, p);
     }
     {
@@ -510,10 +514,11 @@ static int build_plans(Model& m, int B, int mode) {
   return OK;
 }
 
-static int run_bn_finalize(Model& m, const BnRef& bn, int tiles, double count, int training, int update, cudaStream_t s) {
+static int run_bn_finalize(Model& m, const BnRef& bn, int tiles, double count, int training, int update, cudaStream_t s,
+                           const float* stats = nullptr) {
   BnVectors v{bn.vec, bn.vec + bn.C, bn.vec + 2 * bn.C, bn.vec + 3 * bn.C};
   ++g_cilrs_launches;
-  return cuda_status(launch_pdl(bn_finalize_kernel, dim3((bn.C + 31) / 32), dim3(1024), 0, s, (const float*)m.stats, tiles, bn.C, count,
+  return cuda_status(launch_pdl(bn_finalize_kernel, dim3((bn.C + 31) / 32), dim3(1024), 0, s, stats ? stats : (const float*)m.stats, tiles, bn.C, count,
                                 (const float*)(m.params + m.slots[bn.gamma].off), (const float*)(m.params + m.slots[bn.beta].off),
                                 m.buffers + bn.rm_off, m.buffers + bn.rv_off, m.nbt ? m.nbt + bn.nbt_idx : (long long*)nullptr, 0.1f, 1e-5f,
                                 training, update, v));
@@ -568,8 +573,18 @@ static HeadsCtx heads_ctx(const Model& m) {
 }
 
 // re-derive everything that depends on parameter values: packed bf16 conv weights (+ eval-mode BN folding)
+// the repack queued by cilrs_model_refresh_async becomes visible to stream s
+static int pack_join(Model& m, cudaStream_t s) {
+  if (m.pack_pending) {
+    CK(cuda_status(cudaStreamWaitEvent(s, m.ev_pack, 0)));
+    m.pack_pending = false;
+  }
+  return OK;
+}
+
 static int refresh(Model& m, int what, cudaStream_t s) {
   if (!m.params) return ERR_INVALID;
+  CK(pack_join(m, s));
   if (what & 1) {
     CK(cilrs_stem_pack_weight(m.params + m.slots[m.stem.w].off, m.stem.wf, s));
     CK(launch_pack_all(m.params, m.pack_jobs, m.pack_njobs, m.pack_blocks, s));
@@ -611,6 +626,7 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
     bn_relu_maxpool_kernel<<<ew_grid(pool_vec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.unit_vec, m.unit_vec + 64, m.pool_out, nullptr, B, 44,
                                                                         100, 64, 22, 50, kGeom0.Hp, kGeom0.Wp); ++g_cilrs_launches;
     CKL();
+    CK(pack_join(m, s));
     for (auto& blk : m.blocks) {
       if (blk.pl.f_a_flat >= 0) PROF(m, PC_FPROP, s, CK(launch_flat_conv(&m.flat_plans[blk.pl.f_a_flat], s)));
       else PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.old_plans[blk.pl.f_a_old], s)));
@@ -623,29 +639,41 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
     bn_relu_maxpool_kernel<<<ew_grid(pool_vec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.stem.bn.vec, m.stem.bn.vec + 64, m.pool_out,
                                                                         m.pool_arg, B, 44, 100, 64, 22, 50, kGeom0.Hp, kGeom0.Wp); ++g_cilrs_launches;
     CKL();
+    CK(pack_join(m, s));   // the trunk's operands may have been repacked beside the stem (cilrs_model_refresh_async)
     for (auto& blk : m.blocks) {
       // raw conv output + BN vectors: fused in the flat kernel (training), or generic kernel + finalize kernel
-      auto conv_bn = [&](ConvRef& c, int flat_idx, int old_idx) -> int {
+      auto conv_bn = [&](ConvRef& c, int flat_idx, int old_idx, cudaStream_t s, const float* stats = nullptr) -> int {
         const double count = (double)B * c.oh * c.ow;
         if (flat_idx >= 0) {
           PROF(m, PC_FPROP, s, CK(launch_flat_fwd(m, flat_idx, c.bn, count, update_running, s)));
           if (!training) PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, c.bn, 0, count, 0, 0, s)));
         } else {
           PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.old_plans[old_idx], s)));
-          PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, c.bn, conv_gemm_grid(&m.old_plans[old_idx]), count, training, update_running, s)));
+          PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, c.bn, conv_gemm_grid(&m.old_plans[old_idx]), count, training, update_running, s, stats)));
         }
         return OK;
       };
-      CK(conv_bn(blk.a, blk.pl.f_a_flat, blk.pl.f_a_old));
+      // The 1x1 stride-2 downsample convolution (+ its finalize) depends only on the block's input: it runs beside conv_a on the
+      // gradient stream (idle during the forward) and is joined before the block's output BatchNorm reads it.
+      const bool ds_side = blk.has_ds && m.side != nullptr && !m.prof.on;
+      if (ds_side) {
+        CK(cuda_status(cudaEventRecord(m.ev_pack_fork, s)));
+        CK(cuda_status(cudaStreamWaitEvent(m.side, m.ev_pack_fork, 0)));
+        CK(conv_bn(blk.ds, -1, blk.pl.f_ds_old, m.side, m.stats_ds));
+        CK(cuda_status(cudaEventRecord(m.ev_pack, m.side)));
+      }
+      CK(conv_bn(blk.a, blk.pl.f_a_flat, blk.pl.f_a_old, s));
       const int def_a = training && blk.pl.f_a_flat >= 0, def_b = training;
       const bool fused_a = blk.pl.f_a_flat >= 0 && (m.flat_plans[blk.pl.f_a_flat].flags & CF_FUSE);
       const bool fused_b = (m.flat_plans[blk.pl.f_b_flat].flags & CF_FUSE) != 0;
       if (!fused_a)
         PROF(m, PC_BN_FWD, s, CK(run_bn_apply(m, B, blk.a.gout, blk.a.y, blk.a.bn, nullptr, nullptr, nullptr, blk.act_a, 1, blk.bits_a, def_a,
                                               update_running, s)));
-      if (blk.has_ds) CK(conv_bn(blk.ds, -1, blk.pl.f_ds_old));
-      CK(conv_bn(blk.b, blk.pl.f_b_flat, -1));
+      if (blk.has_ds && !ds_side) CK(conv_bn(blk.ds, -1, blk.pl.f_ds_old, s, m.stats_ds));
+      if (ds_side && (m.flat_plans[blk.pl.f_b_flat].flags & CF_FUSE)) CK(cuda_status(cudaStreamWaitEvent(s, m.ev_pack, 0)));
+      CK(conv_bn(blk.b, blk.pl.f_b_flat, -1, s));
       if (fused_b) continue;   // the conv's second pass wrote blk.out and its ReLU bits
+      if (ds_side) CK(cuda_status(cudaStreamWaitEvent(s, m.ev_pack, 0)));
       if (blk.has_ds) PROF(m, PC_BN_FWD, s, CK(run_bn_apply(m, B, blk.b.gout, blk.b.y, blk.b.bn, nullptr, blk.ds.y, &blk.ds.bn, blk.out, 1,
                                                             blk.bits_out, def_b, update_running, s)));
       else PROF(m, PC_BN_FWD, s, CK(run_bn_apply(m, B, blk.b.gout, blk.b.y, blk.b.bn, blk.in, nullptr, nullptr, blk.out, 1, blk.bits_out,
@@ -738,6 +766,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   if (!m.grads) return ERR_INVALID;
   const int frozen = mode == MODE_FROZEN;
   if (part < -1 || part > 4) return ERR_INVALID;
+  CK(pack_join(m, s));
   if (dbg) {
     CK(cuda_status(cudaMemsetAsync(m.acc_bwd, 0, (size_t)m.acc_bwd_bytes, s)));
     // the plans bake the ping-pong buffers in: block 15 reads g0 and writes g1, block 14 reads g1, ...
@@ -770,7 +799,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     }
     // ---- trunk: gradient of the last block's output, then its ReLU mask + BN_b reductions ----
     Block& last = m.blocks.back();
-    avgpool_bwd_kernel<<<(int)((pad_elems(B, last.b.gout, 512) + 255) / 256), 256, 0, s>>>(m.dfeat, m.dfeat2, m.g0, B, 512, last.b.gout); ++g_cilrs_launches;
+    avgpool_bwd_kernel<<<(int)((pad_elems(B, last.b.gout, 512) / 8 + 255) / 256), 256, 0, s>>>(m.dfeat, m.dfeat2, m.g0, B, 512, last.b.gout); ++g_cilrs_launches;
     CKL();
     PROF(m, PC_BN_BWD, s, CK(run_bn_bwd_reduce(m, B, last.b.gout, last.b.bn, m.g0, last.out, last.b.y, s)));
     m.bw_gcur = m.g0; m.bw_gnext = m.g1;
@@ -874,10 +903,12 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
       m.bw_fused_prev = false;
     }
     __nv_bfloat16* t = gcur; gcur = gnext; gnext = t;
+    // the layer group's last weight gradient is queued: permute its accumulator tiles into the OIHW gradients now, under the
+    // data-gradient chain of the layers below (all four at the end of the backward they fought the stem's HBM-bound tail)
+    if (!dbg && bi == part_lo[blk_part]) PROF(m, PC_WGRAD, ws, CK(launch_wgrad_reduce(&m.red_jobs[blk_part], m.grads, ws)));
   }
-  // fold the split-K partial tiles of this part's flat wgrads into the OIHW gradients (one launch per layer group)
-  for (int pt = 0; pt < 4; ++pt)
-    if (part < 0 || part == pt) PROF(m, PC_WGRAD, ws, CK(launch_wgrad_reduce(&m.red_jobs[pt], m.grads, ws)));
+  if (dbg)
+    for (int pt = 0; pt < 4; ++pt) PROF(m, PC_WGRAD, ws, CK(launch_wgrad_reduce(&m.red_jobs[pt], m.grads, ws)));
   if (use_side && !async_part) {
     // join: everything after this call on the caller's stream (allreduce of the part, Adam) sees the finished gradients
     CK(cuda_status(cudaEventRecord(m.ev_join, m.side)));
@@ -1005,6 +1036,8 @@ int cilrs_model_create(cilrs_model** out, int max_batch, void* workspace, size_t
       ok = cudaEventCreateWithFlags(&h->m.ev_ready[i], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&h->m.ev_done[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->m.ev_join, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->m.ev_pack_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->m.ev_pack, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->m.ev_heads, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->m.ev_part, cudaEventDisableTiming) == cudaSuccess;
     if (!ok && h->m.side) { cudaStreamDestroy(h->m.side); h->m.side = nullptr; }
@@ -1022,6 +1055,8 @@ void cilrs_model_destroy(cilrs_model* h) {
       if (h->m.ev_done[i]) cudaEventDestroy(h->m.ev_done[i]);
     }
     if (h->m.ev_join) cudaEventDestroy(h->m.ev_join);
+    if (h->m.ev_pack_fork) cudaEventDestroy(h->m.ev_pack_fork);
+    if (h->m.ev_pack) cudaEventDestroy(h->m.ev_pack);
     if (h->m.ev_heads) cudaEventDestroy(h->m.ev_heads);
     if (h->m.ev_part) cudaEventDestroy(h->m.ev_part);
     cudaStreamDestroy(h->m.side);
@@ -1040,6 +1075,23 @@ int cilrs_model_bind(cilrs_model* h, float* params, float* grads, float* buffers
 int cilrs_model_refresh(cilrs_model* h, int what, void* stream) {
   if (!h) return ERR_INVALID;
   return refresh(h->m, what, (cudaStream_t)stream);
+}
+
+// what = 1 of cilrs_model_refresh, off the critical path: the stem's operand is packed on `stream`, the 36 trunk convolutions'
+// on the model's gradient stream (forked behind everything queued on `stream`); the next cilrs_model_forward* on `stream`
+// waits for them only after its stem convolution + pooling (59 us of packing under 100 us of stem at batch 128).
+int cilrs_model_refresh_async(cilrs_model* h, void* stream) {
+  if (!h || !h->m.params) return ERR_INVALID;
+  Model& m = h->m;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!m.side || m.prof.on) return refresh(m, 1, s);
+  CK(pack_join(m, s));
+  CK(cuda_status(cudaEventRecord(m.ev_pack_fork, s)));
+  CK(cuda_status(cudaStreamWaitEvent(m.side, m.ev_pack_fork, 0)));
+  CK(launch_pack_all(m.params, m.pack_jobs, m.pack_njobs, m.pack_blocks, m.side));
+  CK(cuda_status(cudaEventRecord(m.ev_pack, m.side)));
+  m.pack_pending = true;
+  return cilrs_stem_pack_weight(m.params + m.slots[m.stem.w].off, m.stem.wf, s);
 }
 
 // repack the bf16 operands of the convolutions whose gradients backward part `part` completes (0 = layer4, 1 = layer3,

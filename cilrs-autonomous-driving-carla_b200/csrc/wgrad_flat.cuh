@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
 // 576 contiguous floats to the gradient. All flat convolutions of a backward part are served by one launch (job table).
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(768) wgrad_reduce_kernel(const __grid_constant__ WgradReduceJobs jobs, float* __restrict__ grads) {
-  __shared__ float s_part[8][576];   // [K-slice chain][576] when a CTA serves one output channel, [output channel][576] when it serves several
+  __shared__ __align__(16) float s_part[8][576];   // [K-slice chain][576] when a CTA serves one output channel, [output channel][576] when it serves several
   pdl_entry();
   int j = 0;
   while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.job[j + 1].first_block) ++j;
@@ -177,38 +177,49 @@ __global__ void __launch_bounds__(768) wgrad_reduce_kernel(const __grid_constant
   const int zs = threadIdx.x / 192;  // this thread sums the K slices z = zs, zs + nz, ... (nz = blockDim.x / 192 chains per column)
   const int nz = blockDim.x / 192;
   if (jb.rows > 1) {
-    // Shallow splits (layers 3-4: 6 / 1 K slices): one CTA per output channel was ~20 000 CTAs of three 768-byte reads each -
-    // pure CTA-launch overhead (61-90 us per launch measured). A CTA now serves `rows` (4 / 8) output channels: every load is
-    // issued before the first use, one barrier, `rows` x 2304 contiguous bytes out.
-    const int co0 = cgrp * jb.rows;
-    if (zs == 0) {
-      float acc[8][3];
+    // One accumulator tile per (co block, ci chunk, filter row) (the wgrad kernel's K slices add into it): a CTA serves 8 output
+    // channels = 24 rows of 768 B in, 8 x 2304 contiguous bytes of the OIHW gradient out. Every load (accumulators AND the
+    // gradient it is added to) is a 16-byte vector issued before the first use; the zeroing stores come after ALL loads - placed
+    // between them they alias the next load for the compiler and the kernel degenerated into 24 dependent round trips per
+    // thread (0.8 TB/s, 340 us of kernel time at the end of every step).
+    const int co0 = cgrp * 8;
+    const int tid = threadIdx.x;                 // 192 threads: 6 vectors each of the 24 x 48 accumulator vectors
+    float4 v[6], gv[6];
+    float4* srcp[6];
+    float4* gp[6];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if (r < jb.rows) {
-          const int co = co0 + r, cob = co >> 7, row = co & 127;
+    for (int i = 0; i < 6; ++i) {
+      const int q = tid + i * 192;               // 0..1151
+      const int rt = q / 48, c4 = q - rt * 48;   // (row r, filter row tg) = rt / 3, rt % 3 ; vector inside the 192-wide row
+      const int r = rt / 3, tg = rt - r * 3;
+      const int co = co0 + r, cob = co >> 7, row = co & 127;
+      const int tile = (cob * jb.ci_chunks + cic) * 3 + tg;
+      srcp[i] = (float4*)(jb.scratch + ((size_t)tile * 128 + row) * 192) + c4;
+      v[i] = __ldcg(srcp[i]);
+      // output vector q: row r2 = q / 144, 16-byte vector o4 of its 576 floats
+      const int r2 = q / 144, o4 = q - r2 * 144;
+      gp[i] = (float4*)(grads + jb.grad_off + ((size_t)(co0 + r2) * jb.cin + cic * 64) * 9) + o4;
+      gv[i] = __ldcg(gp[i]);
+    }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int tg = 0; tg < 3; ++tg) {
-            const int tile = (cob * jb.ci_chunks + cic) * 3 + tg;
-            const float* src = jb.scratch + (((size_t)tile * jb.split_z) * 128 + row) * 192 + t;
-            float a = 0.f;
-            for (int z = 0; z < jb.split_z; ++z) a += __ldcg(src + (size_t)z * 128 * 192);
-            if (jb.zero_src) *const_cast<float*>(src) = 0.f;   // the accumulator is ready for the next backward
-            acc[r][tg] = a;
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (r < jb.rows) {
-#pragma unroll
-          for (int tg = 0; tg < 3; ++tg) s_part[r][(t & 63) * 9 + tg * 3 + (t >> 6)] = acc[r][tg];
-        }
+    for (int i = 0; i < 6; ++i) {
+      const int q = tid + i * 192;
+      const int rt = q / 48, c4 = q - rt * 48;
+      const int r = rt / 3, tg = rt - r * 3;
+      const int t0 = c4 * 4;                     // column: tap-in-row (t >> 6), input channel (t & 63); 4 consecutive channels
+      float* d = &s_part[r][(t0 & 63) * 9 + tg * 3 + (t0 >> 6)];
+      d[0] = v[i].x; d[9] = v[i].y; d[18] = v[i].z; d[27] = v[i].w;
+      if (jb.zero_src) __stcg(srcp[i], zero4);   // the accumulator is ready for the next backward
     }
     __syncthreads();
-    for (int r = 0; r < jb.rows; ++r) {
-      float* g = grads + jb.grad_off + ((size_t)(co0 + r) * jb.cin + cic * 64) * 9;
-      for (int o = threadIdx.x; o < 576; o += blockDim.x) g[o] += s_part[r][o];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int q = tid + i * 192;
+      const int r2 = q / 144, o4 = q - r2 * 144;
+      const float4 a = *(const float4*)&s_part[r2][o4 * 4];
+      gv[i].x += a.x; gv[i].y += a.y; gv[i].z += a.z; gv[i].w += a.w;
+      *gp[i] = gv[i];
     }
     return;
   }

@@ -90,6 +90,7 @@ class FusedTrainer:
         self.graph_error = None
         self.skip_optimizer = False   # test hook: leave the exchanged gradient in place (no clip / Adam / repack / zeroing)
         self.optimizer_in_backward = optimizer_in_backward
+        self._opt_in_bwd = bool(optimizer_in_backward) and self.world == 1 and grad_clip == 0   # the variant actually taken
         if use_graph:
             if self.world > 1:
                 # the NCCL allreduces are captured into the graph with the kernels (PyTorch records them on the process
@@ -118,6 +119,10 @@ class FusedTrainer:
         m = self.model
         b = self.batch
         sp = _lib.stream_ptr()
+        if not self._opt_in_bwd:
+            # bf16 operands of the weights the previous step's Adam wrote: the stem's on this stream, the trunk's on the model's
+            # gradient stream beside K0 + the stem convolution (the forward waits for them after its stem) - 59 us off the chain
+            _lib.call("cilrs_model_refresh_async", m._handle, sp)
         if self.frames == "u8":
             _lib.call("cilrs_preprocess_u8", self.d_frames, b, 88, 200, 3, 0, 88, 200, None, None, self.s2d, sp)
             img, s2d = None, self.s2d
@@ -166,14 +171,13 @@ class FusedTrainer:
                 works[-1].wait()
                 self.opt.step(grad_scale=1.0 / self.world, grads_in_arena=True, grads_bf16=self.g16, zero_grad=self.g16 is None,
                               arena_range=(0, cut), advance=False)
-                _lib.call("cilrs_model_refresh", m._handle, 1, sp)
                 self._after_step()
                 return
         else:
             lib = _lib.lib()
             lib.cilrs_model_gradient_stream.restype = ctypes.c_void_p
             lib.cilrs_model_gradient_stream.argtypes = [ctypes.c_void_p]
-            gs_ptr = lib.cilrs_model_gradient_stream(m._handle) if self.optimizer_in_backward else None
+            gs_ptr = lib.cilrs_model_gradient_stream(m._handle) if self._opt_in_bwd else None
             if gs_ptr and self.grad_clip == 0 and not self.skip_optimizer:
                 # Optimizer in the backward (opt-in): once a part's gradients are complete (in the order of the model's gradient
                 # stream) Adam and the bf16 repack of that part run THERE, under the dgrad chain of the lower layers. Layer4 +
@@ -192,7 +196,7 @@ class FusedTrainer:
                 self.opt.step(grads_in_arena=True, zero_grad=True, arena_range=(0, self.part_ranges[1][0]), advance=False)
                 for part in (2, 3, 4):
                     _lib.call("cilrs_model_refresh_part", m._handle, part, sp)
-                self._after_step()
+                self._after_step(repacked=True)
                 return
             _lib.call("cilrs_model_backward", m._handle, b, MODE_TRAIN, -1, *self._backward_args())
         if self.skip_optimizer:
@@ -209,14 +213,14 @@ class FusedTrainer:
             scale_dev = self.norm_out[1:]
         self.opt.step(grad_scale=1.0 / self.world, grad_scale_dev=scale_dev, grads_in_arena=True, grads_bf16=self.g16,
                       zero_grad=self.g16 is None)
-        _lib.call("cilrs_model_refresh", m._handle, 1, sp)
         self._after_step()
 
-    def _after_step(self):
-        # parameters and BatchNorm buffers changed through raw pointers (also on every graph replay): the bf16 operands were
-        # repacked on the stream, but the next eval forward of the module must re-fold its BatchNorm
+    def _after_step(self, repacked=False):
+        # parameters and BatchNorm buffers changed through raw pointers (also on every graph replay): the next step repacks the
+        # bf16 operands itself (first thing, beside the stem); a forward of the MODULE in between must repack (and, in eval
+        # mode, re-fold its BatchNorm) first - unless the optimizer-in-backward variant already repacked on the stream
         m = self.model
-        m.mark_parameters_changed(repacked=True)
+        m.mark_parameters_changed(repacked=repacked)
         m._extra_b += 1
         m._fwd_gen += 1
 
@@ -269,7 +273,7 @@ class FusedTrainer:
             self.opt._sync_hyper(1.0 / self.world)   # lr / weight-decay changes (StepLR) reach the captured kernels here
             self.graph.replay()
             self.opt._step += 1
-            self._after_step()
+            self._after_step(repacked=self._opt_in_bwd)
         else:
             self._device_step()
         return self.loss6

@@ -184,6 +184,10 @@ int cilrs_model_bind(cilrs_model* m, float* params, float* grads, float* buffers
 /* call after parameter values changed. what: bit 0 = repack the bf16 conv operands from the fp32 masters,
  * bit 1 = fold eval-mode BatchNorm (running statistics) into per-channel scale/shift for CILRS_MODE_INFER */
 int cilrs_model_refresh(cilrs_model* m, int what, void* stream);
+/* bit-0 refresh off the critical path: the stem's operand is packed on `stream`, the trunk's on the model's gradient stream
+ * (forked behind the work already queued on `stream`); the next cilrs_model_forward* / _backward / _refresh call on `stream`
+ * waits for it - the forward only after its stem. Must be followed by such a call before a stream capture of `stream` ends. */
+int cilrs_model_refresh_async(cilrs_model* m, void* stream);
 /* bit-0 refresh restricted to the convolutions whose gradients backward part `part` completes (0 = layer4 ... 3 = layer1,
  * 4 = stem): the optimizer step + repack of a finished part can run under the rest of the backward */
 int cilrs_model_refresh_part(cilrs_model* m, int part, void* stream);

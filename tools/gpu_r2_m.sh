@@ -1,7 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_preprocess_gpu.py -q -m gpu --tb=short 2>&1 | tail -2
-for mode in 0 2 1; do
+for mode in 3 4; do
 CILRS_BN_FUSION=$mode timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r2_bench_fuse$mode.json 2> gpurun_out/r2_bench_fuse$mode.err
 python - <<PY
 import json
