@@ -333,6 +333,35 @@ def extra_kernel_lines(torch, model, pk):
         model.flat_gradients().zero_()
     except Exception as ex:
         out["heads"] = {"error": repr(ex)}
+    try:
+        # N3 / N4: the reference loader's per-frame work (cv2.imread + albumentations, notebook/notebook.ipynb:404-407) for one
+        # batch of 128 collector-format frames (200 x 88 JPEG, quality 95): host bytes -> decoded + augmented u8 frames in HBM
+        import time
+        import cv2
+        from cilrs_b200.augment import DeviceAugmenter
+        from cilrs_b200.data import JpegDecoder
+        rng = __import__("numpy").random.default_rng(0)
+        streams = []
+        for i in range(128):
+            img = cv2.GaussianBlur(rng.integers(0, 256, (88, 200, 3), dtype="uint8"), (5, 5), 1.5)
+            img[20:40, 30 + i % 50:90 + i % 50] = rng.integers(0, 256, 3)
+            streams.append(cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 95])[1].tobytes())
+        dec, aug = JpegDecoder(128), DeviceAugmenter(128, seed=0)
+        buf = torch.empty(128, 88, 200, 3, dtype=torch.uint8, device="cuda")
+
+        def run():
+            dec.decode(streams, out=buf)
+            aug(buf)
+        t = _timeit(torch, run)
+        t0 = time.perf_counter()
+        for s_ in streams:
+            cv2.cvtColor(cv2.imdecode(__import__("numpy").frombuffer(s_, dtype="uint8"), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+        t_cpu = time.perf_counter() - t0
+        dec.check()
+        out["n3_decode_augment"] = {"workload": "128 JPEG frames (200x88, q95, %d B avg): host bytes -> decoded + augmented u8 frames" % (sum(map(len, streams)) // 128),
+                                    "ms": t * 1e3, "frames_per_s": 128 / t, "cv2_imdecode_1_thread_frames_per_s": 128 / t_cpu}
+    except Exception as ex:
+        out["n3_decode_augment"] = {"error": repr(ex)}
     return out
 
 
@@ -364,6 +393,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # measurement aid: cap NCCL's persistent CTAs (they take SMs from the 148-CTA convolution grids while an allreduce overlaps
+        # the backward); reported in config.nccl_max_ctas
+        if os.environ.get("CILRS_BENCH_NCCL_MAX_CTAS"):
+            os.environ["NCCL_MAX_CTAS"] = os.environ["CILRS_BENCH_NCCL_MAX_CTAS"]
         dist.init_process_group("nccl", device_id=dev)
     import cilrs_b200  # noqa: F401
     from cilrs_b200 import _lib
@@ -497,6 +530,8 @@ def main():
                    "initial_weights": "reference ctor under torch.manual_seed(0) (%s), loaded via load_state_dict" % init_kind,
                    "allreduce_schedule": trainer.overlap_allreduce if world > 1 else None,
                    "grad_comm": trainer.grad_comm if world > 1 else None,
+                   "async_parts": trainer.async_parts if world > 1 else None,
+                   "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS") if world > 1 else None,
                    "l2": "no explicit flush: one step touches ~0.9 GB of activations + 0.6 GB of optimizer state, > 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps, "input": "uint8 [128,88,200,3] frames + speed/command/targets from pinned host memory"},

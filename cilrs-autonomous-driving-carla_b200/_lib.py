@@ -43,7 +43,8 @@ def lib():
         _lib.cilrs_status_string.restype = ctypes.c_char_p
         _lib.cilrs_status_string.argtypes = [ctypes.c_int]
         for name in ("cilrs_conv_packed_weight_bytes", "cilrs_conv_stats_bytes", "cilrs_stem_packed_weight_bytes",
-                     "cilrs_model_workspace_bytes", "cilrs_conv_flat_workspace_floats", "cilrs_wgrad_flat_workspace_bytes"):
+                     "cilrs_model_workspace_bytes", "cilrs_conv_flat_workspace_floats", "cilrs_wgrad_flat_workspace_bytes",
+                     "cilrs_jpeg_desc_bytes", "cilrs_jpeg_table_set_bytes", "cilrs_jpeg_plane_bytes", "cilrs_augment_param_bytes"):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = ctypes.c_size_t
     return _lib

@@ -346,6 +346,47 @@ int cilrs_grad_sumsq_bf16(const void* g_bf16, long long n, double* partial_ws, u
 /* fp32 gradient range -> bf16 exchange buffer (round to nearest even); zero_source != 0 also clears the fp32 range */
 int cilrs_grad_to_bf16(float* g, void* out_bf16, long long n, int zero_source, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * N3 - input pipeline: baseline JPEG decode on the GPU.
+ * Replaces cv2.imread + cv2.cvtColor(BGR2RGB) of CILRSDataset.__getitem__ (notebook/notebook.ipynb:404-405) for the collector's
+ * frames (model/collect_data.py:685-716: 200 x 88, quality 95, YCbCr 4:2:0, no restart markers); the output is bit-identical
+ * to OpenCV's (libjpeg-turbo defaults: islow inverse DCT, fancy chroma upsampling). Supported: baseline sequential Huffman,
+ * 8 bit, grey / YCbCr 4:4:4 / 4:2:0, Huffman and quantisation table ids 0-1 / 0-3, no restart intervals.
+ * ------------------------------------------------------------------------------------------------------------------------- */
+enum { CILRS_JPEG_OK = 0, CILRS_JPEG_NOT_JPEG = 1, CILRS_JPEG_UNSUPPORTED = 2, CILRS_JPEG_CORRUPT = 3, CILRS_JPEG_SIZE_MISMATCH = 4 };
+size_t cilrs_jpeg_desc_bytes(void);        /* bytes of one image descriptor */
+size_t cilrs_jpeg_table_set_bytes(void);   /* bytes of one derived Huffman table set */
+size_t cilrs_jpeg_plane_bytes(int height, int width);   /* component-plane scratch per image */
+/* HOST: parse n streams that lie at bytes[offsets[i] .. offsets[i + 1]) (offsets 4-byte aligned; a shorter true length is
+ * fine - trailing bytes after EOI are ignored). Writes n descriptors and up to max_sets distinct table sets (host memory; copy
+ * both to the device). A stream that cannot be decoded gets a non-zero status in its descriptor, not an error return. */
+int cilrs_jpeg_prepare(const unsigned char* bytes, const long long* offsets, int n, void* descs_out, void* sets_out, int max_sets,
+                       int* n_sets_out);
+/* HOST: read n files into dst with `threads` threads. offsets must hold 2n + 1 entries: [0..n] = 16-byte aligned starts (and the
+ * total), [n + 1 .. 2n] = the exact end of each stream. */
+int cilrs_jpeg_read_files(const char* const* paths, int n, unsigned char* dst, long long capacity, long long* offsets, int threads);
+/* DEVICE: decode the batch into out_rgb uint8 [n, height, width, 3] (reverse != 0: BGR as cv2.imread returns it). status_dev[i]
+ * receives CILRS_JPEG_* per image (a failed image is written as zeros). Two launches, no synchronisation. */
+int cilrs_jpeg_decode(const unsigned char* bytes_dev, const void* descs_dev, const void* sets_dev, int n, int height, int width,
+                      unsigned char* planes_dev, size_t plane_bytes_per_image, unsigned char* out_rgb, int reverse,
+                      unsigned int* status_dev, void* stream);
+
+/* WeightedRandomSampler(weights, num_samples, replacement=True) (notebook/notebook.ipynb:411-413) on the device: out[i] = the
+ * first row whose cumulative weight exceeds u_i * cdf[n - 1]; u_i = Philox4x32-10(seed, offset + i), 53 bits. cdf_dev: inclusive
+ * prefix sums of the (non-negative) weights, fp64, device. Same distribution as torch.multinomial, not the same random stream. */
+int cilrs_weighted_sample(const double* cdf_dev, long long n, long long num_samples, unsigned long long seed, unsigned long long offset,
+                          long long* out_dev, void* stream);
+
+/* N4 - the training augmentations of notebook/notebook.ipynb:387-394 on uint8 RGB frames [n, height, width, 3] (in == out is
+ * allowed): RandomBrightnessContrast -> HueSaturationValue -> GaussianBlur -> GaussNoise -> CoarseDropout, one CTA per frame,
+ * per-frame parameters (cilrs_augment_param_bytes() each; layout documented in cilrs_b200/augment.py) drawn by the caller.
+ * Point-wise colour transforms and the blur are bit-identical to the cv2 calls albumentations makes with the same parameters;
+ * the noise is N(0, noise_std^2) per value from Philox(seed, offset + ...). Frames of up to 200 KB / 3 bytes. */
+size_t cilrs_augment_param_bytes(void);
+int cilrs_augment_u8(const unsigned char* in, unsigned char* out, const void* params_dev, int n, int height, int width,
+                     unsigned long long seed, unsigned long long offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
