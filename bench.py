@@ -585,11 +585,13 @@ def main():
         achieved = BATCH * (FLOP_FWD + FLOP_DGRAD) / t_gemm / 1e12 if t_gemm > 0 else 0.0
         burst, sustained = pk["bf16_tflops"], pk["bf16_tflops_sustained"]
         traffic, traffic_note = None, None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_flat_traffic.json")))
-            traffic, traffic_note = tj["traffic_bytes_per_launch"], tj["launches"] + " | " + tj["source"]
-        except Exception:
-            pass
+        for tname in ("r02_conv_flat_traffic.json", "r01_conv_flat_traffic.json"):   # the committed ncu --set full capture
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
+                traffic, traffic_note = tj["traffic_bytes_per_launch"], tj["launches"] + " | " + tj["source"]
+                break
+            except Exception:
+                pass
         step_tf = value / world * FLOP_TRAIN / 1e12
         line["roofline"] = {
             "bound": "tensor",

@@ -154,9 +154,17 @@ def test_augment_deterministic_transforms_equal_the_cv2_calls():
     aug = augment.DeviceAugmenter(32, seed=1)
     x = torch.from_numpy(frames).cuda()
     out = aug(x.clone(), params=p).cpu().numpy()
+    bad = []
     for i in range(32):
-        want = AO.apply(frames[i], p[i])
-        assert np.array_equal(out[i], want), (i, int(p["flags"][i]), int(np.abs(out[i].astype(int) - want.astype(int)).max()))
+        want = AO.apply(frames[i], p[i])          # cv2's scalar HSV->RGB path (the same on every host CPU): bit for bit
+        if not np.array_equal(out[i], want):
+            bad.append((i, int(p["flags"][i]), int(np.abs(out[i].astype(int) - want.astype(int)).max())))
+        # OpenCV's vector path (what a wide row gets on an AVX2 host) truncates where its scalar code rounds: one level at most
+        live = AO.apply(frames[i], p[i], vector_path=True)
+        assert np.abs(out[i].astype(int) - live.astype(int)).max() <= 1, i
+        if not (int(p["flags"][i]) & 2):
+            assert np.array_equal(out[i], live), i   # without the HSV transform there is no host dependence at all
+    assert not bad, bad
     assert np.array_equal(out[0], frames[0])
     # out-of-place form leaves the input alone
     y = torch.empty_like(x)
@@ -176,6 +184,7 @@ def test_augment_hsv_round_trip_all_hues():
     out = augment.DeviceAugmenter(21)(torch.from_numpy(frames).cuda(), params=p).cpu().numpy()
     for i in range(21):
         assert np.array_equal(out[i], AO.apply(frames[i], p[i])), i
+        assert np.abs(out[i].astype(int) - AO.apply(frames[i], p[i], vector_path=True).astype(int)).max() <= 1, i
 
 
 def test_augment_noise_statistics_and_dropout():

@@ -3,7 +3,7 @@ set -e
 cd "$(dirname "$0")/.."
 S=cilrs-autonomous-driving-carla_b200/csrc
 mkdir -p /tmp/cilrs_trace
-for f in api conv conv_flat model preprocess; do
+for f in api conv conv_flat model preprocess fp32_path jpeg pipeline; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DCF_TRACE $EXTRA -c $S/$f.cu -o /tmp/cilrs_trace/$f.o &
 done
 wait
