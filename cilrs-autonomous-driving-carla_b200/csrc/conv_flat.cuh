@@ -433,9 +433,11 @@ __global__ void __launch_bounds__(CF_THREADS, 1) conv_flat_kernel(const __grid_c
       if (++acc == p.acc_sets) { acc = 0; accph ^= 1; }
     }
 
-    tma_store_wait_all();  // this warp's output stores have been written
-
     const bool fuse = (p.flags & CF_FUSE) != 0;
+    // The staging tiles have been read by every store; the writes themselves only have to be complete (~1.3 k clocks later in a
+    // CTA trace) when the second pass of CF_FUSE reads them back - otherwise the end of the grid orders them before any consumer
+    if (fuse) tma_store_wait_all(); else tma_store_wait_read();
+
     if (do_stats) {
       // ---- per-CTA partial (the eight warps' sums in a fixed order), then the last CTA to finish folds all partials ----
       const int tid = ew * 32 + lane;  // 0..255

@@ -256,66 +256,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const __nv_bfloat1
 #undef CILRS_BN_APPLY_LOAD
 }
 
-// ---------------------------------------------------------------------------------------------
-// stem: out = maxpool3x3/2 pad 1 ( relu( y*scale + shift ) ), argmax position (0..8) kept for the backward
-// y [B,H,W,C] -> out [B,OH,OW,C], OH = (H+1)/2 ...
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(EW_THREADS) bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
-                                                                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
-                                                                     uint8_t* __restrict__ argmax, int B, int H, int W, int C, int OH,
-                                                                     int OW, int OHp, int OWp) {
-  pdl_entry();
-  const int groups = C >> 3;
-  const long long nvec = (long long)B * OH * OW * groups;
-  const long long stride = (long long)gridDim.x * EW_THREADS;
-  long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
-  const int cg = (int)(i % groups) * 8;
-  const Vec8 sc = loadf8(scale + cg), sh = loadf8(shift + cg);
-  for (; i < nvec; i += stride) {
-    long long pix = i / groups;
-    const int ow = (int)(pix % OW);
-    const int oh = (int)((pix / OW) % OH);
-    const int n = (int)(pix / ((long long)OW * OH));
-    Vec8 best;
-    int bi[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { best.v[k] = -INFINITY; bi[k] = 0; }
-    // all nine window loads are issued before the first comparison
-    uint4 q[9];
-    bool okq[9];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int h = oh * 2 - 1 + r;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int w = ow * 2 - 1 + s;
-        okq[r * 3 + s] = h >= 0 && h < H && w >= 0 && w < W;
-        if (okq[r * 3 + s]) q[r * 3 + s] = *reinterpret_cast<const uint4*>(y + (((long long)n * H + h) * W + w) * C + cg);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        if (!okq[r * 3 + s]) continue;
-        const Vec8 a = unpack8(q[r * 3 + s]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          // round to bf16 first: the comparison must see exactly the values a separate BN+ReLU pass would store
-          const float v = __bfloat162float(__float2bfloat16(fmaxf(fmaf(a.v[k], sc.v[k], sh.v[k]), 0.f)));
-          if (v > best.v[k]) { best.v[k] = v; bi[k] = r * 3 + s; }
-        }
-      }
-    }
-    store8(out + ((((long long)n * OHp + oh) * OWp + ow) * groups) * 8 + cg, best);  // padded-flat output, dense argmax
-    if (argmax) {
-      uint2 u;
-      u.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
-      u.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
-      *reinterpret_cast<uint2*>(argmax + i * 8) = u;
-    }
-  }
-}
+// (the stem's max-pool forward lives in stem_pool.cuh)
 
 // global average pool: x padded-flat [B,Hp,Wp,C] bf16 -> feat [B,C] fp32 (padding pixels are zero, so the sum runs over all of them)
 __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ feat, int B, int C, const PadGeom g) {
@@ -391,49 +332,6 @@ struct BnBwdReduceParams {
   int OHp, OWp;  // stem variant: padded-flat geometry of the pooled gradient g
   PadGeom geom;  // regular variant: padded-flat geometry of g / act / y / dz_out ({1,1,1,1} = dense)
 };
-
-CILRS_DEVINL Vec8 stem_gather_grad(const BnBwdReduceParams& p, int n, int h, int w, int cg) {
-  // gradient reaching conv1-output pixel (h, w): every pool window (oh, ow) that contains it and selected it.
-  // Windows: oh in {h/2, (h+1)/2}, ow in {w/2, (w+1)/2} (the two coincide for even coordinates). All four loads are issued
-  // before any use.
-  Vec8 acc;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc.v[k] = 0.f;
-  uint2 am[4];
-  uint4 gq[4];
-  int code[4];
-  bool ok[4];
-#pragma unroll
-  for (int a = 0; a < 2; ++a) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int oh = (h + a) >> 1, ow = (w + b) >> 1;
-      const int r = h - (oh * 2 - 1), s = w - (ow * 2 - 1);
-      const int q = a * 2 + b;
-      ok[q] = oh < p.OH && ow < p.OW && r >= 0 && r <= 2 && s >= 0 && s <= 2 && !(a == 1 && (h & 1) == 0) && !(b == 1 && (w & 1) == 0);
-      code[q] = r * 3 + s;
-      if (ok[q]) {
-        am[q] = *reinterpret_cast<const uint2*>(p.argmax + (((long long)n * p.OH + oh) * p.OW + ow) * p.C + cg);  // dense codes
-        gq[q] = *reinterpret_cast<const uint4*>(p.g + (((long long)n * p.OHp + oh) * p.OWp + ow) * p.C + cg);
-      }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    if (ok[q]) {
-      const uint32_t gw[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
-      const uint32_t cc = (uint32_t)code[q] * 0x01010101u;
-      const uint32_t m_lo = __vcmpeq4(am[q].x, cc), m_hi = __vcmpeq4(am[q].y, cc);  // 0xFF in every byte whose arg-max is this pixel
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t mk = ((k < 4 ? m_lo : m_hi) >> ((k & 3) * 8)) & 1u;
-        const float gv = (k & 1) ? bf16hi(gw[k >> 1]) : bf16lo(gw[k >> 1]);
-        acc.v[k] = fmaf((float)mk, gv, acc.v[k]);
-      }
-    }
-  }
-  return acc;
-}
 
 template <bool STEM>
 __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(const BnBwdReduceParams p) {
@@ -663,7 +561,7 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(const BnBwd
     CILRS_BN_BWD_LOAD()
   }
   const Vec8 mean = loadf8(p.mean + cg), rstd = loadf8(p.rstd + cg), gamma = loadf8(p.gamma + cg);
-  Vec8 k0, k1, sc, sh;
+  Vec8 k0, k1;
   __shared__ __align__(16) float s_par[2][EW_DEFER_MAX_C];
   if (p.defer.acc_sum) {
     // every CTA derives all channels once from the dgrad epilogue's sums (coalesced), threads pick theirs from shared memory
@@ -688,9 +586,6 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(const BnBwd
       k1.v[k] = p.frozen ? 0.f : bd.v[k] * p.inv_count;
     }
   }
-  if (STEM) { sc = loadf8(p.scale + cg); sh = loadf8(p.shift + cg); }
-  BnBwdReduceParams gp;  // only the fields the stem gather reads
-  if (STEM) { gp.g = p.g; gp.argmax = p.argmax; gp.OH = p.OH; gp.OW = p.OW; gp.OHp = p.OH; gp.OWp = p.OW; gp.C = p.C; }
   if (!STEM) {
     // four vectors per iteration, all loads issued before the first use (see bn_apply_kernel)
     for (;;) {
@@ -724,26 +619,6 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(const BnBwd
       i += 4 * stride;
       if (i >= p.nvec) break;
       CILRS_BN_BWD_LOAD()
-    }
-  } else {
-    for (; i < p.nvec; i += stride) {
-      const Vec8 yv = load8(p.y + i * 8);
-      const long long pix = i / groups;
-      const int w = (int)(pix % p.W);
-      const int h = (int)((pix / p.W) % p.H);
-      const int n = (int)(pix / ((long long)p.W * p.H));
-      Vec8 gv = stem_gather_grad(gp, n, h, w, cg);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (!(fmaf(yv.v[k], sc.v[k], sh.v[k]) > 0.f)) gv.v[k] = 0.f;
-      if (p.dz) store8(p.dz + i * 8, gv);
-      Vec8 ov;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float xhat = (yv.v[k] - mean.v[k]) * rstd.v[k];
-        ov.v[k] = gamma.v[k] * rstd.v[k] * (gv.v[k] - k0.v[k] - xhat * k1.v[k]);
-      }
-      store8(p.dy + i * 8, ov);
     }
   }
 }

@@ -7,6 +7,7 @@
 #include "conv_params.h"
 #include "conv_host.h"
 #include "elementwise.cuh"
+#include "stem_pool.cuh"
 #include "heads_run.cuh"
 #include "adam.cuh"
 #include <new>
@@ -127,6 +128,7 @@ struct Model {
   __nv_bfloat16* x_s2d;
   __nv_bfloat16* pool_out;
   uint8_t* pool_arg;
+  __nv_bfloat16* pool_ysel;   // raw conv1 output at the arg-max of every pool window (padded-flat like pool_out): the stem's BN-backward sums
   float* stats;          // shared stats-partials scratch
   float* stats_ds;       // the same for the downsample convolutions (they run beside conv_a on the gradient stream)
   double* stat_acc;
@@ -276,6 +278,7 @@ static long long carve(Model& m, char* base) {
   carve_conv(bp, m.stem, B);
   m.pool_out = (__nv_bfloat16*)bp.take(pad_elems(B, kGeom0, 64) * 2);
   m.pool_arg = (uint8_t*)bp.take(act_elems(B, 22, 50, 64));
+  m.pool_ysel = (__nv_bfloat16*)bp.take(pad_elems(B, kGeom0, 64) * 2);
   const __nv_bfloat16* prev = m.pool_out;
   for (auto& blk : m.blocks) {
     blk.in = prev;
@@ -623,8 +626,8 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
   const long long pool_vec = act_elems(B, 22, 50, 64) / 8;
   PROF(m, PC_FPROP, s, CK(launch_conv_gemm(&m.old_plans[m.stem_fwd], s)));
   if (mode == MODE_INFER) {
-    bn_relu_maxpool_kernel<<<ew_grid(pool_vec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.unit_vec, m.unit_vec + 64, m.pool_out, nullptr, B, 44,
-                                                                        100, 64, 22, 50, kGeom0.Hp, kGeom0.Wp); ++g_cilrs_launches;
+    bn_relu_maxpool_sel_kernel<<<ew_grid(pool_vec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.unit_vec, m.unit_vec + 64, m.pool_out, nullptr, nullptr,
+                                                                            B, 44, 100, 64, 22, 50, kGeom0.Hp, kGeom0.Wp); ++g_cilrs_launches;
     CKL();
     CK(pack_join(m, s));
     for (auto& blk : m.blocks) {
@@ -636,8 +639,8 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
   } else {
     PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, m.stem.bn, conv_gemm_grid(&m.old_plans[m.stem_fwd]), (double)B * 44 * 100, training,
                                              update_running, s)));
-    bn_relu_maxpool_kernel<<<ew_grid(pool_vec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.stem.bn.vec, m.stem.bn.vec + 64, m.pool_out,
-                                                                        m.pool_arg, B, 44, 100, 64, 22, 50, kGeom0.Hp, kGeom0.Wp); ++g_cilrs_launches;
+    bn_relu_maxpool_sel_kernel<<<ew_grid(pool_vec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.stem.bn.vec, m.stem.bn.vec + 64, m.pool_out, m.pool_arg,
+                                                                            m.pool_ysel, B, 44, 100, 64, 22, 50, kGeom0.Hp, kGeom0.Wp); ++g_cilrs_launches;
     CKL();
     CK(pack_join(m, s));   // the trunk's operands may have been repacked beside the stem (cilrs_model_refresh_async)
     for (auto& blk : m.blocks) {
@@ -918,22 +921,22 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   // ---- stem: max-pool backward + ReLU + BN backward, then wgrad ----
   if (dbg ? dbg_lo < 0 : (part < 0 || part == 4)) {
     const BnRef& bn = m.stem.bn;
-    const long long nvec = act_elems(B, 44, 100, 64) / 8;
-    const int grid = ew_grid(nvec, 64, 4, 2);
-    const int rgrid = 148 * 2;  // 128 registers: two resident CTAs per SM, one wave
+    // sums over the POOL outputs (every pooled gradient lands on exactly one conv1 pixel, whose raw value the forward kept in
+    // pool_ysel): the ordinary reduce kernel on (g, pool_out as the ReLU mask, ysel) - 57 MB instead of a pass over conv1's output
+    const long long pvec = pad_elems(B, kGeom0, 64) / 8;
     BnBwdReduceParams rp{};
-    rp.g = gcur; rp.y = m.stem.y; rp.mean = bn.vec + 2 * 64; rp.rstd = bn.vec + 3 * 64; rp.nvec = nvec; rp.C = 64;
+    rp.g = gcur; rp.act = m.pool_out; rp.y = m.pool_ysel; rp.mean = bn.vec + 2 * 64; rp.rstd = bn.vec + 3 * 64; rp.nvec = pvec; rp.C = 64;
     rp.partial = m.stat_acc; rp.counter = m.counters; rp.bsum = bn.bred; rp.bdot = bn.bred + 64;
-    rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
-    rp.argmax = m.pool_arg; rp.scale = bn.vec; rp.shift = bn.vec + 64; rp.H = 44; rp.W = 100; rp.OH = 22; rp.OW = 50;
-    rp.OHp = kGeom0.Hp; rp.OWp = kGeom0.Wp; rp.geom = kDense;
-    rp.dz_out = m.dy_stem;  // routed + masked gradient, turned into dy in place by the apply pass
-    PROF(m, PC_BN_BWD, s, { ++g_cilrs_launches; CK(cuda_status(launch_pdl(bn_bwd_reduce_kernel<true>, dim3(rgrid), dim3(EW_THREADS), 0, s, rp))); });
-    BnBwdApplyParams ap{};
-    ap.g = m.dy_stem; ap.y = m.stem.y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
-    ap.bsum = rp.bsum; ap.bdot = rp.bdot; ap.inv_count = (float)(1.0 / ((double)B * 4400.0)); ap.frozen = frozen; ap.nvec = nvec;
-    ap.C = 64; ap.dy = m.dy_stem; ap.geom = kDense;
-    PROF(m, PC_BN_BWD, s, { ++g_cilrs_launches; CK(cuda_status(launch_pdl(bn_bwd_apply_kernel<false>, dim3(grid), dim3(EW_THREADS), 0, s, ap))); });
+    rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off; rp.geom = kGeom0;
+    rp.dz_out = gcur;   // in place: g * [pooled activation > 0] - the only place where the stem's ReLU mask matters
+    PROF(m, PC_BN_BWD, s, { ++g_cilrs_launches; CK(cuda_status(launch_pdl(bn_bwd_reduce_kernel<false>, dim3(ew_reduce_grid(pvec, 64)), dim3(EW_THREADS), 0, s, rp))); });
+    // route through the arg-max + ReLU mask + BatchNorm backward in one pass (stem_pool.cuh)
+    StemBwdApplyParams ap{};
+    ap.g = gcur; ap.argmax = m.pool_arg; ap.y = m.stem.y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = m.params + m.slots[bn.gamma].off;
+    ap.bsum = rp.bsum; ap.bdot = rp.bdot; ap.inv_count = (float)(1.0 / ((double)B * 4400.0));
+    ap.frozen = frozen; ap.B = B; ap.H = 44; ap.W = 100; ap.OH = 22; ap.OW = 50; ap.OHp = kGeom0.Hp; ap.OWp = kGeom0.Wp; ap.C = 64; ap.dy = m.dy_stem;
+    const long long nblk = (long long)B * 22 * 50 * 8;
+    PROF(m, PC_BN_BWD, s, { ++g_cilrs_launches; CK(cuda_status(launch_pdl(stem_bwd_apply_kernel, dim3(ew_grid(nblk, 64, 2, 2)), dim3(EW_THREADS), 0, s, ap))); });
     PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, m.stem_wgrad, m.stem.w, s)));
   }
   if (use_side && async_part) {
@@ -1314,15 +1317,53 @@ int cilrs_bn_apply(const void* x, const float* vec, const void* residual, const 
   return cuda_status(cudaGetLastError());
 }
 
-// padded_out != 0: out is padded-flat [batch, OH + 1, OW + 1, C] (its padding pixels are not written); argmax stays dense
-int cilrs_bn_relu_maxpool(const void* y, const float* vec, void* out, uint8_t* argmax, int batch, int H, int W, int C, int padded_out,
-                          void* stream) {
-  if (!y || !vec || !out || C % 64 || batch < 1) return ERR_INVALID;
+// padded_out != 0: out (and ysel) are padded-flat [batch, OH + 1, OW + 1, C] (their padding pixels are not written); argmax stays
+// dense. ysel (optional, needs argmax): the raw y at the arg-max of every window, for cilrs_stem_bn_backward.
+int cilrs_bn_relu_maxpool_sel(const void* y, const float* vec, void* out, uint8_t* argmax, void* ysel, int batch, int H, int W, int C,
+                              int padded_out, void* stream) {
+  if (!y || !vec || !out || C % 64 || batch < 1 || H < 1 || W < 1 || (ysel && !argmax)) return ERR_INVALID;
+  if ((long long)batch * (H + 2) * (W + 2) * C >= (1LL << 31)) return ERR_UNSUPPORTED;   // the kernel indexes with 32 bits
   const int OH = (H + 1) / 2, OW = (W + 1) / 2;
   const long long nvec = (long long)batch * OH * OW * C / 8;
-  bn_relu_maxpool_kernel<<<ew_grid(nvec, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)y, vec, vec + C, (__nv_bfloat16*)out, argmax, batch, H, W, C, OH, OW, padded_out ? OH + 1 : OH,
-      padded_out ? OW + 1 : OW); ++g_cilrs_launches;
+  bn_relu_maxpool_sel_kernel<<<ew_grid(nvec, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y, vec, vec + C, (__nv_bfloat16*)out, argmax, (__nv_bfloat16*)ysel, batch, H, W, C, OH, OW,
+      padded_out ? OH + 1 : OH, padded_out ? OW + 1 : OW); ++g_cilrs_launches;
+  return cuda_status(cudaGetLastError());
+}
+int cilrs_bn_relu_maxpool(const void* y, const float* vec, void* out, uint8_t* argmax, int batch, int H, int W, int C, int padded_out,
+                          void* stream) {
+  return cilrs_bn_relu_maxpool_sel(y, vec, out, argmax, nullptr, batch, H, W, C, padded_out, stream);
+}
+
+// The stem's max-pool + ReLU + BatchNorm backward as the training plan runs it (stem_pool.cuh): sums over the pool outputs
+// (g, act = the pooled activations, ysel from cilrs_bn_relu_maxpool_sel), then one routing + apply pass. H and W even.
+// g / act / ysel: [batch, H/2, W/2, C], padded-flat [batch, H/2 + 1, W/2 + 1, C] when padded != 0; y, dy: dense [batch, H, W, C].
+// workspace / counter as for cilrs_bn_backward.
+int cilrs_stem_bn_backward(void* g, const void* act, const void* ysel, const uint8_t* argmax, const void* y, const float* vec,
+                           const float* gamma, int batch, int H, int W, int C, int padded, int frozen, void* dy, float* dgamma,
+                           float* dbeta, float* workspace, unsigned int* counter, void* stream) {
+  if (!g || !act || !ysel || !argmax || !y || !vec || !gamma || !dy || !workspace || !counter) return ERR_INVALID;
+  if (C % 64 || batch < 1 || H < 2 || W < 2 || (H & 1) || (W & 1)) return ERR_INVALID;
+  if ((long long)batch * (H + 2) * (W + 2) * C >= (1LL << 31)) return ERR_UNSUPPORTED;   // the kernel indexes with 32 bits
+  cudaStream_t s = (cudaStream_t)stream;
+  const int OH = H / 2, OW = W / 2;
+  const PadGeom geom = padded ? PadGeom{OH, OW, OH + 1, OW + 1} : kDense;
+  const long long pvec = (long long)batch * (padded ? (OH + 1) * (OW + 1) : OH * OW) * C / 8;
+  float* bred = workspace + (size_t)EW_MAX_BLOCKS * 2 * C;
+  BnBwdReduceParams rp{};
+  rp.g = (const __nv_bfloat16*)g; rp.act = (const __nv_bfloat16*)act; rp.y = (const __nv_bfloat16*)ysel;
+  rp.mean = vec + 2 * C; rp.rstd = vec + 3 * C; rp.nvec = pvec; rp.C = C; rp.partial = (double*)workspace; rp.counter = counter;
+  rp.bsum = bred; rp.bdot = bred + C; rp.dgamma = dgamma; rp.dbeta = dbeta; rp.geom = geom;
+  rp.dz_out = (__nv_bfloat16*)g;   // g becomes g * [act > 0] in place
+  bn_bwd_reduce_kernel<false><<<ew_reduce_grid(pvec, C), EW_THREADS, 0, s>>>(rp); ++g_cilrs_launches;
+  CKL();
+  StemBwdApplyParams ap{};
+  ap.g = rp.g; ap.argmax = argmax; ap.y = (const __nv_bfloat16*)y; ap.mean = rp.mean; ap.rstd = rp.rstd; ap.gamma = gamma;
+  ap.bsum = rp.bsum; ap.bdot = rp.bdot; ap.inv_count = (float)(1.0 / ((double)batch * H * W));
+  ap.frozen = frozen; ap.B = batch; ap.H = H; ap.W = W; ap.OH = OH; ap.OW = OW; ap.OHp = padded ? OH + 1 : OH; ap.OWp = padded ? OW + 1 : OW;
+  ap.C = C; ap.dy = (__nv_bfloat16*)dy;
+  const long long nblk = (long long)batch * OH * OW * (C / 8);
+  stem_bwd_apply_kernel<<<ew_grid(nblk, C, 2, 2), EW_THREADS, 0, s>>>(ap); ++g_cilrs_launches;
   return cuda_status(cudaGetLastError());
 }
 

@@ -62,11 +62,29 @@ class FusedTrainer:
         _lib.call("cilrs_model_set_dropout_counter", model._handle, self.opt._step_dev)
         if self.world > 1:
             broadcast_parameters(model, 0, process_group)
-        self.d_image = torch.zeros(batch, 3, 88, 200, dtype=torch.float32, device=dev) if frames == "f32" else None
-        self.d_frames = torch.zeros(batch, 88, 200, 3, dtype=torch.uint8, device=dev) if frames == "u8" else None
-        self.d_speed = torch.zeros(batch, dtype=torch.float32, device=dev)
-        self.d_command = torch.zeros(batch, dtype=torch.long, device=dev)
-        self.d_targets = torch.zeros(batch, 3, dtype=torch.float32, device=dev)
+        # The step's static inputs are views of ONE buffer, and a second buffer of the same layout is the staging area of
+        # prefetch_batch(): the next batch's H2D copies run on a copy stream under the current step, load_prefetched() is a single
+        # D2D copy (the reference's DataLoader prefetches the same way: num_workers=2, pin_memory=True, notebook.ipynb:417-420).
+        nb_img = batch * 88 * 200 * 3 * (4 if frames == "f32" else 1)
+        offs, o = [], 0
+        for nbytes in (nb_img, 4 * batch, 8 * batch, 12 * batch):
+            offs.append(o)
+            o += (nbytes + 255) // 256 * 256
+        self._inputs = torch.zeros(o, dtype=torch.uint8, device=dev)
+        self._stage = torch.zeros(o, dtype=torch.uint8, device=dev)
+
+        def views(buf):
+            img = buf[offs[0]:offs[0] + nb_img]
+            img = img.view(torch.float32).view(batch, 3, 88, 200) if frames == "f32" else img.view(batch, 88, 200, 3)
+            return (img, buf[offs[1]:offs[1] + 4 * batch].view(torch.float32), buf[offs[2]:offs[2] + 8 * batch].view(torch.long),
+                    buf[offs[3]:offs[3] + 12 * batch].view(torch.float32).view(batch, 3))
+        img, self.d_speed, self.d_command, self.d_targets = views(self._inputs)
+        self.d_image = img if frames == "f32" else None
+        self.d_frames = img if frames == "u8" else None
+        self._stage_views = views(self._stage)
+        self._copy_stream = None
+        self._staged = None       # event: the staged batch has landed
+        self._stage_free = None   # event: the staging buffer may be overwritten
         self.controls = torch.zeros(batch, 3, dtype=torch.float32, device=dev)
         self.pred_speed = torch.zeros(batch, dtype=torch.float32, device=dev)
         self.dcontrols = torch.zeros(batch, 3, dtype=torch.float32, device=dev)
@@ -282,6 +300,36 @@ class FusedTrainer:
         self.d_speed.copy_(speed, non_blocking=True)
         self.d_command.copy_(command, non_blocking=True)
         self.d_targets.copy_(targets, non_blocking=True)
+
+    def prefetch_batch(self, frames_or_image, speed, command, targets):
+        """Start copying the NEXT batch (pinned host tensors, or device tensors) into the staging buffer on the trainer's copy
+        stream; returns at once. The copies overlap whatever the compute stream is doing - typically the current step.
+        `load_prefetched()` then makes it the step's input. The host tensors must stay untouched until then."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        cs = self._copy_stream
+        if self._stage_free is not None:
+            cs.wait_event(self._stage_free)     # the previous staged batch has been moved out
+        else:
+            cs.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._stage_views, (frames_or_image, speed, command, targets)):
+                dst.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._staged = ev
+
+    def load_prefetched(self):
+        """The batch staged by prefetch_batch() becomes the step's input: one D2D copy on the current stream."""
+        if self._staged is None:
+            raise RuntimeError("cilrs_b200.FusedTrainer.load_prefetched: no batch was prefetched")
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self._staged)
+        self._inputs.copy_(self._stage, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._stage_free = ev
+        self._staged = None
 
     def step(self):
         """One optimisation step on the loaded batch. Returns the device tensor of the 6 loss scalars

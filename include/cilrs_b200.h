@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CILRS_ABI_VERSION 3
+#define CILRS_ABI_VERSION 4
 
 int cilrs_abi_version(void);
 /* human-readable text for a status code returned by any entry point (static storage) */
@@ -296,6 +296,19 @@ int cilrs_bn_apply(const void* x, const float* vec, const void* residual, const 
 /* padded_out != 0: out is padded-flat [batch, (H+1)/2+1, (W+1)/2+1, C] (padding pixels untouched); argmax stays dense */
 int cilrs_bn_relu_maxpool(const void* y, const float* vec, void* out, uint8_t* argmax, int batch, int H, int W, int C,
                           int padded_out, void* stream);
+/* The same pool that also keeps `ysel`, the RAW y at the arg-max of every window (laid out like `out`; needs argmax): with it
+ * the backward of torchvision's bn1 -> relu -> maxpool (model/autonomous_drive.py:365-370) takes its BatchNorm sums over the
+ * pool outputs instead of the 4x larger conv1 output (ABI 4). */
+int cilrs_bn_relu_maxpool_sel(const void* y, const float* vec, void* out, uint8_t* argmax, void* ysel, int batch, int H, int W,
+                              int C, int padded_out, void* stream);
+/* Backward of the stem's bn1 -> relu -> maxpool as the training plan runs it: sums over (g, act = pooled activations, ysel)
+ * - which also overwrite g with g * [act > 0], the ReLU mask where it matters - then one pass that routes it through the
+ * arg-max codes and applies the BatchNorm backward.
+ * g / act / ysel: [batch, H/2, W/2, C] (padded != 0: padded-flat [batch, H/2+1, W/2+1, C]); y, dy: dense [batch, H, W, C];
+ * H, W even. workspace / counter as for cilrs_bn_backward. dgamma / dbeta (optional) are accumulated (+=). (ABI 4) */
+int cilrs_stem_bn_backward(void* g, const void* act, const void* ysel, const uint8_t* argmax, const void* y,
+                           const float* vec, const float* gamma, int batch, int H, int W, int C, int padded, int frozen,
+                           void* dy, float* dgamma, float* dbeta, float* workspace, unsigned int* counter, void* stream);
 /* stem variant (argmax != NULL): pad_h > 0 means the pooled gradient g is padded-flat.
  * workspace: cilrs_bn_backward_workspace_floats(C) floats, 8-byte aligned, the first 4*C ZERO on entry (fp64 accumulators,
  * left zero); counter: zeroed uint32 */

@@ -150,6 +150,88 @@ def test_stem_bn_relu_maxpool_forward_backward(B):
     assert _rel(dgamma, gm.grad) <= 1e-2 and _rel(dbeta, bt.grad) <= 1e-2
 
 
+@pytest.mark.parametrize("B,padded", [(1, 0), (5, 1), (24, 1)])
+def test_stem_pool_with_selected_values_and_fused_backward(B, padded):
+    """The training plan's form of bn1 -> relu -> maxpool and its backward (csrc/stem_pool.cuh): the pool also keeps the raw conv1
+    value at every arg-max, the BatchNorm-backward sums run over the pool outputs, one pass routes + applies. Checked against
+    torch autograd and against the two-pass kernels behind cilrs_bn_backward (an independent implementation of the same maths)."""
+    from cilrs_b200 import _lib, ops
+    gen = torch.Generator(device="cuda").manual_seed(16 + B)
+    img = torch.randn(B, 3, 88, 200, generator=gen, device="cuda")
+    w = torch.randn(64, 3, 7, 7, generator=gen, device="cuda") * (2.0 / 147) ** 0.5
+    y, st = ops.stem_fprop(ops.image_to_s2d(img), ops.stem_pack_weight(w), stats=True)
+    C = 64
+    gamma = 1 + 0.3 * torch.randn(C, generator=gen, device="cuda")
+    gamma[::7] *= -1                                    # negative scales: the pool must not assume a monotone map
+    beta = 0.2 * torch.randn(C, generator=gen, device="cuda")
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    vec = _finalize(st, C, B * 4400, gamma, beta, rm, rv, None, True, 0)
+    sp = _lib.stream_ptr()
+    OHp, OWp = (23, 51) if padded else (22, 50)
+    pooled = torch.zeros(B, OHp, OWp, C, dtype=torch.bfloat16, device="cuda")
+    ysel = torch.full((B, OHp, OWp, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    arg = torch.empty(B, 22, 50, C, dtype=torch.uint8, device="cuda")
+    _lib.call("cilrs_bn_relu_maxpool_sel", y, vec, pooled, arg, ysel, B, 44, 100, C, padded, sp)
+    # reference pool: bf16-rounded activations, first maximum in scan order
+    # (the kernel's y * scale + shift is one fused multiply-add: exact in fp64, then rounded to fp32, then to bf16)
+    a = torch.relu((y.double() * vec[0].double() + vec[1].double()).float()).to(torch.bfloat16)
+    win = F.unfold(F.pad(a.float().permute(0, 3, 1, 2), (1, 1, 1, 1), value=float("-inf")), 3, stride=2).view(B, C, 9, 22, 50)
+    ref_val, ref_idx = win.max(dim=2)                   # torch.max returns the first maximal index on CUDA for exact ties? make it explicit:
+    first = (win == ref_val.unsqueeze(2)).float().argmax(dim=2)
+    assert torch.equal(pooled[:, :22, :50].float().permute(0, 3, 1, 2), ref_val)
+    assert torch.equal(arg.permute(0, 3, 1, 2).long(), first)
+    if padded:
+        assert float(pooled[:, 22:].float().abs().max()) == 0.0 and float(pooled[:, :, 50:].float().abs().max()) == 0.0
+    # ysel = the raw conv output at the arg-max position
+    ywin = F.unfold(F.pad(y.float().permute(0, 3, 1, 2), (1, 1, 1, 1)), 3, stride=2).view(B, C, 9, 22, 50)
+    want_sel = ywin.gather(2, first.unsqueeze(2)).squeeze(2)
+    assert torch.equal(ysel[:, :22, :50].float().permute(0, 3, 1, 2), want_sel)
+
+    gp = torch.randn(B, 22, 50, C, generator=gen, device="cuda").to(torch.bfloat16)
+    g_in = torch.full((B, OHp, OWp, C), 7.0, dtype=torch.bfloat16, device="cuda")   # garbage in the gradient's padding: never read
+    g_in[:, :22, :50] = gp
+    nws = _lib.lib().cilrs_bn_backward_workspace_floats
+    nws.restype = ctypes.c_size_t
+    outs = []
+    for fused in (True, False):
+        dy = torch.full_like(y, float("nan"))
+        dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        ws = torch.zeros(nws(C), device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        if fused:
+            _lib.call("cilrs_stem_bn_backward", g_in.clone(), pooled, ysel, arg, y, vec, gamma, B, 44, 100, C, padded, 0, dy, dgamma, dbeta,
+                      ws, cnt, sp)
+        else:
+            _lib.call("cilrs_bn_backward", gp, None, y, vec, gamma, ctypes.c_longlong(y.numel()), C, ctypes.c_double(B * 4400), 0, dy, None,
+                      dgamma, dbeta, ws, cnt, arg, 44, 100, 0, 0, sp)
+        torch.cuda.synchronize()
+        assert int(cnt) == 0 and float(ws[:4 * C].abs().max()) == 0.0     # accumulators left ready for the next launch
+        outs.append((dy, dgamma, dbeta))
+    (dy_f, dg_f, db_f), (dy_t, dg_t, db_t) = outs
+    assert _rel(dg_f, dg_t) <= 1e-5 and _rel(db_f, db_t) <= 1e-5            # same sums, taken over a quarter of the elements
+    assert _rel(dy_f.float(), dy_t.float()) <= 8e-3 and _l2(dy_f.float(), dy_t.float()) <= 3e-3   # bf16 ulps of the outputs
+    x = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    act = torch.relu(F.batch_norm(x, None, None, gm, bt, True, 0.1, 1e-5))
+    a_r = act + (act.to(torch.bfloat16).float() - act).detach()
+    po = F.max_pool2d(a_r, 3, 2, 1)
+    po.backward(gp.float().permute(0, 3, 1, 2))
+    assert _l2(dy_f.float().permute(0, 3, 1, 2), x.grad) <= 1.5e-2
+    assert _rel(dg_f, gm.grad) <= 1e-2 and _rel(db_f, bt.grad) <= 1e-2
+    # frozen statistics: dy = gamma * rstd * dz only
+    dy0 = torch.empty_like(y)
+    ws = torch.zeros(nws(C), device="cuda")
+    _lib.call("cilrs_stem_bn_backward", g_in.clone(), pooled, ysel, arg, y, vec, gamma, B, 44, 100, C, padded, 1, dy0, None, None, ws,
+              torch.zeros(1, dtype=torch.int32, device="cuda"), sp)
+    dz = torch.zeros(B, C, 46, 102, device="cuda")
+    gm_ = (gp.float() * (pooled[:, :22, :50].float() > 0)).permute(0, 3, 1, 2)
+    for code in range(9):
+        r, s_ = divmod(code, 3)
+        dz[:, :, r:r + 44:2, s_:s_ + 100:2] += gm_ * (first == code)
+    want0 = dz[:, :, 1:45, 1:101] * (gamma * vec[3]).view(1, C, 1, 1)
+    assert _rel(dy0.float().permute(0, 3, 1, 2), want0) <= 8e-3
+
+
 @pytest.mark.parametrize("shape", [(6, 11, 25, 128), (3, 22, 50, 64), (9, 3, 7, 512)])
 def test_padded_flat_layout_bn_apply_and_backward_equal_the_dense_kernels(shape):
     """the same kernels on the padded-flat layout [B,H+1,W+1,C]: identical results on the real pixels, exact zeros on the

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 35
     for n in names:
         assert hasattr(lib, n), "missing export: " + n
-    assert lib.cilrs_abi_version() == 3
+    assert lib.cilrs_abi_version() == 4
     assert lib.cilrs_status_string(2) == b"unsupported shape or configuration"
 
 

@@ -268,6 +268,51 @@ def test_graph_path_follows_the_lr_schedule():
     assert not torch.equal(m.flat_parameters(), snaps[3])
 
 
+def test_prefetched_batches_equal_directly_loaded_ones():
+    """prefetch_batch / load_prefetched (the next batch's H2D copies on a copy stream under the current step, then one D2D copy)
+    must feed the step exactly what load_batch does: same losses and parameters after four steps on four different host
+    batches, graph and eager, uint8 frames and normalised images."""
+    from cilrs_b200.train import FusedTrainer
+    O = _O()
+    sd = O.synthetic_state_dict(0)
+    g = torch.Generator().manual_seed(21)
+    for frames, use_graph in (("u8", True), ("f32", False)):
+        host = []
+        for _ in range(4):
+            img = (torch.randint(0, 256, (8, 88, 200, 3), generator=g, dtype=torch.uint8) if frames == "u8"
+                   else torch.randn(8, 3, 88, 200, generator=g))
+            host.append(tuple(t.pin_memory() for t in (img, torch.rand(8, generator=g), torch.randint(0, 4, (8,), generator=g),
+                                                       torch.rand(8, 3, generator=g))))
+        runs = []
+        for prefetch in (False, True):
+            m = _model(sd, train=True)
+            # eps = 1e-3: with Adam's default 1e-8 a gradient entry at rounding-noise level still moves its weight by +-lr, so
+            # the run-to-run noise of the split-K weight gradients (fp32 rounding) would grow to 1e-2 of the loss in four steps
+            tr = FusedTrainer(m, 8, lr=1e-3, weight_decay=1e-4, eps=1e-3, use_graph=use_graph, frames=frames)
+            losses = []
+            if prefetch:
+                tr.prefetch_batch(*host[0])
+            for i in range(4):
+                if prefetch:
+                    tr.load_prefetched()
+                    if i + 1 < 4:
+                        tr.prefetch_batch(*host[i + 1])
+                else:
+                    tr.load_batch(*host[i])
+                staged = (tr.d_frames if frames == "u8" else tr.d_image, tr.d_speed, tr.d_command, tr.d_targets)
+                assert all(torch.equal(d.cpu(), h) for d, h in zip(staged, host[i])), (frames, prefetch, i)
+                tr.step()
+                losses.append(tr.read_loss()["total"])
+            torch.cuda.synchronize()
+            runs.append((losses, m.flat_parameters().clone()))
+        # (the split-K weight gradients add in L2 in arrival order: two runs agree to fp32 rounding, not bit for bit)
+        assert max(abs(a - b) / abs(b) for a, b in zip(*[r[0] for r in runs])) < 1e-4, (frames, runs[0][0], runs[1][0])
+        assert float((runs[0][1] - runs[1][1]).abs().max()) < 2e-5
+        assert len(set(round(v, 6) for v in runs[0][0])) == 4          # four different batches did go through
+    with pytest.raises(RuntimeError):
+        tr.load_prefetched()                      # nothing staged
+
+
 def test_graph_path_runs_with_dropout_and_draws_new_masks():
     """dropout = 0.5 (notebook.ipynb:480) under use_graph: the mask counter is the device step counter, so every replay draws a
     different mask; keep-rate and 1/(1-p) scaling are checked on the saved activations."""
