@@ -426,27 +426,48 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const float* __restrict__
                                                        int block_base) {
   __shared__ float tile[32][32 * 9 + 1];
   const int bidx = (int)blockIdx.x + block_base;   // (a launch may cover a sub-range of the job table: one backward part)
+  // the job of this block: the last one whose first block is <= bidx (first_block increases). One round trip for up to 64 jobs
+  // (every warp looks for itself) instead of a chain of dependent loads
   int j = 0;
-  while (j + 1 < njobs && bidx >= jobs[j + 1].first_block) ++j;
+  if (njobs <= 64) {
+    const int l = threadIdx.x & 31;
+    const int fb0 = l < njobs ? jobs[l].first_block : 0x7FFFFFFF, fb1 = l + 32 < njobs ? jobs[l + 32].first_block : 0x7FFFFFFF;
+    j = __popc(__ballot_sync(0xFFFFFFFFu, fb0 <= bidx)) + __popc(__ballot_sync(0xFFFFFFFFu, fb1 <= bidx)) - 1;
+    if (j < 0) j = 0;
+  } else {
+    while (j + 1 < njobs && bidx >= jobs[j + 1].first_block) ++j;
+  }
   const PackJob jb = jobs[j];
   const int t_idx = bidx - jb.first_block;
   const int ci_tiles = jb.cin >> 5;
   const int co0 = (t_idx / ci_tiles) * 32, ci0 = (t_idx % ci_tiles) * 32;
   const int kk = jb.kk, run = 32 * kk;
-  const float* w = params + jb.w_off;
-  for (int idx = threadIdx.x; idx < 32 * run; idx += 256) {
-    const int co = idx / run, r = idx - co * run;
-    tile[co][r] = w[((long long)(co0 + co) * jb.cin + ci0) * kk + r];
+  // (ncu, round 2: the first version spent 52 instructions per weight - a division per element in the load loop, 64-bit index
+  //  arithmetic in the store loop - and ran at 50 % issue utilisation, 60 us for 85 MB in + 85 MB out. Loops without divisions:)
+  // load: warp w copies the rows co = w, w + 8, ... (runs of 32 * kk consecutive floats, coalesced)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* w = params + jb.w_off + ((size_t)co0 * jb.cin + ci0) * kk;
+  const unsigned int row_pitch = (unsigned int)jb.cin * kk;
+  for (int co = warp; co < 32; co += 8) {
+    const float* src = w + (size_t)co * row_pitch;
+    for (int r = lane; r < run; r += 32) tile[co][r] = src[r];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 16 * run; idx += 256) {
-    const int a = (idx & 15) * 2, b = (idx >> 4) & 31, t = idx >> 9;  // t < kk; two consecutive elements per 4-byte store
-    // fprop layout [t][co][ci]: a = ci (fastest), b = co
-    *reinterpret_cast<uint32_t*>(jb.wf + ((long long)t * jb.cout + co0 + b) * jb.cin + ci0 + a) =
-        pack_bf16x2(tile[b][a * kk + t], tile[b][(a + 1) * kk + t]);
-    // dgrad layout [t][ci][co]: a = co (fastest), b = ci
-    *reinterpret_cast<uint32_t*>(jb.wd + ((long long)t * jb.cin + ci0 + b) * jb.cout + co0 + a) =
-        pack_bf16x2(tile[a][b * kk + t], tile[a + 1][b * kk + t]);
+  // store: thread (a2 = idx & 15, b = idx >> 4 & 31) writes the element pair (2 a2, 2 a2 + 1) of row b for every tap
+  const int a = (threadIdx.x & 15) * 2, b0 = threadIdx.x >> 4;   // b0 in 0..15; rows b0 and b0 + 16
+  const unsigned int f_pitch = (unsigned int)jb.cout * jb.cin;    // elements per tap in either layout
+#pragma unroll 1
+  for (int t = 0; t < kk; ++t) {
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      const int b = b0 + 16 * hb;
+      // fprop layout [t][co][ci]: a = ci (fastest), b = co
+      *reinterpret_cast<uint32_t*>(jb.wf + (size_t)t * f_pitch + (unsigned int)(co0 + b) * jb.cin + ci0 + a) =
+          pack_bf16x2(tile[b][a * kk + t], tile[b][(a + 1) * kk + t]);
+      // dgrad layout [t][ci][co]: a = co (fastest), b = ci
+      *reinterpret_cast<uint32_t*>(jb.wd + (size_t)t * f_pitch + (unsigned int)(ci0 + b) * jb.cout + co0 + a) =
+          pack_bf16x2(tile[a][b * kk + t], tile[a + 1][b * kk + t]);
+    }
   }
 }
 

@@ -1089,12 +1089,15 @@ int cilrs_model_refresh_async(cilrs_model* h, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (!m.side || m.prof.on) return refresh(m, 1, s);
   CK(pack_join(m, s));
+  // the stem's 64-CTA repack goes first: queued behind the trunk's 2456 CTAs it waited 40 us for a free slot (CUPTI timeline),
+  // and K0 + the whole forward behind it
+  CK(cilrs_stem_pack_weight(m.params + m.slots[m.stem.w].off, m.stem.wf, s));
   CK(cuda_status(cudaEventRecord(m.ev_pack_fork, s)));
   CK(cuda_status(cudaStreamWaitEvent(m.side, m.ev_pack_fork, 0)));
   CK(launch_pack_all(m.params, m.pack_jobs, m.pack_njobs, m.pack_blocks, m.side));
   CK(cuda_status(cudaEventRecord(m.ev_pack, m.side)));
   m.pack_pending = true;
-  return cilrs_stem_pack_weight(m.params + m.slots[m.stem.w].off, m.stem.wf, s);
+  return OK;
 }
 
 // repack the bf16 operands of the convolutions whose gradients backward part `part` completes (0 = layer4, 1 = layer3,
