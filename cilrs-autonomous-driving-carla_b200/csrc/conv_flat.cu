@@ -333,6 +333,26 @@ int launch_flat_conv(const FlatConvParams* p, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // wgrad
 // ------------------------------------------------------------------------------------------------
+static int g_wgrad_cluster = -1;   // -1: not decided yet (environment), 0 / 1
+// clusters of three wgrad_flat3_kernel CTAs that can be resident at once (0: unavailable)
+static int max_clusters3() {
+  static int n = -1;
+  if (n >= 0) return n;
+  n = 0;
+  if (cudaFuncSetAttribute(wgrad_flat3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL) != cudaSuccess) { cudaGetLastError(); return n; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(3 * sm_count()); cfg.blockDim = dim3(WF_THREADS); cfg.dynamicSmemBytes = CG_SMEM_TOTAL;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 3; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&clusters, wgrad_flat3_kernel, &cfg) == cudaSuccess && clusters > 0) n = clusters;
+  else cudaGetLastError();
+  if (getenv("CILRS_FLAT_DEBUG")) fprintf(stderr, "[cilrs wgrad] resident clusters of 3: %d\n", n);
+  return n;
+}
+
 int build_wgrad_flat(WgradFlatParams* p, int batch, const PadGeom& g, int cin, int cout, const void* dy, const void* x, float* scratch) {
   if (batch < 1 || g.H < 1 || g.W < 1 || g.Hp < g.H || g.Wp <= g.W || g.Wp < 3) return ERR_INVALID;
   if (cin % 64 || cout % 64 || cin < 64 || cout < 64) return ERR_UNSUPPORTED;
@@ -360,7 +380,34 @@ int build_wgrad_flat(WgradFlatParams* p, int batch, const PadGeom& g, int cin, i
   p->scratch = scratch;
   int e = encode_2d_map(&p->tmDY, dy, cout, p->total_rows, 64, 128);
   if (e) return e;
-  return encode_2d_map(&p->tmX, x, cin, p->total_rows, 64, p->x_box_rows);
+  e = encode_2d_map(&p->tmX, x, cin, p->total_rows, 64, p->x_box_rows);
+  if (e) return e;
+  // cluster form (wgrad_flat3_kernel): one union slab of 130 + 2 Wp rows serves the three filter rows. OFF by default
+  // (CILRS_WGRAD_CLUSTER=1 / cilrs_set_wgrad_cluster): measured on B200 at batch 128 it is slower - 0.99 ms against 0.93 ms for
+  // the 40 weight-gradient launches of a step, 2.775 against 2.709 ms per step. The kernel was not bound by the crossbar after
+  // all, three CTAs in lock-step lose more than the 2.5x smaller L2 -> SM traffic wins, and only 45 clusters of three SMs are
+  // resident (135 of 148 SMs). Kept as a tested option and as evidence.
+  p->cluster3 = 0;
+  p->wp = g.Wp;
+  p->xu_rows = round_up(130 + 2 * g.Wp, 8);
+  if (g_wgrad_cluster < 0) { const char* env = getenv("CILRS_WGRAD_CLUSTER"); g_wgrad_cluster = (env && env[0] == '1') ? 1 : 0; }
+  const int want = g_wgrad_cluster;
+  const int maxc = want ? max_clusters3() : 0;
+  if (want && p->xu_rows <= 256 && maxc >= p->co_blocks * p->ci_chunks) {
+    // one wave: the K split is what fits the resident clusters (a cluster takes three SMs of ONE GPC, so fewer than
+    // sm_count / 3 fit: with the plain split a few clusters ran as a second wave and the launch took 8 us longer)
+    int z3 = maxc / (p->co_blocks * p->ci_chunks);
+    if (z3 > p->k_tiles) z3 = p->k_tiles;
+    const long long stage3 = 2LL * WG_SLAB + (long long)p->xu_rows * 128;
+    int st3 = (int)((CG_SMEM_TOTAL - 1024 - 256) / stage3);
+    if (st3 > WF_MAX_STAGES) st3 = WF_MAX_STAGES;
+    if (st3 >= 2 && st3 * stage3 >= 128LL * WF_STAGE_PITCH && encode_2d_map(&p->tmXU, x, cin, p->total_rows, 64, p->xu_rows) == OK) {
+      p->stages3 = st3;
+      p->cluster3 = 1;
+      if (z3 < p->split_z) p->split_z = z3;
+    }
+  }
+  return OK;
 }
 
 int launch_wgrad_flat(const WgradFlatParams* p, cudaStream_t s) {
@@ -374,6 +421,16 @@ int launch_wgrad_flat(const WgradFlatParams* p, cudaStream_t s) {
   if ((long long)p->co_blocks * p->ci_chunks * p->tap_groups * 128 * 192 * 4 > WF_SCRATCH_BYTES || !p->scratch) return ERR_WORKSPACE;
   if ((long long)p->num_stages * (2LL * WG_SLAB + (long long)p->x_boxes * p->x_box_rows * 128) < 128LL * WF_STAGE_PITCH) return ERR_UNSUPPORTED;
   ++g_cilrs_launches;
+  if (p->cluster3) {
+    static bool attr3_set = false;
+    if (!attr3_set) {
+      cudaError_t e = cudaFuncSetAttribute(wgrad_flat3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL);
+      if (e != cudaSuccess) return cuda_status(e);
+      attr3_set = true;
+    }
+    // (the same grid: the three filter rows of a work item are the three consecutive CTAs of a cluster)
+    return cuda_status(launch_pdl_cluster(wgrad_flat3_kernel, dim3(grid), dim3(WF_THREADS), CG_SMEM_TOTAL, s, 3, *p));
+  }
   return cuda_status(launch_pdl(wgrad_flat_kernel, dim3(grid), dim3(WF_THREADS), CG_SMEM_TOTAL, s, *p));
 }
 
@@ -416,6 +473,14 @@ long long cilrs_flat_rows(int batch, int H, int W) { return (long long)batch * (
 int cilrs_set_bn_fusion(int enable) {
   const int prev = g_fuse_enabled < 0 ? fuse_default() : g_fuse_enabled;
   g_fuse_enabled = enable < 0 ? 0 : (enable > 4 ? 1 : enable);
+  return prev;
+}
+
+// The weight-gradient kernel as clusters of three CTAs that multicast their operand loads (wgrad_flat3_kernel) on / off for plans
+// built AFTER the call; returns the previous setting. Measurement / test aid: both kernels compute the same sums.
+int cilrs_set_wgrad_cluster(int enable) {
+  const int prev = g_wgrad_cluster < 0 ? 0 : g_wgrad_cluster;
+  g_wgrad_cluster = enable ? 1 : 0;
   return prev;
 }
 

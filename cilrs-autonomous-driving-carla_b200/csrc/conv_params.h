@@ -194,6 +194,12 @@ struct WgradFlatParams {
   int split_z, num_stages;
   int cout, cin;
   float* scratch;                      // split-K partial tiles [tile][z][128][192] fp32 (wgrad_reduce_kernel folds them)
+  // cluster form (wgrad_flat3_kernel): the three filter rows of a (co block, ci chunk, K slice) are one cluster of three CTAs
+  // that multicast their loads to each other
+  int cluster3;                        // 1: launch wgrad_flat3_kernel
+  CUtensorMap tmXU;                    // 2-D (cin, flat pixels), box (64, xu_rows): the union of the three filter rows' slabs
+  int xu_rows, wp;                     // 130 + 2 * Wp rounded up to 8; padded row pitch Wp
+  int stages3;
 };
 
 struct WgradReduceJob {

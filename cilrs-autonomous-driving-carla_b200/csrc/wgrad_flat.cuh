@@ -19,6 +19,7 @@
 //   warp 0 : TMA producer      warp 1 : MMA issuer (whole warp, one elected lane issues)      warps 2..5 : epilogue
 #pragma once
 #include "common.cuh"
+#include "pair.cuh"
 #include "conv_params.h"
 
 namespace cilrs {
@@ -157,6 +158,169 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
     __syncwarp();
     tmem_dealloc(tmem_base, 256);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same contraction with the three filter rows of a (co block, ci chunk, K slice) as ONE CLUSTER of three CTAs.
+// wgrad_flat_kernel is bound by L2 -> SM traffic, not by the tensor core: every dY tile is fetched by 3 x ci_chunks CTAs and
+// every X slab by co_blocks of them (layer3: 115 MB through the crossbar for 12.8 MB of operands, 64 B per clock and SM
+// asked of the L2 by 144 SMs at once). The three CTAs of a cluster need the SAME dY tile and X slabs that are the same pixels
+// shifted by one padded row each (130 rows at -Wp, 0, +Wp): here they load the dY tile and ONE union slab of 130 + 2 Wp rows
+// once per cluster - CTA 0 issues dY half 0, CTA 1 dY half 1, CTA 2 the X slab - with cp.async.bulk.tensor ...
+// .multicast::cluster into all three shared memories (same offsets; every CTA's own `full` barrier counts all bytes), and
+// CTA r's B descriptor starts r * Wp rows into the union slab. A stage may be refilled when all three CTAs are done with
+// it: each MMA warp's tcgen05.commit arrives on the `empty` barrier of all three (multicast, count 3).
+// L2 -> SM bytes per K tile and cluster: 32 KB + (130 + 2 Wp) * 128 B instead of 3 * 49 KB.
+// ------------------------------------------------------------------------------------------------------------------
+CILRS_DEVINL void tma_load_2d_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+CILRS_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
+__global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat3_kernel(const __grid_constant__ WgradFlatParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();   // = filter row: dh = rank - 1
+
+  const int x_bytes = p.xu_rows * 128;
+  const int stage_bytes = 2 * WG_SLAB + x_bytes;
+  uint64_t* bars = (uint64_t*)(smem + (size_t)p.stages3 * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + WF_MAX_STAGES;
+  uint64_t* done_bar = bars + 2 * WF_MAX_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
+
+  pdl_launch_dependents();
+  if (p.m_halves == 1) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int st = 0; st < p.stages3; ++st) {
+      uint4* q = (uint4*)(smem + (size_t)st * stage_bytes + WG_SLAB);
+      for (int i = threadIdx.x; i < WG_SLAB / 16; i += WF_THREADS) q[i] = z;
+    }
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmDY);
+    tma_prefetch_desc(&p.tmXU);
+    for (int i = 0; i < p.stages3; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 3);   // the MMA warps of the three CTAs
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // the peers' barriers are initialised (and their zero slabs written) before anything lands in them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  int wi = blockIdx.x / 3;
+  const int z = wi % p.split_z; wi /= p.split_z;
+  const int cic = wi % p.ci_chunks; wi /= p.ci_chunks;
+  const int cob = wi;
+  const int tg = (int)rank;
+  const int per = (p.k_tiles + p.split_z - 1) / p.split_z;
+  const int kt_begin = z * per;
+  const int kt_end = min(p.k_tiles, kt_begin + per);
+  const uint32_t tx_bytes = (uint32_t)(p.m_halves * WG_SLAB + x_bytes);   // every CTA receives every item
+  // who issues what: dY half 0 -> CTA 0, dY half 1 (128 output channels) -> CTA 1, the X slab -> the next CTA
+  const int x_issuer = p.m_halves;   // 2 (cout >= 128) or 1
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = kt_begin; kt < kt_end; ++kt) {
+        const int k0 = kt * 128;
+        mbar_wait(&empty_bar[stage], phase ^ 1);   // all three CTAs have consumed this stage
+        uint8_t* s = smem + (size_t)stage * stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        if ((int)rank < p.m_halves) tma_load_2d_mc(&p.tmDY, &full_bar[stage], s + rank * WG_SLAB, cob * 128 + (int)rank * 64, k0, 7);
+        if ((int)rank == x_issuer) tma_load_2d_mc(&p.tmXU, &full_bar[stage], s + 2 * WG_SLAB, cic * 64, k0 - p.wp - 1, 7);
+        if (++stage == p.stages3) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (tmem_base != 0) __trap();
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(128, 192, 1, 1);
+    const uint64_t descA0 = umma_desc_sw128(smem_u32(smem), WG_SLAB, 1024);
+    // filter row `rank`: its dw = -1 tap starts rank * Wp pixel rows into the union slab; the three taps are one pixel row apart
+    const uint64_t descB0 = umma_desc_sw128(smem_u32(smem) + 2 * WG_SLAB + rank * (uint32_t)p.wp * 128u, 128, 1024);
+    const uint32_t stage_units = (uint32_t)(stage_bytes >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t first = 1;
+    for (int kt = kt_begin; kt < kt_end; ++kt) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint64_t da = descA0 + (uint64_t)((uint32_t)stage * stage_units);
+      const uint64_t db = descB0 + (uint64_t)((uint32_t)stage * stage_units);
+      if (leader) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16(0u, da + kk * 128, db + kk * 128, idesc, (first && kk == 0) ? 0u : 1u);
+        umma_commit_mc(&empty_bar[stage], 7);
+      }
+      __syncwarp();
+      first = 0;
+      if (++stage == p.stages3) { stage = 0; phase ^= 1; }
+    }
+    if (leader) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tile = (cob * p.ci_chunks + cic) * 3 + tg;
+    float* dst = p.scratch + ((size_t)tile * 128 + row) * 192;
+    if (kt_end > kt_begin) {
+      mbar_wait(done_bar, 0);   // every MMA of THIS CTA has completed
+      tc_fence_after();
+    }
+    // The staging below overwrites stage buffers the peers may still be multicasting into (they can be one K tile behind):
+    // wait until all three CTAs are past their main loops. (All warps of the CTA join the cluster barrier; see below.)
+    cluster_sync_all();
+    if (kt_end > kt_begin) {
+      uint8_t* srow = smem + (size_t)row * WF_STAGE_PITCH;
+      for (int c0 = 0; c0 < 192; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *(uint4*)(srow + (c0 + 4 * j) * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      fence_proxy_async();
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                   ::"l"(dst), "r"(smem_u32(srow)), "r"(768) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+  if (warp < 2) {   // the producer / MMA warps' half of the barrier the epilogue warps wait on above
+    __syncwarp();
+    cluster_sync_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+  cluster_sync_all();   // nobody leaves while a peer's commit may still be arriving on its barriers
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -142,6 +142,10 @@ long long cilrs_flat_rows(int batch, int H, int W);
  * off for plans built after the call; returns the previous setting. Test / measurement aid - both settings compute the same
  * network (replaces the ATen BatchNorm launches under torchvision/models/resnet.py:89-105 either way). */
 int cilrs_set_bn_fusion(int enable);
+/* The flat weight-gradient kernel as clusters of three CTAs (one per filter row) that multicast their TMA loads to each other:
+ * measurement / test aid, off by default (measured slower on B200); applies to plans built after the call; returns the previous
+ * setting (ABI 4). */
+int cilrs_set_wgrad_cluster(int enable);
 size_t cilrs_conv_flat_workspace_floats(int out_c);
 int cilrs_conv_flat(const cilrs_flat_conv_args* a, void* stream);
 /* dw_oihw (fp32 [out_c,in_c,3,3]) += dy^T * shifted(x), both padded-flat. Two launches: the split-K slices add their tiles into

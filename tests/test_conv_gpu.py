@@ -250,13 +250,20 @@ def test_flat_dgrad(case):
 def test_flat_wgrad(case):
     ops = _ops()
     _ref_setup()
+    from cilrs_b200 import _lib
     b, h, w, ci, co = case
     x = _mk((b, ci, h, w), 25).to(torch.bfloat16)
     dy = (_mk((b, co, h, w), 26) * 0.1).to(torch.bfloat16)
-    dw = ops.wgrad_flat(ops.to_padded(_nhwc_bf16(dy.float())), ops.to_padded(_nhwc_bf16(x.float())))
-    torch.cuda.synchronize()
     ref = torch.nn.grad.conv2d_weight(x.float(), (co, ci, 3, 3), dy.float(), padding=1)
-    _report(f"flat_wgrad{case}", dw, ref, 2e-3)
+    # the default kernel (one CTA per filter row) and the opt-in cluster-of-three kernel with multicast loads
+    for cluster in (0, 1):
+        prev = _lib.lib().cilrs_set_wgrad_cluster(cluster)
+        try:
+            dw = ops.wgrad_flat(ops.to_padded(_nhwc_bf16(dy.float())), ops.to_padded(_nhwc_bf16(x.float())))
+            torch.cuda.synchronize()
+        finally:
+            _lib.lib().cilrs_set_wgrad_cluster(prev)
+        _report(f"flat_wgrad{case} cluster={cluster}", dw, ref, 2e-3)
 
 
 def test_flat_inference_epilogue():
