@@ -367,7 +367,22 @@ int build_wgrad_flat(WgradFlatParams* p, int batch, const PadGeom& g, int cin, i
     for (int s = 0; s < 3; ++s) p->tap_shift[r * 3 + s] = (r - 1) * g.Wp + (s - 1);
   split_boxes(128 + 2, &p->x_box_rows, &p->x_boxes);
   const int base = p->co_blocks * p->ci_chunks * p->tap_groups;
-  int z = sm_count() / base;
+  // CTAs of the launch = base * z, the depth of the K split. One CTA per SM is the fastest launch in isolation, but in the step
+  // the weight gradients of layers 1-2 share the GPU with the dgrad / BatchNorm chain, which is the critical path there: with
+  // at most HALF the SMs (74) the step is 40 us shorter (2.71 -> 2.67 ms at batch 128; 66..74 CTAs measure the same, 78 and
+  // more lose it again; layers 3-4 do not care). Measurement aid: CILRS_WGRAD_CTAS="l1,l2,l3,l4" overrides the targets.
+  static int targets[4] = {-1, -1, -1, -1};   // by input channels 64 / 128 / 256 / 512
+  if (targets[0] < 0) {
+    int t[4] = {0, 0, 0, 0};
+    const char* env = getenv("CILRS_WGRAD_CTAS");
+    const int nf = env ? sscanf(env, "%d,%d,%d,%d", &t[0], &t[1], &t[2], &t[3]) : 0;
+    for (int i = 0; i < 4; ++i) {
+      const int v = i < nf ? t[i] : (nf == 1 ? t[0] : 0);
+      targets[i] = v >= 1 ? v : (i < 2 ? sm_count() / 2 : sm_count());
+    }
+  }
+  const int target = targets[cin <= 64 ? 0 : (cin <= 128 ? 1 : (cin <= 256 ? 2 : 3))];
+  int z = target / base;
   if (z < 1) z = 1;
   if (z > p->k_tiles) z = p->k_tiles;
   p->split_z = z;

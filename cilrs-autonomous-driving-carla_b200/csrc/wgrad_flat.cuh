@@ -148,7 +148,9 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat_kernel(const __grid_
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                    ::"l"(dst), "r"(smem_u32(srow)), "r"(768) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      // (the staging rows have been read; the additions themselves complete before the grid does, which is what orders them
+      //  before the fold launch)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     // (a K slice past the end - split_z does not divide the tile count - has nothing to add)
   }
@@ -307,7 +309,9 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad_flat3_kernel(const __grid
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                    ::"l"(dst), "r"(smem_u32(srow)), "r"(768) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      // (the staging rows have been read; the additions themselves complete before the grid does, which is what orders them
+      //  before the fold launch)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
   }
   if (warp < 2) {   // the producer / MMA warps' half of the barrier the epilogue warps wait on above

@@ -1,0 +1,10 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+for c in 74,74,148,148 66,66,148,148 72,72,148,148 78,78,148,148 84,84,148,148 74,66,148,148 66,74,148,148 74,74,148,148; do
+CILRS_WGRAD_CTAS=$c timeout 600 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r2x_bench.json 2> gpurun_out/r2x_bench.err; echo -n "ctas=$c exit $? "
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/r2x_bench.json').read().strip().splitlines()[-1])
+print('ms/step %.4f'%d['ms_per_step'], 'fps %.0f'%d['value'], 'e2e %.0f'%d['e2e']['value'], 'wgrad eager ms', d['roofline']['breakdown_ms']['conv_wgrad']['ms'])
+PY
+done
