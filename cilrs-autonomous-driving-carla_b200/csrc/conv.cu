@@ -3,6 +3,7 @@
 #include "wgrad_gemm.cuh"
 #include "conv_params.h"
 #include "conv_host.h"
+#include <stdlib.h>
 #include <cudaTypedefs.h>
 #include <string.h>
 
@@ -307,7 +308,12 @@ int build_wgrad(WgradParams* p, const cilrs_conv_desc* d, const void* dy, const 
       p->tap_id[t] = (int16_t)t;
     }
   const int base = p->co_blocks * p->ci_chunks * p->tap_groups;
-  int z = num_sms() / base;
+  // CTAs of the launch = base * z. Three quarters of the SMs: these launches (stride-2 and 1x1 convolutions at the stage
+  // transitions) run beside the BatchNorm-backward reduce / apply of the transition, which needs SMs of its own (measured at
+  // batch 128: 2.669 ms per step with 148, 2.653 with 111, 2.660 with 74 or 48). CILRS_WGRAD_GEMM_CTAS overrides the target.
+  static int target = -1;
+  if (target < 0) { const char* env = getenv("CILRS_WGRAD_GEMM_CTAS"); target = env ? atoi(env) : 0; if (target < 1) target = num_sms() * 3 / 4; }
+  int z = target / base;
   if (z < 1) z = 1;
   if (z > b.m_tiles()) z = b.m_tiles();
   p->split_z = z;
