@@ -912,12 +912,16 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   }
   if (dbg)
     for (int pt = 0; pt < 4; ++pt) PROF(m, PC_WGRAD, ws, CK(launch_wgrad_reduce(&m.red_jobs[pt], m.grads, ws)));
-  if (use_side && !async_part) {
-    // join: everything after this call on the caller's stream (allreduce of the part, Adam) sees the finished gradients
-    CK(cuda_status(cudaEventRecord(m.ev_join, m.side)));
-    CK(cuda_status(cudaStreamWaitEvent(s, m.ev_join, 0)));
-    for (int i = 0; i < 6; ++i) m.pending[i] = false;
-  }
+  static const bool join_early = getenv("CILRS_JOIN_EARLY") != nullptr;   // measurement aid: the round-1 order (join before the stem)
+  auto join_side = [&]() -> int {
+    if (use_side && !async_part) {
+      CK(cuda_status(cudaEventRecord(m.ev_join, m.side)));
+      CK(cuda_status(cudaStreamWaitEvent(s, m.ev_join, 0)));
+      for (int i = 0; i < 6; ++i) m.pending[i] = false;
+    }
+    return OK;
+  };
+  if (join_early) CK(join_side());
   // ---- stem: max-pool backward + ReLU + BN backward, then wgrad ----
   if (dbg ? dbg_lo < 0 : (part < 0 || part == 4)) {
     const BnRef& bn = m.stem.bn;
@@ -939,6 +943,10 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     PROF(m, PC_BN_BWD, s, { ++g_cilrs_launches; CK(cuda_status(launch_pdl(stem_bwd_apply_kernel, dim3(ew_grid(nblk, 64, 2, 2)), dim3(EW_THREADS), 0, s, ap))); });
     PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, m.stem_wgrad, m.stem.w, s)));
   }
+  // join: everything after this call on the caller's stream (allreduce of the part, Adam) sees the finished gradients.
+  // AFTER the stem's kernels, which read nothing the gradient stream writes: joined before them, the stem's reduce waited
+  // 25 us for layer1's last weight gradient and its fold (CUPTI timeline).
+  if (!join_early) CK(join_side());
   if (use_side && async_part) {
     CK(cuda_status(cudaEventRecord(m.ev_part, s)));
     CK(cuda_status(cudaStreamWaitEvent(m.side, m.ev_part, 0)));
