@@ -414,7 +414,8 @@ def main():
                            use_graph=(not args.no_graph),
                            overlap_allreduce=os.environ.get("CILRS_BENCH_ALLREDUCE", "two"),       # measurement aids
                            grad_comm=os.environ.get("CILRS_BENCH_GRAD_COMM", "bf16"),
-                           async_parts=os.environ.get("CILRS_BENCH_ASYNC_PARTS", "0") == "1")
+                           async_parts=os.environ.get("CILRS_BENCH_ASYNC_PARTS", "0") == "1",
+                           adam_beside_stem=os.environ.get("CILRS_BENCH_ADAM_BESIDE_STEM", "0") == "1")
 
     # synthetic batches, per-rank seed (rank 0's are the ones the CPU arm sees)
     POOL = 4

@@ -768,7 +768,7 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   if (B != m.planB || mode != m.planMode) return ERR_INVALID;  // must follow a forward with keep_for_backward
   if (!m.grads) return ERR_INVALID;
   const int frozen = mode == MODE_FROZEN;
-  if (part < -1 || part > 4) return ERR_INVALID;
+  if (part < -1 || part > 6) return ERR_INVALID;   // 5 / 6: the two halves of part 4 (stem: BatchNorm backward | weight gradient)
   CK(pack_join(m, s));
   if (dbg) {
     CK(cuda_status(cudaMemsetAsync(m.acc_bwd, 0, (size_t)m.acc_bwd_bytes, s)));
@@ -923,7 +923,9 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
   };
   if (join_early) CK(join_side());
   // ---- stem: max-pool backward + ReLU + BN backward, then wgrad ----
-  if (dbg ? dbg_lo < 0 : (part < 0 || part == 4)) {
+  const bool stem_ew = dbg ? dbg_lo < 0 : (part < 0 || part == 4 || part == 5);
+  const bool stem_wg = dbg ? dbg_lo < 0 : (part < 0 || part == 4 || part == 6);
+  if (stem_ew) {
     const BnRef& bn = m.stem.bn;
     // sums over the POOL outputs (every pooled gradient lands on exactly one conv1 pixel, whose raw value the forward kept in
     // pool_ysel): the ordinary reduce kernel on (g, pool_out as the ReLU mask, ysel) - 57 MB instead of a pass over conv1's output
@@ -941,8 +943,8 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     ap.frozen = frozen; ap.B = B; ap.H = 44; ap.W = 100; ap.OH = 22; ap.OW = 50; ap.OHp = kGeom0.Hp; ap.OWp = kGeom0.Wp; ap.C = 64; ap.dy = m.dy_stem;
     const long long nblk = (long long)B * 22 * 50 * 8;
     PROF(m, PC_BN_BWD, s, { ++g_cilrs_launches; CK(cuda_status(launch_pdl(stem_bwd_apply_kernel, dim3(ew_grid(nblk, 64, 2, 2)), dim3(EW_THREADS), 0, s, ap))); });
-    PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, m.stem_wgrad, m.stem.w, s)));
   }
+  if (stem_wg) PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, m.stem_wgrad, m.stem.w, s)));
   // join: everything after this call on the caller's stream (allreduce of the part, Adam) sees the finished gradients.
   // AFTER the stem's kernels, which read nothing the gradient stream writes: joined before them, the stem's reduce waited
   // 25 us for layer1's last weight gradient and its fold (CUPTI timeline).

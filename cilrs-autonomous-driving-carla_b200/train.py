@@ -229,10 +229,13 @@ class FusedTrainer:
                     self.opt._sync_hyper(1.0)
                     for part in range(4):
                         _lib.call("cilrs_model_backward_part_async", m._handle, b, MODE_TRAIN, part, *self._backward_args())
+                    # part 5 = the stem's max-pool / BatchNorm backward (HBM-bound, main stream); the gradient stream is made to wait
+                    # for it, so Adam starts exactly when conv1's weight gradient (part 6: L2-bound, 5 % DRAM) does
+                    _lib.call("cilrs_model_backward_part_async", m._handle, b, MODE_TRAIN, 5, *self._backward_args())
                     cut = self.part_ranges[3][0]      # the stem's parameters come first in the arena: [0, cut)
                     with torch.cuda.stream(gstream):  # ordered behind every gradient of layers 1-4 and the heads
                         self.opt.step(grads_in_arena=True, zero_grad=True, arena_range=(cut, g.numel()))
-                    _lib.call("cilrs_model_backward_part_async", m._handle, b, MODE_TRAIN, 4, *self._backward_args())
+                    _lib.call("cilrs_model_backward_part_async", m._handle, b, MODE_TRAIN, 6, *self._backward_args())
                     _lib.call("cilrs_model_backward_join", m._handle, sp)
                     self.opt.step(grads_in_arena=True, zero_grad=True, arena_range=(0, cut), advance=False)
                     self._after_step()

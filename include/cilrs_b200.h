@@ -216,7 +216,9 @@ int cilrs_model_forward_loss(cilrs_model* m, int batch, int mode, const float* i
                              float* out6, float* dcontrols, float* dspeed, void* stream);
 /* gradients of a scalar w.r.t. controls / pred_speed in, parameter gradients accumulated into `grads`.
  * part = -1 runs the whole backward; parts 0..4 (heads+layer4, layer3, layer2, layer1, stem; in that order) let the
- * host start the allreduce of the gradient range a part completed while the next part runs (data parallelism). */
+ * host start the allreduce of the gradient range a part completed while the next part runs (data parallelism).
+ * Parts 5 and 6 are the two halves of part 4 (5: the stem's max-pool / ReLU / BatchNorm backward, 6: conv1's weight
+ * gradient), for a caller that wants to start the optimizer between them (ABI 4). */
 int cilrs_model_backward(cilrs_model* m, int batch, int mode, int part, const float* dcontrols, const float* dspeed,
                          const float* speed, const long long* command, float dropout_p, void* stream);
 /* first parameter-tensor index (into cilrs_model_param_layout) whose gradient backward part `part` completes;
