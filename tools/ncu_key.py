@@ -10,11 +10,11 @@ want = ['gpu__time_duration.sum', 'sm__cycles_elapsed.max', 'sm__cycles_active.a
 for f in sys.argv[1:]:
     out = subprocess.run(['ncu', '-i', f, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     r = list(csv.reader(out.splitlines()))
-    hdr = r[0]
+    hdr, units = r[0], r[1]
     print('==', f)
     for row in r[2:]:
-        for h, v in zip(hdr, row):
+        for h, v, un in zip(hdr, row, units):
             if h == 'Kernel Name':
                 print(' --', v[:80])
             if any(h == w or h.startswith(w + '.') and h.count('.') == w.count('.') for w in want) or h in want:
-                print('   %-86s %s' % (h, v))
+                print('   %-86s %s %s' % (h, v, un))
