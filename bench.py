@@ -16,7 +16,8 @@ tensor-core convs with fp32 accumulate, fp32 master weights / heads / optimizer.
   roofline     : the implicit-GEMM conv kernels (conv_flat_kernel: 58 of the 77 fprop+dgrad launches, conv_gemm_kernel: stem /
                  stride-2 / 1x1): algorithmic conv FLOPs / time inside those launches (CUDA events around every launch of
                  one eager step; the launches also carry the fused BN statistics / ReLU mask / BN-backward reductions)
-  cpu_baseline : the oracle port of the reference step (torch fp32 on the host cores), rank 0 / N=1 only
+  cpu_baseline : the reference's own `class CILRS` train step (oracle/_ref, extracted at build() time; the oracle port only if that
+                 file is absent) in torch fp32 on ALL host cores, bounded sample, rank 0 / N=1 only
 """
 import argparse
 import json
