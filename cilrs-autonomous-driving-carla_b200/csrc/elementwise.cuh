@@ -645,9 +645,9 @@ inline int ew_reduce_grid(long long nvec, int C) {
 inline int ew_grid(long long nvec, int C, int per_thread = 2, int ctas_per_sm = 3) {
   (void)C;
   long long blocks = (nvec + (long long)EW_THREADS * per_thread - 1) / ((long long)EW_THREADS * per_thread);
-  if (blocks > EW_MAX_BLOCKS) blocks = EW_MAX_BLOCKS;
   // the 4-way unrolled streaming kernels: exactly the resident CTAs (bn_apply: 70 registers -> 3 per SM, bn_bwd_apply: 123 -> 2)
-  if (per_thread == 4 && blocks > 148 * ctas_per_sm) blocks = 148 * ctas_per_sm;
+  if (per_thread == 4) { if (blocks > 148 * ctas_per_sm) blocks = 148 * ctas_per_sm; }
+  else if (blocks > EW_MAX_BLOCKS) blocks = EW_MAX_BLOCKS;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }

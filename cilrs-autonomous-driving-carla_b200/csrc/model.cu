@@ -542,7 +542,12 @@ static int run_bn_apply(Model& m, int B, const PadGeom& g, const __nv_bfloat16* 
     d.momentum = 0.1f; d.eps = 1e-5f; d.update_running = update_running;
   }
   ++g_cilrs_launches;
-  return cuda_status(launch_pdl(bn_apply_kernel, dim3(ew_grid(nvec, bn.C, 4)), dim3(EW_THREADS), 0, s, x, (const float*)bn.vec,
+  // CTAs per SM the grid is capped at. Three are resident (70 registers), but measured in the step at batch 128 TWO is the
+  // sweet spot: 2.636 ms per step with 3, 2.585 with 2, 2.66 with 1 or 6 (every CTA pays the deferred finalize in its prologue,
+  // and the CTAs of the convolution it follows are still draining when it starts). CILRS_EW_FWD_CAP overrides.
+  static int cap_f = -1;
+  if (cap_f < 0) { const char* e = getenv("CILRS_EW_FWD_CAP"); cap_f = e ? atoi(e) : 2; if (cap_f < 1) cap_f = 2; }
+  return cuda_status(launch_pdl(bn_apply_kernel, dim3(ew_grid(nvec, bn.C, 4, cap_f)), dim3(EW_THREADS), 0, s, x, (const float*)bn.vec,
                                 (const float*)(bn.vec + bn.C), res, x2, (const float*)(bn2 ? bn2->vec : nullptr),
                                 (const float*)(bn2 ? bn2->vec + bn2->C : nullptr), out, nvec, bn.C, relu, g, bits, d));
 }
@@ -748,7 +753,9 @@ static int run_bn_bwd_apply(Model& m, int B, const PadGeom& g, const BnRef& bn, 
     ap.defer.dgamma = m.grads + m.slots[bn.gamma].off; ap.defer.dbeta = m.grads + m.slots[bn.beta].off;
   }
   ++g_cilrs_launches;
-  return cuda_status(launch_pdl(bn_bwd_apply_kernel<false>, dim3(ew_grid(nvec, bn.C, 4, 2)), dim3(EW_THREADS), 0, s, ap));
+  static int cap_b = -1;   // CTAs per SM the backward apply grid is capped at (2 = the resident CTAs; 1 measured the same, 4 and 8 slower)
+  if (cap_b < 0) { const char* e = getenv("CILRS_EW_BWD_CAP"); cap_b = e ? atoi(e) : 2; if (cap_b < 1) cap_b = 2; }
+  return cuda_status(launch_pdl(bn_bwd_apply_kernel<false>, dim3(ew_grid(nvec, bn.C, 4, cap_b)), dim3(EW_THREADS), 0, s, ap));
 }
 
 static int heads_backward(Model& m, int B, const float* dcontrols, const float* dspeed, const float* speed,
