@@ -367,6 +367,18 @@ enum FwdMode { MODE_TRAIN = 0, MODE_FROZEN = 1, MODE_INFER = 2 };
   } while (0)
 #define CKL() CK(cuda_status(cudaGetLastError()))
 
+// launch-geometry knobs of the stem's elementwise kernels and the stand-alone reduce (CTAs per SM; measurement aids)
+static int env_cap(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : dflt;
+  return v >= 1 ? v : dflt;
+}
+static int capped_grid(long long blocks, int per_sm) {
+  const long long cap = 148LL * per_sm;
+  if (blocks > cap) blocks = cap;
+  return blocks < 1 ? 1 : (int)blocks;
+}
+
 static int add_old(Model& m, const ConvGemmParams& p) { m.old_plans.push_back(p); return (int)m.old_plans.size() - 1; }
 static int add_flat(Model& m, const FlatConvParams& p) { m.flat_plans.push_back(p); return (int)m.flat_plans.size() - 1; }
 
@@ -644,7 +656,8 @@ static int forward(Model& m, int B, int mode, const float* image, const void* x_
   } else {
     PROF(m, PC_BN_FWD, s, CK(run_bn_finalize(m, m.stem.bn, conv_gemm_grid(&m.old_plans[m.stem_fwd]), (double)B * 44 * 100, training,
                                              update_running, s)));
-    bn_relu_maxpool_sel_kernel<<<ew_grid(pool_vec, 64), EW_THREADS, 0, s>>>(m.stem.y, m.stem.bn.vec, m.stem.bn.vec + 64, m.pool_out, m.pool_arg,
+    static const int pool_cap = env_cap("CILRS_EW_POOL_CAP", 4);
+    bn_relu_maxpool_sel_kernel<<<capped_grid(ew_grid(pool_vec, 64), pool_cap), EW_THREADS, 0, s>>>(m.stem.y, m.stem.bn.vec, m.stem.bn.vec + 64, m.pool_out, m.pool_arg,
                                                                             m.pool_ysel, B, 44, 100, 64, 22, 50, kGeom0.Hp, kGeom0.Wp); ++g_cilrs_launches;
     CKL();
     CK(pack_join(m, s));   // the trunk's operands may have been repacked beside the stem (cilrs_model_refresh_async)
@@ -736,7 +749,8 @@ static int run_bn_bwd_reduce(Model& m, int B, const PadGeom& g, const BnRef& bn,
   rp.dgamma = m.grads + m.slots[bn.gamma].off; rp.dbeta = m.grads + m.slots[bn.beta].off;
   rp.dz_out = grad; rp.geom = g;
   ++g_cilrs_launches;
-  return cuda_status(launch_pdl(bn_bwd_reduce_kernel<false>, dim3(ew_reduce_grid(nvec, bn.C)), dim3(EW_THREADS), 0, s, rp));
+  static const int red_cap = env_cap("CILRS_EW_REDUCE_CAP", 2);
+  return cuda_status(launch_pdl(bn_bwd_reduce_kernel<false>, dim3(capped_grid(ew_reduce_grid(nvec, bn.C), red_cap)), dim3(EW_THREADS), 0, s, rp));
 }
 
 // dy = gamma * rstd * (dz - bsum/n - xhat * bdot/n)   (frozen: gamma * rstd * dz); dz is already ReLU-masked
@@ -949,7 +963,8 @@ static int backward(Model& m, int B, int mode, int part, const float* dcontrols,
     ap.bsum = rp.bsum; ap.bdot = rp.bdot; ap.inv_count = (float)(1.0 / ((double)B * 4400.0));
     ap.frozen = frozen; ap.B = B; ap.H = 44; ap.W = 100; ap.OH = 22; ap.OW = 50; ap.OHp = kGeom0.Hp; ap.OWp = kGeom0.Wp; ap.C = 64; ap.dy = m.dy_stem;
     const long long nblk = (long long)B * 22 * 50 * 8;
-    PROF(m, PC_BN_BWD, s, { ++g_cilrs_launches; CK(cuda_status(launch_pdl(stem_bwd_apply_kernel, dim3(ew_grid(nblk, 64, 2, 2)), dim3(EW_THREADS), 0, s, ap))); });
+    static const int stem_cap = env_cap("CILRS_EW_STEM_CAP", 4);
+    PROF(m, PC_BN_BWD, s, { ++g_cilrs_launches; CK(cuda_status(launch_pdl(stem_bwd_apply_kernel, dim3(capped_grid(ew_grid(nblk, 64, 2, 2), stem_cap)), dim3(EW_THREADS), 0, s, ap))); });
   }
   if (stem_wg) PROF(m, PC_WGRAD, s, CK(run_wgrad_old(m, m.stem_wgrad, m.stem.w, s)));
   // join: everything after this call on the caller's stream (allreduce of the part, Adam) sees the finished gradients.
