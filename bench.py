@@ -178,6 +178,17 @@ def reference_initial_state_dict():
     return O.synthetic_state_dict(0, perturb_bn=False), "port"
 
 
+def own_initial_state_dict():
+    """Random-init weights for OUR arm, made by our own module's constructor under torch.manual_seed(0) (the reference's
+    initialisers: kaiming fan_out convs, BN 1/0, default Linear init - tests/test_host_cpu.py) - nothing under oracle/ is touched.
+    The CPU leg loads this very state_dict into the reference's class (strict), so both start from the same weights."""
+    import torch
+    from cilrs_b200.model import CILRS
+    torch.manual_seed(0)
+    m = CILRS(num_commands=4, dropout=0.0)
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}, "cilrs_b200.CILRS ctor"
+
+
 def cpu_reference_step_rate(batch, steps, warmup, state_dict=None, batches=None):
     """The reference's train step on the host cores, ALL of them (torch.set_num_threads(os.cpu_count()): torchrun exports
     OMP_NUM_THREADS=1, which must not apply to this arm): `model(imgs, speeds, cmds)` -> loss -> zero_grad -> backward ->
@@ -406,8 +417,8 @@ def main():
 
     lib = _lib.lib()
     lib.cilrs_launch_count.restype = ctypes.c_longlong
-    # random-init weights as the reference constructs them, loaded through the checkpoint interface (both arms start equal)
-    init_sd, init_kind = reference_initial_state_dict()
+    # random-init weights from our own constructor, loaded through the checkpoint interface (the CPU leg loads the same ones)
+    init_sd, init_kind = own_initial_state_dict()
     model = CILRS(num_commands=4, dropout=0.0)
     model.load_state_dict(init_sd, strict=True)
     model = model.to(dev)
@@ -538,7 +549,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                    "cuda_graph": trainer.graph is not None, "cuda_graph_error": trainer.graph_error, "settle_steps": settle,
-                   "initial_weights": "reference ctor under torch.manual_seed(0) (%s), loaded via load_state_dict" % init_kind,
+                   "initial_weights": "%s under torch.manual_seed(0), loaded via load_state_dict (the CPU leg loads the same state_dict)" % init_kind,
                    "allreduce_schedule": trainer.overlap_allreduce if world > 1 else None,
                    "grad_comm": trainer.grad_comm if world > 1 else None,
                    "async_parts": trainer.async_parts if world > 1 else None,

@@ -5,8 +5,8 @@ import torch
 import cilrs_b200  # noqa
 from cilrs_b200.model import CILRS
 from cilrs_b200.train import FusedTrainer
-from oracle import cilrs_oracle as O
-sd = O.synthetic_state_dict(0)
+torch.manual_seed(0)
+sd = {k: v.clone() for k, v in CILRS(num_commands=4, dropout=0.0).state_dict().items()}   # one random initialisation for every run
 g = torch.Generator().manual_seed(21)
 host = []
 for _ in range(4):

@@ -10,7 +10,7 @@ from cilrs_b200.train import FusedTrainer
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 dev = torch.device("cuda", 0)
-sd, _ = bench.reference_initial_state_dict()
+sd, _ = bench.own_initial_state_dict()
 model = CILRS(num_commands=4, dropout=0.0)
 model.load_state_dict(sd, strict=True)
 model = model.to(dev)
